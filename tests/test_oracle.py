@@ -1,0 +1,163 @@
+"""The oracle against the reference-generated golden vectors and against itself (CPU only)."""
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import GOLDEN, rel_inf
+from oracle import layers_np as O
+from oracle import ref_loader
+
+
+def test_rescale_matches_reference_vectors(graph_l4):
+    for L, Lt in zip(graph_l4["L"], graph_l4["Lt"]):
+        mine = O.rescale_L(L, 2)
+        mine.sort_indices()
+        assert mine.dtype == Lt.dtype == np.float32
+        assert np.array_equal(mine.indptr, Lt.indptr) and np.array_equal(mine.indices, Lt.indices)
+        assert np.array_equal(mine.data, Lt.data)
+        assert abs(mine.diagonal()).max() == 0  # lmax=2 => zero diagonal, SURVEY A.4
+
+
+def test_chebyshev_recursion_matches_reference_graph_chebyshev(graph_l4):
+    """graph.chebyshev (graph.py:155-172) ran in the build container; bit-exact restatement."""
+    z = np.load(os.path.join(GOLDEN, "ref_chebyshev.npz"))
+    for name in "abcde":
+        lvl, K = (int(v) for v in z["meta_" + name])
+        Xt = O.chebyshev_basis(graph_l4["Lt"][lvl], z["X_" + name], K)
+        assert Xt.dtype == np.float32
+        assert np.array_equal(Xt, z["Xt_" + name]), name
+
+
+def test_chebyshev5_equals_chebyshev2_and_einsum(graph_l4):
+    """The TF-op transcription (chebyshev5) and the py_func route (chebyshev2) are the same filter,
+    and the W row order is f*K + k."""
+    rng = np.random.RandomState(0)
+    L = graph_l4["L"][2]
+    x = rng.randn(3, 100, 6).astype(np.float32)
+    W = rng.randn(6 * 4, 5).astype(np.float32)
+    y5 = O.chebyshev5(x, L, W, 4, np.float64)
+    y2 = O.chebyshev2(x, L, W, 4, np.float64)
+    assert rel_inf(y5, y2) < 1e-13
+    Lt = graph_l4["Lt"][2].astype(np.float64)
+    T = [x.astype(np.float64)]
+    T.append(np.einsum("mn,bnf->bmf", Lt.toarray(), T[0]))
+    for _ in range(2, 4):
+        T.append(2 * np.einsum("mn,bnf->bmf", Lt.toarray(), T[-1]) - T[-2])
+    T = np.stack(T, -1)  # [B, M, Fin, K]
+    ref = np.einsum("bmfk,fko->bmo", T, W.astype(np.float64).reshape(6, 4, 5))
+    assert rel_inf(y5, ref) < 1e-13
+    # K = 1 is a per-vertex dense layer: no neighbour mixing
+    W1 = rng.randn(6, 5).astype(np.float32)
+    assert rel_inf(O.chebyshev5(x, L, W1, 1, np.float64), x.astype(np.float64) @ W1) < 1e-14
+
+
+def test_fourier_is_U_W_Ut(graph_l4):
+    rng = np.random.RandomState(1)
+    L = graph_l4["L"][3]
+    M = L.shape[0]
+    x = rng.randn(2, M, 3)
+    W = rng.randn(M, 4, 3)
+    lamb, U = np.linalg.eigh(L.toarray().astype(np.float64))
+    xh = np.einsum("nm,bnf->bmf", U, x)
+    yh = np.einsum("mof,bmf->bmo", W, xh)
+    ref = np.einsum("nm,bmo->bno", U, yh)
+    got = O.filter_in_fourier(x, U.T, W, np.float64)
+    assert rel_inf(got, ref) < 1e-12
+
+
+def test_mpool_same_padding_and_first_max():
+    x = np.array([[[1.0], [3.0], [3.0], [2.0], [5.0], [0.0]]])  # M = 6
+    y, a = O.mpool1(x, 4, with_argmax=True)  # ceil(6/4)=2, pad 2 -> one before, one after
+    assert y[0, :, 0].tolist() == [3.0, 5.0]
+    assert a[0, :, 0].tolist() == [2, 1]  # window 0 = [pad, x0, x1, x2]: first max (x1) at offset 2
+    y, a = O.mpool1(x, 2, with_argmax=True)
+    assert y[0, :, 0].tolist() == [3.0, 3.0, 5.0] and a[0, :, 0].tolist() == [1, 0, 0]
+    dy = np.ones((1, 3, 1))
+    assert O.mpool1_bwd(dy, a, 2, 6)[0, :, 0].tolist() == [0, 1, 1, 0, 1, 0]
+    assert O.mpool1(x, 1) is x
+
+
+def test_backward_against_finite_differences(graph_l4):
+    rng = np.random.RandomState(3)
+    for filt, brelu, lvl, Fin, Fout, K, p in (("chebyshev5", "b1relu", 3, 3, 4, 4, 2),
+                                               ("chebyshev5", "b2relu", 4, 2, 3, 3, 1),
+                                               ("fourier", "b1relu", 4, 2, 3, 0, 1)):
+        L = graph_l4["L"][lvl]
+        M = L.shape[0]
+        x = rng.randn(2, M, Fin)
+        W = rng.randn(M, Fout, Fin) if filt == "fourier" else rng.randn(Fin * K, Fout)
+        b = rng.randn(M, Fout) if brelu == "b2relu" else rng.randn(Fout)
+        dy = rng.randn(2, M // p, Fout)
+        pr = [dict(W=W, b=b, K=K, p=p)]
+
+        def f(x_, W_, b_):
+            y = O.conv_stack(x_, [L], [dict(W=W_, b=b_, K=K, p=p)], filter=filt, brelu=brelu, dtype=np.float64)
+            return float((y * dy).sum())
+
+        _, tr = O.conv_stack(x, [L], pr, filter=filt, brelu=brelu, dtype=np.float64, keep=True)
+        dx, g = O.conv_stack_bwd(tr, [L], pr, dy, filter=filt, brelu=brelu, dtype=np.float64, first_needs_dx=True)
+        eps = 1e-6
+        for arr, grad, which in ((x, dx, 0), (W, g[0]["dW"], 1), (b, g[0]["db"], 2)):
+            for _ in range(6):
+                idx = tuple(rng.randint(0, s) for s in arr.shape)
+                hi, lo = arr.copy(), arr.copy()
+                hi[idx] += eps
+                lo[idx] -= eps
+                args_hi = [x, W, b]
+                args_lo = [x, W, b]
+                args_hi[which], args_lo[which] = hi, lo
+                num = (f(*args_hi) - f(*args_lo)) / (2 * eps)
+                assert abs(num - grad[idx]) < 1e-5 * max(1.0, abs(num)), (filt, which, idx)
+
+
+def test_layer_cases_reproduce(graph_l4, layer_cases):
+    """The committed oracle vectors are reproduced by the oracle as it stands."""
+    for name, c in layer_cases.items():
+        lvl, B, Fin, Fout, K, p = (int(v) for v in c["meta"])
+        filt, brelu = str(c["kind"]).split("/")
+        L = graph_l4["L"][lvl]
+        pr = [dict(W=c["W"], b=c["b"], K=K, p=p)]
+        y, tr = O.conv_stack(c["x"], [L], pr, filter=filt, brelu=brelu, dtype=np.float64, keep=True)
+        if filt == "fourier":
+            # eigenvectors of a degenerate spectrum are host-BLAS dependent: rebuild with the stored basis
+            z = O.filter_in_fourier(c["x"], c["Ut"], c["W"], np.float64)
+            a = O.b1relu(z, c["b"]) if brelu == "b1relu" else O.b2relu(z, c["b"])
+            y, am = O.mpool1(a, p, with_argmax=True)
+            assert rel_inf(y, c["y64"]) < 1e-5, name
+            continue
+        assert rel_inf(y, c["y64"]) < 1e-12, name
+        assert np.array_equal(tr[0]["argmax"], c["argmax"]), name
+        # as-run fp32 oracle vs fp64 truth: the noise floor the 1e-4 bar sits above
+        assert rel_inf(c["y32"], c["y64"]) < 2e-5, name
+
+
+def test_select_laplacians_and_head():
+    assert O.select_laplacians(list("abcde"), [4, 4]) == ["a", "c"]
+    assert O.select_laplacians(list("ab"), [1, 1, 1, 1, 1, 1]) == ["a"] * 6
+    assert O.select_laplacians(list("abcdefg"), [1, 4, 1, 4, 1, 4]) == ["a", "a", "c", "c", "e", "e"]
+    rng = np.random.RandomState(5)
+    x = rng.randn(4, 25, 32)
+    fcs = [(rng.randn(25, 8), rng.randn(8)), (rng.randn(8, 22), rng.randn(22))]
+    out = O.head(x, fcs, np.float64)
+    assert out.shape == (4, 22)
+    ref = np.maximum(x.mean(-1) @ fcs[0][0] + fcs[0][1], 0) @ fcs[1][0] + fcs[1][1]
+    assert rel_inf(out, ref) < 1e-14
+    lab = np.array([0, 5, 20, 3])
+    l = O.loss(out, lab, [fcs[0][0]], 5e-4)
+    p = np.exp(out - out.max(1, keepdims=True))
+    p /= p.sum(1, keepdims=True)
+    assert abs(l - (-np.log(p[np.arange(4), lab]).mean() + 5e-4 * 0.5 * (fcs[0][0] ** 2).sum())) < 1e-12
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference sources only exist in the build container")
+def test_oracle_against_live_reference(graph_l4):
+    """Container-only: the reference's functions executed now agree with the oracle bit for bit."""
+    graph, coarsening = ref_loader.load()
+    rng = np.random.RandomState(21)
+    for lvl, K in ((0, 5), (2, 8), (4, 3)):
+        L = graph_l4["L"][lvl]
+        Lt_ref = graph.rescale_L(sp.csr_matrix(L, copy=True), lmax=2)
+        X = rng.randn(L.shape[0], 9).astype(np.float32)
+        assert np.array_equal(graph.chebyshev(Lt_ref, X, K), O.chebyshev_basis(O.rescale_L(L), X, K))
