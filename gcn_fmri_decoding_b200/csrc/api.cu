@@ -1,0 +1,329 @@
+// extern "C" entry points of libgcnb200.so: argument validation, kernel-family dispatch, and the
+// small stand-alone kernels (b1relu/b2relu, mpool1, perm gather, mean over filters).
+#include <algorithm>
+#include <atomic>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace gcnb {
+
+static thread_local char g_err[512] = "no error";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+int device_info(DeviceInfo* out) {
+  static std::mutex mu;
+  static DeviceInfo cache[64];
+  static bool have[64] = {false};
+  int dev = 0;
+  GCNB_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) {
+    set_error("device ordinal %d out of range", dev);
+    return GCNB_ERR_INVALID;
+  }
+  std::lock_guard<std::mutex> lock(mu);
+  if (!have[dev]) {
+    GCNB_CUDA(cudaDeviceGetAttribute(&cache[dev].sm_count, cudaDevAttrMultiProcessorCount, dev));
+    GCNB_CUDA(cudaDeviceGetAttribute(&cache[dev].smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    have[dev] = true;
+  }
+  *out = cache[dev];
+  return GCNB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stand-alone elementwise kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void k_brelu_fwd(const float* __restrict__ x, const float* __restrict__ bias, float* __restrict__ y,
+                            long long total, int M, int F, int bias_mode) {
+  const long long MF = (long long)M * F;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    float v = x[i];
+    if (bias_mode == GCNB_BIAS_PER_FILTER) v += bias[i % F];
+    else if (bias_mode == GCNB_BIAS_PER_VERTEX) v += bias[i % MF];
+    y[i] = fmaxf(v, 0.f);
+  }
+}
+
+__global__ void k_brelu_bwd(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dx,
+                            long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    dx[i] = y[i] > 0.f ? dy[i] : 0.f;
+}
+
+// db2[m*F+o] = sum_b dx[b][m][o]  (fixed order over b)
+__global__ void k_bias_grad_vertex(const float* __restrict__ dx, float* __restrict__ db2, int B, long long MF) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < MF; i += (long long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += dx[(long long)b * MF + i];
+    db2[i] = s;
+  }
+}
+
+__global__ void k_bias_grad_filter(const float* __restrict__ db2, float* __restrict__ db, int M, int F) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= F) return;
+  float s = 0.f;
+  for (int m = 0; m < M; ++m) s += db2[(long long)m * F + o];
+  db[o] = s;
+}
+
+__global__ void k_mpool_fwd(const float* __restrict__ x, float* __restrict__ y, uint8_t* __restrict__ argmax, int B,
+                            int M, int F, int p) {
+  const int Mo = (M + p - 1) / p;
+  const int before = (Mo * p - M) / 2;
+  const long long total = (long long)B * Mo * F;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int o = (int)(i % F);
+    const int j = (int)((i / F) % Mo);
+    const int b = (int)(i / ((long long)F * Mo));
+    float best = -INFINITY;
+    int bi = 0;
+    for (int w = 0; w < p; ++w) {
+      const int m = j * p - before + w;
+      if (m < 0 || m >= M) continue;
+      const float v = x[((long long)b * M + m) * F + o];
+      if (v > best) { best = v; bi = w; }
+    }
+    y[i] = best;
+    if (argmax) argmax[i] = (uint8_t)bi;
+  }
+}
+
+__global__ void k_mpool_bwd(const float* __restrict__ dy, const uint8_t* __restrict__ argmax, float* __restrict__ dx,
+                            int B, int M, int F, int p) {
+  const int Mo = (M + p - 1) / p;
+  const int before = (Mo * p - M) / 2;
+  const long long total = (long long)B * Mo * F;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int o = (int)(i % F);
+    const int j = (int)((i / F) % Mo);
+    const int b = (int)(i / ((long long)F * Mo));
+    const int am = argmax[i];
+    const float g = dy[i];
+    for (int w = 0; w < p; ++w) {
+      const int m = j * p - before + w;
+      if (m < 0 || m >= M) continue;
+      dx[((long long)b * M + m) * F + o] = (w == am) ? g : 0.f;
+    }
+  }
+}
+
+__global__ void k_perm_gather(const float* __restrict__ x, const int32_t* __restrict__ perm, float* __restrict__ y,
+                              int B, int M_in, int M_out, int F) {
+  const long long total = (long long)B * M_out * F;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)(i % F);
+    const int m = (int)((i / F) % M_out);
+    const int b = (int)(i / ((long long)F * M_out));
+    const int src = perm[m];
+    y[i] = (src >= 0 && src < M_in) ? x[((long long)b * M_in + src) * F + f] : 0.f;
+  }
+}
+
+// y[r] = mean_f x[r][f]  -- one warp per row, shuffle tree (fixed order)
+__global__ void k_mean_f_fwd(const float* __restrict__ x, float* __restrict__ y, long long rows, int F) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp; r < rows; r += nwarps) {
+    float s = 0.f;
+    for (int f = lane; f < F; f += 32) s += x[r * F + f];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if (lane == 0) y[r] = s / (float)F;
+  }
+}
+
+__global__ void k_mean_f_bwd(const float* __restrict__ dy, float* __restrict__ dx, long long rows, int F) {
+  const long long total = rows * F;
+  const float inv = 1.f / (float)F;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    dx[i] = dy[i / F] * inv;
+}
+
+static inline unsigned grid_for(long long total, int block = 256) {
+  return (unsigned)std::max<long long>(1, std::min<long long>(ceil_div_ll(total, block), 148 * 16));
+}
+
+static bool is_pow2(int v) { return v >= 1 && (v & (v - 1)) == 0; }
+
+static int check_layer(const char* who, const gcnb_csr* L, int B, int Fin, int Fout, int K, int p, int bias_mode,
+                       const float* bias) {
+  GCNB_REQUIRE(L != nullptr && L->rowptr && (L->nnz == 0 || (L->col && L->val)), "%s: NULL operator", who);
+  GCNB_REQUIRE(L->M >= 1 && L->nnz >= 0, "%s: bad operator size M=%d nnz=%d", who, L->M, L->nnz);
+  GCNB_REQUIRE(B >= 1 && Fin >= 1 && Fout >= 1, "%s: B, Fin, Fout must be >= 1 (got %d, %d, %d)", who, B, Fin, Fout);
+  GCNB_REQUIRE(K >= 1, "%s: polynomial order K must be >= 1 (got %d)", who, K);
+  GCNB_REQUIRE(is_pow2(p) && p <= 128, "%s: pooling size must be a power of 2 in [1,128] (got %d)", who, p);
+  GCNB_REQUIRE(bias_mode >= GCNB_BIAS_NONE && bias_mode <= GCNB_BIAS_PER_VERTEX, "%s: bad bias_mode %d", who, bias_mode);
+  GCNB_REQUIRE(bias_mode == GCNB_BIAS_NONE || bias != nullptr, "%s: bias is NULL but bias_mode=%d", who, bias_mode);
+  return GCNB_OK;
+}
+
+}  // namespace gcnb
+
+using namespace gcnb;
+
+extern "C" {
+
+int gcnb_version(void) { return 100; }
+
+const char* gcnb_last_error_string(void) { return g_err; }
+
+unsigned long long gcnb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int gcnb_cheb_fused_supported(int B, int M, int nnz, int Fin, int Fout, int K, int p, int backward, int need_dx) {
+  LayerShape s{B, M, nnz, Fin, Fout, K, p};
+  return backward ? (fused_bwd_supported(s, need_dx != 0) ? 1 : 0) : (fused_fwd_supported(s) ? 1 : 0);
+}
+
+size_t gcnb_cheb_workspace_bytes(int B, int M, int nnz, int Fin, int Fout, int K, int p, int backward, int need_dx,
+                                 int algo) {
+  LayerShape s{B, M, nnz, Fin, Fout, K, p};
+  const bool fused_ok = backward ? fused_bwd_supported(s, need_dx != 0) : fused_fwd_supported(s);
+  if (algo == GCNB_ALGO_FUSED || (algo == GCNB_ALGO_AUTO && fused_ok))
+    return fused_ok ? fused_cheb_workspace(s, backward != 0, need_dx != 0) : 0;
+  return general_cheb_workspace(s, backward != 0, need_dx != 0);
+}
+
+int gcnb_cheb_fwd_f32(const float* x, const int32_t* perm, int M_in, const gcnb_csr* L, const float* W,
+                      const float* bias, float* y, uint8_t* argmax, int B, int Fin, int Fout, int K, int p,
+                      int bias_mode, int relu, int algo, void* workspace, size_t workspace_bytes,
+                      gcnb_stream_t stream) {
+  int rc = check_layer("gcnb_cheb_fwd_f32", L, B, Fin, Fout, K, p, bias_mode, bias);
+  if (rc) return rc;
+  GCNB_REQUIRE(x && W && y, "gcnb_cheb_fwd_f32: x, W and y must not be NULL");
+  GCNB_REQUIRE(perm != nullptr || M_in == L->M, "gcnb_cheb_fwd_f32: without perm, M_in (%d) must equal M (%d)", M_in,
+               L->M);
+  GCNB_REQUIRE(M_in >= 1, "gcnb_cheb_fwd_f32: M_in must be >= 1");
+  LayerShape s{B, L->M, L->nnz, Fin, Fout, K, p};
+  Workspace ws(workspace, workspace_bytes);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool fused_ok = fused_fwd_supported(s);
+  if (algo == GCNB_ALGO_FUSED && !fused_ok) {
+    set_error("gcnb_cheb_fwd_f32: fused kernels do not support B=%d M=%d nnz=%d Fin=%d Fout=%d K=%d p=%d", B, s.M,
+              s.nnz, Fin, Fout, K, p);
+    return GCNB_ERR_INVALID;
+  }
+  if (algo == GCNB_ALGO_FUSED || (algo == GCNB_ALGO_AUTO && fused_ok))
+    return fused_cheb_fwd(x, perm, M_in, *L, W, bias, y, argmax, s, bias_mode, relu, ws, st);
+  return general_cheb_fwd(x, perm, M_in, *L, W, bias, y, argmax, s, bias_mode, relu, ws, st);
+}
+
+int gcnb_cheb_bwd_f32(const float* x, const int32_t* perm, int M_in, const float* y, const uint8_t* argmax,
+                      const float* dy, const gcnb_csr* L,
+                      const gcnb_csr* Lt, const float* W, float* dx, float* dW, float* db, int B, int Fin,
+                      int Fout, int K, int p, int bias_mode, int relu, int algo, void* workspace,
+                      size_t workspace_bytes, gcnb_stream_t stream) {
+  int rc = check_layer("gcnb_cheb_bwd_f32", L, B, Fin, Fout, K, p, bias_mode, reinterpret_cast<const float*>(1));
+  if (rc) return rc;
+  GCNB_REQUIRE(x && y && dy && W && dW, "gcnb_cheb_bwd_f32: x, y, dy, W and dW must not be NULL");
+  GCNB_REQUIRE(p == 1 || argmax != nullptr, "gcnb_cheb_bwd_f32: argmax is required when p > 1");
+  GCNB_REQUIRE(perm != nullptr || M_in == L->M, "gcnb_cheb_bwd_f32: without perm, M_in (%d) must equal M (%d)", M_in,
+               L->M);
+  GCNB_REQUIRE(bias_mode == GCNB_BIAS_NONE || db != nullptr, "gcnb_cheb_bwd_f32: db is NULL but bias_mode=%d", bias_mode);
+  GCNB_REQUIRE(dx == nullptr || K == 1 || (Lt && Lt->M == L->M && Lt->nnz == L->nnz),
+               "gcnb_cheb_bwd_f32: dx needs the transposed operator Lt with the same M and nnz");
+  LayerShape s{B, L->M, L->nnz, Fin, Fout, K, p};
+  Workspace ws(workspace, workspace_bytes);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool fused_ok = fused_bwd_supported(s, dx != nullptr);
+  if (algo == GCNB_ALGO_FUSED && !fused_ok) {
+    set_error("gcnb_cheb_bwd_f32: fused kernels do not support B=%d M=%d nnz=%d Fin=%d Fout=%d K=%d p=%d", B, s.M,
+              s.nnz, Fin, Fout, K, p);
+    return GCNB_ERR_INVALID;
+  }
+  if (algo == GCNB_ALGO_FUSED || (algo == GCNB_ALGO_AUTO && fused_ok))
+    return fused_cheb_bwd(x, perm, M_in, y, argmax, dy, *L, Lt, W, dx, dW, db, s, bias_mode, relu, ws, st);
+  return general_cheb_bwd(x, perm, M_in, y, argmax, dy, *L, Lt, W, dx, dW, db, s, bias_mode, relu, ws, st);
+}
+
+int gcnb_brelu_fwd_f32(const float* x, const float* bias, float* y, int B, int M, int F, int bias_mode,
+                       gcnb_stream_t stream) {
+  GCNB_REQUIRE(x && y && B >= 1 && M >= 1 && F >= 1, "gcnb_brelu_fwd_f32: bad arguments");
+  GCNB_REQUIRE(bias_mode == GCNB_BIAS_NONE || bias, "gcnb_brelu_fwd_f32: bias is NULL");
+  const long long total = (long long)B * M * F;
+  k_brelu_fwd<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, bias, y, total, M, F, bias_mode);
+  GCNB_LAUNCH_CHECK("k_brelu_fwd");
+  return GCNB_OK;
+}
+
+int gcnb_brelu_bwd_f32(const float* dy, const float* y, float* dx, float* db, int B, int M, int F, int bias_mode,
+                       void* workspace, size_t workspace_bytes, gcnb_stream_t stream) {
+  GCNB_REQUIRE(dy && y && dx && B >= 1 && M >= 1 && F >= 1, "gcnb_brelu_bwd_f32: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long total = (long long)B * M * F, MF = (long long)M * F;
+  k_brelu_bwd<<<grid_for(total), 256, 0, st>>>(dy, y, dx, total);
+  GCNB_LAUNCH_CHECK("k_brelu_bwd");
+  if (bias_mode == GCNB_BIAS_NONE || db == nullptr) return GCNB_OK;
+  float* db2 = db;
+  if (bias_mode == GCNB_BIAS_PER_FILTER) {
+    Workspace ws(workspace, workspace_bytes);
+    db2 = ws.take<float>((size_t)MF);
+    if (!db2) {
+      set_error("gcnb_brelu_bwd_f32: b1relu needs a workspace of M*F floats (+256 B)");
+      return GCNB_ERR_WORKSPACE;
+    }
+  }
+  k_bias_grad_vertex<<<grid_for(MF), 256, 0, st>>>(dx, db2, B, MF);
+  GCNB_LAUNCH_CHECK("k_bias_grad_vertex");
+  if (bias_mode == GCNB_BIAS_PER_FILTER) {
+    k_bias_grad_filter<<<ceil_div(F, 128), 128, 0, st>>>(db2, db, M, F);
+    GCNB_LAUNCH_CHECK("k_bias_grad_filter");
+  }
+  return GCNB_OK;
+}
+
+int gcnb_mpool_fwd_f32(const float* x, float* y, uint8_t* argmax, int B, int M, int F, int p, gcnb_stream_t stream) {
+  GCNB_REQUIRE(x && y && B >= 1 && M >= 1 && F >= 1, "gcnb_mpool_fwd_f32: bad arguments");
+  GCNB_REQUIRE(is_pow2(p) && p <= 128, "gcnb_mpool_fwd_f32: pooling size must be a power of 2 in [1,128] (got %d)", p);
+  const long long total = (long long)B * ceil_div(M, p) * F;
+  k_mpool_fwd<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, argmax, B, M, F, p);
+  GCNB_LAUNCH_CHECK("k_mpool_fwd");
+  return GCNB_OK;
+}
+
+int gcnb_mpool_bwd_f32(const float* dy, const uint8_t* argmax, float* dx, int B, int M, int F, int p,
+                       gcnb_stream_t stream) {
+  GCNB_REQUIRE(dy && argmax && dx && B >= 1 && M >= 1 && F >= 1, "gcnb_mpool_bwd_f32: bad arguments");
+  GCNB_REQUIRE(is_pow2(p) && p <= 128, "gcnb_mpool_bwd_f32: pooling size must be a power of 2 in [1,128] (got %d)", p);
+  const long long total = (long long)B * ceil_div(M, p) * F;
+  k_mpool_bwd<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(dy, argmax, dx, B, M, F, p);
+  GCNB_LAUNCH_CHECK("k_mpool_bwd");
+  return GCNB_OK;
+}
+
+int gcnb_perm_gather_f32(const float* x, const int32_t* perm, float* y, int B, int M_in, int M_out, int F,
+                         gcnb_stream_t stream) {
+  GCNB_REQUIRE(x && perm && y && B >= 1 && M_in >= 1 && M_out >= M_in && F >= 1,
+               "gcnb_perm_gather_f32: bad arguments (need M_out >= M_in, coarsening.py:254)");
+  const long long total = (long long)B * M_out * F;
+  k_perm_gather<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, perm, y, B, M_in, M_out, F);
+  GCNB_LAUNCH_CHECK("k_perm_gather");
+  return GCNB_OK;
+}
+
+int gcnb_mean_f_fwd_f32(const float* x, float* y, int rows, int F, gcnb_stream_t stream) {
+  GCNB_REQUIRE(x && y && rows >= 1 && F >= 1, "gcnb_mean_f_fwd_f32: bad arguments");
+  k_mean_f_fwd<<<grid_for((long long)rows * 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, rows, F);
+  GCNB_LAUNCH_CHECK("k_mean_f_fwd");
+  return GCNB_OK;
+}
+
+int gcnb_mean_f_bwd_f32(const float* dy, float* dx, int rows, int F, gcnb_stream_t stream) {
+  GCNB_REQUIRE(dy && dx && rows >= 1 && F >= 1, "gcnb_mean_f_bwd_f32: bad arguments");
+  k_mean_f_bwd<<<grid_for((long long)rows * F), 256, 0, static_cast<cudaStream_t>(stream)>>>(dy, dx, rows, F);
+  GCNB_LAUNCH_CHECK("k_mean_f_bwd");
+  return GCNB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,104 @@
+// Shared helpers of the gcnb200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/gcnb200.h"
+
+namespace gcnb {
+
+void set_error(const char* fmt, ...);
+void count_launch();  // diagnostic counter behind gcnb_launch_count()
+
+#define GCNB_REQUIRE(cond, ...)      \
+  do {                               \
+    if (!(cond)) {                   \
+      gcnb::set_error(__VA_ARGS__);  \
+      return GCNB_ERR_INVALID;       \
+    }                                \
+  } while (0)
+
+#define GCNB_CUDA(expr)                                                         \
+  do {                                                                          \
+    cudaError_t e_ = (expr);                                                    \
+    if (e_ != cudaSuccess) {                                                    \
+      gcnb::set_error("%s failed: %s", #expr, cudaGetErrorString(e_));          \
+      return GCNB_ERR_CUDA;                                                     \
+    }                                                                           \
+  } while (0)
+
+// Launch errors are surfaced right after enqueue; no synchronisation.
+#define GCNB_LAUNCH_CHECK(name)                                                 \
+  do {                                                                          \
+    gcnb::count_launch();                                                       \
+    cudaError_t e_ = cudaGetLastError();                                        \
+    if (e_ != cudaSuccess) {                                                    \
+      gcnb::set_error("launch of %s failed: %s", name, cudaGetErrorString(e_)); \
+      return GCNB_ERR_CUDA;                                                     \
+    }                                                                           \
+  } while (0)
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
+
+// Bump allocator over the caller's workspace.
+struct Workspace {
+  char* base;
+  size_t size;
+  size_t used;
+  Workspace(void* p, size_t n) : base(static_cast<char*>(p)), size(n), used(0) {}
+  template <typename T>
+  T* take(size_t count) {
+    size_t off = align_up(used, 256);
+    size_t end = off + count * sizeof(T);
+    used = end;
+    if (end > size || base == nullptr) return nullptr;
+    return reinterpret_cast<T*>(base + off);
+  }
+};
+
+struct LayerShape {
+  int B, M, nnz, Fin, Fout, K, p;
+};
+
+// Device properties the dispatch needs, queried once per device.
+struct DeviceInfo {
+  int sm_count;
+  int smem_optin;
+};
+int device_info(DeviceInfo* out);
+
+// ---- general (HBM-resident) path, general.cu ------------------------------------------------
+size_t general_cheb_workspace(const LayerShape& s, bool backward, bool need_dx);
+int general_cheb_fwd(const float* x, const int32_t* perm, int M_in, const gcnb_csr& L, const float* W,
+                     const float* bias, float* y, uint8_t* argmax, const LayerShape& s, int bias_mode, int relu,
+                     Workspace& ws, cudaStream_t st);
+int general_cheb_bwd(const float* x, const int32_t* perm, int M_in, const float* y, const uint8_t* argmax, const float* dy, const gcnb_csr& L,
+                     const gcnb_csr* Lt, const float* W, float* dx, float* dW, float* db, const LayerShape& s,
+                     int bias_mode, int relu, Workspace& ws, cudaStream_t st);
+
+// pieces shared with the spectral path
+int launch_to_node_major(const float* x, const int32_t* perm, float* X0, int B, int M, int M_in, int F,
+                         cudaStream_t st);
+int launch_from_node_major(const float* Xn, float* x, int B, int M, int F, cudaStream_t st);
+int launch_epilogue(const float* Zn, const float* bias, float* y, uint8_t* argmax, int B, int M, int F, int p,
+                    int bias_mode, int relu, cudaStream_t st);
+int launch_dz(const float* dy, const float* y, const uint8_t* argmax, float* dZn, int B, int M, int F, int p,
+              int relu, cudaStream_t st);
+int launch_db(const float* dZn, float* db, float* scratch_MF, int B, int M, int F, int bias_mode, cudaStream_t st);
+
+// ---- fused (shared-memory resident) path, fused_fwd.cu / fused_bwd.cu ------------------------
+bool fused_fwd_supported(const LayerShape& s);
+bool fused_bwd_supported(const LayerShape& s, bool need_dx);
+size_t fused_cheb_workspace(const LayerShape& s, bool backward, bool need_dx);
+int fused_cheb_fwd(const float* x, const int32_t* perm, int M_in, const gcnb_csr& L, const float* W,
+                   const float* bias, float* y, uint8_t* argmax, const LayerShape& s, int bias_mode, int relu,
+                   Workspace& ws, cudaStream_t st);
+int fused_cheb_bwd(const float* x, const int32_t* perm, int M_in, const float* y, const uint8_t* argmax, const float* dy, const gcnb_csr& L,
+                   const gcnb_csr* Lt, const float* W, float* dx, float* dW, float* db, const LayerShape& s,
+                   int bias_mode, int relu, Workspace& ws, cudaStream_t st);
+
+}  // namespace gcnb

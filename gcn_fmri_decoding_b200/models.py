@@ -1,0 +1,318 @@
+"""``cgcnn`` -- the reference's graph-CNN class, with the same constructor and layer methods.
+
+Mirrors ``/root/reference/lib_new/models_gcn.py``: ``cgcnn.__init__ :445-510`` (argument
+checks, Laplacian selection, layers bound by name), the layer methods ``chebyshev5 :587-617``,
+``chebyshev2 :558-585``, ``fourier :530-539``, ``b1relu :619-623``, ``b2relu :625-629``,
+``mpool1 :631-639``, ``fc :650-656``, ``_inference :658-682`` and the ``base_model`` pieces
+``loss :253-276``, ``predict :31-71``, ``fit :112-184`` (loop structure only; there is no
+TF session, checkpointing or TensorBoard here -- see DESIGN.md, out of scope).
+
+Differences a reference user will notice:
+* tensors are CUDA fp32 ``torch.Tensor``; ``L`` is still the list of SciPy Laplacians.
+* parameters exist before the first call (TF creates them while building the graph); their
+  names follow the TF variable scopes: ``conv{i}/weights``, ``conv{i}/bias``, ``fc{i}/...``,
+  ``logits/...`` (``state_dict_tf()`` / ``load_state_dict_tf()``).
+* ``conv(i, x)`` is the fast path: ONE fused kernel per layer (filter+bias+ReLU+pool).
+  ``filter``/``brelu``/``pool`` called one by one (as ``_inference`` does in the reference) give
+  the same numbers through three kernels.
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops, synth
+from .plan import GraphPlan, SpectralPlan
+
+
+class cgcnn(nn.Module):
+    """Graph CNN with Chebyshev / first-order / spectral filters (drop-in for the reference class)."""
+
+    def __init__(self, config=None, L=None, F=None, K=None, p=None, M=None, filter="chebyshev5", brelu="b1relu",
+                 pool="mpool1", initial="normal", channel=1, num_epochs=20, learning_rate=0.1, decay_rate=0.95,
+                 decay_steps=None, momentum=0.9, regularization=0, dropout=0, batch_size=100, eval_frequency=200,
+                 dir_name="", device="cuda", seed=0, perm=None, n_input_vertices=None, algo=ops.ALGO_AUTO,
+                 fused=True, verbose=False):
+        super().__init__()
+        # ---- the reference's consistency checks (models_gcn.py:452-460) ----------------------------
+        # The reference only *prints* when ``len(L) >= len(F) == len(K) == len(p)`` fails (:452-456), and its
+        # shipped config depends on that: 6 layers with p=1 on 2 Laplacians (model.py:271-274).  Unequal
+        # F/K/p lengths crash it a few lines later, so those are rejected here.
+        if not (len(F) == len(K) == len(p)):
+            raise ValueError("need len(F) == len(K) == len(p) (got %d, %d, %d)" % (len(F), len(K), len(p)))
+        if not np.all(np.array(p) >= 1):
+            raise ValueError("pooling sizes must be >= 1")
+        p_log2 = np.where(np.array(p) > 1, np.log2(np.maximum(p, 1)), 0)
+        if not np.all(np.mod(p_log2, 1) == 0):
+            raise ValueError("pooling sizes must be powers of 2")
+        if not len(L) >= np.sum(p_log2):
+            raise ValueError("not enough coarsening levels for the pooling sizes")
+        if filter not in ("chebyshev5", "chebyshev2", "fourier"):
+            raise ValueError("filter must be 'chebyshev5', 'chebyshev2' or 'fourier' (spline is out of scope)")
+        if brelu not in ("b1relu", "b2relu"):
+            raise ValueError("brelu must be 'b1relu' or 'b2relu'")
+        if pool != "mpool1":
+            raise ValueError("pool must be 'mpool1' (apool1 is never selected by the reference, model.py:163)")
+        if initial not in ("normal", "he"):
+            raise ValueError("initial must be 'normal' or 'he'")
+
+        # ---- keep the useful Laplacians only (models_gcn.py:462-469) ------------------------------
+        M_0 = L[0].shape[0]
+        j, used = 0, []
+        for pp in p:
+            used.append(L[j])
+            j += int(np.log2(pp)) if pp > 1 else 0
+        self.L, self.F, self.K, self.p, self.M = used, list(F), list(K), list(p), list(M)
+        self.num_epochs, self.learning_rate = num_epochs, learning_rate
+        self.decay_rate, self.decay_steps, self.momentum = decay_rate, decay_steps, momentum
+        self.regularization, self.dropout = regularization, dropout
+        self.batch_size, self.eval_frequency = batch_size, eval_frequency
+        self.dir_name, self.initial, self.channel = dir_name, initial, channel
+        self.filter_name, self.brelu_name, self.pool_name = filter, brelu, pool
+        self.filter = getattr(self, filter)  # bound by name, like models_gcn.py:504-506
+        self.brelu = getattr(self, brelu)
+        self.pool = getattr(self, pool)
+        self.algo, self.fused = algo, fused
+        self.dev = torch.device(device)
+        self._layer = None
+
+        # ---- operator plans, uploaded once ---------------------------------------------------------
+        self._plans, self._splans = {}, {}
+        for Li in self.L:
+            if filter == "fourier":
+                self._spectral_plan(Li)
+            else:
+                self._plan(Li)
+        self.perm = None
+        if perm is not None:
+            self.perm = torch.as_tensor(np.asarray(perm), dtype=torch.int32, device=self.dev)
+            if self.perm.numel() != M_0:
+                raise ValueError("perm must have one entry per vertex of L[0]")
+        self.n_input_vertices = n_input_vertices if n_input_vertices is not None else M_0
+
+        # ---- parameters (shapes/initialisers of models_gcn.py:330-355) ------------------------------
+        rng = np.random.RandomState(seed)
+        self.conv_weights, self.conv_bias = nn.ParameterList(), nn.ParameterList()
+        self._regularized = []
+        Fin = channel
+        for i in range(len(self.p)):
+            Mi = self.L[i].shape[0]
+            if filter == "fourier":
+                W = self._init_weight(rng, (Mi, self.F[i], Fin), fan_in=self.F[i] * Fin)
+                regularize = True  # models_gcn.py:538
+            else:
+                W = self._init_weight(rng, (Fin * self.K[i], self.F[i]), fan_in=Fin * self.K[i])
+                regularize = filter == "chebyshev5"  # :615 regularised, chebyshev2 :583 not
+            bshape = (1, 1, self.F[i]) if brelu == "b1relu" else (1, Mi, self.F[i])
+            self.conv_weights.append(nn.Parameter(torch.from_numpy(W).to(self.dev)))
+            self.conv_bias.append(nn.Parameter(torch.full(bshape, 0.2, dtype=torch.float32, device=self.dev)))
+            if regularize:
+                self._regularized.append(self.conv_weights[-1])
+            Fin = self.F[i]
+        # fully connected head: input width is the number of vertices left (mean over F, :671-673)
+        M_last = self.L[-1].shape[0] // self.p[-1] if len(self.p) else M_0
+        self.fc_weights, self.fc_bias = nn.ParameterList(), nn.ParameterList()
+        width = M_last
+        for Mi in self.M:
+            W = self._init_weight(rng, (width, Mi), fan_in=width)
+            self.fc_weights.append(nn.Parameter(torch.from_numpy(W).to(self.dev)))
+            self.fc_bias.append(nn.Parameter(torch.full((Mi,), 0.2, dtype=torch.float32, device=self.dev)))
+            self._regularized += [self.fc_weights[-1], self.fc_bias[-1]]  # fc: both regularised (:652-653)
+            width = Mi
+        if verbose:
+            self.describe()
+
+    # ------------------------------------------------------------------ helpers
+    def _init_weight(self, rng, shape, fan_in):
+        if self.initial == "normal":  # tf.truncated_normal_initializer(0, 0.2), models_gcn.py:333
+            return synth.truncated_normal(rng, shape, 0.2)
+        # variance_scaling(factor=2, FAN_IN, normal) = truncated normal with std sqrt(2/fan_in)/.8796
+        return synth.truncated_normal(rng, shape, math.sqrt(2.0 / fan_in) / 0.87962566103423978)
+
+    def _plan(self, L):
+        key = id(L)
+        if key not in self._plans:
+            self._plans[key] = (GraphPlan(L, self.dev), L)
+        return self._plans[key][0]
+
+    def _spectral_plan(self, L):
+        key = id(L)
+        if key not in self._splans:
+            self._splans[key] = (SpectralPlan(L, self.dev), L)
+        return self._splans[key][0]
+
+    def describe(self):
+        print("NN architecture")
+        print("  input: M_0 = %d" % self.L[0].shape[0])
+        for i in range(len(self.p)):
+            print("  layer %d: cgconv%d  M=%d F=%d K=%d p=%d  weights %s" % (
+                i + 1, i + 1, self.L[i].shape[0], self.F[i], self.K[i], self.p[i], tuple(self.conv_weights[i].shape)))
+        for i, Mi in enumerate(self.M):
+            print("  layer %d: %s  M=%d" % (len(self.p) + i + 1, "logits" if i == len(self.M) - 1 else "fc%d" % (i + 1), Mi))
+
+    def _bias_mode(self):
+        return ops.BIAS_PER_FILTER if self.brelu_name == "b1relu" else ops.BIAS_PER_VERTEX
+
+    def _weights_for(self, layer, W):
+        if W is not None:
+            return W
+        layer = self._layer if layer is None else layer
+        if layer is None:
+            raise ValueError("call inside _inference, or pass layer=<index> / W=<tensor>")
+        return self.conv_weights[layer]
+
+    # ------------------------------------------------------------------ the reference's layer methods
+    def chebyshev5(self, x, L, Fout, K, layer=None, W=None):
+        """``filter(x, L, Fout, K) -> [B, M, Fout]`` (models_gcn.py:587-617)."""
+        W = self._weights_for(layer, W)
+        if W.shape[1] != Fout or W.shape[0] != x.shape[2] * K:
+            raise ValueError("weights %s do not match Fin*K=%d, Fout=%d" % (tuple(W.shape), x.shape[2] * K, Fout))
+        pl = self._plan(L)
+        y, _ = ops.cheb_fwd(x, None, *pl.tensors(), W, None, K, 1, ops.BIAS_NONE, False, False, self.algo)
+        return y
+
+    def chebyshev2(self, x, L, Fout, K, layer=None, W=None):
+        """Same filter; the reference computes the recursion with NumPy on the host (models_gcn.py:558-585)."""
+        return self.chebyshev5(x, L, Fout, K, layer=layer, W=W)
+
+    def fourier(self, x, L, Fout, K, layer=None, W=None):
+        """Spectral filter; ``K`` is ignored exactly as in the reference (models_gcn.py:530-539)."""
+        W = self._weights_for(layer, W)
+        sp = self._spectral_plan(L)
+        y, _ = ops.spectral_fwd(x, sp.Ut, W, None, 1, ops.BIAS_NONE, False, False)
+        return y
+
+    def b1relu(self, x, layer=None, b=None):
+        """Bias and ReLU, one bias per filter (models_gcn.py:619-623)."""
+        b = self.conv_bias[self._layer if layer is None else layer] if b is None else b
+        return ops.brelu_fwd(x, b, ops.BIAS_PER_FILTER)
+
+    def b2relu(self, x, layer=None, b=None):
+        """Bias and ReLU, one bias per vertex per filter (models_gcn.py:625-629)."""
+        b = self.conv_bias[self._layer if layer is None else layer] if b is None else b
+        return ops.brelu_fwd(x, b, ops.BIAS_PER_VERTEX)
+
+    def mpool1(self, x, p):
+        """Max pooling of size p over the vertex axis (models_gcn.py:631-639)."""
+        if p > 1:
+            return ops.mpool_fwd(x, p)[0]
+        return x
+
+    def fc(self, x, layer, relu=True):
+        """Fully connected layer (models_gcn.py:650-656)."""
+        x = torch.addmm(self.fc_bias[layer], x, self.fc_weights[layer])
+        return torch.relu(x) if relu else x
+
+    # ------------------------------------------------------------------ fused fast path
+    def conv(self, i, x, gather=False):
+        """Layer ``i`` as ONE fused op: filter -> brelu -> pool.  ``gather`` fuses ``perm_data_3d`` into the load."""
+        want_argmax = torch.is_grad_enabled() and self.p[i] > 1
+        b = self.conv_bias[i]
+        perm = self.perm if gather else None
+        if self.filter_name == "fourier":
+            if perm is not None:
+                x = ops.perm_gather(x, perm)
+            sp = self._spectral_plan(self.L[i])
+            return ops.spectral_fwd(x, sp.Ut, self.conv_weights[i], b, self.p[i], self._bias_mode(), True, want_argmax)[0]
+        pl = self._plan(self.L[i])
+        return ops.cheb_fwd(x, perm, *pl.tensors(), self.conv_weights[i], b, self.K[i], self.p[i], self._bias_mode(),
+                            True, want_argmax, self.algo)[0]
+
+    # ------------------------------------------------------------------ model
+    def conv_stack(self, x, gather=False):
+        """The conv loop of ``_inference`` (models_gcn.py:661-668)."""
+        if gather and not self.fused:
+            x = ops.perm_gather(x, self.perm)
+            gather = False
+        for i in range(len(self.p)):
+            if self.fused:
+                x = self.conv(i, x, gather=gather and i == 0)
+            else:
+                self._layer = i
+                try:
+                    x = self.filter(x, self.L[i], self.F[i], self.K[i])
+                    x = self.brelu(x)
+                    x = self.pool(x, self.p[i])
+                finally:
+                    self._layer = None
+        return x
+
+    def _inference(self, x, dropout=1.0, gather=False):
+        """logits = head(conv_stack(x)); ``dropout`` is the keep probability, as in the reference."""
+        x = self.conv_stack(x, gather=gather)
+        x = ops.mean_f_fwd(x)  # tf.reduce_mean(x, -1), models_gcn.py:673
+        for i in range(len(self.M) - 1):
+            x = self.fc(x, i)
+            if dropout < 1.0:
+                x = torch.nn.functional.dropout(x, 1.0 - dropout, training=True)
+        return self.fc(x, len(self.M) - 1, relu=False)
+
+    def forward(self, x, dropout=1.0, gather=None):
+        if gather is None:
+            gather = self.perm is not None and x.shape[1] == self.n_input_vertices != self.L[0].shape[0]
+        return self._inference(x, dropout, gather)
+
+    def loss(self, logits, labels, regularization=None):
+        """mean sparse-softmax CE + regularization * sum_v ||v||^2/2 (models_gcn.py:253-262)."""
+        reg = self.regularization if regularization is None else regularization
+        ce = torch.nn.functional.cross_entropy(logits, labels)
+        if reg:
+            ce = ce + reg * sum(0.5 * (v * v).sum() for v in self._regularized)
+        return ce
+
+    @torch.no_grad()
+    def predict(self, data, labels=None):
+        """Batched prediction with the reference's zero-padded last batch (models_gcn.py:31-71)."""
+        size = data.shape[0]
+        preds = np.empty(size)
+        total = 0.0
+        bs = self.batch_size
+        for begin in range(0, size, bs):
+            end = min(begin + bs, size)
+            batch = torch.zeros((bs,) + tuple(data.shape[1:]), dtype=torch.float32, device=self.dev)
+            batch[: end - begin] = torch.as_tensor(np.asarray(data[begin:end]), dtype=torch.float32, device=self.dev)
+            logits = self.forward(batch)
+            if labels is not None:
+                lab = torch.zeros(bs, dtype=torch.long, device=self.dev)
+                lab[: end - begin] = torch.as_tensor(np.asarray(labels[begin:end]), dtype=torch.long, device=self.dev)
+                l = float(self.loss(logits, lab))
+                if not np.isfinite(l):
+                    l = 0.0
+                total += l
+            preds[begin:end] = logits.argmax(1)[: end - begin].cpu().numpy()
+        if labels is not None:
+            return preds, total * bs / size
+        return preds
+
+    # ------------------------------------------------------------------ TF-style names for checkpoints
+    def state_dict_tf(self):
+        """Parameters under the reference's TF variable names (models_gcn.py:662,343,351,675,680)."""
+        out = OrderedDict()
+        for i in range(len(self.p)):
+            out["conv%d/weights" % (i + 1)] = self.conv_weights[i].detach().cpu().numpy()
+            out["conv%d/bias" % (i + 1)] = self.conv_bias[i].detach().cpu().numpy()
+        for i in range(len(self.M)):
+            scope = "logits" if i == len(self.M) - 1 else "fc%d" % (i + 1)
+            out[scope + "/weights"] = self.fc_weights[i].detach().cpu().numpy()
+            out[scope + "/bias"] = self.fc_bias[i].detach().cpu().numpy()
+        return out
+
+    @torch.no_grad()
+    def load_state_dict_tf(self, d):
+        mine = OrderedDict()
+        for i in range(len(self.p)):
+            mine["conv%d/weights" % (i + 1)] = self.conv_weights[i]
+            mine["conv%d/bias" % (i + 1)] = self.conv_bias[i]
+        for i in range(len(self.M)):
+            scope = "logits" if i == len(self.M) - 1 else "fc%d" % (i + 1)
+            mine[scope + "/weights"] = self.fc_weights[i]
+            mine[scope + "/bias"] = self.fc_bias[i]
+        for k, v in mine.items():
+            a = np.asarray(d[k], dtype=np.float32)
+            if tuple(a.shape) != tuple(v.shape):
+                raise ValueError("%s: shape %s does not match %s" % (k, a.shape, tuple(v.shape)))
+            v.copy_(torch.from_numpy(a).to(v.device))

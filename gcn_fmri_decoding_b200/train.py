@@ -1,0 +1,164 @@
+"""Training step, TF-style Adam and batch-sharded data parallelism.
+
+* ``TFAdam`` -- ``tf.train.AdamOptimizer(learning_rate=0.001)`` as hard-coded by the reference
+  (``/root/reference/lib_new/models_gcn.py:294``): ``lr_t = lr*sqrt(1-b2^t)/(1-b1^t)``,
+  ``v -= lr_t * m / (sqrt(v) + eps)`` ("epsilon hat" form, which differs from ``torch.optim.Adam``).
+* ``Trainer`` -- one training step = forward, loss (``:253-262``), backward, optimiser
+  (``:298-305``); with ``world_size > 1`` every rank takes its slice of the global batch, the
+  Laplacians and weights are replicated and ONE all-reduce of a flat gradient buffer averages
+  the gradients.  The reference has no distributed code; this is the only
+  collective the path needs.
+* ``fit`` -- the reference's step loop (``:112-184``) without sessions/checkpoints/summaries.
+"""
+from __future__ import annotations
+
+import collections
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+class TFAdam:
+    """TensorFlow-1.x Adam on a flat parameter list (multi-tensor ``_foreach`` ops)."""
+
+    def __init__(self, params, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8):
+        self.params = [p for p in params]
+        self.lr, self.b1, self.b2, self.eps = lr, beta1, beta2, eps
+        self.m = [torch.zeros_like(p) for p in self.params]
+        self.v = [torch.zeros_like(p) for p in self.params]
+        dev = self.params[0].device
+        # step-dependent scalars live on the device so that a captured CUDA graph can replay the step
+        self.b1_pow = torch.ones((), device=dev)
+        self.b2_pow = torch.ones((), device=dev)
+
+    @torch.no_grad()
+    def step(self, grads=None):
+        grads = [p.grad for p in self.params] if grads is None else grads
+        self.b1_pow.mul_(self.b1)
+        self.b2_pow.mul_(self.b2)
+        lr_t = self.lr * torch.sqrt(1 - self.b2_pow) / (1 - self.b1_pow)
+        torch._foreach_mul_(self.m, self.b1)
+        torch._foreach_add_(self.m, grads, alpha=1 - self.b1)
+        torch._foreach_mul_(self.v, self.b2)
+        torch._foreach_addcmul_(self.v, grads, grads, value=1 - self.b2)
+        denom = torch._foreach_sqrt(self.v)
+        torch._foreach_add_(denom, self.eps)
+        upd = torch._foreach_div(self.m, denom)
+        torch._foreach_mul_(upd, -lr_t)
+        torch._foreach_add_(self.params, upd)
+
+    def zero_grad(self):
+        for p in self.params:
+            p.grad = None
+
+
+class Trainer:
+    """Forward + loss + backward + (all-reduce) + Adam for a ``cgcnn``; optionally CUDA-graph captured."""
+
+    def __init__(self, model, lr=1e-3, distributed=None, use_cuda_graph=False):
+        self.model = model
+        self.params = [p for p in model.parameters()]
+        self.opt = TFAdam(self.params, lr=lr)
+        self.distributed = dist.is_available() and dist.is_initialized() if distributed is None else distributed
+        self.world = dist.get_world_size() if self.distributed else 1
+        sizes = [p.numel() for p in self.params]
+        self.flat_grad = torch.zeros(sum(sizes), dtype=torch.float32, device=self.params[0].device)
+        self.grad_views = []
+        off = 0
+        for p, n in zip(self.params, sizes):
+            self.grad_views.append(self.flat_grad[off:off + n].view_as(p))
+            off += n
+        self.use_cuda_graph = use_cuda_graph
+        self._graph = None
+        self._static = None
+        if self.distributed:  # start from identical weights on every rank
+            for p in self.params:
+                dist.broadcast(p.data, src=0)
+
+    def _step_impl(self, x, labels, dropout):
+        logits = self.model(x, dropout=dropout)
+        loss = self.model.loss(logits, labels)
+        grads = torch.autograd.grad(loss, self.params)
+        torch._foreach_copy_(self.grad_views, grads)
+        if self.world > 1:
+            # gradients of the local-batch mean; the global-batch mean is their average over ranks.
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM)
+            self.flat_grad.mul_(1.0 / self.world)
+        self.opt.step(self.grad_views)
+        return loss.detach(), logits.detach()
+
+    def step(self, x, labels, dropout=1.0):
+        """One optimisation step on the local shard ``x [b, M, channel]``; returns (loss, logits)."""
+        if not self.use_cuda_graph:
+            return self._step_impl(x, labels, dropout)
+        if self._graph is None:
+            self._static = (torch.empty_like(x), torch.empty_like(labels))
+            self._static[0].copy_(x)
+            self._static[1].copy_(labels)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            state = self._snapshot()
+            with torch.cuda.stream(side):
+                for _ in range(3):  # warm up allocator / lazy init outside the capture
+                    self._step_impl(self._static[0], self._static[1], dropout)
+            torch.cuda.current_stream().wait_stream(side)
+            self._restore(state)
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self._out = self._step_impl(self._static[0], self._static[1], dropout)
+            self._restore(state)
+        self._static[0].copy_(x, non_blocking=True)
+        self._static[1].copy_(labels, non_blocking=True)
+        self._graph.replay()
+        return self._out
+
+    def _snapshot(self):
+        return ([p.detach().clone() for p in self.params], [m.clone() for m in self.opt.m],
+                [v.clone() for v in self.opt.v], self.opt.b1_pow.clone(), self.opt.b2_pow.clone())
+
+    def _restore(self, s):
+        with torch.no_grad():
+            for p, q in zip(self.params, s[0]):
+                p.copy_(q)
+            for a, b in zip(self.opt.m, s[1]):
+                a.copy_(b)
+            for a, b in zip(self.opt.v, s[2]):
+                a.copy_(b)
+            self.opt.b1_pow.copy_(s[3])
+            self.opt.b2_pow.copy_(s[4])
+
+
+def shard(n, rank, world):
+    """Contiguous slice of ``range(n)`` rank ``rank`` of ``world`` owns (windows [r*n/G, (r+1)*n/G))."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def fit(model, train_data, train_labels, val_data=None, val_labels=None, trainer=None, seed=0, verbose=True):
+    """The reference's training loop (models_gcn.py:112-184): epochs of random batches from a deque of
+    shuffled indices, dropout keep-prob ``model.dropout``, periodic validation.  Returns the loss history."""
+    trainer = trainer or Trainer(model)
+    rng = np.random.RandomState(seed)
+    n = train_data.shape[0]
+    num_steps = int(model.num_epochs * n / model.batch_size)
+    indices = collections.deque()
+    losses, t0 = [], time.time()
+    dev = model.dev
+    for step in range(1, num_steps + 1):
+        if len(indices) < model.batch_size:
+            indices.extend(rng.permutation(n))
+        idx = [indices.popleft() for _ in range(model.batch_size)]
+        x = torch.as_tensor(np.asarray(train_data[idx]), dtype=torch.float32, device=dev)
+        y = torch.as_tensor(np.asarray(train_labels[idx]), dtype=torch.long, device=dev)
+        loss, _ = trainer.step(x, y, dropout=model.dropout if model.dropout else 1.0)
+        losses.append(float(loss))
+        if verbose and (step % model.eval_frequency == 0 or step == num_steps):
+            msg = "step %d / %d (epoch %.2f): loss %.4f" % (step, num_steps, step * model.batch_size / n, losses[-1])
+            if val_data is not None:
+                pred, vloss = model.predict(val_data, val_labels)
+                msg += "  val acc %.2f%% loss %.4f" % (100.0 * float(np.mean(pred == np.asarray(val_labels))), vloss)
+            print(msg + "  (%.1fs)" % (time.time() - t0))
+    return losses

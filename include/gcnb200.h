@@ -1,0 +1,153 @@
+/*
+ * gcnb200.h -- C ABI of the B200 (sm_100a) graph-convolution kernels.
+ *
+ * This is the drop-in boundary for the graph-convolution hot path of
+ * zhangyu2ustc/GCN_fmri_decoding.  The reference has no FFI: its layers are Python
+ * methods that emit TensorFlow-1.x ops (lib_new/models_gcn.py).  Each entry point below
+ * replaces the TF op sequence of one reference method (cited per function); the Python
+ * host side (gcn_fmri_decoding_b200/_lib.py, ops.py) binds them with ctypes and mirrors
+ * the reference's method names and arguments.  INTEGRATION.md shows the stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer unless named h_*.
+ *  - tensors are dense, row-major, fp32: x[B][M][Fin], y[B][Mo][Fout] with Mo = ceil(M/p).
+ *  - the caller owns every buffer, including the workspace (size from *_workspace_bytes);
+ *    the library never allocates or frees device memory and keeps no pointer after return.
+ *  - all work is enqueued on `stream` (a cudaStream_t); no host synchronisation, no
+ *    allocation, no stream creation inside: every call is CUDA-graph capturable.
+ *  - return value: GCNB_OK (0) or a negative code; gcnb_last_error_string() (thread local)
+ *    describes the last failure.  Nothing throws or aborts.
+ *  - re-entrant; no global mutable state besides the thread-local error string and the
+ *    one-time per-device kernel attribute setup.
+ */
+#ifndef GCNB200_H
+#define GCNB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define GCNB_API __attribute__((visibility("default")))
+#else
+#define GCNB_API
+#endif
+
+#define GCNB_OK 0
+#define GCNB_ERR_INVALID (-1)   /* bad argument / unsupported shape */
+#define GCNB_ERR_WORKSPACE (-2) /* workspace too small or misaligned */
+#define GCNB_ERR_CUDA (-3)      /* a CUDA runtime call or launch failed */
+
+/* bias_mode: how the bias of b1relu / b2relu is indexed (models_gcn.py:619-629) */
+#define GCNB_BIAS_NONE 0
+#define GCNB_BIAS_PER_FILTER 1 /* b1relu: bias[Fout]    */
+#define GCNB_BIAS_PER_VERTEX 2 /* b2relu: bias[M][Fout] */
+
+/* algo: kernel family selection.  AUTO picks FUSED when the graph and a tile of samples
+ * fit in shared memory, GENERAL (HBM-resident operator and state) otherwise. */
+#define GCNB_ALGO_AUTO 0
+#define GCNB_ALGO_GENERAL 1
+#define GCNB_ALGO_FUSED 2
+
+typedef void* gcnb_stream_t; /* cudaStream_t */
+
+/* A rescaled Laplacian L~ = L/(lmax/2) - I in CSR (graph.py:146-152 output, rows sorted by
+ * column as tf.sparse_reorder leaves them, models_gcn.py:593-596).  Device arrays. */
+typedef struct gcnb_csr {
+  const int32_t* rowptr; /* [M+1] */
+  const int32_t* col;    /* [nnz] */
+  const float* val;      /* [nnz] */
+  int32_t M;
+  int32_t nnz;
+} gcnb_csr;
+
+GCNB_API int gcnb_version(void);
+GCNB_API const char* gcnb_last_error_string(void);
+/* Number of kernels this library has enqueued in this process so far (diagnostic; monotonic). */
+GCNB_API unsigned long long gcnb_launch_count(void);
+
+/* 1 if the fused shared-memory kernels can take this layer shape, else 0. */
+GCNB_API int gcnb_cheb_fused_supported(int B, int M, int nnz, int Fin, int Fout, int K, int p, int backward, int need_dx);
+
+/* Bytes of workspace gcnb_cheb_{fwd,bwd}_f32 need for this shape (256-byte aligned pointer). */
+GCNB_API size_t gcnb_cheb_workspace_bytes(int B, int M, int nnz, int Fin, int Fout, int K, int p, int backward, int need_dx,
+                                 int algo);
+
+/*
+ * Fused ChebyNet layer, forward:  filter -> bias -> ReLU -> max-pool.
+ * Replaces cgcnn.chebyshev5 (models_gcn.py:587-617) / cgcnn.chebyshev2 (:558-585, same math)
+ * followed by b1relu/b2relu (:619-629) and mpool1 (:631-639), i.e. one iteration of the
+ * conv loop at :658-668.
+ *
+ *   X_0 = x, X_1 = L~ X_0, X_k = 2 L~ X_{k-1} - X_{k-2}
+ *   z[b,m,o] = sum_{f,k} X_k[b,m,f] * W[f*K + k, o]          (W row order of :611-615)
+ *   a = relu ? max(z + bias, 0) : z + bias
+ *   y[b,j,o] = max_{i<p} a[b, j*p+i, o],  argmax[b,j,o] = first i attaining it (uint8)
+ *
+ * perm (nullable): if given, x is the un-permuted data x_raw[B][M_in][Fin] and the kernel reads
+ *   row perm[m] (zero when perm[m] >= M_in) -- coarsening.perm_data_3d (coarsening.py:244-265)
+ *   fused into the load.  With perm == NULL, M_in must equal M.
+ * bias (nullable iff bias_mode == NONE); argmax (nullable: not written); p >= 1, power of 2.
+ */
+GCNB_API int gcnb_cheb_fwd_f32(const float* x, const int32_t* perm, int M_in, const gcnb_csr* L, const float* W,
+                      const float* bias, float* y, uint8_t* argmax, int B, int Fin, int Fout, int K, int p,
+                      int bias_mode, int relu, int algo, void* workspace, size_t workspace_bytes,
+                      gcnb_stream_t stream);
+
+/*
+ * Backward of the fused layer (what tf.gradients builds for it, models_gcn.py:298-303).
+ *   g  = dy * [y > 0] (if relu)            routed to row j*p + argmax (MaxPoolGrad), dz elsewhere 0
+ *   db = sum_b,m dz (PER_FILTER) | sum_b dz (PER_VERTEX)
+ *   dW[f*K+k, o] = sum_{b,m} X_k[b,m,f] dz[b,m,o]           (X_k recomputed from x)
+ *   dx = sum_k T_k(L~^T) (dz W_k^T)                          (needs Lt = CSR of L~^T; skipped if dx NULL)
+ * x / perm / M_in as in the forward (the gather is repeated when X_k is recomputed); dx, if
+ * requested, is the gradient w.r.t. the permuted layer input [B][M][Fin].
+ * dW / db are overwritten (not accumulated).  db may be NULL when bias_mode == NONE.
+ */
+GCNB_API int gcnb_cheb_bwd_f32(const float* x, const int32_t* perm, int M_in, const float* y, const uint8_t* argmax,
+                      const float* dy, const gcnb_csr* L,
+                      const gcnb_csr* Lt, const float* W, float* dx, float* dW, float* db, int B, int Fin,
+                      int Fout, int K, int p, int bias_mode, int relu, int algo, void* workspace,
+                      size_t workspace_bytes, gcnb_stream_t stream);
+
+/*
+ * Spectral layer (cgcnn.fourier + filter_in_fourier, models_gcn.py:512-539) with the same fused
+ * bias/ReLU/pool epilogue.  Ut[M][M] is the transposed eigenvector matrix (row i = i-th
+ * eigenvector), exactly the constant the reference builds at :536.  W[M][Fout][Fin].
+ *   xh = Ut x ; yh[b,m,o] = sum_f W[m,o,f] xh[b,m,f] ; z = Ut^T yh
+ */
+GCNB_API size_t gcnb_spectral_workspace_bytes(int B, int M, int Fin, int Fout, int p, int backward);
+GCNB_API int gcnb_spectral_fwd_f32(const float* x, const float* Ut, const float* W, const float* bias, float* y,
+                          uint8_t* argmax, int B, int M, int Fin, int Fout, int p, int bias_mode, int relu,
+                          void* workspace, size_t workspace_bytes, gcnb_stream_t stream);
+GCNB_API int gcnb_spectral_bwd_f32(const float* x, const float* y, const uint8_t* argmax, const float* dy, const float* Ut,
+                          const float* W, float* dx, float* dW, float* db, int B, int M, int Fin, int Fout, int p,
+                          int bias_mode, int relu, void* workspace, size_t workspace_bytes, gcnb_stream_t stream);
+
+/* Stand-alone pieces, for callers that invoke the reference methods one by one. */
+/* b1relu / b2relu (models_gcn.py:619-629): y = max(x + bias, 0). */
+GCNB_API int gcnb_brelu_fwd_f32(const float* x, const float* bias, float* y, int B, int M, int F, int bias_mode,
+                       gcnb_stream_t stream);
+/* dx = dy * [y > 0]; db as above.  workspace: M*F floats (PER_FILTER only), may be NULL otherwise. */
+GCNB_API int gcnb_brelu_bwd_f32(const float* dy, const float* y, float* dx, float* db, int B, int M, int F, int bias_mode,
+                       void* workspace, size_t workspace_bytes, gcnb_stream_t stream);
+/* mpool1 (models_gcn.py:631-639): tf.nn.max_pool SAME over the vertex axis, any M (ragged tail padded). */
+GCNB_API int gcnb_mpool_fwd_f32(const float* x, float* y, uint8_t* argmax, int B, int M, int F, int p, gcnb_stream_t stream);
+GCNB_API int gcnb_mpool_bwd_f32(const float* dy, const uint8_t* argmax, float* dx, int B, int M, int F, int p,
+                       gcnb_stream_t stream);
+/* coarsening.perm_data_3d (coarsening.py:244-265) on the device, fp32 in / fp32 out. */
+GCNB_API int gcnb_perm_gather_f32(const float* x, const int32_t* perm, float* y, int B, int M_in, int M_out, int F,
+                         gcnb_stream_t stream);
+
+/* Head pieces ("next" rows of the scope table): reduce_mean over the filter axis (models_gcn.py:673). */
+GCNB_API int gcnb_mean_f_fwd_f32(const float* x, float* y, int rows, int F, gcnb_stream_t stream);
+GCNB_API int gcnb_mean_f_bwd_f32(const float* dy, float* dx, int rows, int F, gcnb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GCNB200_H */

@@ -319,3 +319,39 @@ def conv_stack_bwd(trace, Ls, params, dy, filter="chebyshev5", brelu="b1relu", d
         grads[i] = dict(dW=dW, db=db)
         dy = dx
     return dy, grads
+
+
+# ----------------------------------------------------------------------------- whole training step (CPU baseline)
+def network_step(x, labels, Ls, params, fcs, regularization, filter="chebyshev5", brelu="b1relu", dtype=np.float32):
+    """Forward + loss + backward of the whole network (conv stack, mean over F, FC head, CE + L2).
+
+    What one ``sess.run([op_train, ...])`` computes up to the optimiser update (models_gcn.py:146, :298-303).
+    Returns ``(loss, conv_grads, fc_grads)``.  Used as the CPU baseline and by the gradient parity test.
+    """
+    h, trace = conv_stack(x, Ls, params, filter=filter, brelu=brelu, dtype=dtype, keep=True)
+    F_last = h.shape[-1]
+    acts = [h.mean(axis=-1, dtype=dtype)]
+    for i, (W, b) in enumerate(fcs):
+        z = acts[-1] @ np.asarray(W, dtype) + np.asarray(b, dtype)
+        acts.append(np.maximum(z, 0) if i < len(fcs) - 1 else z)
+    logits = acts[-1]
+    regs = [np.asarray(p["W"]) for p in params if filter != "chebyshev2"] + [v for Wb in fcs for v in Wb]
+    value = loss(logits.astype(np.float64), labels, regs, regularization)
+    B = x.shape[0]
+    pz = np.exp(logits - logits.max(axis=1, keepdims=True))
+    pz /= pz.sum(axis=1, keepdims=True)
+    pz[np.arange(B), labels] -= 1
+    d = (pz / B).astype(dtype)
+    fc_grads = [None] * len(fcs)
+    for i in range(len(fcs) - 1, -1, -1):
+        W, b = fcs[i]
+        if i < len(fcs) - 1:
+            d = d * (acts[i + 1] > 0)
+        fc_grads[i] = (acts[i].T @ d + regularization * np.asarray(W, dtype), d.sum(0) + regularization * np.asarray(b, dtype))
+        d = d @ np.asarray(W, dtype).T
+    dh = np.repeat(d[:, :, None], F_last, axis=2) / dtype(F_last)
+    _, conv_grads = conv_stack_bwd(trace, Ls, params, dh, filter=filter, brelu=brelu, dtype=dtype)
+    if filter != "chebyshev2":
+        for g, p in zip(conv_grads, params):
+            g["dW"] = g["dW"] + regularization * np.asarray(p["W"], dtype)
+    return value, conv_grads, fc_grads

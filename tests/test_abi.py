@@ -1,0 +1,93 @@
+"""CPU-side checks of the boundary: the C-ABI library loads and exports every declared symbol;
+host-side validation raises like the reference's asserts.  No compute calls (no GPU here)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def test_library_exports_every_declared_symbol():
+    from gcn_fmri_decoding_b200 import _lib
+
+    header = open(os.path.join(ROOT, "include", "gcnb200.h")).read()
+    declared = set(re.findall(r"GCNB_API\s+[\w\s\*]+?\b(gcnb_\w+)\s*\(", header))
+    assert len(declared) >= 15
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = _lib.lib()  # raises if the .so is missing: the product has no fallback
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.gcnb_version() >= 100
+    assert isinstance(_lib.last_error(), str)
+
+
+def test_workspace_queries_are_pure_host_calls():
+    from gcn_fmri_decoding_b200 import _lib
+
+    lib = _lib.lib()
+    fwd = lib.gcnb_cheb_workspace_bytes(512, 400, 3684, 15, 32, 5, 4, 0, 0, _lib.ALGO_GENERAL)
+    bwd = lib.gcnb_cheb_workspace_bytes(512, 400, 3684, 15, 32, 5, 4, 1, 1, _lib.ALGO_GENERAL)
+    assert fwd >= 4 * (5 * 400 * 512 * 15 + 400 * 512 * 32)
+    assert bwd > fwd
+    assert lib.gcnb_spectral_workspace_bytes(8, 100, 8, 16, 4, 1) > lib.gcnb_spectral_workspace_bytes(8, 100, 8, 16, 4, 0)
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from gcn_fmri_decoding_b200 import _lib
+
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libgcnb200.so")
+    with pytest.raises(_lib.GcnbError, match="no CPU fallback"):
+        _lib.lib()
+
+
+def test_constructor_checks_mirror_reference(graph_l4):
+    """cgcnn.__init__ validation (models_gcn.py:452-460) -- raised before any device work."""
+    from gcn_fmri_decoding_b200.models import cgcnn
+
+    L = graph_l4["L"]
+    with pytest.raises(ValueError, match="len"):
+        cgcnn(L=L, F=[32, 32], K=[5], p=[4, 4], M=[22], device="cpu")
+    with pytest.raises(ValueError, match="powers of 2"):
+        cgcnn(L=L, F=[32], K=[5], p=[3], M=[22], device="cpu")
+    with pytest.raises(ValueError, match="coarsening levels"):
+        cgcnn(L=L[:2], F=[32, 32], K=[5, 5], p=[4, 4], M=[22], device="cpu")
+    with pytest.raises(ValueError, match="filter"):
+        cgcnn(L=L, F=[32], K=[5], p=[4], M=[22], filter="spline", device="cpu")
+    with pytest.raises(ValueError, match="pool"):
+        cgcnn(L=L, F=[32], K=[5], p=[4], M=[22], pool="apool1", device="cpu")
+
+
+def test_model_parameter_layout_and_tf_names(graph_l4):
+    """Shapes and names a reference checkpoint maps onto; host tensors only."""
+    from gcn_fmri_decoding_b200.models import cgcnn
+
+    m = cgcnn(L=graph_l4["L"], F=[32, 32], K=[5, 5], p=[4, 4], M=[512, 256, 22], channel=15, device="cpu")
+    assert [l.shape[0] for l in m.L] == [400, 100]  # L[0] and L[2] (models_gcn.py:462-469)
+    sd = m.state_dict_tf()
+    assert list(sd) == ["conv1/weights", "conv1/bias", "conv2/weights", "conv2/bias", "fc1/weights", "fc1/bias",
+                        "fc2/weights", "fc2/bias", "logits/weights", "logits/bias"]
+    assert sd["conv1/weights"].shape == (75, 32) and sd["conv2/weights"].shape == (160, 32)
+    assert sd["conv1/bias"].shape == (1, 1, 32) and sd["fc1/weights"].shape == (25, 512)
+    assert sum(v.size for v in sd.values()) == 157878  # SURVEY 8e message size
+    assert np.all(sd["conv1/bias"] == np.float32(0.2)) and abs(sd["conv1/weights"]).max() <= 0.4 + 1e-6
+    m2 = cgcnn(L=graph_l4["L"], F=[32, 32], K=[5, 5], p=[4, 4], M=[512, 256, 22], channel=15, device="cpu", seed=3)
+    m2.load_state_dict_tf(sd)
+    assert all(np.array_equal(a, b) for a, b in zip(sd.values(), m2.state_dict_tf().values()))
+    b2 = cgcnn(L=graph_l4["L"][:2], F=[32] * 6, K=[5] * 6, p=[1] * 6, M=[512, 256, 22], channel=15,
+               brelu="b2relu", device="cpu")
+    assert b2.state_dict_tf()["conv3/bias"].shape == (1, 400, 32)
+    four = cgcnn(L=graph_l4["L"][2:], F=[8], K=[100], p=[2], M=[22], channel=4, filter="fourier", device="cpu")
+    assert four.state_dict_tf()["conv1/weights"].shape == (100, 8, 4)
+
+
+def test_layers_refuse_cpu_tensors(graph_l4):
+    import torch
+
+    from gcn_fmri_decoding_b200.models import cgcnn
+
+    m = cgcnn(L=graph_l4["L"][4:], F=[4], K=[2], p=[1], M=[3], channel=2, device="cpu")
+    with pytest.raises((ValueError, NotImplementedError, RuntimeError)):
+        m(torch.zeros(2, 25, 2))

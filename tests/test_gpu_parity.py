@@ -1,0 +1,421 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle.  Run on the B200 box: -m gpu.
+
+Bars:
+* integer work -- permutation/padding, pooled arg-max bytes: bit-exact;
+* floating point -- ||y - y_ref||_inf / ||y_ref||_inf <= 1e-4 against the fp64 oracle
+  (TOL below); the as-run fp32 oracle's own distance to fp64 is the noise floor.
+Arg-max note: where the fp64 window maximum leads the runner-up by less than fp32 rounding
+noise (ARGMAX_GAP, relative to the tensor's max), either index is a correct fp32 answer; such
+windows are counted, required to be rare, and excluded from the exact comparison.
+"""
+import numpy as np
+import pytest
+
+from conftest import rel_inf
+from oracle import layers_np as O
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+ARGMAX_GAP = 2e-5
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+def T(a, dev, dtype=torch.float32):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype, device=dev)
+
+
+def algos_for(B, M, nnz, Fin, Fout, K, p, backward=False, need_dx=True):
+    from gcn_fmri_decoding_b200 import _lib
+
+    out = [_lib.ALGO_GENERAL]
+    if _lib.lib().gcnb_cheb_fused_supported(B, M, nnz, Fin, Fout, K, p, int(backward), int(need_dx)):
+        out.append(_lib.ALGO_FUSED)
+    return out
+
+
+def check_argmax(got, a64, p, name=""):
+    """got: uint8 [B, Mo, F]; a64: fp64 pre-pool activation [B, M, F] (M % p == 0)."""
+    B, M, F = a64.shape
+    win = a64.reshape(B, M // p, p, F)
+    ref = win.argmax(2)
+    srt = np.sort(win, axis=2)
+    gap = srt[:, :, -1, :] - srt[:, :, -2, :]
+    scale = np.abs(a64).max()
+    bad = got.astype(np.int64) != ref
+    # a disagreement is only admissible on a (near-)tie that is not an exact tie
+    assert not np.any(bad & (gap > ARGMAX_GAP * scale)), name
+    assert not np.any(bad & (gap == 0)), name  # exact ties (e.g. all-zero after ReLU): first index, bit-exact
+    assert bad.mean() < 1e-3, name
+
+
+def run_layer(dev, L, x, W, b, K, p, brelu, algo, perm=None, dy=None, need_dx=True):
+    from gcn_fmri_decoding_b200 import ops
+    from gcn_fmri_decoding_b200.plan import GraphPlan
+
+    pl = GraphPlan(L, dev)
+    mode = ops.BIAS_PER_FILTER if brelu == "b1relu" else ops.BIAS_PER_VERTEX
+    xt = T(x, dev).requires_grad_(need_dx)
+    Wt = T(W, dev).requires_grad_(True)
+    bt = T(b, dev).requires_grad_(True)
+    pt = None if perm is None else T(perm, dev, torch.int32)
+    y, am = ops.cheb_fwd(xt, pt, *pl.tensors(), Wt, bt, K, p, mode, True, True, algo)
+    out = dict(y=y.detach().cpu().numpy(), argmax=am.cpu().numpy())
+    if dy is not None:
+        y.backward(T(dy, dev))
+        out.update(dW=Wt.grad.cpu().numpy(), db=bt.grad.cpu().numpy().reshape(np.shape(b)))
+        if need_dx:
+            out["dx"] = xt.grad.cpu().numpy()
+    return out
+
+
+# ------------------------------------------------------------------------------------------ golden cases
+def test_golden_layer_cases(dev, graph_l4, layer_cases):
+    for name, c in layer_cases.items():
+        filt, brelu = str(c["kind"]).split("/")
+        if filt == "fourier":
+            continue
+        lvl, B, Fin, Fout, K, p = (int(v) for v in c["meta"])
+        L = graph_l4["L"][lvl]
+        for algo in algos_for(B, L.shape[0], graph_l4["Lt"][lvl].nnz, Fin, Fout, K, p, True, True):
+            r = run_layer(dev, L, c["x"], c["W"], c["b"], K, p, brelu, algo, dy=c["dy"])
+            tag = "%s algo=%d" % (name, algo)
+            assert rel_inf(r["y"], c["y64"]) <= TOL, tag
+            assert rel_inf(r["dW"], c["dW64"]) <= TOL, tag
+            assert rel_inf(r["db"], c["db64"]) <= TOL, tag
+            assert rel_inf(r["dx"], c["dx64"]) <= TOL, tag
+            if p > 1:
+                a64 = O.b1relu(c["z64"], c["b"]) if brelu == "b1relu" else O.b2relu(c["z64"], c["b"])
+                check_argmax(r["argmax"], a64, p, tag)
+
+
+def test_golden_spectral_cases(dev, layer_cases):
+    from gcn_fmri_decoding_b200 import ops
+
+    for name, c in layer_cases.items():
+        filt, brelu = str(c["kind"]).split("/")
+        if filt != "fourier":
+            continue
+        lvl, B, Fin, Fout, K, p = (int(v) for v in c["meta"])
+        mode = ops.BIAS_PER_FILTER if brelu == "b1relu" else ops.BIAS_PER_VERTEX
+        xt, Wt, bt = (T(c[k], dev).requires_grad_(True) for k in ("x", "W", "b"))
+        y, am = ops.spectral_fwd(xt, T(c["Ut"], dev), Wt, bt, p, mode, True, True)
+        y.backward(T(c["dy"], dev))
+        # reference values recomputed in fp64 from the stored fp32 basis (eigenvectors are host-BLAS dependent)
+        pr = dict(W=c["W"], b=c["b"], K=K, p=p)
+        z = O.filter_in_fourier(c["x"], c["Ut"], c["W"], np.float64)
+        a = O.b1relu(z, c["b"]) if brelu == "b1relu" else O.b2relu(z, c["b"])
+        yref, amref = O.mpool1(a, p, with_argmax=True)
+        dz, db = O.brelu_bwd(O.mpool1_bwd(c["dy"].astype(np.float64), amref, p, a.shape[1]), a, brelu == "b2relu")
+        dx, dW = O.fourier_bwd(c["x"], c["Ut"], c["W"], dz, np.float64)
+        assert rel_inf(y.detach().cpu().numpy(), yref) <= TOL, name
+        assert rel_inf(xt.grad.cpu().numpy(), dx) <= TOL, name
+        assert rel_inf(Wt.grad.cpu().numpy(), dW) <= TOL, name
+        assert rel_inf(bt.grad.cpu().numpy().reshape(db.shape), db) <= TOL, name
+        if p > 1:
+            check_argmax(am.cpu().numpy(), a, p, name)
+
+
+# ------------------------------------------------------------------------------------------ live oracle sweeps
+SWEEP = [
+    # lvl, B, Fin, Fout, K, p, brelu
+    (0, 6, 15, 32, 5, 4, "b1relu"),   # config 2, layer 1 shape
+    (2, 9, 32, 32, 5, 4, "b1relu"),   # config 2, layer 2 shape
+    (0, 3, 15, 32, 5, 1, "b2relu"),   # production-like b2relu, no pooling
+    (0, 4, 15, 32, 2, 4, "b1relu"),   # config 3a, K=2
+    (0, 4, 15, 32, 1, 4, "b1relu"),   # K=1 "firstorder" 
+    (2, 5, 32, 32, 2, 4, "b2relu"),
+    (1, 3, 7, 24, 10, 2, "b1relu"),
+    (3, 5, 32, 16, 20, 2, "b2relu"),
+    (4, 7, 3, 8, 25, 1, "b1relu"),
+    (2, 1, 1, 1, 3, 1, "b1relu"),     # degenerate widths
+    (2, 2, 33, 40, 3, 2, "b1relu"),   # widths that are not multiples of 8
+    (1, 2, 64, 64, 3, 8, "b1relu"),
+]
+
+
+@pytest.mark.parametrize("lvl,B,Fin,Fout,K,p,brelu", SWEEP)
+def test_cheb_layer_vs_oracle(dev, graph_l4, lvl, B, Fin, Fout, K, p, brelu):
+    rng = np.random.RandomState(100 + lvl * 7 + K)
+    L = graph_l4["L"][lvl]
+    M = L.shape[0]
+    x = rng.randn(B, M, Fin).astype(np.float32)
+    W = (rng.randn(Fin * K, Fout) * 0.2).astype(np.float32)
+    b = (0.2 + 0.1 * rng.randn(*((M, Fout) if brelu == "b2relu" else (Fout,)))).astype(np.float32)
+    dy = rng.randn(B, M // p, Fout).astype(np.float32)
+    pr = [dict(W=W, b=b, K=K, p=p)]
+    y64, tr = O.conv_stack(x, [L], pr, brelu=brelu, dtype=np.float64, keep=True)
+    dx64, g64 = O.conv_stack_bwd(tr, [L], pr, dy, brelu=brelu, dtype=np.float64, first_needs_dx=True)
+    y32 = O.conv_stack(x, [L], pr, brelu=brelu, dtype=np.float32)
+    for algo in algos_for(B, M, graph_l4["Lt"][lvl].nnz, Fin, Fout, K, p, True, True):
+        r = run_layer(dev, L, x, W, b, K, p, brelu, algo, dy=dy)
+        tag = "algo=%d" % algo
+        err = rel_inf(r["y"], y64)
+        assert err <= TOL, (tag, err, "fp32 oracle noise floor", rel_inf(y32, y64))
+        assert rel_inf(r["dW"], g64[0]["dW"]) <= TOL, tag
+        assert rel_inf(r["db"], g64[0]["db"]) <= TOL, tag
+        assert rel_inf(r["dx"], dx64) <= TOL, tag
+        if p > 1:
+            check_argmax(r["argmax"], tr[0]["a"], p, tag)
+        # no-dx variant (layer 1 of a network) gives the same dW/db
+        r2 = run_layer(dev, L, x, W, b, K, p, brelu, algo, dy=dy, need_dx=False)
+        assert np.array_equal(r2["dW"], r["dW"]) and np.array_equal(r2["db"], r["db"]), tag
+
+
+@pytest.mark.parametrize("levels", [0, 1, 2, 4])
+def test_fused_perm_gather_all_graph_sizes(dev, levels):
+    """M in {360, 372, 384, 400}: raw [B,360,15] windows, perm_data_3d fused into the layer-1 load."""
+    from gcn_fmri_decoding_b200 import graclus, synth
+
+    A, gs, perm, L = synth.brain_graph(levels)
+    M = L[0].shape[0]
+    rng = np.random.RandomState(5)
+    xraw = synth.bold_windows(5, seed=3)
+    W = (rng.randn(15 * 5, 32) * 0.2).astype(np.float32)
+    b = np.full(32, 0.2, np.float32)
+    p = 2 if levels else 1
+    xp = graclus.perm_data_3d(xraw, perm).astype(np.float32) if perm is not None else xraw
+    y64, tr = O.conv_stack(xp, [L[0]], [dict(W=W, b=b, K=5, p=p)], dtype=np.float64, keep=True)
+    for algo in algos_for(5, M, 3684, 15, 32, 5, p):
+        if perm is None:
+            r = run_layer(dev, L[0], xraw, W, b, 5, p, "b1relu", algo)
+        else:
+            r = run_layer(dev, L[0], xraw, W, b, 5, p, "b1relu", algo, perm=np.asarray(perm))
+        assert rel_inf(r["y"], y64) <= TOL, (levels, algo)
+        if p > 1:
+            check_argmax(r["argmax"], tr[0]["a"], p)
+
+
+def test_perm_gather_bit_exact(dev, graph_l4):
+    import os
+
+    from conftest import GOLDEN
+    from gcn_fmri_decoding_b200 import ops
+
+    z = np.load(os.path.join(GOLDEN, "ref_fourier_perm.npz"))
+    got = ops.perm_gather(T(z["x"], dev), T(graph_l4["perm"], dev, torch.int32)).cpu().numpy()
+    assert got.dtype == np.float32 and np.array_equal(got, z["x_perm"].astype(np.float32))
+    with pytest.raises(ValueError):
+        ops.perm_gather(T(z["x"], dev), T(np.arange(10), dev, torch.int32))
+
+
+@pytest.mark.parametrize("M,p", [(10, 4), (7, 2), (16, 8), (5, 1), (33, 16)])
+def test_standalone_brelu_mpool_ragged(dev, M, p):
+    """b1relu/b2relu and mpool1 one by one, including ragged M (tf SAME padding)."""
+    from gcn_fmri_decoding_b200 import ops
+
+    rng = np.random.RandomState(M * 10 + p)
+    x = rng.randn(3, M, 6).astype(np.float32)
+    b1 = rng.randn(6).astype(np.float32)
+    b2 = rng.randn(M, 6).astype(np.float32)
+    for b, mode, per_vertex in ((b1, ops.BIAS_PER_FILTER, False), (b2, ops.BIAS_PER_VERTEX, True)):
+        xt, bt = T(x, dev).requires_grad_(True), T(b, dev).requires_grad_(True)
+        a = ops.brelu_fwd(xt, bt, mode)
+        y, am = ops.mpool_fwd(a, p)
+        a_ref = O.b2relu(x, b) if per_vertex else O.b1relu(x, b)
+        y_ref, am_ref = O.mpool1(a_ref, p, with_argmax=True)
+        assert np.array_equal(a.detach().cpu().numpy(), a_ref)  # one add and one max: bit-exact
+        assert np.array_equal(y.detach().cpu().numpy(), y_ref)
+        if p > 1:
+            assert np.array_equal(am.cpu().numpy(), am_ref)
+        dy = rng.randn(*y_ref.shape).astype(np.float32)
+        y.backward(T(dy, dev))
+        da = O.mpool1_bwd(dy, am_ref, p, M) if p > 1 else dy
+        dz, db = O.brelu_bwd(da.astype(np.float64), a_ref, per_vertex)
+        assert rel_inf(xt.grad.cpu().numpy(), dz) <= 1e-6
+        assert rel_inf(bt.grad.cpu().numpy(), db) <= 1e-5
+
+
+def test_error_behaviour(dev, graph_l4):
+    """Shape/dtype/arity violations raise ValueError, like the reference's asserts."""
+    from gcn_fmri_decoding_b200 import ops
+    from gcn_fmri_decoding_b200.plan import GraphPlan
+
+    pl = GraphPlan(graph_l4["L"][4], dev)
+    x = torch.zeros(2, 25, 3, device=dev)
+    W = torch.zeros(9, 4, device=dev)
+    b = torch.zeros(4, device=dev)
+    with pytest.raises(ValueError):  # W rows != Fin*K
+        ops.cheb_fwd(x, None, *pl.tensors(), W, b, 2, 1, ops.BIAS_PER_FILTER, True, False, 0)
+    with pytest.raises(ValueError):  # wrong vertex count
+        ops.cheb_fwd(torch.zeros(2, 24, 3, device=dev), None, *pl.tensors(), W, b, 3, 1, ops.BIAS_PER_FILTER, True, False, 0)
+    with pytest.raises(ValueError):  # pooling size not a power of two
+        ops.cheb_fwd(x, None, *pl.tensors(), W, b, 3, 3, ops.BIAS_PER_FILTER, True, False, 0)
+    with pytest.raises(ValueError):  # float64 input
+        ops.cheb_fwd(x.double(), None, *pl.tensors(), W, b, 3, 1, ops.BIAS_PER_FILTER, True, False, 0)
+    with pytest.raises(ValueError):  # K < 1
+        ops.cheb_fwd(x, None, *pl.tensors(), torch.zeros(0, 4, device=dev), b, 0, 1, ops.BIAS_PER_FILTER, True, False, 0)
+    y, _ = ops.cheb_fwd(x, None, *pl.tensors(), W, b, 3, 1, ops.BIAS_PER_FILTER, True, False, 0)
+    assert y.shape == (2, 25, 4) and float(y.abs().sum()) == 0.0
+
+
+# ------------------------------------------------------------------------------------------ whole model
+def build_model(graph, F, K, p, Mfc, filt, brelu, dev, fused=True, perm=None, algo=0):
+    from gcn_fmri_decoding_b200.models import cgcnn
+
+    return cgcnn(L=graph["L"], F=F, K=K, p=p, M=Mfc, filter=filt, brelu=brelu, channel=15, device=dev, seed=7,
+                 regularization=5e-4, batch_size=16, perm=perm, n_input_vertices=360, fused=fused, algo=algo)
+
+
+def oracle_logits(model, xperm, dtype=np.float64):
+    sd = model.state_dict_tf()
+    n = len(model.p)
+    params = [dict(W=sd["conv%d/weights" % (i + 1)], b=sd["conv%d/bias" % (i + 1)].reshape(
+        (-1, model.F[i]) if model.brelu_name == "b2relu" else (model.F[i],)), K=model.K[i], p=model.p[i]) for i in range(n)]
+    h = O.conv_stack(xperm, model.L, params, filter=model.filter_name, brelu=model.brelu_name, dtype=dtype)
+    names = ["fc%d" % (i + 1) for i in range(len(model.M) - 1)] + ["logits"]
+    return O.head(h, [(sd[s + "/weights"], sd[s + "/bias"]) for s in names], dtype)
+
+
+@pytest.mark.parametrize("cfg", ["config2", "config1_b2", "config1_b1", "config3_k2", "config3_k1"])
+def test_model_logits_and_argmax(dev, graph_l1, graph_l4, cfg):
+    """Whole network (conv stack + head) against the oracle: logits within TOL, identical arg-max over 22 columns."""
+    from gcn_fmri_decoding_b200 import graclus, synth
+
+    if cfg == "config2":
+        g, F, K, p, filt, brelu = graph_l4, [32, 32], [5, 5], [4, 4], "chebyshev5", "b1relu"
+    elif cfg.startswith("config1"):
+        g, F, K, p, filt = graph_l1, [32] * 6, [5] * 6, [1] * 6, "chebyshev5"
+        brelu = "b2relu" if cfg.endswith("b2") else "b1relu"
+    elif cfg == "config3_k2":
+        g, F, K, p, filt, brelu = graph_l4, [32, 32], [2, 2], [4, 4], "chebyshev2", "b1relu"
+    else:
+        g, F, K, p, filt, brelu = graph_l4, [32, 32], [1, 1], [4, 4], "chebyshev5", "b1relu"
+    xraw = synth.bold_windows(16, seed=11)
+    xperm = graclus.perm_data_3d(xraw, g["perm"]).astype(np.float32)
+    model = build_model(g, F, K, p, [512, 256, 22], filt, brelu, dev, perm=g["perm"])
+    ref = oracle_logits(model, xperm)
+    with torch.no_grad():
+        fused_from_raw = model(T(xraw, dev)).cpu().numpy()          # gather fused into layer 1
+        fused_from_perm = model(T(xperm, dev), gather=False).cpu().numpy()
+        model.fused = False
+        unfused = model(T(xperm, dev), gather=False).cpu().numpy()   # filter / brelu / pool one by one
+    for got in (fused_from_raw, fused_from_perm, unfused):
+        assert got.shape == (16, 22)
+        assert rel_inf(got, ref) <= TOL
+        assert np.array_equal(got.argmax(1), ref.argmax(1))
+    assert np.array_equal(fused_from_raw, fused_from_perm)
+
+
+def test_model_spectral(dev, graph_l4):
+    from gcn_fmri_decoding_b200 import graclus, synth
+
+    g = graph_l4
+    xraw = synth.bold_windows(8, seed=12)
+    xperm = graclus.perm_data_3d(xraw, g["perm"]).astype(np.float32)
+    model = build_model(g, [32, 32], [0, 0], [4, 4], [512, 256, 22], "fourier", "b1relu", dev, perm=g["perm"])
+    sd = model.state_dict_tf()
+    # oracle with the very basis the model uses
+    h = xperm
+    for i in range(2):
+        Ut = model._spectral_plan(model.L[i]).Ut.cpu().numpy()
+        z = O.filter_in_fourier(h, Ut, sd["conv%d/weights" % (i + 1)], np.float64)
+        h = O.mpool1(O.b1relu(z, sd["conv%d/bias" % (i + 1)]), 4)
+    ref = O.head(h, [(sd[s + "/weights"], sd[s + "/bias"]) for s in ("fc1", "fc2", "logits")], np.float64)
+    with torch.no_grad():
+        got = model(T(xraw, dev)).cpu().numpy()
+    assert rel_inf(got, ref) <= TOL and np.array_equal(got.argmax(1), ref.argmax(1))
+
+
+def test_training_step_gradients_match_oracle(dev, graph_l4):
+    """Full backward through both conv layers and the head: dW/db of every conv layer against the oracle."""
+    from gcn_fmri_decoding_b200 import graclus, synth
+
+    g = graph_l4
+    B = 12
+    xraw = synth.bold_windows(B, seed=13)
+    labels = synth.labels(B, seed=13)
+    xperm = graclus.perm_data_3d(xraw, g["perm"]).astype(np.float32)
+    model = build_model(g, [32, 32], [5, 5], [4, 4], [512, 256, 22], "chebyshev5", "b1relu", dev, perm=g["perm"])
+    logits = model(T(xraw, dev))
+    loss = model.loss(logits, T(labels, dev, torch.long))
+    loss.backward()
+    # oracle: forward in fp64, softmax-CE gradient, head backward, conv backward
+    sd = {k: v.astype(np.float64) for k, v in model.state_dict_tf().items()}
+    params = [dict(W=sd["conv%d/weights" % (i + 1)], b=sd["conv%d/bias" % (i + 1)].reshape(32), K=5, p=4) for i in range(2)]
+    h, tr = O.conv_stack(xperm, model.L, params, dtype=np.float64, keep=True)
+    hm = h.mean(-1)
+    a1 = np.maximum(hm @ sd["fc1/weights"] + sd["fc1/bias"], 0)
+    a2 = np.maximum(a1 @ sd["fc2/weights"] + sd["fc2/bias"], 0)
+    lg = a2 @ sd["logits/weights"] + sd["logits/bias"]
+    regs = [sd["conv1/weights"], sd["conv2/weights"]] + [sd[s + t] for s in ("fc1", "fc2", "logits") for t in ("/weights", "/bias")]
+    assert abs(float(loss) - O.loss(lg, labels, regs, 5e-4)) <= 1e-4 * abs(float(loss))
+    pz = np.exp(lg - lg.max(1, keepdims=True))
+    pz /= pz.sum(1, keepdims=True)
+    pz[np.arange(B), labels] -= 1
+    dlg = pz / B
+    da2 = (dlg @ sd["logits/weights"].T) * (a2 > 0)
+    da1 = (da2 @ sd["fc2/weights"].T) * (a1 > 0)
+    dhm = da1 @ sd["fc1/weights"].T
+    dh = np.repeat(dhm[:, :, None], 32, 2) / 32
+    _, grads = O.conv_stack_bwd(tr, model.L, params, dh, dtype=np.float64)
+    for i in range(2):
+        gW = grads[i]["dW"] + 5e-4 * sd["conv%d/weights" % (i + 1)]
+        assert rel_inf(model.conv_weights[i].grad.cpu().numpy(), gW) <= TOL, i
+        assert rel_inf(model.conv_bias[i].grad.cpu().numpy().reshape(32), grads[i]["db"]) <= TOL, i
+
+
+# ------------------------------------------------------------------------------------------ full-size properties
+def test_full_size_properties(dev, graph_l4):
+    """BASELINE config-2 sizes (B=512): determinism, batch independence, linearity of the filter,
+    agreement of the two kernel families, pooled output = max over the un-pooled output."""
+    from gcn_fmri_decoding_b200 import ops
+    from gcn_fmri_decoding_b200.plan import GraphPlan
+
+    rng = np.random.RandomState(0)
+    B = 512
+    for lvl, Fin in ((0, 15), (2, 32)):
+        L = graph_l4["L"][lvl]
+        M = L.shape[0]
+        pl = GraphPlan(L, dev)
+        x1 = torch.randn(B, M, Fin, device=dev)
+        x2 = torch.randn(B, M, Fin, device=dev)
+        W = T((rng.randn(Fin * 5, 32) * 0.2).astype(np.float32), dev)
+        b = torch.full((32,), 0.2, device=dev)
+        outs = {}
+        for algo in algos_for(B, M, pl.nnz, Fin, 32, 5, 4):
+            y, am = ops.cheb_fwd(x1, None, *pl.tensors(), W, b, 5, 4, ops.BIAS_PER_FILTER, True, True, algo)
+            y_again, am_again = ops.cheb_fwd(x1, None, *pl.tensors(), W, b, 5, 4, ops.BIAS_PER_FILTER, True, True, algo)
+            assert torch.equal(y, y_again) and torch.equal(am, am_again)  # deterministic
+            ysub, _ = ops.cheb_fwd(x1[100:103].contiguous(), None, *pl.tensors(), W, b, 5, 4, ops.BIAS_PER_FILTER, True,
+                                   True, algo)
+            assert torch.allclose(ysub, y[100:103], rtol=0, atol=2e-5 * float(y.abs().max()))  # batch independence
+            # un-pooled activation, pooled by hand, must give the same values and arg-max
+            a, _ = ops.cheb_fwd(x1, None, *pl.tensors(), W, b, 5, 1, ops.BIAS_PER_FILTER, True, False, algo)
+            win = a.view(B, M // 4, 4, 32)
+            assert torch.equal(win.max(2).values, y)
+            assert torch.equal(win.argmax(2).to(torch.uint8)[win.max(2).values > 0], am[y > 0])
+            # linearity of the bare filter: f(2 x1 - 3 x2) = 2 f(x1) - 3 f(x2)
+            f = lambda t: ops.cheb_fwd(t, None, *pl.tensors(), W, None, 5, 1, ops.BIAS_NONE, False, False, algo)[0]
+            lhs, rhs = f(2 * x1 - 3 * x2), 2 * f(x1) - 3 * f(x2)
+            assert float((lhs - rhs).abs().max()) <= 1e-4 * float(rhs.abs().max())
+            outs[algo] = y
+        ys = list(outs.values())
+        for other in ys[1:]:
+            assert float((other - ys[0]).abs().max()) <= 1e-4 * float(ys[0].abs().max())
+
+
+def test_large_graph_general_path(dev):
+    """Vertex-level graph (config 5 family, scaled down): HBM-resident operator, K=25."""
+    from gcn_fmri_decoding_b200 import synth
+
+    L = synth.fibonacci_sphere_graph(3000, 6)
+    rng = np.random.RandomState(9)
+    x = rng.randn(3, 3000, 15).astype(np.float32)
+    W = (rng.randn(15 * 25, 32) * 0.05).astype(np.float32)
+    b = np.full(32, 0.2, np.float32)
+    dy = rng.randn(3, 3000, 32).astype(np.float32)
+    pr = [dict(W=W, b=b, K=25, p=1)]
+    y64, tr = O.conv_stack(x, [L], pr, dtype=np.float64, keep=True)
+    dx64, g64 = O.conv_stack_bwd(tr, [L], pr, dy, dtype=np.float64, first_needs_dx=True)
+    r = run_layer(dev, L, x, W, b, 25, 1, "b1relu", 0, dy=dy)
+    assert rel_inf(r["y"], y64) <= TOL
+    assert rel_inf(r["dW"], g64[0]["dW"]) <= TOL
+    assert rel_inf(r["dx"], dx64) <= TOL
