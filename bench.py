@@ -352,18 +352,29 @@ def main():
             dy1 = [torch.randn_like(ys1[i][0]) for i in range(n1)]
 
             def timed(fn, n, reps=3):
-                for i in range(3):
-                    fn(i % n)
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                """GPU seconds per call: the n calls (one per ring slot) are captured into a CUDA graph and the
+                graph replays are bracketed by CUDA events on the launching stream, so host launch overhead
+                (tens of microseconds per Python op call) is not counted as kernel time."""
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    for i in range(3):
+                        fn(i % n)
+                torch.cuda.current_stream().wait_stream(side)
                 c0 = lib.gcnb_launch_count()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    for i in range(n):
+                        fn(i)
+                per_call = (lib.gcnb_launch_count() - c0) / n
+                g.replay()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 torch.cuda.synchronize()
                 a.record()
                 for r in range(reps):
-                    for i in range(n):
-                        fn(i)
+                    g.replay()
                 b.record()
                 torch.cuda.synchronize()
-                per_call = (lib.gcnb_launch_count() - c0) / (reps * n)
                 return a.elapsed_time(b) * 1e-3 / (reps * n), per_call
 
             specs = [

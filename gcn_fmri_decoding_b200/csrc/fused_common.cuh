@@ -166,13 +166,14 @@ __device__ __forceinline__ void build_operator(const int32_t* __restrict__ rowpt
   __syncthreads();
 }
 
-// One recursion step for all rows dealt to this warp:
-//   dst[r] = first ? L src : 2 L src - dst[r]        (columns: the warp's CW columns, 4 per lane)
+// One recursion step for all rows dealt to this warp (columns: the warp's CW columns, 4 per lane):
+//   dst[r] = alpha * (A src)[r] - (use_old ? dst[r] : 0)
+// forward:  X_1 = L X_0 (alpha 1), X_k = 2 L X_{k-1} - X_{k-2};  adjoint (Clenshaw): b_k = 2 L^T b_{k+1} - b_{k+2}.
 // `part`/`nparts`: this warp's share of the row groups (round robin over the length-sorted order).
 template <int LPR>
 __device__ __noinline__ void spmm_rows(const OperatorSmem& op, const unsigned char* __restrict__ src,
-                                          unsigned char* __restrict__ dst, int Mpad, int col_byte, int part, int nparts,
-                                          bool first) {
+                                       unsigned char* __restrict__ dst, int Mpad, int col_byte, int part, int nparts,
+                                       float alpha, bool use_old) {
   constexpr int RPW = 32 / LPR;
   const int lane = threadIdx.x & 31;
   const int q = lane / LPR, sub = lane % LPR;
@@ -213,11 +214,26 @@ __device__ __noinline__ void spmm_rows(const OperatorSmem& op, const unsigned ch
     }
     a0.x += a1.x; a0.y += a1.y; a0.z += a1.z; a0.w += a1.w;
     float4* out = reinterpret_cast<float4*>(d + info.z);
-    if (!first) {
+    if (use_old) {
       const float4 o = *out;
-      a0.x = fmaf(2.f, a0.x, -o.x); a0.y = fmaf(2.f, a0.y, -o.y); a0.z = fmaf(2.f, a0.z, -o.z); a0.w = fmaf(2.f, a0.w, -o.w);
+      a0.x = fmaf(alpha, a0.x, -o.x); a0.y = fmaf(alpha, a0.y, -o.y); a0.z = fmaf(alpha, a0.z, -o.z); a0.w = fmaf(alpha, a0.w, -o.w);
+    } else {
+      a0.x *= alpha; a0.y *= alpha; a0.z *= alpha; a0.w *= alpha;
     }
     *out = a0;
+  }
+}
+
+// LPR = CW/4 lanes per row with CW the number of slab columns a warp works on (8 .. 128)
+__device__ __forceinline__ void spmm_dispatch(int LPR, const OperatorSmem& op, const unsigned char* src,
+                                              unsigned char* dst, int Mpad, int col_byte, int part, int nparts,
+                                              float alpha, bool use_old) {
+  switch (LPR) {
+    case 2: spmm_rows<2>(op, src, dst, Mpad, col_byte, part, nparts, alpha, use_old); break;
+    case 4: spmm_rows<4>(op, src, dst, Mpad, col_byte, part, nparts, alpha, use_old); break;
+    case 8: spmm_rows<8>(op, src, dst, Mpad, col_byte, part, nparts, alpha, use_old); break;
+    case 16: spmm_rows<16>(op, src, dst, Mpad, col_byte, part, nparts, alpha, use_old); break;
+    default: spmm_rows<32>(op, src, dst, Mpad, col_byte, part, nparts, alpha, use_old); break;
   }
 }
 

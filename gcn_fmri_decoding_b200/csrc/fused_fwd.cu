@@ -29,6 +29,7 @@ struct FwdParams {
   int off_wfrag, off_slab;  // byte offsets into dynamic smem (operator image at 0)
   int off_stage;            // raw staging buffer for the TMA bulk prefetch of the next tile (0 = none)
   int log2p;
+  int debug;  // profiling aid: bit0 skip sparse step, bit1 skip contraction, bit2 skip stores
 };
 
 // one step of the pooled first-maximum reduction across lanes whose row index differs in one bit
@@ -134,17 +135,15 @@ __global__ void __launch_bounds__((SLOTS * NT > 8) ? 512 : 896, 1) k_cheb_fwd_fu
 
     for (int k = 0; k < P.K; ++k) {
       unsigned char* cur = (k & 1) ? slabB : slabA;  // holds X_k after the sparse step below
-      if (k > 0) {
+      if (k > 0 && !(P.debug & 1)) {
         const unsigned char* src = (k & 1) ? slabA : slabB;
-        if (G.LPR == 8) spmm_rows<8>(op, src, cur, G.Mpad, col_byte, rw, G.RW, k == 1);
-        else if (G.LPR == 16) spmm_rows<16>(op, src, cur, G.Mpad, col_byte, rw, G.RW, k == 1);
-        else spmm_rows<32>(op, src, cur, G.Mpad, col_byte, rw, G.RW, k == 1);
+        spmm_dispatch(G.LPR, op, src, cur, G.Mpad, col_byte, rw, G.RW, k == 1 ? 1.f : 2.f, k > 1);
         __syncthreads();  // X_k complete (rows of this phase are not the rows of the tensor-core phase)
       }
       // ---- contraction of the warp's own row tiles of X_k with the taps of order k --------------------
       const float4* wk = wfrag + (size_t)k * KS * NT * 32 + lane;
       const float* curf = reinterpret_cast<const float*>(cur) + g * RS + sg * G.WS * FP + t;
-      for (int ks = 0; ks < KS; ++ks) {
+      for (int ks = 0; ks < ((P.debug & 2) ? 0 : KS); ++ks) {
         uint32_t ah[SLOTS][4], al[SLOTS][4];
 #pragma unroll
         for (int a = 0; a < SLOTS; ++a) {
@@ -180,7 +179,7 @@ __global__ void __launch_bounds__((SLOTS * NT > 8) ? 512 : 896, 1) k_cheb_fwd_fu
       const int tt = a / G.WS, s = a - tt * G.WS;
       const int rt = rw + tt * G.RW;
       const int b = b0 + sg * G.WS + s;
-      const bool live = (a < G.TPW * G.WS) && rt < G.RT && b < P.B;  // warp-uniform
+      const bool live = (a < G.TPW * G.WS) && rt < G.RT && b < P.B && !(P.debug & 4);  // warp-uniform
       if (!live) continue;
 #pragma unroll
       for (int n = 0; n < NT; ++n) {
@@ -374,6 +373,7 @@ int fused_cheb_fwd(const float* x, const int32_t* perm, int M_in, const gcnb_csr
   P.ntiles = ceil_div(s.B, pl.g.S);
   P.off_wfrag = pl.off_wfrag; P.off_slab = pl.off_slab; P.off_stage = pl.off_stage;
   P.log2p = 0;
+  P.debug = env_int("GCNB_FWD_DEBUG", 0);
   while ((1 << P.log2p) < s.p) ++P.log2p;
 #define GCNB_FWD_CASE(nt, sl) \
   if (pl.NT == nt && pl.SLOTS == sl) return launch_fwd<nt, sl>(P, pl, st);

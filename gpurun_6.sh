@@ -1,0 +1,2 @@
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15
+TAG=fused python tools/time_layers.py
