@@ -275,14 +275,13 @@ def main():
     value = world * BATCH * args.steps / (ms_total * 1e-3)
     if sampler:
         sampler.mark()
-    # keep the GPU under the same load for >= 1.5 s so that nvidia-smi (100 ms period) sees the clocks
-    if rank == 0 and ms_total < 1500:
-        t_end = time.time() + 1.5
-        i = 0
-        while time.time() < t_end:
+    # keep the GPU under the same load for >= 1.5 s so that nvidia-smi (100 ms period) sees the clocks.
+    # Every rank runs the same number of extra steps (the step contains a collective).
+    if ms_total < 1500:
+        extra = int(min(20000, np.ceil(1500.0 / max(ms_total / args.steps, 1e-3))))
+        for i in range(extra):
             trainer.step(ring_x[i % R], ring_y[i % R])
-            i += 1
-            if i % 50 == 0:
+            if i % 50 == 49:
                 torch.cuda.synchronize()
         torch.cuda.synchronize()
         if sampler:
@@ -429,8 +428,9 @@ def main():
             "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
             "roofline": roofline, "cpu_baseline": cpu,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()  # rank 0 is the only one doing the roofline / CPU legs; the others wait here
         dist.destroy_process_group()
 
 
