@@ -214,7 +214,7 @@ def main():
 
     from gcn_fmri_decoding_b200 import _lib, ops, synth
     from gcn_fmri_decoding_b200.models import cgcnn
-    from gcn_fmri_decoding_b200.train import Trainer
+    from gcn_fmri_decoding_b200.train import FusedTrainer
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -231,7 +231,8 @@ def main():
     A, gs, perm, L = synth.brain_graph(4)
     model = cgcnn(L=L, F=F, K=K, p=P, M=MFC, channel=15, device=dev, seed=7, regularization=REG, batch_size=BATCH,
                   perm=perm, n_input_vertices=360, algo=args.algo)
-    trainer = Trainer(model, use_cuda_graph=not args.no_graph)
+    # dropout keep-probability 0.5 on the FC layers, as the reference trains (model.py:169, models_gcn.py:145)
+    trainer = FusedTrainer(model, use_cuda_graph=not args.no_graph, dropout=0.5)
 
     # ring of distinct resident batches: R x 11.06 MB of raw windows  (> 2 x 126 MB L2)
     R = 25
@@ -246,15 +247,17 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # launches of this library per step (counted on an eager step; a graph replays the same launches)
-    eager = Trainer(model, use_cuda_graph=False, distributed=False)
-    state = eager._snapshot()
+    # launches of this library per step (counted on an eager step outside the timed region, state restored;
+    # the CUDA graph replays exactly these launches).  world > 1: the eager step contains the all-reduce, every
+    # rank runs it.
+    snap = [t.clone() for t in (trainer.flat_p, trainer.flat_m, trainer.flat_v, trainer.state)]
     c0 = lib.gcnb_launch_count()
-    eager._step_impl(ring_x[0], ring_y[0], 1.0)
+    trainer._step_impl(ring_x[0], ring_y[0])
     torch.cuda.synchronize()
     launches_per_step = int(lib.gcnb_launch_count() - c0)
-    eager._restore(state)
-    del eager
+    with torch.no_grad():
+        for t, q in zip((trainer.flat_p, trainer.flat_m, trainer.flat_v, trainer.state), snap):
+            t.copy_(q)
 
     sampler = ClockSampler(local) if rank == 0 else None
     for i in range(args.warmup):
@@ -421,7 +424,8 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": BATCH * world, "parallelism": "dp%d" % world,
                        "l2_policy": "inputs rotate through a ring of %d distinct batches (%.0f MB > 2x L2)" % (R, R * 11.06),
-                       "cuda_graph": not args.no_graph, "algo": args.algo, "final_loss": final_loss},
+                       "cuda_graph": not args.no_graph, "algo": args.algo, "dropout_keep": 0.5,
+                       "final_loss": final_loss},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "windows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "wall_s": wall},

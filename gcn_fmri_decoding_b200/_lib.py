@@ -45,6 +45,9 @@ SIGNATURES = {
     "gcnb_perm_gather_f32": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),
     "gcnb_mean_f_fwd_f32": (_i, [_p, _p, _i, _i, _p]),
     "gcnb_mean_f_bwd_f32": (_i, [_p, _p, _i, _i, _p]),
+    "gcnb_softmax_xent_f32": (_i, [_p, _p, _p, _p, _p, _i, _i, _p]),
+    "gcnb_adam_tf_f32": (_i, [_p, _p, _p, _p, _p, _p, C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_float,
+                              C.c_float, C.c_float, _p]),
 }
 
 _lib = None

@@ -35,6 +35,7 @@ struct BwdParams {
   const float* W;
   float* dx;       // nullable
   float* dw_part;  // [grid][K][chunks][256]
+  float* db_part;  // [grid][FoP] per-filter bias-gradient partials (nullable)
   int B, Fin, Fout, K, p, log2p, relu;
   TileGeom g;      // FP/KS/RS describe the X slabs
   int FoP, RSz;    // padded Fout, dZ slab stride
@@ -96,6 +97,8 @@ __global__ void __launch_bounds__(896, 1) k_cheb_bwd_fused(const BwdParams P) {
   const int lrow = lane >> fp_shift, lf = lane & (FP - 1), rows_per_instr = 32 >> fp_shift;
   const int per_sample = P.M_in * P.Fin;
 
+  float dbacc = 0.f;  // this thread's filter (o = tid % FoP is the same in every iteration: FoP | blockDim)
+
   for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
     const int b0 = tile * G.S;
     __syncthreads();
@@ -127,6 +130,7 @@ __global__ void __launch_bounds__(896, 1) k_cheb_bwd_fused(const BwdParams P) {
           if (P.relu && !(__ldg(P.y + gi) > 0.f)) gval = 0.f;
           if (P.argmax != nullptr && P.p > 1) am = __ldg(P.argmax + gi);
         }
+        dbacc += gval;
         float* dst = dZ + (size_t)(j << P.log2p) * RSz + s * FoP + o;
         for (int i = 0; i < P.p; ++i) dst[(size_t)i * RSz] = (i == am) ? gval : 0.f;
       }
@@ -286,22 +290,43 @@ __global__ void __launch_bounds__(896, 1) k_cheb_bwd_fused(const BwdParams P) {
   __syncthreads();
   float* out = P.dw_part + (size_t)blockIdx.x * P.K * NCH * 256;
   for (int i = tid; i < P.K * NCH * 256; i += blockDim.x) out[i] = dWs[i];
+  if (P.db_part != nullptr) {  // per-filter bias gradient of this CTA: threads -> filters in fixed order
+    scratch[tid] = dbacc;
+    __syncthreads();
+    if (tid < FoP) {
+      float sum = 0.f;
+      for (int i = tid; i < (int)blockDim.x; i += FoP) sum += scratch[i];
+      P.db_part[(size_t)blockIdx.x * FoP + tid] = sum;
+    }
+  }
 }
 
-// dW[(f*K + k)*Fout + o] = sum over CTAs of the chunked partials (fixed order)
+// dW[(f*K + k)*Fout + o] = sum over CTAs of the chunked partials; one warp per output element, lanes stride over
+// the CTAs, fixed-order shuffle tree.  The trailing warps reduce the per-filter bias-gradient partials.
 __global__ void k_dw_from_partials(const float* __restrict__ part, float* __restrict__ dW, int nblocks, int K, int MT,
-                                   int NT, int Fin, int Fout) {
+                                   int NT, int Fin, int Fout, const float* __restrict__ db_part, float* __restrict__ db,
+                                   int FoP) {
   const int NCH = MT * NT / 2;
   const int total = K * NCH * 256;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w < total) {
     float s = 0.f;
-    for (int b = 0; b < nblocks; ++b) s += part[(size_t)b * total + i];
-    const int e = i & 255, chunk = (i >> 8) % NCH, k = i / (256 * NCH);
+    for (int b = lane; b < nblocks; b += 32) s += part[(size_t)b * total + w];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    const int e = w & 255, chunk = (w >> 8) % NCH, k = w / (256 * NCH);
     const int m = chunk / (NT / 2), np = chunk % (NT / 2);
-    const int reg = e >> 5, lane = e & 31, gg = lane >> 2, tt = lane & 3;
+    const int reg = e >> 5, ln = e & 31, gg = ln >> 2, tt = ln & 3;
     const int n = 2 * np + (reg >> 2), c = reg & 3;
     const int f = m * 16 + gg + ((c & 2) ? 8 : 0), o = n * 8 + 2 * tt + (c & 1);
-    if (f < Fin && o < Fout) dW[((size_t)f * K + k) * Fout + o] = s;
+    if (lane == 0 && f < Fin && o < Fout) dW[((size_t)f * K + k) * Fout + o] = s;
+  } else if (db_part != nullptr && w < total + Fout) {
+    const int o = w - total;
+    float s = 0.f;
+    for (int b = lane; b < nblocks; b += 32) s += db_part[(size_t)b * FoP + o];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if (lane == 0) db[o] = s;
   }
 }
 
@@ -355,7 +380,7 @@ __global__ void k_db_final(const float* __restrict__ part, float* __restrict__ d
 // host side
 // ------------------------------------------------------------------------------------------------
 static const size_t kSmemBudgetBwd = 225 * 1024;
-static const int kDbChunks = 8;
+static const int kDbChunks = 64;
 
 struct BwdPlan {
   bool ok;
@@ -451,7 +476,7 @@ size_t fused_cheb_workspace(const LayerShape& s, bool backward, bool need_dx) {
   if (!backward) return 256;
   const BwdPlan pl = plan_bwd(s, need_dx);
   if (!pl.ok) return 0;
-  const size_t part = (size_t)148 * 2 * s.K * pl.nchunks * 256 * 4;  // up to 296 CTAs
+  const size_t part = (size_t)148 * 2 * (s.K * pl.nchunks * 256 + 32) * 4;  // up to 296 CTAs (+ bias partials)
   const size_t dbp = (size_t)kDbChunks * s.M * s.Fout * 4;
   return align_up(part, 256) + align_up(dbp, 256) + 512;
 }
@@ -480,8 +505,9 @@ int fused_cheb_bwd(const float* x, const int32_t* perm, int M_in, const float* y
   const int ntiles = ceil_div(s.B, pl.g.S);
   const int grid = std::min(ntiles, std::min(di.sm_count, 296));
   float* part = ws.take<float>((size_t)grid * s.K * pl.nchunks * 256);
+  float* dbf = ws.take<float>((size_t)grid * 32);
   float* dbp = ws.take<float>((size_t)kDbChunks * s.M * s.Fout);
-  if (!part || !dbp) {
+  if (!part || !dbp || !dbf) {
     set_error("workspace too small for the fused backward path");
     return GCNB_ERR_WORKSPACE;
   }
@@ -489,7 +515,8 @@ int fused_cheb_bwd(const float* x, const int32_t* perm, int M_in, const float* y
   P.x = x; P.perm = perm; P.M_in = M_in; P.y = y; P.argmax = argmax; P.dy = dy;
   P.rowptr = L.rowptr; P.col = L.col; P.val = L.val; P.nnz = L.nnz;
   P.rowptr_t = Lt ? Lt->rowptr : nullptr; P.col_t = Lt ? Lt->col : nullptr; P.val_t = Lt ? Lt->val : nullptr;
-  P.W = W; P.dx = dx; P.dw_part = part;
+  const bool db_fused = bias_mode == GCNB_BIAS_PER_FILTER && db != nullptr;
+  P.W = W; P.dx = dx; P.dw_part = part; P.db_part = db_fused ? dbf : nullptr;
   P.B = s.B; P.Fin = s.Fin; P.Fout = s.Fout; P.K = s.K; P.p = s.p; P.relu = relu;
   P.log2p = 0;
   while ((1 << P.log2p) < s.p) ++P.log2p;
@@ -510,10 +537,12 @@ int fused_cheb_bwd(const float* x, const int32_t* perm, int M_in, const float* y
   }
   {
     const int total = s.K * pl.nchunks * 256;
-    k_dw_from_partials<<<ceil_div(total, 256), 256, 0, st>>>(part, dW, grid, s.K, pl.MT, pl.NT, s.Fin, s.Fout);
+    const int warps = total + (db_fused ? s.Fout : 0);
+    k_dw_from_partials<<<ceil_div(warps * 32, 256), 256, 0, st>>>(part, dW, grid, s.K, pl.MT, pl.NT, s.Fin, s.Fout,
+                                                                  P.db_part, db, pl.FoP);
     GCNB_LAUNCH_CHECK("k_dw_from_partials");
   }
-  if (bias_mode != GCNB_BIAS_NONE && db != nullptr) {
+  if (bias_mode == GCNB_BIAS_PER_VERTEX && db != nullptr) {
     const int Mo = s.M / s.p;
     const int bchunk = ceil_div(s.B, kDbChunks);
     const int nch = ceil_div(s.B, bchunk);

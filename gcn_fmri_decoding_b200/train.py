@@ -162,3 +162,160 @@ def fit(model, train_data, train_labels, val_data=None, val_labels=None, trainer
                 msg += "  val acc %.2f%% loss %.4f" % (100.0 * float(np.mean(pred == np.asarray(val_labels))), vloss)
             print(msg + "  (%.1fs)" % (time.time() - t0))
     return losses
+
+
+class FusedTrainer:
+    """The training step with an explicit (autograd-free) schedule and as few launches as possible.
+
+    forward : fused conv launches (``ops.cheb_fwd`` / ``spectral_fwd``) -> mean over F -> FC stack (cuBLAS) ->
+              ``gcnb_softmax_xent_f32`` (loss and dlogits in one pass)
+    backward: FC stack written straight into one flat gradient buffer -> fused conv backward launches
+    update  : one all-reduce of the flat buffer (world > 1) -> ``gcnb_adam_tf_f32`` over the flat parameter buffer with
+              the L2 term of ``models_gcn.py:260-262`` folded in (``g += reg * p`` on the regularised tensors).
+    The whole step is captured once and replayed as a CUDA graph.  Parameters of the model become views into one flat
+    buffer.  Gradients equal those of ``Trainer`` (autograd) -- see ``tests/test_gpu_parity.py``.
+    """
+
+    def __init__(self, model, lr=1e-3, distributed=None, use_cuda_graph=True, dropout=1.0, beta1=0.9, beta2=0.999,
+                 eps=1e-8):
+        import ctypes as C
+
+        from . import _lib, ops
+
+        self.model, self.lr, self.b1, self.b2, self.eps = model, lr, beta1, beta2, eps
+        self.C, self._lib, self.ops = C, _lib, ops
+        self.keep = float(dropout) if dropout else 1.0
+        self.distributed = dist.is_available() and dist.is_initialized() if distributed is None else distributed
+        self.world = dist.get_world_size() if self.distributed else 1
+        self.params = [p for p in model.parameters()]
+        dev = self.params[0].device
+        sizes = [p.numel() for p in self.params]
+        self.n = sum(sizes)
+        self.flat_p = torch.empty(self.n, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(self.n, dtype=torch.float32, device=dev)
+        self.flat_m = torch.zeros(self.n, dtype=torch.float32, device=dev)
+        self.flat_v = torch.zeros(self.n, dtype=torch.float32, device=dev)
+        self.decay = torch.zeros(self.n, dtype=torch.uint8, device=dev)
+        self.state = torch.tensor([1.0, 1.0, 0.0], dtype=torch.float32, device=dev)
+        regularized = {id(p) for p in model._regularized}
+        self.gview = {}
+        off = 0
+        with torch.no_grad():
+            for p, n in zip(self.params, sizes):
+                self.flat_p[off:off + n].copy_(p.detach().reshape(-1))
+                p.data = self.flat_p[off:off + n].view_as(p)
+                self.gview[id(p)] = self.flat_g[off:off + n].view_as(p)
+                if id(p) in regularized:
+                    self.decay[off:off + n] = 1
+                off += n
+        if self.distributed:
+            dist.broadcast(self.flat_p, src=0)
+        self.use_cuda_graph = use_cuda_graph
+        self._graph = None
+        self._loss = torch.zeros((), dtype=torch.float32, device=dev)
+
+    # -- one step, eagerly ---------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def _step_impl(self, x, labels):
+        m, ops, C = self.model, self.ops, self.C
+        lib = self._lib.lib()
+        stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+        nconv, nfc = len(m.p), len(m.M)
+        mode = m._bias_mode()
+        gather = m.perm is not None and x.shape[1] == m.n_input_vertices != m.L[0].shape[0]
+        # ---- forward: conv stack ----
+        saved, h = [], x
+        for i in range(nconv):
+            perm = m.perm if (gather and i == 0) else None
+            if m.filter_name == "fourier":
+                if perm is not None:
+                    h = ops.perm_gather(h, perm)
+                sp = m._spectral_plan(m.L[i])
+                y, am = ops.spectral_fwd(h, sp.Ut, m.conv_weights[i], m.conv_bias[i], m.p[i], mode, True, True)
+                saved.append((h, None, y, am, sp))
+            else:
+                pl = m._plan(m.L[i])
+                y, am = ops.cheb_fwd(h, perm, *pl.tensors(), m.conv_weights[i], m.conv_bias[i], m.K[i], m.p[i], mode,
+                                     True, True, m.algo)
+                saved.append((h, perm, y, am, pl))
+            h = y
+        # ---- forward: head ----
+        acts = [ops.mean_f_fwd(h)]
+        masks = []
+        for i in range(nfc - 1):
+            a = torch.addmm(m.fc_bias[i], acts[-1], m.fc_weights[i]).relu_()
+            if self.keep < 1.0:
+                a, mask = torch.native_dropout(a, 1.0 - self.keep, True)
+                masks.append(mask)
+            acts.append(a)
+        logits = torch.addmm(m.fc_bias[nfc - 1], acts[-1], m.fc_weights[nfc - 1])
+        B, ncls = logits.shape
+        d = torch.empty_like(logits)
+        rows = torch.empty(B, dtype=torch.float32, device=x.device)
+        rc = lib.gcnb_softmax_xent_f32(C.c_void_p(logits.data_ptr()), C.c_void_p(labels.data_ptr()),
+                                       C.c_void_p(self._loss.data_ptr()), C.c_void_p(d.data_ptr()),
+                                       C.c_void_p(rows.data_ptr()), B, ncls, stream)
+        self._lib.check(rc, "gcnb_softmax_xent_f32")
+        # ---- backward: head, gradients land in the flat buffer ----
+        for i in range(nfc - 1, -1, -1):
+            torch.mm(acts[i].t(), d, out=self.gview[id(m.fc_weights[i])])
+            torch.sum(d, 0, out=self.gview[id(m.fc_bias[i])])
+            d = torch.mm(d, m.fc_weights[i].t())
+            if i > 0:
+                if self.keep < 1.0:
+                    d = torch.ops.aten.native_dropout_backward(d, masks[i - 1], 1.0 / self.keep)
+                d = torch.ops.aten.threshold_backward(d, acts[i], 0.0)
+        dy = torch.ops.gcn_b200.mean_f_bwd(d, h.shape[-1])
+        # ---- backward: conv stack ----
+        for i in range(nconv - 1, -1, -1):
+            hin, perm, y, am, pl = saved[i]
+            need_dx = i > 0
+            if m.filter_name == "fourier":
+                dx, dW, db = torch.ops.gcn_b200.spectral_bwd(hin, y, am, dy, pl.Ut, m.conv_weights[i], m.p[i], mode, True,
+                                                             need_dx)
+            else:
+                dx, dW, db = torch.ops.gcn_b200.cheb_bwd(hin, perm, y, am, dy, *pl.tensors(), m.conv_weights[i], m.K[i],
+                                                         m.p[i], mode, True, need_dx, m.algo)
+            self.gview[id(m.conv_weights[i])].copy_(dW)
+            self.gview[id(m.conv_bias[i])].copy_(db.view_as(m.conv_bias[i]))
+            dy = dx
+        # ---- update ----
+        if self.world > 1:
+            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM)
+        rc = lib.gcnb_adam_tf_f32(C.c_void_p(self.flat_p.data_ptr()), C.c_void_p(self.flat_g.data_ptr()),
+                                  C.c_void_p(self.flat_m.data_ptr()), C.c_void_p(self.flat_v.data_ptr()),
+                                  C.c_void_p(self.decay.data_ptr()), C.c_void_p(self.state.data_ptr()), self.n, self.lr,
+                                  self.b1, self.b2, self.eps, float(m.regularization or 0.0), 1.0 / self.world, stream)
+        self._lib.check(rc, "gcnb_adam_tf_f32")
+        return self._loss, logits
+
+    def regularization_term(self):
+        """``regularization * sum_v ||v||^2 / 2`` over the regularised tensors (reported with the loss, not needed by the step)."""
+        with torch.no_grad():
+            return float(self.model.regularization or 0.0) * 0.5 * float((self.flat_p * self.flat_p * self.decay).sum())
+
+    def step(self, x, labels, dropout=None):
+        """One optimisation step on the local shard; returns (cross-entropy loss tensor, logits).  ``labels`` int64."""
+        if not self.use_cuda_graph:
+            return self._step_impl(x, labels)
+        if self._graph is None:
+            self._sx, self._sl = torch.empty_like(x), torch.empty_like(labels)
+            self._sx.copy_(x)
+            self._sl.copy_(labels)
+            snap = [t.clone() for t in (self.flat_p, self.flat_m, self.flat_v, self.state)]
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    self._step_impl(self._sx, self._sl)
+            torch.cuda.current_stream().wait_stream(side)
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self._out = self._step_impl(self._sx, self._sl)
+            with torch.no_grad():
+                for t, s in zip((self.flat_p, self.flat_m, self.flat_v, self.state), snap):
+                    t.copy_(s)
+        self._sx.copy_(x, non_blocking=True)
+        self._sl.copy_(labels, non_blocking=True)
+        self._graph.replay()
+        return self._out

@@ -147,6 +147,25 @@ GCNB_API int gcnb_perm_gather_f32(const float* x, const int32_t* perm, float* y,
 GCNB_API int gcnb_mean_f_fwd_f32(const float* x, float* y, int rows, int F, gcnb_stream_t stream);
 GCNB_API int gcnb_mean_f_bwd_f32(const float* dy, float* dx, int rows, int F, gcnb_stream_t stream);
 
+/*
+ * Sparse softmax cross-entropy, forward and backward in one pass (models_gcn.py:253-259):
+ *   loss = mean_b (logsumexp(logits[b]) - logits[b][labels[b]]);  dlogits = (softmax - onehot) / B  (nullable).
+ * loss_rows[B] is scratch for the per-row losses (fixed-order mean).
+ */
+GCNB_API int gcnb_softmax_xent_f32(const float* logits, const int64_t* labels, float* loss, float* dlogits,
+                          float* loss_rows, int B, int C, gcnb_stream_t stream);
+
+/*
+ * tf.train.AdamOptimizer step (models_gcn.py:294, TF-1.x "epsilon hat" form) over one flat buffer of n parameters:
+ *   g' = g * gscale + reg * p (only where decay[i] != 0; the L2 term of models_gcn.py:260-262)
+ *   m = b1 m + (1-b1) g';  v = b2 v + (1-b2) g'^2;  p -= lr sqrt(1-b2^t)/(1-b1^t) * m / (sqrt(v) + eps)
+ * state[3] (device) holds {b1^t, b2^t, lr_t}; initialise to {1, 1, 0}.  The step counter lives on the device so
+ * that a captured CUDA graph can replay the step.
+ */
+GCNB_API int gcnb_adam_tf_f32(float* p, const float* g, float* m, float* v, const uint8_t* decay, float* state,
+                     long long n, float lr, float beta1, float beta2, float eps, float reg, float gscale,
+                     gcnb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

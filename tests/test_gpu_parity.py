@@ -365,6 +365,30 @@ def test_training_step_gradients_match_oracle(dev, graph_l4):
         assert rel_inf(model.conv_bias[i].grad.cpu().numpy().reshape(32), grads[i]["db"]) <= TOL, i
 
 
+def test_fused_trainer_matches_autograd_trainer(dev, graph_l4):
+    """The explicit few-launch training step (FusedTrainer: custom xent + flat TF-Adam kernels, L2 folded into the
+    update) gives the same parameters after a step as the autograd step with the multi-tensor TFAdam."""
+    from gcn_fmri_decoding_b200 import synth
+    from gcn_fmri_decoding_b200.train import FusedTrainer, Trainer
+
+    g = graph_l4
+    x = T(synth.bold_windows(32, seed=21), dev)
+    y = T(synth.labels(32, seed=21), dev, torch.long)
+    for graph in (False, True):
+        a = build_model(g, [32, 32], [5, 5], [4, 4], [512, 256, 22], "chebyshev5", "b1relu", dev, perm=g["perm"])
+        b = build_model(g, [32, 32], [5, 5], [4, 4], [512, 256, 22], "chebyshev5", "b1relu", dev, perm=g["perm"])
+        ta = Trainer(a, distributed=False)
+        tb = FusedTrainer(b, distributed=False, use_cuda_graph=graph, dropout=1.0)
+        for _ in range(3):
+            la, _ = ta.step(x, y)
+            lb, _ = tb.step(x, y)
+        torch.cuda.synchronize()
+        assert abs(float(la) - (float(lb) + tb.regularization_term())) <= 2e-3 * abs(float(la))
+        for pa, pb in zip(a.parameters(), b.parameters()):
+            # three Adam steps of size 1e-3: compare the *updates*
+            assert float((pa - pb).abs().max()) <= 2e-5, graph
+
+
 # ------------------------------------------------------------------------------------------ full-size properties
 def test_full_size_properties(dev, graph_l4):
     """BASELINE config-2 sizes (B=512): determinism, batch independence, linearity of the filter,
