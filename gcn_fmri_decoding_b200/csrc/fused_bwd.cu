@@ -118,9 +118,10 @@ __global__ void __launch_bounds__(896, 1) k_cheb_bwd_fused(const BwdParams P) {
     {
       // pooled elements (s, j, o) of the tile, o fastest (coalesced); padded filters and rows are zeroed
       const int MoP = G.Mpad >> P.log2p;
-      const int total = G.S * MoP * FoP;
-      for (int e = tid; e < total; e += blockDim.x) {
-        const int o = e % FoP, j = (e / FoP) % MoP, s = e / (FoP * MoP);
+      const int fo_shift = FoP == 16 ? 4 : 5;
+      const int o = tid & (FoP - 1);
+      for (int rj = tid >> fo_shift; rj < G.S * MoP; rj += blockDim.x >> fo_shift) {
+        const int s = rj / MoP, j = rj - s * MoP;
         const int b = b0 + s;
         float gval = 0.f;
         int am = 0;
@@ -196,9 +197,17 @@ __global__ void __launch_bounds__(896, 1) k_cheb_bwd_fused(const BwdParams P) {
           }
           __syncthreads();
           for (int e = tid; e < 256; e += blockDim.x) {
-            float sum = 0.f;
-            for (int w = 0; w < nwarps; ++w) sum += scratch[w * 256 + e];
-            dWs[((size_t)k * NCH + m * (NT / 2) + np) * 256 + e] += sum;
+            // fixed association, four independent chains (the loads are independent, only the adds chain)
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+            int w = 0;
+            for (; w + 4 <= nwarps; w += 4) {
+              s0 += scratch[w * 256 + e];
+              s1 += scratch[(w + 1) * 256 + e];
+              s2 += scratch[(w + 2) * 256 + e];
+              s3 += scratch[(w + 3) * 256 + e];
+            }
+            for (; w < nwarps; ++w) s0 += scratch[w * 256 + e];
+            dWs[((size_t)k * NCH + m * (NT / 2) + np) * 256 + e] += (s0 + s1) + (s2 + s3);
           }
           __syncthreads();
         }

@@ -188,6 +188,20 @@ __device__ __noinline__ void spmm_rows(const OperatorSmem& op, const unsigned ch
     const int2* e = op.ent + info.x;
     float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
     int it = 0;
+    // four neighbours per trip: the four entry loads and the four data loads are independent (ILP); even entries
+    // accumulate into a0, odd ones into a1 -- the same association as the two-at-a-time loops below
+    for (; it + 4 <= nmin; it += 4) {
+      const int2 e0 = e[it], e1 = e[it + 1], e2 = e[it + 2], e3 = e[it + 3];
+      const float4 x0 = *reinterpret_cast<const float4*>(s + e0.x);
+      const float4 x1 = *reinterpret_cast<const float4*>(s + e1.x);
+      const float4 x2 = *reinterpret_cast<const float4*>(s + e2.x);
+      const float4 x3 = *reinterpret_cast<const float4*>(s + e3.x);
+      const float v0 = __int_as_float(e0.y), v1 = __int_as_float(e1.y), v2 = __int_as_float(e2.y), v3 = __int_as_float(e3.y);
+      a0.x = fmaf(v0, x0.x, a0.x); a0.y = fmaf(v0, x0.y, a0.y); a0.z = fmaf(v0, x0.z, a0.z); a0.w = fmaf(v0, x0.w, a0.w);
+      a1.x = fmaf(v1, x1.x, a1.x); a1.y = fmaf(v1, x1.y, a1.y); a1.z = fmaf(v1, x1.z, a1.z); a1.w = fmaf(v1, x1.w, a1.w);
+      a0.x = fmaf(v2, x2.x, a0.x); a0.y = fmaf(v2, x2.y, a0.y); a0.z = fmaf(v2, x2.z, a0.z); a0.w = fmaf(v2, x2.w, a0.w);
+      a1.x = fmaf(v3, x3.x, a1.x); a1.y = fmaf(v3, x3.y, a1.y); a1.z = fmaf(v3, x3.z, a1.z); a1.w = fmaf(v3, x3.w, a1.w);
+    }
     for (; it + 2 <= nmin; it += 2) {
       const int2 e0 = e[it], e1 = e[it + 1];
       const float4 x0 = *reinterpret_cast<const float4*>(s + e0.x);

@@ -28,19 +28,10 @@ struct FwdParams {
   int ntiles;
   int off_wfrag, off_slab;  // byte offsets into dynamic smem (operator image at 0)
   int off_stage;            // raw staging buffer for the TMA bulk prefetch of the next tile (0 = none)
+  int off_misc;             // int src_row[Mpad] (gather table, -1 = zero row) followed by float bias_f[64]
   int log2p;
   int debug;  // profiling aid: bit0 skip sparse step, bit1 skip contraction, bit2 skip stores
 };
-
-// one step of the pooled first-maximum reduction across lanes whose row index differs in one bit
-__device__ __forceinline__ void pool_step(float& v, int& idx, int lane_xor) {
-  const float ov = __shfl_xor_sync(0xffffffffu, v, lane_xor);
-  const int oi = __shfl_xor_sync(0xffffffffu, idx, lane_xor);
-  if (ov > v || (ov == v && oi < idx)) {
-    v = ov;
-    idx = oi;
-  }
-}
 
 // register-heavy instances (many accumulator fragments) run with at most 16 warps
 template <int NT, int SLOTS>
@@ -89,6 +80,19 @@ __global__ void __launch_bounds__((SLOTS * NT > 8) ? 512 : 896, 1) k_cheb_fwd_fu
     wfrag[idx] = make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(l0), __uint_as_float(l1));
   }
 
+  int* src_row = reinterpret_cast<int*>(smem + P.off_misc);
+  float* bias_f = reinterpret_cast<float*>(src_row + G.Mpad);
+  for (int m = tid; m < G.Mpad; m += blockDim.x) {
+    int src = -1;
+    if (m < G.M) {
+      src = P.perm ? __ldg(P.perm + m) : m;
+      if (src >= P.M_in) src = -1;  // fake vertex: stays zero (coarsening.py:260-264)
+    }
+    src_row[m] = src;
+  }
+  for (int o = tid; o < 64; o += blockDim.x)
+    bias_f[o] = (P.bias_mode == GCNB_BIAS_PER_FILTER && o < P.Fout) ? __ldg(P.bias + o) : 0.f;
+
   const int col_byte = sg * G.WS * FP * 4;  // first column of this warp's sample group
   const int Mo = G.M / P.p;
   // loader geometry: FP is a power of two; 32/FP rows per warp instruction
@@ -106,10 +110,8 @@ __global__ void __launch_bounds__((SLOTS * NT > 8) ? 512 : 896, 1) k_cheb_fwd_fu
       const float* xb = staged ? stage + s * per_sample : P.x + (long long)b * per_sample;
       for (int m = warp * rows_per_instr + lrow; m < G.Mpad; m += nwarps * rows_per_instr) {
         float v = 0.f;
-        if (b < P.B && m < G.M && lf < P.Fin) {
-          const int src = P.perm ? __ldg(P.perm + m) : m;
-          if (src < P.M_in) v = staged ? xb[src * P.Fin + lf] : __ldg(xb + (long long)src * P.Fin + lf);
-        }
+        const int src = src_row[m];
+        if (b < P.B && src >= 0 && lf < P.Fin) v = staged ? xb[src * P.Fin + lf] : __ldg(xb + (long long)src * P.Fin + lf);
         reinterpret_cast<float*>(slabA)[m * RS + s * FP + lf] = v;
       }
     }
@@ -133,17 +135,12 @@ __global__ void __launch_bounds__((SLOTS * NT > 8) ? 512 : 896, 1) k_cheb_fwd_fu
 #pragma unroll
         for (int c = 0; c < 4; ++c) acc[a][n][c] = 0.f;
 
-    for (int k = 0; k < P.K; ++k) {
-      unsigned char* cur = (k & 1) ? slabB : slabA;  // holds X_k after the sparse step below
-      if (k > 0 && !(P.debug & 1)) {
-        const unsigned char* src = (k & 1) ? slabA : slabB;
-        spmm_dispatch(G.LPR, op, src, cur, G.Mpad, col_byte, rw, G.RW, k == 1 ? 1.f : 2.f, k > 1);
-        __syncthreads();  // X_k complete (rows of this phase are not the rows of the tensor-core phase)
-      }
-      // ---- contraction of the warp's own row tiles of X_k with the taps of order k --------------------
+    // Contraction of the warp's own row tiles of X_k (in slab `cur`) with the taps of order k.
+    auto contract = [&](int k, const unsigned char* cur) {
+      if (P.debug & 2) return;
       const float4* wk = wfrag + (size_t)k * KS * NT * 32 + lane;
       const float* curf = reinterpret_cast<const float*>(cur) + g * RS + sg * G.WS * FP + t;
-      for (int ks = 0; ks < ((P.debug & 2) ? 0 : KS); ++ks) {
+      for (int ks = 0; ks < KS; ++ks) {
         uint32_t ah[SLOTS][4], al[SLOTS][4];
 #pragma unroll
         for (int a = 0; a < SLOTS; ++a) {
@@ -169,75 +166,65 @@ __global__ void __launch_bounds__((SLOTS * NT > 8) ? 512 : 896, 1) k_cheb_fwd_fu
           for (int a = 0; a < SLOTS; ++a) mma_3xtf32(acc[a][n], ah[a], al[a], bh0, bh1, bl0, bl1);
         }
       }
-      // no barrier here: the next sparse step reads `cur` and overwrites the other slab, whose last
-      // readers (sparse step k, contraction k-1) are all behind the barrier above.
-    }
+    };
 
-    // ---- epilogue: bias, ReLU, max-pool over p consecutive vertices (first maximum wins), store -------
+    // Step k: the sparse step that produces X_k (shared-memory / FFMA pipes) and the contraction of X_{k-1} (tensor
+    // pipe) are independent -- both only read X_{k-1}.  Odd warps run them in one order, even warps in the other,
+    // so at any time about half of the CTA feeds each pipe.  One barrier per order.
+    for (int k = 1; k < P.K; ++k) {
+      unsigned char* cur = (k & 1) ? slabB : slabA;         // receives X_k (holds X_{k-2})
+      const unsigned char* prev = (k & 1) ? slabA : slabB;  // X_{k-1}
+      if (warp & 1) contract(k - 1, prev);
+      if (!(P.debug & 1)) spmm_dispatch(G.LPR, op, prev, cur, G.Mpad, col_byte, rw, G.RW, k == 1 ? 1.f : 2.f, k > 1);
+      if (!(warp & 1)) contract(k - 1, prev);
+      __syncthreads();
+    }
+    contract(P.K - 1, ((P.K - 1) & 1) ? slabB : slabA);
+
+    // ---- epilogue: bias, ReLU, max-pool over p consecutive vertices (first maximum wins), store -------------
+    // The accumulator fragments of one (row tile, sample) go through the warp's own 16 rows of the slab that is
+    // no longer needed (X_{K-2}); then lane = filter: p values per pooled row are read back conflict free, the
+    // pooled row is stored as one coalesced 128-byte line (arg-max bytes: 32 bytes).  Only __syncwarp is needed.
+    {
+      float* fs = reinterpret_cast<float*>(((P.K - 1) & 1) ? slabA : slabB);
 #pragma unroll
-    for (int a = 0; a < SLOTS; ++a) {
-      const int tt = a / G.WS, s = a - tt * G.WS;
-      const int rt = rw + tt * G.RW;
-      const int b = b0 + sg * G.WS + s;
-      const bool live = (a < G.TPW * G.WS) && rt < G.RT && b < P.B && !(P.debug & 4);  // warp-uniform
-      if (!live) continue;
+      for (int a = 0; a < SLOTS; ++a) {
+        const int tt = a / G.WS, s = a - tt * G.WS;
+        const int rt = rw + tt * G.RW;
+        const int b = b0 + sg * G.WS + s;
+        const bool live = (a < G.TPW * G.WS) && rt < G.RT && b < P.B && !(P.debug & 4);  // warp-uniform
+        if (!live) continue;
+        // own 16 rows, own column range (warps of other sample groups share the rows): CW = WS*FP >= 32 columns
+        float* tile_s = fs + (size_t)rt * 16 * RS + sg * G.WS * FP;
 #pragma unroll
-      for (int n = 0; n < NT; ++n) {
-        const int o = n * 8 + 2 * t;
-        float pv[2][2];
-        int pi[2][2];
+        for (int c0 = 0; c0 < NT; c0 += 4) {  // 32 filters at a time
+          __syncwarp();
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {  // h = 0: rows g (c0,c1); h = 1: rows g+8 (c2,c3)
-          const int r = rt * 16 + g + 8 * h;
-          float v0 = acc[a][n][2 * h], v1 = acc[a][n][2 * h + 1];
-          if (P.bias_mode == GCNB_BIAS_PER_FILTER) {
-            if (o < P.Fout) v0 += __ldg(P.bias + o);
-            if (o + 1 < P.Fout) v1 += __ldg(P.bias + o + 1);
-          } else if (P.bias_mode == GCNB_BIAS_PER_VERTEX && r < G.M) {
-            if (o < P.Fout) v0 += __ldg(P.bias + (long long)r * P.Fout + o);
-            if (o + 1 < P.Fout) v1 += __ldg(P.bias + (long long)r * P.Fout + o + 1);
+          for (int n = c0; n < c0 + 4 && n < NT; ++n) {
+            *reinterpret_cast<float2*>(tile_s + g * RS + (n - c0) * 8 + 2 * t) = make_float2(acc[a][n][0], acc[a][n][1]);
+            *reinterpret_cast<float2*>(tile_s + (g + 8) * RS + (n - c0) * 8 + 2 * t) = make_float2(acc[a][n][2], acc[a][n][3]);
           }
-          if (P.relu) {
-            v0 = fmaxf(v0, 0.f);
-            v1 = fmaxf(v1, 0.f);
-          }
-          pv[h][0] = v0;
-          pv[h][1] = v1;
-          pi[h][0] = pi[h][1] = (g + 8 * h) & (P.p - 1);
-        }
-        for (int step = 1; step < P.p && step < 8; step <<= 1) {
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            pool_step(pv[h][0], pi[h][0], 4 * step);
-            pool_step(pv[h][1], pi[h][1], 4 * step);
-          }
-        }
-        if (P.p == 16) {  // rows 0-7 against rows 8-15 (strictly greater: the lower half wins ties)
-#pragma unroll
-          for (int c = 0; c < 2; ++c)
-            if (pv[1][c] > pv[0][c]) {
-              pv[0][c] = pv[1][c];
-              pi[0][c] = pi[1][c];
-            }
-        }
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          if (P.p == 16 && h == 1) break;
-          const int r = rt * 16 + g + 8 * h;
-          if ((r & (P.p - 1)) != 0 || r >= G.M) continue;
-          const long long oidx = ((long long)b * Mo + (r >> P.log2p)) * P.Fout + o;
-          if (o + 1 < P.Fout && (P.Fout & 1) == 0) {
-            *reinterpret_cast<float2*>(P.y + oidx) = make_float2(pv[h][0], pv[h][1]);
-            if (P.argmax)
-              *reinterpret_cast<uchar2*>(P.argmax + oidx) = make_uchar2((unsigned char)pi[h][0], (unsigned char)pi[h][1]);
-          } else {
-            if (o < P.Fout) {
-              P.y[oidx] = pv[h][0];
-              if (P.argmax) P.argmax[oidx] = (uint8_t)pi[h][0];
-            }
-            if (o + 1 < P.Fout) {
-              P.y[oidx + 1] = pv[h][1];
-              if (P.argmax) P.argmax[oidx + 1] = (uint8_t)pi[h][1];
+          __syncwarp();
+          const int o = c0 * 8 + lane;
+          if (o < P.Fout && lane < (NT - c0) * 8) {
+            const float bf = bias_f[o];
+            for (int j = 0; j < (16 >> P.log2p); ++j) {
+              const int r0 = rt * 16 + (j << P.log2p);
+              if (r0 >= G.M) break;
+              float best = -INFINITY;
+              int bi = 0;
+              for (int i = 0; i < P.p; ++i) {
+                float v = tile_s[((j << P.log2p) + i) * RS + lane] + bf;
+                if (P.bias_mode == GCNB_BIAS_PER_VERTEX) v += __ldg(P.bias + (long long)(r0 + i) * P.Fout + o);
+                if (P.relu) v = fmaxf(v, 0.f);
+                if (v > best) {  // strict: the first maximum keeps the slot
+                  best = v;
+                  bi = i;
+                }
+              }
+              const long long oidx = ((long long)b * Mo + (r0 >> P.log2p)) * P.Fout + o;
+              P.y[oidx] = best;
+              if (P.argmax) P.argmax[oidx] = (uint8_t)bi;
             }
           }
         }
@@ -256,7 +243,7 @@ struct FwdPlan {
   TileGeom g;
   int NT, SLOTS;
   size_t smem;
-  int off_wfrag, off_slab, off_stage;
+  int off_wfrag, off_slab, off_stage, off_misc;
   bool staged;
 };
 
@@ -279,7 +266,8 @@ static FwdPlan plan_fwd(const LayerShape& s, int M_in, bool x_aligned16) {
   g.FP = s.Fin <= 8 ? 8 : (s.Fin <= 16 ? 16 : 32);
   g.KS = g.FP / 8;
   pl.NT = s.Fout <= 16 ? 2 : (s.Fout <= 32 ? 4 : 8);
-  const size_t fixed = operator_smem_bytes(g.Mpad, s.nnz) + (size_t)s.K * g.KS * pl.NT * 32 * 16;
+  const size_t misc = (size_t)g.Mpad * 4 + 64 * 4;
+  const size_t fixed = operator_smem_bytes(g.Mpad, s.nnz) + (size_t)s.K * g.KS * pl.NT * 32 * 16 + misc;
   // Candidates: WS samples per warp (CW = WS*FP columns in {32,64,128}) x SG sample groups.
   // Prefer the configuration with the fewest shared-memory wavefronts per nonzero (large CW), subject to
   // registers (SLOTS*NT accumulator fragments), warps (<= 28, or <= 16 for heavy instances) and smem.
@@ -300,7 +288,7 @@ static FwdPlan plan_fwd(const LayerShape& s, int M_in, bool x_aligned16) {
                              env_int("GCNB_FWD_NOSTAGE", 0) == 0;
       if (can_stage) need += stage_bytes;
       for (int heavy = 0; heavy < 2; ++heavy) {
-        const int maxw = heavy ? 16 : 28;
+        const int maxw = heavy ? 16 : env_int("GCNB_FWD_MAXW", 28);
         int rwn = std::min(g.RT, maxw / sgn);
         if (rwn < 1) continue;
         const int tpw = ceil_div(g.RT, rwn);
@@ -334,7 +322,8 @@ static FwdPlan plan_fwd(const LayerShape& s, int M_in, bool x_aligned16) {
   }
   if (best_score < 0) return pl;
   pl.off_wfrag = (int)operator_smem_bytes(g.Mpad, s.nnz);
-  pl.off_slab = pl.off_wfrag + s.K * g.KS * pl.NT * 32 * 16;
+  pl.off_misc = pl.off_wfrag + s.K * g.KS * pl.NT * 32 * 16;
+  pl.off_slab = pl.off_misc + (int)misc;
   pl.off_stage = pl.staged ? pl.off_slab + 2 * g.Mpad * g.RS * 4 + 16 : 0;
   pl.ok = true;
   return pl;
@@ -371,7 +360,7 @@ int fused_cheb_fwd(const float* x, const int32_t* perm, int M_in, const gcnb_csr
   P.B = s.B; P.Fin = s.Fin; P.Fout = s.Fout; P.K = s.K; P.p = s.p; P.bias_mode = bias_mode; P.relu = relu;
   P.g = pl.g;
   P.ntiles = ceil_div(s.B, pl.g.S);
-  P.off_wfrag = pl.off_wfrag; P.off_slab = pl.off_slab; P.off_stage = pl.off_stage;
+  P.off_wfrag = pl.off_wfrag; P.off_slab = pl.off_slab; P.off_stage = pl.off_stage; P.off_misc = pl.off_misc;
   P.log2p = 0;
   P.debug = env_int("GCNB_FWD_DEBUG", 0);
   while ((1 << P.log2p) < s.p) ++P.log2p;
