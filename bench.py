@@ -225,6 +225,8 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.lib()
 
@@ -434,8 +436,20 @@ def main():
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.barrier()  # rank 0 is the only one doing the roofline / CPU legs; the others wait here
-        dist.destroy_process_group()
+        # Rank 0 alone runs the roofline / CPU legs; the others wait for it on the rendezvous store (a host-side
+        # wait: no collective is left pending on the device).  The processes then leave without tearing the
+        # communicator down: destroying a process group whose collectives live in captured CUDA graphs can hang.
+        import datetime
+
+        store = dist.distributed_c10d._get_default_store()
+        if rank == 0:
+            store.set("gcnb_bench_done", "1")
+        else:
+            store.wait(["gcnb_bench_done"], datetime.timedelta(minutes=30))
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
