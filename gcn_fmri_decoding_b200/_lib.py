@@ -33,8 +33,8 @@ SIGNATURES = {
     "gcnb_launch_count": (C.c_ulonglong, []),
     "gcnb_cheb_fused_supported": (_i, [_i] * 9),
     "gcnb_cheb_workspace_bytes": (_z, [_i] * 10),
-    "gcnb_cheb_fwd_f32": (_i, [_p, _p, _i, _CSRP, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _z, _p]),
-    "gcnb_cheb_bwd_f32": (_i, [_p, _p, _i, _p, _p, _p, _CSRP, _CSRP, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _z, _p]),
+    "gcnb_cheb_fwd_f32": (_i, [_p, _p, _i, _CSRP, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _z, _p]),
+    "gcnb_cheb_bwd_f32": (_i, [_p, _p, _i, _p, _p, _p, _i, _CSRP, _CSRP, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _z, _p]),
     "gcnb_spectral_workspace_bytes": (_z, [_i] * 6),
     "gcnb_spectral_fwd_f32": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _z, _p]),
     "gcnb_spectral_bwd_f32": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _z, _p]),
@@ -45,9 +45,13 @@ SIGNATURES = {
     "gcnb_perm_gather_f32": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),
     "gcnb_mean_f_fwd_f32": (_i, [_p, _p, _i, _i, _p]),
     "gcnb_mean_f_bwd_f32": (_i, [_p, _p, _i, _i, _p]),
-    "gcnb_softmax_xent_f32": (_i, [_p, _p, _p, _p, _p, _i, _i, _p]),
+    "gcnb_softmax_xent_f32": (_i, [_p, _p, _p, _p, _p, _i, _i, _p, C.c_float, C.c_float, C.c_float, _p]),
+    "gcnb_relu_dropout_fwd_f32": (_i, [_p, C.c_longlong, _i, _i, C.c_float, C.c_uint, _p, _p]),
+    "gcnb_relu_dropout_bwd_f32": (_i, [_p, _p, C.c_longlong, _i, _i, _i, C.c_float, _p]),
+    "gcnb_colsum_multi_f32": (_i, [_p, _p, _p, _p, _i, _p]),
+    "gcnb_gemm_f32": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "gcnb_adam_tf_f32": (_i, [_p, _p, _p, _p, _p, _p, C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_float,
-                              C.c_float, C.c_float, _p]),
+                              C.c_float, C.c_float, _i, _p]),
 }
 
 _lib = None

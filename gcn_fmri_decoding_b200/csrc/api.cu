@@ -155,6 +155,18 @@ static inline unsigned grid_for(long long total, int block = 256) {
   return (unsigned)std::max<long long>(1, std::min<long long>(ceil_div_ll(total, block), 148 * 16));
 }
 
+int launch_mean_f(const float* x, float* y, long long rows, int F, cudaStream_t st) {
+  k_mean_f_fwd<<<grid_for(rows * 32), 256, 0, st>>>(x, y, rows, F);
+  GCNB_LAUNCH_CHECK("k_mean_f_fwd");
+  return GCNB_OK;
+}
+
+int launch_mean_f_bwd(const float* dy, float* dx, long long rows, int F, cudaStream_t st) {
+  k_mean_f_bwd<<<grid_for(rows * F), 256, 0, st>>>(dy, dx, rows, F);
+  GCNB_LAUNCH_CHECK("k_mean_f_bwd");
+  return GCNB_OK;
+}
+
 static bool is_pow2(int v) { return v >= 1 && (v & (v - 1)) == 0; }
 
 static int check_layer(const char* who, const gcnb_csr* L, int B, int Fin, int Fout, int K, int p, int bias_mode,
@@ -192,12 +204,13 @@ size_t gcnb_cheb_workspace_bytes(int B, int M, int nnz, int Fin, int Fout, int K
   const bool fused_ok = backward ? fused_bwd_supported(s, need_dx != 0) : fused_fwd_supported(s);
   if (algo == GCNB_ALGO_FUSED || (algo == GCNB_ALGO_AUTO && fused_ok))
     return fused_ok ? fused_cheb_workspace(s, backward != 0, need_dx != 0) : 0;
-  return general_cheb_workspace(s, backward != 0, need_dx != 0);
+  return general_cheb_workspace(s, backward != 0, need_dx != 0) +
+         (backward ? align_up((size_t)B * ceil_div(M, p) * Fout * sizeof(float), 256) + 256 : 0);
 }
 
 int gcnb_cheb_fwd_f32(const float* x, const int32_t* perm, int M_in, const gcnb_csr* L, const float* W,
-                      const float* bias, float* y, uint8_t* argmax, int B, int Fin, int Fout, int K, int p,
-                      int bias_mode, int relu, int algo, void* workspace, size_t workspace_bytes,
+                      const float* bias, float* y, uint8_t* argmax, float* y_mean, int B, int Fin, int Fout, int K,
+                      int p, int bias_mode, int relu, int algo, void* workspace, size_t workspace_bytes,
                       gcnb_stream_t stream) {
   int rc = check_layer("gcnb_cheb_fwd_f32", L, B, Fin, Fout, K, p, bias_mode, bias);
   if (rc) return rc;
@@ -214,13 +227,19 @@ int gcnb_cheb_fwd_f32(const float* x, const int32_t* perm, int M_in, const gcnb_
               s.nnz, Fin, Fout, K, p);
     return GCNB_ERR_INVALID;
   }
-  if (algo == GCNB_ALGO_FUSED || (algo == GCNB_ALGO_AUTO && fused_ok))
-    return fused_cheb_fwd(x, perm, M_in, *L, W, bias, y, argmax, s, bias_mode, relu, ws, st);
-  return general_cheb_fwd(x, perm, M_in, *L, W, bias, y, argmax, s, bias_mode, relu, ws, st);
+  const long long pooled_rows = (long long)B * ceil_div(s.M, p);
+  if (algo == GCNB_ALGO_FUSED || (algo == GCNB_ALGO_AUTO && fused_ok)) {
+    rc = fused_cheb_fwd(x, perm, M_in, *L, W, bias, y, argmax, y_mean, s, bias_mode, relu, ws, st);
+    if (rc == GCNB_OK && y_mean != nullptr && Fout > 32) rc = launch_mean_f(y, y_mean, pooled_rows, Fout, st);
+    return rc;
+  }
+  rc = general_cheb_fwd(x, perm, M_in, *L, W, bias, y, argmax, s, bias_mode, relu, ws, st);
+  if (rc == GCNB_OK && y_mean != nullptr) rc = launch_mean_f(y, y_mean, pooled_rows, Fout, st);
+  return rc;
 }
 
 int gcnb_cheb_bwd_f32(const float* x, const int32_t* perm, int M_in, const float* y, const uint8_t* argmax,
-                      const float* dy, const gcnb_csr* L,
+                      const float* dy, int dy_is_mean, const gcnb_csr* L,
                       const gcnb_csr* Lt, const float* W, float* dx, float* dW, float* db, int B, int Fin,
                       int Fout, int K, int p, int bias_mode, int relu, int algo, void* workspace,
                       size_t workspace_bytes, gcnb_stream_t stream) {
@@ -243,7 +262,18 @@ int gcnb_cheb_bwd_f32(const float* x, const int32_t* perm, int M_in, const float
     return GCNB_ERR_INVALID;
   }
   if (algo == GCNB_ALGO_FUSED || (algo == GCNB_ALGO_AUTO && fused_ok))
-    return fused_cheb_bwd(x, perm, M_in, y, argmax, dy, *L, Lt, W, dx, dW, db, s, bias_mode, relu, ws, st);
+    return fused_cheb_bwd(x, perm, M_in, y, argmax, dy, *L, Lt, W, dx, dW, db, s, bias_mode, relu, dy_is_mean, ws, st);
+  if (dy_is_mean) {  // the general path works on the full gradient: expand dy/Fout over the filters first
+    const long long pooled_rows = (long long)B * ceil_div(s.M, p);
+    float* full = ws.take<float>((size_t)pooled_rows * Fout);
+    if (!full) {
+      set_error("gcnb_cheb_bwd_f32: workspace too small");
+      return GCNB_ERR_WORKSPACE;
+    }
+    rc = launch_mean_f_bwd(dy, full, pooled_rows, Fout, st);
+    if (rc) return rc;
+    dy = full;
+  }
   return general_cheb_bwd(x, perm, M_in, y, argmax, dy, *L, Lt, W, dx, dW, db, s, bias_mode, relu, ws, st);
 }
 

@@ -37,6 +37,7 @@ struct BwdParams {
   float* dw_part;  // [grid][K][chunks][256]
   float* db_part;  // [grid][FoP] per-filter bias-gradient partials (nullable)
   int B, Fin, Fout, K, p, log2p, relu;
+  int dy_is_mean;  // dy is [B][M/p]: the gradient of the mean over filters (every filter gets dy/Fout)
   TileGeom g;      // FP/KS/RS describe the X slabs
   int FoP, RSz;    // padded Fout, dZ slab stride
   int ntiles;
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(896, 1) k_cheb_bwd_fused(const BwdParams P) {
         int am = 0;
         if (b < P.B && j < Mo && o < P.Fout) {
           const long long gi = ((long long)b * Mo + j) * P.Fout + o;
-          gval = __ldg(P.dy + gi);
+          gval = P.dy_is_mean ? __ldg(P.dy + (long long)b * Mo + j) / (float)P.Fout : __ldg(P.dy + gi);
           if (P.relu && !(__ldg(P.y + gi) > 0.f)) gval = 0.f;
           if (P.argmax != nullptr && P.p > 1) am = __ldg(P.argmax + gi);
         }
@@ -341,7 +342,8 @@ __global__ void k_dw_from_partials(const float* __restrict__ part, float* __rest
 
 // bias gradient, stage 1: part[chunk][m][o] = sum over the samples of the chunk of dZ[b][m][o]
 __global__ void k_db_partial(const float* __restrict__ dy, const float* __restrict__ y, const uint8_t* __restrict__ argmax,
-                             float* __restrict__ part, int B, int M, int Fout, int p, int log2p, int relu, int bchunk) {
+                             float* __restrict__ part, int B, int M, int Fout, int p, int log2p, int relu, int bchunk,
+                             int dy_is_mean) {
   const int Mo = M >> log2p;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;  // pooled element (j, o)
   if (e >= Mo * Fout) return;
@@ -352,7 +354,7 @@ __global__ void k_db_partial(const float* __restrict__ dy, const float* __restri
   for (int i = 0; i < 16; ++i) acc[i] = 0.f;
   for (int b = blo; b < bhi; ++b) {
     const long long gi = ((long long)b * Mo + j) * Fout + o;
-    float g = __ldg(dy + gi);
+    float g = dy_is_mean ? __ldg(dy + (long long)b * Mo + j) / (float)Fout : __ldg(dy + gi);
     if (relu && !(__ldg(y + gi) > 0.f)) g = 0.f;
     const int am = (argmax != nullptr && p > 1) ? __ldg(argmax + gi) : 0;
 #pragma unroll
@@ -501,7 +503,7 @@ static int launch_bwd(const BwdParams& P, const BwdPlan& pl, int grid, cudaStrea
 
 int fused_cheb_bwd(const float* x, const int32_t* perm, int M_in, const float* y, const uint8_t* argmax, const float* dy,
                    const gcnb_csr& L, const gcnb_csr* Lt, const float* W, float* dx, float* dW, float* db,
-                   const LayerShape& s, int bias_mode, int relu, Workspace& ws, cudaStream_t st) {
+                   const LayerShape& s, int bias_mode, int relu, int dy_is_mean, Workspace& ws, cudaStream_t st) {
   const bool need_dx = dx != nullptr;
   const BwdPlan pl = plan_bwd(s, need_dx);
   if (!pl.ok) {
@@ -526,7 +528,7 @@ int fused_cheb_bwd(const float* x, const int32_t* perm, int M_in, const float* y
   P.rowptr_t = Lt ? Lt->rowptr : nullptr; P.col_t = Lt ? Lt->col : nullptr; P.val_t = Lt ? Lt->val : nullptr;
   const bool db_fused = bias_mode == GCNB_BIAS_PER_FILTER && db != nullptr;
   P.W = W; P.dx = dx; P.dw_part = part; P.db_part = db_fused ? dbf : nullptr;
-  P.B = s.B; P.Fin = s.Fin; P.Fout = s.Fout; P.K = s.K; P.p = s.p; P.relu = relu;
+  P.B = s.B; P.Fin = s.Fin; P.Fout = s.Fout; P.K = s.K; P.p = s.p; P.relu = relu; P.dy_is_mean = dy_is_mean;
   P.log2p = 0;
   while ((1 << P.log2p) < s.p) ++P.log2p;
   P.g = pl.g; P.FoP = pl.FoP; P.RSz = pl.RSz; P.ntiles = ntiles; P.nchunks = pl.nchunks;
@@ -556,7 +558,7 @@ int fused_cheb_bwd(const float* x, const int32_t* perm, int M_in, const float* y
     const int bchunk = ceil_div(s.B, kDbChunks);
     const int nch = ceil_div(s.B, bchunk);
     dim3 grid_db(ceil_div(Mo * s.Fout, 128), nch);
-    k_db_partial<<<grid_db, 128, 0, st>>>(dy, y, argmax, dbp, s.B, s.M, s.Fout, s.p, P.log2p, relu, bchunk);
+    k_db_partial<<<grid_db, 128, 0, st>>>(dy, y, argmax, dbp, s.B, s.M, s.Fout, s.p, P.log2p, relu, bchunk, dy_is_mean);
     GCNB_LAUNCH_CHECK("k_db_partial");
     const int n = bias_mode == GCNB_BIAS_PER_VERTEX ? s.M * s.Fout : s.Fout * 32;
     k_db_final<<<ceil_div(n, 128), 128, 0, st>>>(dbp, db, nch, s.M, s.Fout, bias_mode == GCNB_BIAS_PER_VERTEX);

@@ -22,6 +22,7 @@ struct FwdParams {
   const float* W;
   const float* bias;
   float* y;
+  float* y_mean;  // nullable: mean over the filters of the pooled output, [B][M/p] (models_gcn.py:673 fused)
   uint8_t* argmax;
   int B, Fin, Fout, K, p, bias_mode, relu;
   TileGeom g;
@@ -206,13 +207,14 @@ __global__ void __launch_bounds__((SLOTS * NT > 8) ? 512 : 896, 1) k_cheb_fwd_fu
           }
           __syncwarp();
           const int o = c0 * 8 + lane;
-          if (o < P.Fout && lane < (NT - c0) * 8) {
-            const float bf = bias_f[o];
-            for (int j = 0; j < (16 >> P.log2p); ++j) {
-              const int r0 = rt * 16 + (j << P.log2p);
-              if (r0 >= G.M) break;
-              float best = -INFINITY;
-              int bi = 0;
+          const bool valid = o < P.Fout && lane < (NT - c0) * 8;
+          const float bf = valid ? bias_f[o] : 0.f;
+          for (int j = 0; j < (16 >> P.log2p); ++j) {
+            const int r0 = rt * 16 + (j << P.log2p);
+            if (r0 >= G.M) break;  // warp-uniform
+            float best = -INFINITY;
+            int bi = 0;
+            if (valid) {
               for (int i = 0; i < P.p; ++i) {
                 float v = tile_s[((j << P.log2p) + i) * RS + lane] + bf;
                 if (P.bias_mode == GCNB_BIAS_PER_VERTEX) v += __ldg(P.bias + (long long)(r0 + i) * P.Fout + o);
@@ -225,6 +227,12 @@ __global__ void __launch_bounds__((SLOTS * NT > 8) ? 512 : 896, 1) k_cheb_fwd_fu
               const long long oidx = ((long long)b * Mo + (r0 >> P.log2p)) * P.Fout + o;
               P.y[oidx] = best;
               if (P.argmax) P.argmax[oidx] = (uint8_t)bi;
+            }
+            if (P.y_mean != nullptr) {  // Fout <= 32 (one chunk): fixed-order shuffle tree over the filters
+              float sm = valid ? best : 0.f;
+#pragma unroll
+              for (int d = 16; d > 0; d >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, d);
+              if (lane == 0) P.y_mean[(long long)b * Mo + (r0 >> P.log2p)] = sm / (float)P.Fout;
             }
           }
         }
@@ -345,8 +353,8 @@ static int launch_fwd(const FwdParams& P, const FwdPlan& pl, cudaStream_t st) {
 }
 
 int fused_cheb_fwd(const float* x, const int32_t* perm, int M_in, const gcnb_csr& L, const float* W,
-                   const float* bias, float* y, uint8_t* argmax, const LayerShape& s, int bias_mode, int relu,
-                   Workspace& ws, cudaStream_t st) {
+                   const float* bias, float* y, uint8_t* argmax, float* y_mean, const LayerShape& s, int bias_mode,
+                   int relu, Workspace& ws, cudaStream_t st) {
   (void)ws;
   const FwdPlan pl = plan_fwd(s, M_in, (reinterpret_cast<uintptr_t>(x) & 15) == 0);
   if (!pl.ok) {
@@ -356,7 +364,7 @@ int fused_cheb_fwd(const float* x, const int32_t* perm, int M_in, const gcnb_csr
   FwdParams P;
   P.x = x; P.perm = perm; P.M_in = M_in;
   P.rowptr = L.rowptr; P.col = L.col; P.val = L.val; P.nnz = L.nnz;
-  P.W = W; P.bias = bias; P.y = y; P.argmax = argmax;
+  P.W = W; P.bias = bias; P.y = y; P.argmax = argmax; P.y_mean = s.Fout <= 32 ? y_mean : nullptr;
   P.B = s.B; P.Fin = s.Fin; P.Fout = s.Fout; P.K = s.K; P.p = s.p; P.bias_mode = bias_mode; P.relu = relu;
   P.g = pl.g;
   P.ntiles = ceil_div(s.B, pl.g.S);

@@ -1,0 +1,152 @@
+// Dense fp32 GEMM on the tensor cores with fp32-level accuracy (3-pass error-compensated TF32, mma.sync m16n8k8).
+//
+//   C[M x N] = op(A)[M x K] * op(B)[K x N] (+ bias[N] broadcast over rows),   row-major, arbitrary leading dimensions
+//
+// Used for the two dense graph-Fourier transforms of the spectral layer (models_gcn.py:512-528: [M,M] x [M, B*F]) and
+// for the small FC GEMMs of the training step, where a single-pass TF32 GEMM would break the 1e-4 parity bar and the
+// SIMT sgemm is several times slower.  64x64x16 CTA tiles, 4 warps (2x2), 32x32 per warp, double-buffered shared
+// memory filled with guarded loads (any M, N, K, any alignment, either operand transposed).
+#include <algorithm>
+
+#include "fused_common.cuh"
+
+namespace gcnb {
+
+constexpr int GBM = 64, GBN = 64, GBK = 16;
+constexpr int GAS = GBK + 4;  // A tile row stride: 20 -> fragment rows hit distinct banks
+constexpr int GBS = GBN + 8;  // B tile row stride: 72 -> 8t + g distinct
+
+struct GemmArgs {
+  const float* A;
+  const float* B;
+  float* C;
+  const float* bias;
+  int M, N, K, lda, ldb, ldc, ta, tb;
+};
+
+__device__ __forceinline__ float gemm_a(const GemmArgs& g, int m, int k) {
+  if (m >= g.M || k >= g.K) return 0.f;
+  return g.ta ? __ldg(g.A + (long long)k * g.lda + m) : __ldg(g.A + (long long)m * g.lda + k);
+}
+
+__device__ __forceinline__ float gemm_b(const GemmArgs& g, int k, int n) {
+  if (k >= g.K || n >= g.N) return 0.f;
+  return g.tb ? __ldg(g.B + (long long)n * g.ldb + k) : __ldg(g.B + (long long)k * g.ldb + n);
+}
+
+__global__ void __launch_bounds__(128) k_gemm_3xtf32(const GemmArgs g) {
+  __shared__ float As[2][GBM * GAS];
+  __shared__ float Bs[2][GBK * GBS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gq = lane >> 2, t = lane & 3;
+  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+  const int m0 = blockIdx.y * GBM, n0 = blockIdx.x * GBN;
+
+  float acc[2][4][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[i][j][c] = 0.f;
+
+  // register staging of the next tile (8 A + 8 B values per thread); consecutive threads walk the operand's
+  // contiguous axis
+  float ra[8], rb[8];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int idx = tid + i * 128;  // 0..1023
+      int m, k;
+      if (g.ta) { k = idx >> 6; m = idx & 63; } else { m = idx >> 4; k = idx & 15; }
+      ra[i] = gemm_a(g, m0 + m, k0 + k);
+      int kb, n;
+      if (g.tb) { n = idx >> 4; kb = idx & 15; } else { kb = idx >> 6; n = idx & 63; }
+      rb[i] = gemm_b(g, k0 + kb, n0 + n);
+    }
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int idx = tid + i * 128;
+      int m, k;
+      if (g.ta) { k = idx >> 6; m = idx & 63; } else { m = idx >> 4; k = idx & 15; }
+      As[buf][m * GAS + k] = ra[i];
+      int kb, n;
+      if (g.tb) { n = idx >> 4; kb = idx & 15; } else { kb = idx >> 6; n = idx & 63; }
+      Bs[buf][kb * GBS + n] = rb[i];
+    }
+  };
+
+  const int nk = (g.K + GBK - 1) / GBK;
+  fetch(0);
+  stash(0);
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) fetch((kt + 1) * GBK);  // global loads in flight while the tensor cores work on `buf`
+    const float* as = As[buf];
+    const float* bs = Bs[buf];
+#pragma unroll
+    for (int ks = 0; ks < GBK; ks += 8) {
+      uint32_t ah[2][4], al[2][4];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const float* p = as + (wm + i * 16 + gq) * GAS + ks + t;
+        split_trunc(p[0], ah[i][0], al[i][0]);
+        split_trunc(p[8 * GAS], ah[i][1], al[i][1]);
+        split_trunc(p[4], ah[i][2], al[i][2]);
+        split_trunc(p[8 * GAS + 4], ah[i][3], al[i][3]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float* p = bs + (ks + t) * GBS + wn + j * 8 + gq;
+        uint32_t bh0, bl0, bh1, bl1;
+        split_trunc(p[0], bh0, bl0);
+        split_trunc(p[4 * GBS], bh1, bl1);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) mma_3xtf32(acc[i][j], ah[i], al[i], bh0, bh1, bl0, bl1);
+      }
+    }
+    if (kt + 1 < nk) stash(buf ^ 1);
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + wn + j * 8 + 2 * t;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int m = m0 + wm + i * 16 + gq + 8 * h;
+        if (m >= g.M) continue;
+        float v0 = acc[i][j][2 * h], v1 = acc[i][j][2 * h + 1];
+        if (g.bias != nullptr) {
+          if (n < g.N) v0 += __ldg(g.bias + n);
+          if (n + 1 < g.N) v1 += __ldg(g.bias + n + 1);
+        }
+        float* c = g.C + (long long)m * g.ldc + n;
+        if (n < g.N) c[0] = v0;
+        if (n + 1 < g.N) c[1] = v1;
+      }
+    }
+}
+
+int launch_gemm(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int lda, int ldb, int ldc,
+                int ta, int tb, cudaStream_t st) {
+  GemmArgs g{A, B, C, bias, M, N, K, lda, ldb, ldc, ta, tb};
+  dim3 grid((unsigned)ceil_div(N, GBN), (unsigned)ceil_div(M, GBM));
+  k_gemm_3xtf32<<<grid, 128, 0, st>>>(g);
+  GCNB_LAUNCH_CHECK("k_gemm_3xtf32");
+  return GCNB_OK;
+}
+
+}  // namespace gcnb
+
+extern "C" int gcnb_gemm_f32(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int lda,
+                             int ldb, int ldc, int transA, int transB, gcnb_stream_t stream) {
+  GCNB_REQUIRE(A && B && C && M >= 1 && N >= 1 && K >= 1, "gcnb_gemm_f32: bad arguments");
+  GCNB_REQUIRE(lda >= (transA ? M : K) && ldb >= (transB ? K : N) && ldc >= N, "gcnb_gemm_f32: leading dimension too small");
+  return gcnb::launch_gemm(A, B, C, bias, M, N, K, lda, ldb, ldc, transA, transB, static_cast<cudaStream_t>(stream));
+}

@@ -43,12 +43,112 @@ __global__ void k_mean_rows(const float* __restrict__ v, float* __restrict__ out
   if (threadIdx.x == 0) out[0] = red[0] / (float)n;
 }
 
-// state[0] = beta1^t, state[1] = beta2^t, state[2] = lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t)
-__global__ void k_adam_tick(float* state, float lr, float b1, float b2) {
+// state[0] = beta1^t, state[1] = beta2^t, state[2] = lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t), state[3] = t
+__device__ __forceinline__ void adam_tick(float* state, float lr, float b1, float b2) {
   const float p1 = state[0] * b1, p2 = state[1] * b2;
   state[0] = p1;
   state[1] = p2;
   state[2] = lr * sqrtf(1.f - p2) / (1.f - p1);
+  state[3] += 1.f;
+}
+
+__global__ void k_adam_tick(float* state, float lr, float b1, float b2) { adam_tick(state, lr, b1, b2); }
+
+// Single-CTA variant of the cross-entropy (B up to a few thousand rows): rows strided over the warps, fixed-order
+// block reduction of the mean, optional optimiser clock tick -- one launch for loss, dlogits and the clock.
+__global__ void __launch_bounds__(1024) k_softmax_xent_1cta(const float* __restrict__ logits,
+                                                            const long long* __restrict__ labels, float* __restrict__ loss,
+                                                            float* __restrict__ dlogits, int B, int C, float scale,
+                                                            float* adam_state, float lr, float b1, float b2) {
+  __shared__ float red[32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  float mine = 0.f;
+  for (int row = warp; row < B; row += nw) {
+    const float* z = logits + (long long)row * C;
+    float mx = -INFINITY;
+    for (int c = lane; c < C; c += 32) mx = fmaxf(mx, z[c]);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    float se = 0.f;
+    for (int c = lane; c < C; c += 32) se += expf(z[c] - mx);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) se += __shfl_xor_sync(0xffffffffu, se, d);
+    const float lse = mx + logf(se);
+    const int lab = (int)labels[row];
+    if (dlogits != nullptr)
+      for (int c = lane; c < C; c += 32)
+        dlogits[(long long)row * C + c] = (expf(z[c] - lse) - (c == lab ? 1.f : 0.f)) * scale;
+    mine += lse - z[lab];
+  }
+  if (lane == 0) red[warp] = mine;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < nw; ++w) s += red[w];
+    loss[0] = s / (float)B;
+    if (adam_state != nullptr) adam_tick(adam_state, lr, b1, b2);
+  }
+}
+
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {  // murmur3 finaliser
+  x ^= x >> 16;
+  x *= 0x85ebca6bu;
+  x ^= x >> 13;
+  x *= 0xc2b2ae35u;
+  x ^= x >> 16;
+  return x;
+}
+
+__global__ void k_relu_dropout_fwd(float* __restrict__ x, long long rows, int cols, int ld, float keep, float inv_keep,
+                                   uint32_t seed, const float* __restrict__ step) {
+  const long long total = rows * cols;
+  const uint32_t key = mix32(seed ^ mix32((uint32_t)(step ? step[3] : 0.f) + 0x9e3779b9u));
+  const uint32_t thresh = keep >= 1.f ? 0xffffffffu : (uint32_t)(keep * 4294967296.0);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols;
+    const int c = (int)(i - r * cols);
+    float v = fmaxf(x[r * ld + c], 0.f);
+    if (keep < 1.f) v = (mix32((uint32_t)i * 0x9e3779b1u + key) < thresh) ? v * inv_keep : 0.f;
+    x[r * ld + c] = v;
+  }
+}
+
+__global__ void k_relu_dropout_bwd(float* __restrict__ d, const float* __restrict__ act, long long rows, int cols, int ld_d,
+                                   int ld_act, float inv_keep) {
+  const long long total = rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols;
+    const int c = (int)(i - r * cols);
+    d[r * ld_d + c] = act[r * ld_act + c] > 0.f ? d[r * ld_d + c] * inv_keep : 0.f;
+  }
+}
+
+struct ColsumArgs {
+  const float* m[4];
+  float* out[4];
+  int rows[4], cols[4];
+  int block_begin[5];  // blocks of 32 columns, prefix over the matrices
+};
+
+// block = (matrix, 32-column chunk): 8 row groups x 32 lanes, fixed-order combine
+__global__ void __launch_bounds__(256) k_colsum_multi(ColsumArgs a) {
+  __shared__ float red[256];
+  int mi = 0;
+  while (mi < 3 && (int)blockIdx.x >= a.block_begin[mi + 1]) ++mi;
+  const int c0 = ((int)blockIdx.x - a.block_begin[mi]) * 32;
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int c = c0 + lane, R = a.rows[mi], Cn = a.cols[mi];
+  float s = 0.f;
+  if (c < Cn)
+    for (int r = grp; r < R; r += 8) s += a.m[mi][(long long)r * Cn + c];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  if (grp == 0 && c < Cn) {
+    float t = 0.f;
+#pragma unroll
+    for (int g2 = 0; g2 < 8; ++g2) t += red[g2 * 32 + lane];
+    a.out[mi][c] = t;
+  }
 }
 
 // g_total = g * gscale + reg * p (where decay[i] != 0);  m, v, p updated in place (TF "epsilon hat" form)
@@ -75,9 +175,19 @@ using namespace gcnb;
 extern "C" {
 
 int gcnb_softmax_xent_f32(const float* logits, const int64_t* labels, float* loss, float* dlogits, float* loss_rows,
-                          int B, int C, gcnb_stream_t stream) {
+                          int B, int C, float* adam_state, float lr, float beta1, float beta2, gcnb_stream_t stream) {
   GCNB_REQUIRE(logits && labels && loss && loss_rows && B >= 1 && C >= 1, "gcnb_softmax_xent_f32: bad arguments");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (B <= 8192) {
+    k_softmax_xent_1cta<<<1, 1024, 0, st>>>(logits, reinterpret_cast<const long long*>(labels), loss, dlogits, B, C,
+                                            1.f / (float)B, adam_state, lr, beta1, beta2);
+    GCNB_LAUNCH_CHECK("k_softmax_xent_1cta");
+    return GCNB_OK;
+  }
+  if (adam_state != nullptr) {
+    k_adam_tick<<<1, 1, 0, st>>>(adam_state, lr, beta1, beta2);
+    GCNB_LAUNCH_CHECK("k_adam_tick");
+  }
   k_softmax_xent<<<ceil_div(B * 32, 256), 256, 0, st>>>(logits, reinterpret_cast<const long long*>(labels), loss_rows,
                                                        dlogits, B, C, 1.f / (float)B);
   GCNB_LAUNCH_CHECK("k_softmax_xent");
@@ -86,12 +196,52 @@ int gcnb_softmax_xent_f32(const float* logits, const int64_t* labels, float* los
   return GCNB_OK;
 }
 
+int gcnb_relu_dropout_fwd_f32(float* x, long long rows, int cols, int ld, float keep, unsigned seed, const float* step,
+                              gcnb_stream_t stream) {
+  GCNB_REQUIRE(x && rows >= 1 && cols >= 1 && ld >= cols && keep > 0.f, "gcnb_relu_dropout_fwd_f32: bad arguments");
+  const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(ceil_div_ll(rows * cols, 256), 148 * 8));
+  k_relu_dropout_fwd<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, rows, cols, ld, keep, 1.f / keep, seed, step);
+  GCNB_LAUNCH_CHECK("k_relu_dropout_fwd");
+  return GCNB_OK;
+}
+
+int gcnb_relu_dropout_bwd_f32(float* d, const float* act, long long rows, int cols, int ld_d, int ld_act, float keep,
+                              gcnb_stream_t stream) {
+  GCNB_REQUIRE(d && act && rows >= 1 && cols >= 1 && keep > 0.f, "gcnb_relu_dropout_bwd_f32: bad arguments");
+  const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(ceil_div_ll(rows * cols, 256), 148 * 8));
+  k_relu_dropout_bwd<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(d, act, rows, cols, ld_d, ld_act,
+                                                                           keep >= 1.f ? 1.f : 1.f / keep);
+  GCNB_LAUNCH_CHECK("k_relu_dropout_bwd");
+  return GCNB_OK;
+}
+
+int gcnb_colsum_multi_f32(const float* const* mats, float* const* outs, const int* rows, const int* cols, int count,
+                          gcnb_stream_t stream) {
+  GCNB_REQUIRE(mats && outs && rows && cols && count >= 1 && count <= 4, "gcnb_colsum_multi_f32: 1..4 matrices");
+  ColsumArgs a;
+  a.block_begin[0] = 0;
+  for (int i = 0; i < 4; ++i) {
+    const bool on = i < count;
+    a.m[i] = on ? mats[i] : nullptr;
+    a.out[i] = on ? outs[i] : nullptr;
+    a.rows[i] = on ? rows[i] : 0;
+    a.cols[i] = on ? cols[i] : 0;
+    a.block_begin[i + 1] = a.block_begin[i] + (on ? ceil_div(cols[i], 32) : 0);
+  }
+  k_colsum_multi<<<a.block_begin[4], 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  GCNB_LAUNCH_CHECK("k_colsum_multi");
+  return GCNB_OK;
+}
+
 int gcnb_adam_tf_f32(float* p, const float* g, float* m, float* v, const uint8_t* decay, float* state, long long n,
-                     float lr, float beta1, float beta2, float eps, float reg, float gscale, gcnb_stream_t stream) {
+                     float lr, float beta1, float beta2, float eps, float reg, float gscale, int tick,
+                     gcnb_stream_t stream) {
   GCNB_REQUIRE(p && g && m && v && state && n >= 1, "gcnb_adam_tf_f32: bad arguments");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  k_adam_tick<<<1, 1, 0, st>>>(state, lr, beta1, beta2);
-  GCNB_LAUNCH_CHECK("k_adam_tick");
+  if (tick) {
+    k_adam_tick<<<1, 1, 0, st>>>(state, lr, beta1, beta2);
+    GCNB_LAUNCH_CHECK("k_adam_tick");
+  }
   const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(ceil_div_ll(n, 256), 148 * 8));
   k_adam_tf<<<grid, 256, 0, st>>>(p, g, m, v, decay, state, n, beta1, beta2, eps, reg, gscale);
   GCNB_LAUNCH_CHECK("k_adam_tf");

@@ -7,8 +7,7 @@
 // Everything runs in the vertex-major layout Xn[m][b*F + f] so that both transforms are plain
 // row-major GEMMs over all samples at once (no per-sample batching, no transposes of the data
 // besides the one pass in and one pass out).  Backward recomputes xh.
-// TODO(perf): the two dense transforms are FFMA-tiled here; they are the tensor-core candidates
-// of this layer.
+// The two dense transforms run on the tensor cores (3-pass TF32 split, gemm.cu) -- SURVEY 8a row a3.
 #include <algorithm>
 
 #include "common.cuh"
@@ -71,8 +70,11 @@ __global__ void __launch_bounds__(256) k_sgemm(const float* __restrict__ A, cons
   }
 }
 
+// The two graph-Fourier transforms run on the tensor cores (3xTF32, gemm.cu) when the column count fits an int;
+// the FFMA kernel above is the fallback for gigantic batches.
 static int launch_sgemm(bool ta, const float* A, const float* Bm, float* C, int Mr, long long N, int Kd, int lda,
                         cudaStream_t st) {
+  if (N < (1LL << 30)) return launch_gemm(A, Bm, C, nullptr, Mr, (int)N, Kd, lda, (int)N, (int)N, ta ? 1 : 0, 0, st);
   dim3 grid((unsigned)ceil_div_ll(N, 64), (unsigned)ceil_div(Mr, 64));
   if (ta)
     k_sgemm<true><<<grid, 256, 0, st>>>(A, Bm, C, Mr, N, Kd, lda);

@@ -177,7 +177,7 @@ class FusedTrainer:
     """
 
     def __init__(self, model, lr=1e-3, distributed=None, use_cuda_graph=True, dropout=1.0, beta1=0.9, beta2=0.999,
-                 eps=1e-8):
+                 eps=1e-8, own_gemm=False):
         import ctypes as C
 
         from . import _lib, ops
@@ -185,6 +185,7 @@ class FusedTrainer:
         self.model, self.lr, self.b1, self.b2, self.eps = model, lr, beta1, beta2, eps
         self.C, self._lib, self.ops = C, _lib, ops
         self.keep = float(dropout) if dropout else 1.0
+        self.own_gemm = own_gemm
         self.distributed = dist.is_available() and dist.is_initialized() if distributed is None else distributed
         self.world = dist.get_world_size() if self.distributed else 1
         self.params = [p for p in model.parameters()]
@@ -196,7 +197,7 @@ class FusedTrainer:
         self.flat_m = torch.zeros(self.n, dtype=torch.float32, device=dev)
         self.flat_v = torch.zeros(self.n, dtype=torch.float32, device=dev)
         self.decay = torch.zeros(self.n, dtype=torch.uint8, device=dev)
-        self.state = torch.tensor([1.0, 1.0, 0.0], dtype=torch.float32, device=dev)
+        self.state = torch.tensor([1.0, 1.0, 0.0, 0.0], dtype=torch.float32, device=dev)  # b1^t, b2^t, lr_t, t
         regularized = {id(p) for p in model._regularized}
         self.gview = {}
         off = 0
@@ -220,72 +221,115 @@ class FusedTrainer:
         m, ops, C = self.model, self.ops, self.C
         lib = self._lib.lib()
         stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+        vp = lambda t: C.c_void_p(t.data_ptr())
         nconv, nfc = len(m.p), len(m.M)
         mode = m._bias_mode()
+        cheb = m.filter_name != "fourier"
         gather = m.perm is not None and x.shape[1] == m.n_input_vertices != m.L[0].shape[0]
-        # ---- forward: conv stack ----
-        saved, h = [], x
+        # ---- forward: conv stack (the last layer also emits the mean over its filters = the head's input) ----
+        saved, h, h0 = [], x, None
         for i in range(nconv):
             perm = m.perm if (gather and i == 0) else None
-            if m.filter_name == "fourier":
+            last = i == nconv - 1
+            if cheb:
+                pl = m._plan(m.L[i])
+                if last:
+                    y, am, h0 = ops.cheb_fwd_mean(h, perm, pl.rowptr, pl.col, pl.val, m.conv_weights[i], m.conv_bias[i],
+                                                  m.K[i], m.p[i], mode, True, m.algo)
+                else:
+                    y, am = ops.cheb_fwd(h, perm, *pl.tensors(), m.conv_weights[i], m.conv_bias[i], m.K[i], m.p[i], mode,
+                                         True, True, m.algo)
+                saved.append((h, perm, y, am, pl))
+            else:
                 if perm is not None:
                     h = ops.perm_gather(h, perm)
                 sp = m._spectral_plan(m.L[i])
                 y, am = ops.spectral_fwd(h, sp.Ut, m.conv_weights[i], m.conv_bias[i], m.p[i], mode, True, True)
                 saved.append((h, None, y, am, sp))
-            else:
-                pl = m._plan(m.L[i])
-                y, am = ops.cheb_fwd(h, perm, *pl.tensors(), m.conv_weights[i], m.conv_bias[i], m.K[i], m.p[i], mode,
-                                     True, True, m.algo)
-                saved.append((h, perm, y, am, pl))
             h = y
+        if h0 is None:
+            h0 = ops.mean_f_fwd(h)
         # ---- forward: head ----
-        acts = [ops.mean_f_fwd(h)]
-        masks = []
+        def gemm(A, Bm, out, bias, M_, N_, K_, ta, tb):
+            rc = lib.gcnb_gemm_f32(vp(A), vp(Bm), vp(out), None if bias is None else vp(bias), M_, N_, K_, A.shape[1],
+                                   Bm.shape[1], out.shape[1], ta, tb, stream)
+            self._lib.check(rc, "gcnb_gemm_f32")
+            return out
+
+        # The FC GEMMs are plain library GEMMs (cuBLAS fp32): at B=512 they are a few microseconds each and launch
+        # bound; the in-house 3xTF32 kernel (`gemm`, used by the spectral layer) pays off only for large operands.
+        use_own_gemm = self.own_gemm
+
+        def fc_fwd(i, a_in):
+            W = m.fc_weights[i]
+            if not use_own_gemm:
+                return torch.addmm(m.fc_bias[i], a_in, W)
+            out = torch.empty((a_in.shape[0], W.shape[1]), dtype=torch.float32, device=x.device)
+            return gemm(a_in, W, out, m.fc_bias[i], a_in.shape[0], W.shape[1], W.shape[0], 0, 0)
+
+        acts = [h0]
         for i in range(nfc - 1):
-            a = torch.addmm(m.fc_bias[i], acts[-1], m.fc_weights[i]).relu_()
-            if self.keep < 1.0:
-                a, mask = torch.native_dropout(a, 1.0 - self.keep, True)
-                masks.append(mask)
+            a = fc_fwd(i, acts[-1])
+            rc = lib.gcnb_relu_dropout_fwd_f32(vp(a), a.shape[0], a.shape[1], a.shape[1], self.keep, 0x5eed + i,
+                                               vp(self.state), stream)
+            self._lib.check(rc, "gcnb_relu_dropout_fwd_f32")
             acts.append(a)
-        logits = torch.addmm(m.fc_bias[nfc - 1], acts[-1], m.fc_weights[nfc - 1])
+        logits = fc_fwd(nfc - 1, acts[-1])
         B, ncls = logits.shape
         d = torch.empty_like(logits)
         rows = torch.empty(B, dtype=torch.float32, device=x.device)
-        rc = lib.gcnb_softmax_xent_f32(C.c_void_p(logits.data_ptr()), C.c_void_p(labels.data_ptr()),
-                                       C.c_void_p(self._loss.data_ptr()), C.c_void_p(d.data_ptr()),
-                                       C.c_void_p(rows.data_ptr()), B, ncls, stream)
+        # loss, dlogits and the optimiser clock in one launch
+        rc = lib.gcnb_softmax_xent_f32(vp(logits), vp(labels), vp(self._loss), vp(d), vp(rows), B, ncls, vp(self.state),
+                                       self.lr, self.b1, self.b2, stream)
         self._lib.check(rc, "gcnb_softmax_xent_f32")
-        # ---- backward: head, gradients land in the flat buffer ----
+        # ---- backward: head; weight gradients land in the flat buffer, the bias gradients in one launch at the end ----
+        ds = [None] * nfc
         for i in range(nfc - 1, -1, -1):
-            torch.mm(acts[i].t(), d, out=self.gview[id(m.fc_weights[i])])
-            torch.sum(d, 0, out=self.gview[id(m.fc_bias[i])])
-            d = torch.mm(d, m.fc_weights[i].t())
+            ds[i] = d
+            W = m.fc_weights[i]
+            if use_own_gemm:
+                gemm(acts[i], d, self.gview[id(W)], None, W.shape[0], W.shape[1], d.shape[0], 1, 0)   # dW = a^T d
+                dn = torch.empty((d.shape[0], W.shape[0]), dtype=torch.float32, device=x.device)
+                d = gemm(d, W, dn, None, d.shape[0], W.shape[0], W.shape[1], 0, 1)                    # dx = d W^T
+            else:
+                torch.mm(acts[i].t(), d, out=self.gview[id(W)])
+                d = torch.mm(d, W.t())
             if i > 0:
-                if self.keep < 1.0:
-                    d = torch.ops.aten.native_dropout_backward(d, masks[i - 1], 1.0 / self.keep)
-                d = torch.ops.aten.threshold_backward(d, acts[i], 0.0)
-        dy = torch.ops.gcn_b200.mean_f_bwd(d, h.shape[-1])
-        # ---- backward: conv stack ----
+                rc = lib.gcnb_relu_dropout_bwd_f32(vp(d), vp(acts[i]), d.shape[0], d.shape[1], d.shape[1], d.shape[1],
+                                                   self.keep, stream)
+                self._lib.check(rc, "gcnb_relu_dropout_bwd_f32")
+        for lo in range(0, nfc, 4):
+            grp = list(range(lo, min(nfc, lo + 4)))
+            n = len(grp)
+            mats = (C.c_void_p * n)(*[ds[i].data_ptr() for i in grp])
+            outs = (C.c_void_p * n)(*[self.gview[id(m.fc_bias[i])].data_ptr() for i in grp])
+            rws = (C.c_int * n)(*[ds[i].shape[0] for i in grp])
+            cls = (C.c_int * n)(*[ds[i].shape[1] for i in grp])
+            rc = lib.gcnb_colsum_multi_f32(mats, outs, rws, cls, n, stream)
+            self._lib.check(rc, "gcnb_colsum_multi_f32")
+        # ---- backward: conv stack (d is the gradient of the mean over filters of the last layer) ----
+        dy, dy_is_mean = d, True
+        if not cheb:
+            dy, dy_is_mean = torch.ops.gcn_b200.mean_f_bwd(d, h.shape[-1]), False
         for i in range(nconv - 1, -1, -1):
             hin, perm, y, am, pl = saved[i]
             need_dx = i > 0
-            if m.filter_name == "fourier":
+            gW, gb = self.gview[id(m.conv_weights[i])], self.gview[id(m.conv_bias[i])]
+            if cheb:
+                dx = ops.cheb_bwd_into(hin, perm, y, am, dy, dy_is_mean, *pl.tensors(), m.conv_weights[i], gW, gb, m.K[i],
+                                       m.p[i], mode, True, need_dx, m.algo)
+            else:
                 dx, dW, db = torch.ops.gcn_b200.spectral_bwd(hin, y, am, dy, pl.Ut, m.conv_weights[i], m.p[i], mode, True,
                                                              need_dx)
-            else:
-                dx, dW, db = torch.ops.gcn_b200.cheb_bwd(hin, perm, y, am, dy, *pl.tensors(), m.conv_weights[i], m.K[i],
-                                                         m.p[i], mode, True, need_dx, m.algo)
-            self.gview[id(m.conv_weights[i])].copy_(dW)
-            self.gview[id(m.conv_bias[i])].copy_(db.view_as(m.conv_bias[i]))
-            dy = dx
+                gW.copy_(dW)
+                gb.copy_(db.view_as(gb))
+            dy, dy_is_mean = dx, False
         # ---- update ----
         if self.world > 1:
             dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM)
-        rc = lib.gcnb_adam_tf_f32(C.c_void_p(self.flat_p.data_ptr()), C.c_void_p(self.flat_g.data_ptr()),
-                                  C.c_void_p(self.flat_m.data_ptr()), C.c_void_p(self.flat_v.data_ptr()),
-                                  C.c_void_p(self.decay.data_ptr()), C.c_void_p(self.state.data_ptr()), self.n, self.lr,
-                                  self.b1, self.b2, self.eps, float(m.regularization or 0.0), 1.0 / self.world, stream)
+        rc = lib.gcnb_adam_tf_f32(vp(self.flat_p), vp(self.flat_g), vp(self.flat_m), vp(self.flat_v), vp(self.decay),
+                                  vp(self.state), self.n, self.lr, self.b1, self.b2, self.eps,
+                                  float(m.regularization or 0.0), 1.0 / self.world, 0, stream)
         self._lib.check(rc, "gcnb_adam_tf_f32")
         return self._loss, logits
 

@@ -92,10 +92,12 @@ GCNB_API size_t gcnb_cheb_workspace_bytes(int B, int M, int nnz, int Fin, int Fo
  *   row perm[m] (zero when perm[m] >= M_in) -- coarsening.perm_data_3d (coarsening.py:244-265)
  *   fused into the load.  With perm == NULL, M_in must equal M.
  * bias (nullable iff bias_mode == NONE); argmax (nullable: not written); p >= 1, power of 2.
+ * y_mean (nullable): also write mean_o y[b,j,o] as [B][M/p] -- tf.reduce_mean(x, -1) of the last conv layer
+ *   (models_gcn.py:673) fused into the epilogue.
  */
 GCNB_API int gcnb_cheb_fwd_f32(const float* x, const int32_t* perm, int M_in, const gcnb_csr* L, const float* W,
-                      const float* bias, float* y, uint8_t* argmax, int B, int Fin, int Fout, int K, int p,
-                      int bias_mode, int relu, int algo, void* workspace, size_t workspace_bytes,
+                      const float* bias, float* y, uint8_t* argmax, float* y_mean, int B, int Fin, int Fout, int K,
+                      int p, int bias_mode, int relu, int algo, void* workspace, size_t workspace_bytes,
                       gcnb_stream_t stream);
 
 /*
@@ -107,9 +109,11 @@ GCNB_API int gcnb_cheb_fwd_f32(const float* x, const int32_t* perm, int M_in, co
  * x / perm / M_in as in the forward (the gather is repeated when X_k is recomputed); dx, if
  * requested, is the gradient w.r.t. the permuted layer input [B][M][Fin].
  * dW / db are overwritten (not accumulated).  db may be NULL when bias_mode == NONE.
+ * dy_is_mean != 0: dy is [B][M/p], the gradient of the mean over filters (every filter receives dy/Fout);
+ *   the adjoint of y_mean above.
  */
 GCNB_API int gcnb_cheb_bwd_f32(const float* x, const int32_t* perm, int M_in, const float* y, const uint8_t* argmax,
-                      const float* dy, const gcnb_csr* L,
+                      const float* dy, int dy_is_mean, const gcnb_csr* L,
                       const gcnb_csr* Lt, const float* W, float* dx, float* dW, float* db, int B, int Fin,
                       int Fout, int K, int p, int bias_mode, int relu, int algo, void* workspace,
                       size_t workspace_bytes, gcnb_stream_t stream);
@@ -151,19 +155,40 @@ GCNB_API int gcnb_mean_f_bwd_f32(const float* dy, float* dx, int rows, int F, gc
  * Sparse softmax cross-entropy, forward and backward in one pass (models_gcn.py:253-259):
  *   loss = mean_b (logsumexp(logits[b]) - logits[b][labels[b]]);  dlogits = (softmax - onehot) / B  (nullable).
  * loss_rows[B] is scratch for the per-row losses (fixed-order mean).
+ * adam_state (nullable): if given, the kernel also advances the optimiser clock {b1^t, b2^t, lr_t, t} of
+ *   gcnb_adam_tf_f32 (one launch less per training step); pass the same lr/beta1/beta2 as to the update.
  */
 GCNB_API int gcnb_softmax_xent_f32(const float* logits, const int64_t* labels, float* loss, float* dlogits,
-                          float* loss_rows, int B, int C, gcnb_stream_t stream);
+                          float* loss_rows, int B, int C, float* adam_state, float lr, float beta1, float beta2,
+                          gcnb_stream_t stream);
+
+/* C[M x N] = op(A) op(B) (+ bias[N]); row-major, fp32 in/out, tensor cores with a 3-pass TF32 split (fp32-level
+ * accuracy).  The dense transforms of the spectral layer and the FC layers of the training step use it. */
+GCNB_API int gcnb_gemm_f32(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int lda,
+                  int ldb, int ldc, int transA, int transB, gcnb_stream_t stream);
+
+/* y = dropout(relu(x)) in place on x[rows][ld] (first `cols` columns): keep-probability `keep`, kept values scaled by
+ * 1/keep (tf.nn.relu + tf.nn.dropout, models_gcn.py:655,677).  Counter-based generator keyed by (seed, *step, index);
+ * step is a device counter so that CUDA-graph replays draw fresh masks.  keep >= 1 is a plain ReLU. */
+GCNB_API int gcnb_relu_dropout_fwd_f32(float* x, long long rows, int cols, int ld, float keep, unsigned seed,
+                              const float* step, gcnb_stream_t stream);
+/* d = (act > 0) ? d / keep : 0 in place (act = output of the forward; act > 0 <=> ReLU active and kept). */
+GCNB_API int gcnb_relu_dropout_bwd_f32(float* d, const float* act, long long rows, int cols, int ld_d, int ld_act,
+                              float keep, gcnb_stream_t stream);
+/* out_i[c] = sum_r m_i[r][c] for up to 4 row-major matrices in one launch (bias gradients of the FC layers). */
+GCNB_API int gcnb_colsum_multi_f32(const float* const* mats, float* const* outs, const int* rows, const int* cols,
+                          int count, gcnb_stream_t stream);
 
 /*
  * tf.train.AdamOptimizer step (models_gcn.py:294, TF-1.x "epsilon hat" form) over one flat buffer of n parameters:
  *   g' = g * gscale + reg * p (only where decay[i] != 0; the L2 term of models_gcn.py:260-262)
  *   m = b1 m + (1-b1) g';  v = b2 v + (1-b2) g'^2;  p -= lr sqrt(1-b2^t)/(1-b1^t) * m / (sqrt(v) + eps)
- * state[3] (device) holds {b1^t, b2^t, lr_t}; initialise to {1, 1, 0}.  The step counter lives on the device so
- * that a captured CUDA graph can replay the step.
+ * state[4] (device) holds {b1^t, b2^t, lr_t, t}; initialise to {1, 1, 0, 0}.  The step counter lives on the device so
+ * that a captured CUDA graph can replay the step.  tick != 0: advance the clock here (an extra 1-thread launch);
+ * tick == 0: the clock was already advanced this step by gcnb_softmax_xent_f32.
  */
 GCNB_API int gcnb_adam_tf_f32(float* p, const float* g, float* m, float* v, const uint8_t* decay, float* state,
-                     long long n, float lr, float beta1, float beta2, float eps, float reg, float gscale,
+                     long long n, float lr, float beta1, float beta2, float eps, float reg, float gscale, int tick,
                      gcnb_stream_t stream);
 
 #ifdef __cplusplus

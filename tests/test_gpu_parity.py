@@ -366,27 +366,119 @@ def test_training_step_gradients_match_oracle(dev, graph_l4):
 
 
 def test_fused_trainer_matches_autograd_trainer(dev, graph_l4):
-    """The explicit few-launch training step (FusedTrainer: custom xent + flat TF-Adam kernels, L2 folded into the
-    update) gives the same parameters after a step as the autograd step with the multi-tensor TFAdam."""
+    """The explicit few-launch training step (FusedTrainer: fused mean, custom xent, flat TF-Adam with the L2 term
+    folded in) produces the gradients of the autograd step, and the same parameters after a few Adam steps wherever
+    the gradient is not numerically zero (Adam's m/sqrt(v) amplifies rounding noise on those)."""
     from gcn_fmri_decoding_b200 import synth
     from gcn_fmri_decoding_b200.train import FusedTrainer, Trainer
 
     g = graph_l4
     x = T(synth.bold_windows(32, seed=21), dev)
     y = T(synth.labels(32, seed=21), dev, torch.long)
-    for graph in (False, True):
+    for graph, own in ((False, False), (True, False), (False, True)):
         a = build_model(g, [32, 32], [5, 5], [4, 4], [512, 256, 22], "chebyshev5", "b1relu", dev, perm=g["perm"])
         b = build_model(g, [32, 32], [5, 5], [4, 4], [512, 256, 22], "chebyshev5", "b1relu", dev, perm=g["perm"])
         ta = Trainer(a, distributed=False)
-        tb = FusedTrainer(b, distributed=False, use_cuda_graph=graph, dropout=1.0)
-        for _ in range(3):
-            la, _ = ta.step(x, y)
-            lb, _ = tb.step(x, y)
+        tb = FusedTrainer(b, distributed=False, use_cuda_graph=graph, dropout=1.0, own_gemm=own)
+        p0 = tb.flat_p.clone()
+        la, _ = ta.step(x, y)
+        lb, _ = tb.step(x, y)
         torch.cuda.synchronize()
-        assert abs(float(la) - (float(lb) + tb.regularization_term())) <= 2e-3 * abs(float(la))
-        for pa, pb in zip(a.parameters(), b.parameters()):
-            # three Adam steps of size 1e-3: compare the *updates*
-            assert float((pa - pb).abs().max()) <= 2e-5, graph
+        reg_before = 5e-4 * 0.5 * float((p0 * p0 * tb.decay).sum())
+        assert abs(float(la) - (float(lb) + reg_before)) <= 1e-4 * abs(float(la))
+        g_auto = ta.flat_grad                                   # d(CE + L2)/dp
+        g_fused = tb.flat_g + 5e-4 * p0 * tb.decay              # the update kernel adds the L2 term itself
+        scale = float(g_auto.abs().max())
+        assert float((g_auto - g_fused).abs().max()) <= 1e-4 * scale, (graph, own)
+        for _ in range(2):
+            ta.step(x, y)
+            tb.step(x, y)
+        torch.cuda.synchronize()
+        pa = torch.cat([p.detach().reshape(-1) for p in a.parameters()])
+        big = g_auto.abs() > 1e-3 * scale
+        assert float((pa - tb.flat_p)[big].abs().max()) <= 2e-4, (graph, own)  # three steps of size 1e-3
+
+
+def test_head_pieces(dev, graph_l4):
+    """Fused mean over filters (forward) / mean-form dy (backward), ReLU+dropout, column sums, xent -- against NumPy."""
+    import ctypes as C
+
+    from gcn_fmri_decoding_b200 import _lib, ops
+    from gcn_fmri_decoding_b200.plan import GraphPlan
+
+    lib = _lib.lib()
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    rng = np.random.RandomState(4)
+    L = graph_l4["L"][2]
+    pl = GraphPlan(L, dev)
+    x = T(rng.randn(6, 100, 32).astype(np.float32), dev)
+    W = T((rng.randn(160, 32) * 0.2).astype(np.float32), dev)
+    b = T(np.full(32, 0.2, np.float32), dev)
+    for algo in algos_for(6, 100, pl.nnz, 32, 32, 5, 4, True, True):
+        y, am, ym = ops.cheb_fwd_mean(x, None, pl.rowptr, pl.col, pl.val, W, b, 5, 4, ops.BIAS_PER_FILTER, True, algo)
+        y2, am2 = ops.cheb_fwd(x, None, *pl.tensors(), W, b, 5, 4, ops.BIAS_PER_FILTER, True, True, algo)
+        assert torch.equal(y, y2) and torch.equal(am, am2)
+        assert float((ym - y.mean(-1)).abs().max()) <= 1e-5 * float(y.abs().max())
+        dm = T(rng.randn(6, 25).astype(np.float32), dev)
+        full = (dm / 32).unsqueeze(-1).expand(6, 25, 32).contiguous()
+        ref = torch.ops.gcn_b200.cheb_bwd(x, None, y, am, full, *pl.tensors(), W, 5, 4, ops.BIAS_PER_FILTER, True, True, algo)
+        gW, gb = torch.empty_like(W), torch.empty(32, device=dev)
+        dx = ops.cheb_bwd_into(x, None, y, am, dm, True, *pl.tensors(), W, gW, gb, 5, 4, ops.BIAS_PER_FILTER, True, True, algo)
+        for got, want in ((dx, ref[0]), (gW, ref[1]), (gb, ref[2])):
+            assert float((got - want).abs().max()) <= 1e-5 * float(want.abs().max()), algo
+    # ReLU + dropout: kept fraction, scaling, fresh mask per step, deterministic for a given step
+    a = T(rng.randn(512, 512).astype(np.float32), dev)
+    state = torch.tensor([1.0, 1.0, 0.0, 3.0], device=dev)
+    o1, o2 = a.clone(), a.clone()
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    assert lib.gcnb_relu_dropout_fwd_f32(vp(o1), 512, 512, 512, 0.5, 7, vp(state), stream) == 0
+    assert lib.gcnb_relu_dropout_fwd_f32(vp(o2), 512, 512, 512, 0.5, 7, vp(state), stream) == 0
+    assert torch.equal(o1, o2)
+    pos = a > 0
+    kept = (o1 > 0) & pos
+    assert abs(float(kept.sum()) / float(pos.sum()) - 0.5) < 0.01
+    assert torch.allclose(o1[kept], 2 * a[kept]) and float(o1[~pos].abs().max()) == 0.0
+    state[3] = 4.0
+    o3 = a.clone()
+    lib.gcnb_relu_dropout_fwd_f32(vp(o3), 512, 512, 512, 0.5, 7, vp(state), stream)
+    assert not torch.equal(o1, o3)
+    d = T(rng.randn(512, 512).astype(np.float32), dev)
+    d0 = d.clone()
+    lib.gcnb_relu_dropout_bwd_f32(vp(d), vp(o1), 512, 512, 512, 512, 0.5, stream)
+    assert torch.equal(d, torch.where(o1 > 0, 2 * d0, torch.zeros_like(d0)))
+    o4 = a.clone()
+    lib.gcnb_relu_dropout_fwd_f32(vp(o4), 512, 512, 512, 1.0, 7, vp(state), stream)
+    assert torch.equal(o4, torch.relu(a))
+    # column sums of several matrices in one launch
+    ms = [T(rng.randn(512, n).astype(np.float32), dev) for n in (512, 256, 22)]
+    outs = [torch.empty(n, device=dev) for n in (512, 256, 22)]
+    rc = lib.gcnb_colsum_multi_f32((C.c_void_p * 3)(*[t.data_ptr() for t in ms]), (C.c_void_p * 3)(*[t.data_ptr() for t in outs]),
+                                   (C.c_int * 3)(512, 512, 512), (C.c_int * 3)(512, 256, 22), 3, stream)
+    assert rc == 0
+    for mm_, oo in zip(ms, outs):
+        assert float((oo - mm_.double().sum(0).float()).abs().max()) <= 1e-4
+    # tensor-core GEMM (3xTF32): all four transpose combinations, ragged sizes, bias
+    for (Mg, Ng, Kg, ta, tb) in ((512, 256, 512, 0, 0), (25, 512, 512, 1, 0), (512, 25, 512, 0, 1), (67, 45, 33, 1, 1), (400, 7680, 400, 1, 0)):
+        A = T(rng.randn(*((Kg, Mg) if ta else (Mg, Kg))).astype(np.float32), dev)
+        Bm = T(rng.randn(*((Ng, Kg) if tb else (Kg, Ng))).astype(np.float32), dev)
+        bias = T(rng.randn(Ng).astype(np.float32), dev)
+        Cc = torch.empty(Mg, Ng, device=dev)
+        rc = lib.gcnb_gemm_f32(vp(A), vp(Bm), vp(Cc), vp(bias), Mg, Ng, Kg, A.shape[1], Bm.shape[1], Ng, ta, tb, stream)
+        assert rc == 0
+        ref = (A.double().t() if ta else A.double()) @ (Bm.double().t() if tb else Bm.double()) + bias.double()
+        assert float((Cc.double() - ref).abs().max()) <= 2e-6 * float(ref.abs().max()), (Mg, Ng, Kg, ta, tb)
+    # cross-entropy forward+backward and the optimiser clock
+    lg = T(rng.randn(512, 22).astype(np.float32) * 3, dev)
+    lab = T(rng.randint(0, 21, 512), dev, torch.long)
+    loss, dl, rows = torch.zeros((), device=dev), torch.empty_like(lg), torch.empty(512, device=dev)
+    st2 = torch.tensor([1.0, 1.0, 0.0, 0.0], device=dev)
+    assert lib.gcnb_softmax_xent_f32(vp(lg), vp(lab), vp(loss), vp(dl), vp(rows), 512, 22, vp(st2), 1e-3, 0.9, 0.999, stream) == 0
+    lgr = lg.clone().double().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(lgr, lab)
+    ref.backward()
+    assert abs(float(loss) - float(ref)) <= 1e-5 * float(ref)
+    assert float((dl.double() - lgr.grad).abs().max()) <= 1e-7
+    assert np.allclose(st2.cpu().numpy(), [0.9, 0.999, 1e-3 * np.sqrt(1 - 0.999) / (1 - 0.9), 1.0], rtol=1e-5)
 
 
 # ------------------------------------------------------------------------------------------ full-size properties
