@@ -193,6 +193,11 @@ const char* gcnb_last_error_string(void) { return g_err; }
 
 unsigned long long gcnb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+int gcnb_cheb_stack_width(int B, int M, int nnz, int Fin, int Fout, int K, int p) {
+  LayerShape s{B, M, nnz, Fin, Fout, K, p};
+  return (fused_fwd_supported(s) && stack_dw_supported(s)) ? fused_feature_pad(Fin) : 0;
+}
+
 int gcnb_cheb_fused_supported(int B, int M, int nnz, int Fin, int Fout, int K, int p, int backward, int need_dx) {
   LayerShape s{B, M, nnz, Fin, Fout, K, p};
   return backward ? (fused_bwd_supported(s, need_dx != 0) ? 1 : 0) : (fused_fwd_supported(s) ? 1 : 0);
@@ -203,15 +208,16 @@ size_t gcnb_cheb_workspace_bytes(int B, int M, int nnz, int Fin, int Fout, int K
   LayerShape s{B, M, nnz, Fin, Fout, K, p};
   const bool fused_ok = backward ? fused_bwd_supported(s, need_dx != 0) : fused_fwd_supported(s);
   if (algo == GCNB_ALGO_FUSED || (algo == GCNB_ALGO_AUTO && fused_ok))
-    return fused_ok ? fused_cheb_workspace(s, backward != 0, need_dx != 0) : 0;
+    return fused_ok ? std::max(fused_cheb_workspace(s, backward != 0, need_dx != 0), backward ? stack_dw_workspace(s) : 0)
+                    : 0;
   return general_cheb_workspace(s, backward != 0, need_dx != 0) +
          (backward ? align_up((size_t)B * ceil_div(M, p) * Fout * sizeof(float), 256) + 256 : 0);
 }
 
 int gcnb_cheb_fwd_f32(const float* x, const int32_t* perm, int M_in, const gcnb_csr* L, const float* W,
-                      const float* bias, float* y, uint8_t* argmax, float* y_mean, int B, int Fin, int Fout, int K,
-                      int p, int bias_mode, int relu, int algo, void* workspace, size_t workspace_bytes,
-                      gcnb_stream_t stream) {
+                      const float* bias, float* y, uint8_t* argmax, float* y_mean, float* xstack, int B, int Fin,
+                      int Fout, int K, int p, int bias_mode, int relu, int algo, void* workspace,
+                      size_t workspace_bytes, gcnb_stream_t stream) {
   int rc = check_layer("gcnb_cheb_fwd_f32", L, B, Fin, Fout, K, p, bias_mode, bias);
   if (rc) return rc;
   GCNB_REQUIRE(x && W && y, "gcnb_cheb_fwd_f32: x, W and y must not be NULL");
@@ -229,17 +235,18 @@ int gcnb_cheb_fwd_f32(const float* x, const int32_t* perm, int M_in, const gcnb_
   }
   const long long pooled_rows = (long long)B * ceil_div(s.M, p);
   if (algo == GCNB_ALGO_FUSED || (algo == GCNB_ALGO_AUTO && fused_ok)) {
-    rc = fused_cheb_fwd(x, perm, M_in, *L, W, bias, y, argmax, y_mean, s, bias_mode, relu, ws, st);
+    rc = fused_cheb_fwd(x, perm, M_in, *L, W, bias, y, argmax, y_mean, xstack, s, bias_mode, relu, ws, st);
     if (rc == GCNB_OK && y_mean != nullptr && Fout > 32) rc = launch_mean_f(y, y_mean, pooled_rows, Fout, st);
     return rc;
   }
+  GCNB_REQUIRE(xstack == nullptr, "gcnb_cheb_fwd_f32: xstack is only produced by the fused kernels (see gcnb_cheb_fused_supported)");
   rc = general_cheb_fwd(x, perm, M_in, *L, W, bias, y, argmax, s, bias_mode, relu, ws, st);
   if (rc == GCNB_OK && y_mean != nullptr) rc = launch_mean_f(y, y_mean, pooled_rows, Fout, st);
   return rc;
 }
 
 int gcnb_cheb_bwd_f32(const float* x, const int32_t* perm, int M_in, const float* y, const uint8_t* argmax,
-                      const float* dy, int dy_is_mean, const gcnb_csr* L,
+                      const float* dy, int dy_is_mean, const float* xstack, const gcnb_csr* L,
                       const gcnb_csr* Lt, const float* W, float* dx, float* dW, float* db, int B, int Fin,
                       int Fout, int K, int p, int bias_mode, int relu, int algo, void* workspace,
                       size_t workspace_bytes, gcnb_stream_t stream) {
@@ -255,6 +262,8 @@ int gcnb_cheb_bwd_f32(const float* x, const int32_t* perm, int M_in, const float
   LayerShape s{B, L->M, L->nnz, Fin, Fout, K, p};
   Workspace ws(workspace, workspace_bytes);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (xstack != nullptr && dx == nullptr && algo != GCNB_ALGO_GENERAL && stack_dw_supported(s))
+    return stack_dw(xstack, y, argmax, dy, dy_is_mean, dW, db, s, bias_mode, relu, ws, st);
   const bool fused_ok = fused_bwd_supported(s, dx != nullptr);
   if (algo == GCNB_ALGO_FUSED && !fused_ok) {
     set_error("gcnb_cheb_bwd_f32: fused kernels do not support B=%d M=%d nnz=%d Fin=%d Fout=%d K=%d p=%d", B, s.M,

@@ -95,8 +95,19 @@ bool fused_fwd_supported(const LayerShape& s);
 bool fused_bwd_supported(const LayerShape& s, bool need_dx);
 size_t fused_cheb_workspace(const LayerShape& s, bool backward, bool need_dx);
 int fused_cheb_fwd(const float* x, const int32_t* perm, int M_in, const gcnb_csr& L, const float* W,
-                   const float* bias, float* y, uint8_t* argmax, float* y_mean, const LayerShape& s, int bias_mode,
-                   int relu, Workspace& ws, cudaStream_t st);
+                   const float* bias, float* y, uint8_t* argmax, float* y_mean, float* xstack, const LayerShape& s,
+                   int bias_mode, int relu, Workspace& ws, cudaStream_t st);
+// padded feature width of the fused kernels' slabs / of the X_k stack (8, 16 or 32; 0 = not supported)
+int fused_feature_pad(int Fin);
+int launch_dw_from_partials(const float* part, float* dW, int nblocks, int K, int MT, int NT, int Fin, int Fout,
+                            const float* db_part, float* db, int FoP, cudaStream_t st);
+size_t db_vertex_workspace(const LayerShape& s);
+int launch_db_vertex(const float* dy, const float* y, const uint8_t* argmax, float* db, const LayerShape& s, int relu,
+                     int dy_is_mean, Workspace& ws, cudaStream_t st);
+bool stack_dw_supported(const LayerShape& s);
+size_t stack_dw_workspace(const LayerShape& s);
+int stack_dw(const float* xstack, const float* y, const uint8_t* argmax, const float* dy, int dy_is_mean, float* dW,
+             float* db, const LayerShape& s, int bias_mode, int relu, Workspace& ws, cudaStream_t st);
 int fused_cheb_bwd(const float* x, const int32_t* perm, int M_in, const float* y, const uint8_t* argmax, const float* dy, const gcnb_csr& L,
                    const gcnb_csr* Lt, const float* W, float* dx, float* dW, float* db, const LayerShape& s,
                    int bias_mode, int relu, int dy_is_mean, Workspace& ws, cudaStream_t st);

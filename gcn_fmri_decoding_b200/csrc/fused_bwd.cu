@@ -43,6 +43,7 @@ struct BwdParams {
   int ntiles;
   int nchunks;     // MT*NT/2 accumulator chunks of 256 floats
   int off_opT, off_wfragT, off_dws, off_scratch, off_dz, off_slab;
+  int debug;  // profiling aid: bit0 skip sparse steps, bit1 skip dW contraction, bit2 skip reduction, bit3 skip dx phase
 };
 
 // MT = FP/16 (1 or 2) m-tiles over the input features, NT = FoP/8 n-tiles over the filters.
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(896, 1) k_cheb_bwd_fused(const BwdParams P) {
       unsigned char* cur = (k & 1) ? slabB : slabA;
       if (k > 0) {
         const unsigned char* src = (k & 1) ? slabA : slabB;
-        spmm_dispatch(G.LPR, opL, src, cur, G.Mpad, col_byte, rw, G.RW, k == 1 ? 1.f : 2.f, k > 1);
+        if (!(P.debug & 1)) spmm_dispatch(G.LPR, opL, src, cur, G.Mpad, col_byte, rw, G.RW, k == 1 ? 1.f : 2.f, k > 1);
         __syncthreads();
       }
       float acc[MT][NT][4];
@@ -159,7 +160,7 @@ __global__ void __launch_bounds__(896, 1) k_cheb_bwd_fused(const BwdParams P) {
       for (int a = 0; a < SLOTS; ++a) {
         const int tt = a / G.WS, s = a - tt * G.WS;
         const int rt = rw + tt * G.RW;
-        if (!(a < G.TPW * G.WS && rt < G.RT)) continue;
+        if (!(a < G.TPW * G.WS && rt < G.RT) || (P.debug & 2)) continue;
         const int scol = (sg * G.WS + s);
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2) {
@@ -187,7 +188,7 @@ __global__ void __launch_bounds__(896, 1) k_cheb_bwd_fused(const BwdParams P) {
       }
       // ---- warps -> CTA: fixed-order reduction through the scratch, two n-tiles (256 floats) per round --------
 #pragma unroll
-      for (int m = 0; m < MT; ++m) {
+      for (int m = 0; m < ((P.debug & 4) ? 0 : MT); ++m) {
 #pragma unroll
         for (int np = 0; np < NT / 2; ++np) {
           float* mine = scratch + (size_t)warp * 256 + lane;
@@ -216,7 +217,7 @@ __global__ void __launch_bounds__(896, 1) k_cheb_bwd_fused(const BwdParams P) {
     }
 
     // ---- phase B: dx by the Clenshaw form of the adjoint recursion ---------------------------------------------
-    if (need_dx) {
+    if (need_dx && !(P.debug & 8)) {
       const int KSo = FoP / 8;
       for (int k = P.K - 1; k >= 0; --k) {
         const int step = P.K - 1 - k;                       // 0, 1, 2, ...
@@ -447,6 +448,7 @@ static BwdPlan plan_bwd(const LayerShape& s, bool need_dx) {
       // slab strides: RS/8 odd keeps the transposed fragment loads of the dW contraction conflict free
       int RS = S * g.FP + 8;
       if ((RS / 8) % 2 == 0) RS += 8;
+      if (S * g.FP == 16) RS = 16;  // 64-byte rows: alternate bank halves in the sparse step (measured best)
       int RSz = S * pl.FoP + 8;
       if ((RSz / 8) % 2 == 0) RSz += 8;
       const size_t need = op_bytes * ((need_dx && s.K > 1) ? 2 : 1) + wfragT + dws + (size_t)nw * 256 * 4 +
@@ -483,13 +485,44 @@ static BwdPlan plan_bwd(const LayerShape& s, bool need_dx) {
 
 bool fused_bwd_supported(const LayerShape& s, bool need_dx) { return plan_bwd(s, need_dx).ok; }
 
+int launch_dw_from_partials(const float* part, float* dW, int nblocks, int K, int MT, int NT, int Fin, int Fout,
+                            const float* db_part, float* db, int FoP, cudaStream_t st) {
+  const int total = K * (MT * NT / 2) * 256;
+  const int warps = total + (db_part != nullptr ? Fout : 0);
+  k_dw_from_partials<<<ceil_div(warps * 32, 256), 256, 0, st>>>(part, dW, nblocks, K, MT, NT, Fin, Fout, db_part, db, FoP);
+  GCNB_LAUNCH_CHECK("k_dw_from_partials");
+  return GCNB_OK;
+}
+
+size_t db_vertex_workspace(const LayerShape& s) { return align_up((size_t)kDbChunks * s.M * s.Fout * 4, 256) + 256; }
+
+// per-vertex bias gradient (b2relu): two-stage column sum over the pooled tensors
+int launch_db_vertex(const float* dy, const float* y, const uint8_t* argmax, float* db, const LayerShape& s, int relu,
+                     int dy_is_mean, Workspace& ws, cudaStream_t st) {
+  float* dbp = ws.take<float>((size_t)kDbChunks * s.M * s.Fout);
+  if (!dbp) {
+    set_error("workspace too small for the bias gradient");
+    return GCNB_ERR_WORKSPACE;
+  }
+  int log2p = 0;
+  while ((1 << log2p) < s.p) ++log2p;
+  const int Mo = s.M / s.p;
+  const int bchunk = ceil_div(s.B, kDbChunks);
+  const int nch = ceil_div(s.B, bchunk);
+  dim3 grid_db(ceil_div(Mo * s.Fout, 128), nch);
+  k_db_partial<<<grid_db, 128, 0, st>>>(dy, y, argmax, dbp, s.B, s.M, s.Fout, s.p, log2p, relu, bchunk, dy_is_mean);
+  GCNB_LAUNCH_CHECK("k_db_partial");
+  k_db_final<<<ceil_div(s.M * s.Fout, 128), 128, 0, st>>>(dbp, db, nch, s.M, s.Fout, 1);
+  GCNB_LAUNCH_CHECK("k_db_final");
+  return GCNB_OK;
+}
+
 size_t fused_cheb_workspace(const LayerShape& s, bool backward, bool need_dx) {
   if (!backward) return 256;
   const BwdPlan pl = plan_bwd(s, need_dx);
   if (!pl.ok) return 0;
   const size_t part = (size_t)148 * 2 * (s.K * pl.nchunks * 256 + 32) * 4;  // up to 296 CTAs (+ bias partials)
-  const size_t dbp = (size_t)kDbChunks * s.M * s.Fout * 4;
-  return align_up(part, 256) + align_up(dbp, 256) + 512;
+  return align_up(part, 256) + db_vertex_workspace(s) + 512;
 }
 
 template <int MT, int NT, int SLOTS>
@@ -517,8 +550,7 @@ int fused_cheb_bwd(const float* x, const int32_t* perm, int M_in, const float* y
   const int grid = std::min(ntiles, std::min(di.sm_count, 296));
   float* part = ws.take<float>((size_t)grid * s.K * pl.nchunks * 256);
   float* dbf = ws.take<float>((size_t)grid * 32);
-  float* dbp = ws.take<float>((size_t)kDbChunks * s.M * s.Fout);
-  if (!part || !dbp || !dbf) {
+  if (!part || !dbf) {
     set_error("workspace too small for the fused backward path");
     return GCNB_ERR_WORKSPACE;
   }
@@ -534,6 +566,7 @@ int fused_cheb_bwd(const float* x, const int32_t* perm, int M_in, const float* y
   P.g = pl.g; P.FoP = pl.FoP; P.RSz = pl.RSz; P.ntiles = ntiles; P.nchunks = pl.nchunks;
   P.off_opT = pl.off_opT; P.off_wfragT = pl.off_wfragT; P.off_dws = pl.off_dws; P.off_scratch = pl.off_scratch;
   P.off_dz = pl.off_dz; P.off_slab = pl.off_slab;
+  P.debug = env_int_b("GCNB_BWD_DEBUG", 0);
   rc = GCNB_ERR_INVALID;
 #define GCNB_BWD_CASE(mt, nt, sl) \
   if (pl.MT == mt && pl.NT == nt && pl.SLOTS == sl) rc = launch_bwd<mt, nt, sl>(P, pl, grid, st);
@@ -546,24 +579,9 @@ int fused_cheb_bwd(const float* x, const int32_t* perm, int M_in, const float* y
     if (rc == GCNB_ERR_INVALID) set_error("fused backward: no kernel instance for MT=%d NT=%d SLOTS=%d", pl.MT, pl.NT, pl.SLOTS);
     return rc;
   }
-  {
-    const int total = s.K * pl.nchunks * 256;
-    const int warps = total + (db_fused ? s.Fout : 0);
-    k_dw_from_partials<<<ceil_div(warps * 32, 256), 256, 0, st>>>(part, dW, grid, s.K, pl.MT, pl.NT, s.Fin, s.Fout,
-                                                                  P.db_part, db, pl.FoP);
-    GCNB_LAUNCH_CHECK("k_dw_from_partials");
-  }
-  if (bias_mode == GCNB_BIAS_PER_VERTEX && db != nullptr) {
-    const int Mo = s.M / s.p;
-    const int bchunk = ceil_div(s.B, kDbChunks);
-    const int nch = ceil_div(s.B, bchunk);
-    dim3 grid_db(ceil_div(Mo * s.Fout, 128), nch);
-    k_db_partial<<<grid_db, 128, 0, st>>>(dy, y, argmax, dbp, s.B, s.M, s.Fout, s.p, P.log2p, relu, bchunk, dy_is_mean);
-    GCNB_LAUNCH_CHECK("k_db_partial");
-    const int n = bias_mode == GCNB_BIAS_PER_VERTEX ? s.M * s.Fout : s.Fout * 32;
-    k_db_final<<<ceil_div(n, 128), 128, 0, st>>>(dbp, db, nch, s.M, s.Fout, bias_mode == GCNB_BIAS_PER_VERTEX);
-    GCNB_LAUNCH_CHECK("k_db_final");
-  }
+  rc = launch_dw_from_partials(part, dW, grid, s.K, pl.MT, pl.NT, s.Fin, s.Fout, P.db_part, db, pl.FoP, st);
+  if (rc) return rc;
+  if (bias_mode == GCNB_BIAS_PER_VERTEX && db != nullptr) return launch_db_vertex(dy, y, argmax, db, s, relu, dy_is_mean, ws, st);
   return GCNB_OK;
 }
 

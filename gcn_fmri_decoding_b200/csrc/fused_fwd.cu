@@ -22,6 +22,7 @@ struct FwdParams {
   const float* W;
   const float* bias;
   float* y;
+  float* xstack;  // nullable: X_k for all k as [K][B][M][FP] (training: lets the weight gradient skip the recursion)
   float* y_mean;  // nullable: mean over the filters of the pooled output, [B][M/p] (models_gcn.py:673 fused)
   uint8_t* argmax;
   int B, Fin, Fout, K, p, bias_mode, relu;
@@ -169,17 +170,35 @@ __global__ void __launch_bounds__((SLOTS * NT > 8) ? 512 : 896, 1) k_cheb_fwd_fu
       }
     };
 
+    // Optional: keep the basis for the backward pass.  X_k sits untouched in its slab during step k+1, so each warp
+    // streams its share of rows out at the start of that step (no extra barrier).
+    auto spill = [&](int k, const unsigned char* slab) {
+      if (P.xstack == nullptr) return;
+      const int q4 = FP >> 2;  // float4 per (row, sample)
+      const int per_row = G.S * q4;
+      for (int idx = tid; idx < G.M * per_row; idx += blockDim.x) {
+        const int m = idx / per_row, rem = idx - m * per_row;
+        const int s = rem / q4, q = rem - s * q4;
+        const int b = b0 + s;
+        if (b >= P.B) continue;
+        const float4 v = *reinterpret_cast<const float4*>(slab + ((size_t)m * RS + s * FP + 4 * q) * 4);
+        *reinterpret_cast<float4*>(P.xstack + (((size_t)k * P.B + b) * G.M + m) * FP + 4 * q) = v;
+      }
+    };
+
     // Step k: the sparse step that produces X_k (shared-memory / FFMA pipes) and the contraction of X_{k-1} (tensor
     // pipe) are independent -- both only read X_{k-1}.  Odd warps run them in one order, even warps in the other,
     // so at any time about half of the CTA feeds each pipe.  One barrier per order.
     for (int k = 1; k < P.K; ++k) {
       unsigned char* cur = (k & 1) ? slabB : slabA;         // receives X_k (holds X_{k-2})
       const unsigned char* prev = (k & 1) ? slabA : slabB;  // X_{k-1}
+      spill(k - 1, prev);
       if (warp & 1) contract(k - 1, prev);
       if (!(P.debug & 1)) spmm_dispatch(G.LPR, op, prev, cur, G.Mpad, col_byte, rw, G.RW, k == 1 ? 1.f : 2.f, k > 1);
       if (!(warp & 1)) contract(k - 1, prev);
       __syncthreads();
     }
+    spill(P.K - 1, ((P.K - 1) & 1) ? slabB : slabA);
     contract(P.K - 1, ((P.K - 1) & 1) ? slabB : slabA);
 
     // ---- epilogue: bias, ReLU, max-pool over p consecutive vertices (first maximum wins), store -------------
@@ -353,8 +372,8 @@ static int launch_fwd(const FwdParams& P, const FwdPlan& pl, cudaStream_t st) {
 }
 
 int fused_cheb_fwd(const float* x, const int32_t* perm, int M_in, const gcnb_csr& L, const float* W,
-                   const float* bias, float* y, uint8_t* argmax, float* y_mean, const LayerShape& s, int bias_mode,
-                   int relu, Workspace& ws, cudaStream_t st) {
+                   const float* bias, float* y, uint8_t* argmax, float* y_mean, float* xstack, const LayerShape& s,
+                   int bias_mode, int relu, Workspace& ws, cudaStream_t st) {
   (void)ws;
   const FwdPlan pl = plan_fwd(s, M_in, (reinterpret_cast<uintptr_t>(x) & 15) == 0);
   if (!pl.ok) {
@@ -365,6 +384,7 @@ int fused_cheb_fwd(const float* x, const int32_t* perm, int M_in, const gcnb_csr
   P.x = x; P.perm = perm; P.M_in = M_in;
   P.rowptr = L.rowptr; P.col = L.col; P.val = L.val; P.nnz = L.nnz;
   P.W = W; P.bias = bias; P.y = y; P.argmax = argmax; P.y_mean = s.Fout <= 32 ? y_mean : nullptr;
+  P.xstack = xstack;
   P.B = s.B; P.Fin = s.Fin; P.Fout = s.Fout; P.K = s.K; P.p = s.p; P.bias_mode = bias_mode; P.relu = relu;
   P.g = pl.g;
   P.ntiles = ceil_div(s.B, pl.g.S);

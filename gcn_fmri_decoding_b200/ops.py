@@ -84,7 +84,7 @@ def cheb_fwd(x: Tensor, perm: Optional[Tensor], rowptr: Tensor, col: Tensor, val
     ws = _workspace(nbytes, x.device)
     csr = csr_struct(rowptr, col, val)
     rc = L.gcnb_cheb_fwd_f32(_ptr(x), _ptr(perm), M_in, C.byref(csr), _ptr(W), _ptr(bias), _ptr(y), _ptr(argmax), None,
-                             B, Fin, Fout, K, p, bias_mode, int(relu), algo, _ptr(ws), ws.numel(), _stream(x))
+                             None, B, Fin, Fout, K, p, bias_mode, int(relu), algo, _ptr(ws), ws.numel(), _stream(x))
     _lib.check(rc, "gcnb_cheb_fwd_f32")
     return y, argmax
 
@@ -116,7 +116,7 @@ def cheb_bwd(x: Tensor, perm: Optional[Tensor], y: Tensor, argmax: Tensor, dy: T
     ws = _workspace(nbytes, x.device)
     csr = csr_struct(rowptr, col, val)
     csr_t = csr_struct(rowptr_t, col_t, val_t)
-    rc = L.gcnb_cheb_bwd_f32(_ptr(x), _ptr(perm), M_in, _ptr(y), _ptr(argmax), _ptr(dy), 0, C.byref(csr),
+    rc = L.gcnb_cheb_bwd_f32(_ptr(x), _ptr(perm), M_in, _ptr(y), _ptr(argmax), _ptr(dy), 0, None, C.byref(csr),
                              C.byref(csr_t), _ptr(W), _ptr(dx), _ptr(dW), _ptr(db), B, Fin, Fout, K, p, bias_mode,
                              int(relu), algo, _ptr(ws), ws.numel(), _stream(x))
     _lib.check(rc, "gcnb_cheb_bwd_f32")
@@ -136,7 +136,8 @@ def _(x, perm, y, argmax, dy, rowptr, col, val, rowptr_t, col_t, val_t, W, K, p,
 # gradients are written straight into caller-provided views of the flat gradient buffer.
 @torch.library.custom_op("gcn_b200::cheb_fwd_mean", mutates_args=(), device_types="cuda")
 def cheb_fwd_mean(x: Tensor, perm: Optional[Tensor], rowptr: Tensor, col: Tensor, val: Tensor, W: Tensor,
-                  bias: Optional[Tensor], K: int, p: int, bias_mode: int, relu: bool, algo: int) -> Tuple[Tensor, Tensor, Tensor]:
+                  bias: Optional[Tensor], K: int, p: int, bias_mode: int, relu: bool, algo: int,
+                  want_stack: bool = False) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
     _check_x(x)
     x = x.contiguous()
     B, M_in, Fin = x.shape
@@ -147,27 +148,30 @@ def cheb_fwd_mean(x: Tensor, perm: Optional[Tensor], rowptr: Tensor, col: Tensor
     argmax = torch.empty((B, Mo, Fout) if p > 1 else (0,), dtype=torch.uint8, device=x.device)
     ymean = torch.empty((B, Mo), dtype=torch.float32, device=x.device)
     L = _lib.lib()
+    FP = L.gcnb_cheb_stack_width(B, M, val.numel(), Fin, Fout, K, p) if (want_stack and algo != ALGO_GENERAL) else 0
+    stack = torch.empty((K, B, M, FP) if FP else (0,), dtype=torch.float32, device=x.device)
     ws = _workspace(L.gcnb_cheb_workspace_bytes(B, M, val.numel(), Fin, Fout, K, p, 0, 0, algo), x.device)
     csr = csr_struct(rowptr, col, val)
     rc = L.gcnb_cheb_fwd_f32(_ptr(x), _ptr(perm), M_in, C.byref(csr), _ptr(W), _ptr(bias), _ptr(y), _ptr(argmax),
-                             _ptr(ymean), B, Fin, Fout, K, p, bias_mode, int(relu), algo, _ptr(ws), ws.numel(), _stream(x))
+                             _ptr(ymean), _ptr(stack), B, Fin, Fout, K, p, bias_mode, int(relu), algo, _ptr(ws), ws.numel(),
+                             _stream(x))
     _lib.check(rc, "gcnb_cheb_fwd_f32")
-    return y, argmax, ymean
+    return y, argmax, ymean, stack
 
 
 @cheb_fwd_mean.register_fake
-def _(x, perm, rowptr, col, val, W, bias, K, p, bias_mode, relu, algo):
+def _(x, perm, rowptr, col, val, W, bias, K, p, bias_mode, relu, algo, want_stack=False):
     B = x.shape[0]
     Mo = _pooled(rowptr.numel() - 1, p)
     return (x.new_empty((B, Mo, W.shape[1])), x.new_empty((B, Mo, W.shape[1]) if p > 1 else (0,), dtype=torch.uint8),
-            x.new_empty((B, Mo)))
+            x.new_empty((B, Mo)), x.new_empty((0,)))
 
 
 @torch.library.custom_op("gcn_b200::cheb_bwd_into", mutates_args=("dW_out", "db_out"), device_types="cuda")
 def cheb_bwd_into(x: Tensor, perm: Optional[Tensor], y: Tensor, argmax: Tensor, dy: Tensor, dy_is_mean: bool,
                   rowptr: Tensor, col: Tensor, val: Tensor, rowptr_t: Tensor, col_t: Tensor, val_t: Tensor, W: Tensor,
                   dW_out: Tensor, db_out: Tensor, K: int, p: int, bias_mode: int, relu: bool, need_dx: bool,
-                  algo: int) -> Tensor:
+                  algo: int, stack: Optional[Tensor] = None) -> Tensor:
     x = x.contiguous()
     dy = dy.contiguous()
     B, M_in, Fin = x.shape
@@ -180,7 +184,8 @@ def cheb_bwd_into(x: Tensor, perm: Optional[Tensor], y: Tensor, argmax: Tensor, 
     ws = _workspace(L.gcnb_cheb_workspace_bytes(B, M, val.numel(), Fin, Fout, K, p, 1, int(need_dx), algo), x.device)
     csr = csr_struct(rowptr, col, val)
     csr_t = csr_struct(rowptr_t, col_t, val_t)
-    rc = L.gcnb_cheb_bwd_f32(_ptr(x), _ptr(perm), M_in, _ptr(y), _ptr(argmax), _ptr(dy), int(dy_is_mean), C.byref(csr),
+    rc = L.gcnb_cheb_bwd_f32(_ptr(x), _ptr(perm), M_in, _ptr(y), _ptr(argmax), _ptr(dy), int(dy_is_mean), _ptr(stack),
+                             C.byref(csr),
                              C.byref(csr_t), _ptr(W), _ptr(dx), _ptr(dW_out), _ptr(db_out), B, Fin, Fout, K, p, bias_mode,
                              int(relu), algo, _ptr(ws), ws.numel(), _stream(x))
     _lib.check(rc, "gcnb_cheb_bwd_f32")
@@ -189,7 +194,7 @@ def cheb_bwd_into(x: Tensor, perm: Optional[Tensor], y: Tensor, argmax: Tensor, 
 
 @cheb_bwd_into.register_fake
 def _(x, perm, y, argmax, dy, dy_is_mean, rowptr, col, val, rowptr_t, col_t, val_t, W, dW_out, db_out, K, p, bias_mode,
-      relu, need_dx, algo):
+      relu, need_dx, algo, stack=None):
     return x.new_empty((x.shape[0], rowptr.numel() - 1, x.shape[2]) if need_dx else (0,))
 
 

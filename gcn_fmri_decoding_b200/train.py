@@ -177,7 +177,7 @@ class FusedTrainer:
     """
 
     def __init__(self, model, lr=1e-3, distributed=None, use_cuda_graph=True, dropout=1.0, beta1=0.9, beta2=0.999,
-                 eps=1e-8, own_gemm=False):
+                 eps=1e-8, own_gemm=False, save_basis=True):
         import ctypes as C
 
         from . import _lib, ops
@@ -186,6 +186,7 @@ class FusedTrainer:
         self.C, self._lib, self.ops = C, _lib, ops
         self.keep = float(dropout) if dropout else 1.0
         self.own_gemm = own_gemm
+        self.save_basis = save_basis
         self.distributed = dist.is_available() and dist.is_initialized() if distributed is None else distributed
         self.world = dist.get_world_size() if self.distributed else 1
         self.params = [p for p in model.parameters()]
@@ -233,19 +234,19 @@ class FusedTrainer:
             last = i == nconv - 1
             if cheb:
                 pl = m._plan(m.L[i])
+                # first layer: keep the Chebyshev basis (its backward needs no dx, so dW becomes one streamed GEMM);
+                # last layer: also emit the mean over the filters
+                y, am, hm, stack = ops.cheb_fwd_mean(h, perm, pl.rowptr, pl.col, pl.val, m.conv_weights[i], m.conv_bias[i],
+                                                     m.K[i], m.p[i], mode, True, m.algo, i == 0 and self.save_basis)
                 if last:
-                    y, am, h0 = ops.cheb_fwd_mean(h, perm, pl.rowptr, pl.col, pl.val, m.conv_weights[i], m.conv_bias[i],
-                                                  m.K[i], m.p[i], mode, True, m.algo)
-                else:
-                    y, am = ops.cheb_fwd(h, perm, *pl.tensors(), m.conv_weights[i], m.conv_bias[i], m.K[i], m.p[i], mode,
-                                         True, True, m.algo)
-                saved.append((h, perm, y, am, pl))
+                    h0 = hm
+                saved.append((h, perm, y, am, pl, stack if stack.numel() else None))
             else:
                 if perm is not None:
                     h = ops.perm_gather(h, perm)
                 sp = m._spectral_plan(m.L[i])
                 y, am = ops.spectral_fwd(h, sp.Ut, m.conv_weights[i], m.conv_bias[i], m.p[i], mode, True, True)
-                saved.append((h, None, y, am, sp))
+                saved.append((h, None, y, am, sp, None))
             h = y
         if h0 is None:
             h0 = ops.mean_f_fwd(h)
@@ -312,12 +313,12 @@ class FusedTrainer:
         if not cheb:
             dy, dy_is_mean = torch.ops.gcn_b200.mean_f_bwd(d, h.shape[-1]), False
         for i in range(nconv - 1, -1, -1):
-            hin, perm, y, am, pl = saved[i]
+            hin, perm, y, am, pl, stack = saved[i]
             need_dx = i > 0
             gW, gb = self.gview[id(m.conv_weights[i])], self.gview[id(m.conv_bias[i])]
             if cheb:
                 dx = ops.cheb_bwd_into(hin, perm, y, am, dy, dy_is_mean, *pl.tensors(), m.conv_weights[i], gW, gb, m.K[i],
-                                       m.p[i], mode, True, need_dx, m.algo)
+                                       m.p[i], mode, True, need_dx, m.algo, stack)
             else:
                 dx, dW, db = torch.ops.gcn_b200.spectral_bwd(hin, y, am, dy, pl.Ut, m.conv_weights[i], m.p[i], mode, True,
                                                              need_dx)

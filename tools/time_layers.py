@@ -55,4 +55,9 @@ if "b2" in which:
     out.append("L2 bwd %.1f" % timeit(lambda i: torch.ops.gcn_b200.cheb_bwd(xs[i], None, y2[i][0], y2[i][1], dy2[i], *pl2.tensors(), W2, 5, 4, 1, True, True, algo), n2))
 if "b1" in which:
     out.append("L1 bwd %.1f" % timeit(lambda i: torch.ops.gcn_b200.cheb_bwd(xr[i], permt, y1[i][0], y1[i][1], dy1[i], *pl1.tensors(), W1, 5, 4, 1, True, False, algo), n1))
+if "s1" in which:
+    st = [ops.cheb_fwd_mean(xr[i], permt, pl1.rowptr, pl1.col, pl1.val, W1, b, 5, 4, 1, True, algo, True) for i in range(4)]
+    out.append("L1 fwd+stack %.1f" % timeit(lambda i: ops.cheb_fwd_mean(xr[i], permt, pl1.rowptr, pl1.col, pl1.val, W1, b, 5, 4, 1, True, algo, True), n1))
+    gW, gb = torch.empty_like(W1), torch.empty(32, device=dev)
+    out.append("L1 bwd(stack) %.1f" % timeit(lambda i: ops.cheb_bwd_into(xr[i], permt, y1[i][0], y1[i][1], dy1[i], False, *pl1.tensors(), W1, gW, gb, 5, 4, 1, True, False, algo, st[i % 4][3]), n1))
 print(os.environ.get("TAG", ""), "us:", "  ".join(out))
