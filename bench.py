@@ -204,6 +204,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--algo", type=int, default=0, help="0 auto, 1 general (HBM) kernels, 2 fused kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cublas-fc", action="store_true", help="FC GEMMs through cuBLAS fp32 instead of the in-house 3xTF32 kernel")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -234,7 +235,7 @@ def main():
     model = cgcnn(L=L, F=F, K=K, p=P, M=MFC, channel=15, device=dev, seed=7, regularization=REG, batch_size=BATCH,
                   perm=perm, n_input_vertices=360, algo=args.algo)
     # dropout keep-probability 0.5 on the FC layers, as the reference trains (model.py:169, models_gcn.py:145)
-    trainer = FusedTrainer(model, use_cuda_graph=not args.no_graph, dropout=0.5)
+    trainer = FusedTrainer(model, use_cuda_graph=not args.no_graph, dropout=0.5, own_gemm=not args.cublas_fc)
 
     # ring of distinct resident batches: R x 11.06 MB of raw windows  (> 2 x 126 MB L2)
     R = 25

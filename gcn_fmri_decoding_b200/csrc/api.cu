@@ -208,7 +208,7 @@ size_t gcnb_cheb_workspace_bytes(int B, int M, int nnz, int Fin, int Fout, int K
   LayerShape s{B, M, nnz, Fin, Fout, K, p};
   const bool fused_ok = backward ? fused_bwd_supported(s, need_dx != 0) : fused_fwd_supported(s);
   if (algo == GCNB_ALGO_FUSED || (algo == GCNB_ALGO_AUTO && fused_ok))
-    return fused_ok ? std::max(fused_cheb_workspace(s, backward != 0, need_dx != 0), backward ? stack_dw_workspace(s) : 0)
+    return fused_ok ? fused_cheb_workspace(s, backward != 0, need_dx != 0) + (backward ? stack_dw_workspace(s) + 512 : 0)
                     : 0;
   return general_cheb_workspace(s, backward != 0, need_dx != 0) +
          (backward ? align_up((size_t)B * ceil_div(M, p) * Fout * sizeof(float), 256) + 256 : 0);
@@ -265,13 +265,20 @@ int gcnb_cheb_bwd_f32(const float* x, const int32_t* perm, int M_in, const float
   if (xstack != nullptr && dx == nullptr && algo != GCNB_ALGO_GENERAL && stack_dw_supported(s))
     return stack_dw(xstack, y, argmax, dy, dy_is_mean, dW, db, s, bias_mode, relu, ws, st);
   const bool fused_ok = fused_bwd_supported(s, dx != nullptr);
+  if (xstack != nullptr && dx != nullptr && algo != GCNB_ALGO_GENERAL && fused_ok && stack_dw_supported(s)) {
+    // saved basis: the weight gradient is one streamed GEMM; the fused kernel only runs the adjoint recursion for dx
+    rc = stack_dw(xstack, y, argmax, dy, dy_is_mean, dW, db, s, bias_mode, relu, ws, st);
+    if (rc) return rc;
+    Workspace ws2(static_cast<char*>(workspace) + align_up(ws.used, 256), workspace_bytes - align_up(ws.used, 256));
+    return fused_cheb_bwd(x, perm, M_in, y, argmax, dy, *L, Lt, W, dx, dW, db, s, bias_mode, relu, dy_is_mean, true, ws2, st);
+  }
   if (algo == GCNB_ALGO_FUSED && !fused_ok) {
     set_error("gcnb_cheb_bwd_f32: fused kernels do not support B=%d M=%d nnz=%d Fin=%d Fout=%d K=%d p=%d", B, s.M,
               s.nnz, Fin, Fout, K, p);
     return GCNB_ERR_INVALID;
   }
   if (algo == GCNB_ALGO_FUSED || (algo == GCNB_ALGO_AUTO && fused_ok))
-    return fused_cheb_bwd(x, perm, M_in, y, argmax, dy, *L, Lt, W, dx, dW, db, s, bias_mode, relu, dy_is_mean, ws, st);
+    return fused_cheb_bwd(x, perm, M_in, y, argmax, dy, *L, Lt, W, dx, dW, db, s, bias_mode, relu, dy_is_mean, false, ws, st);
   if (dy_is_mean) {  // the general path works on the full gradient: expand dy/Fout over the filters first
     const long long pooled_rows = (long long)B * ceil_div(s.M, p);
     float* full = ws.take<float>((size_t)pooled_rows * Fout);

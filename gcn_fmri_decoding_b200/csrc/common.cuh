@@ -110,7 +110,7 @@ int stack_dw(const float* xstack, const float* y, const uint8_t* argmax, const f
              float* db, const LayerShape& s, int bias_mode, int relu, Workspace& ws, cudaStream_t st);
 int fused_cheb_bwd(const float* x, const int32_t* perm, int M_in, const float* y, const uint8_t* argmax, const float* dy, const gcnb_csr& L,
                    const gcnb_csr* Lt, const float* W, float* dx, float* dW, float* db, const LayerShape& s,
-                   int bias_mode, int relu, int dy_is_mean, Workspace& ws, cudaStream_t st);
+                   int bias_mode, int relu, int dy_is_mean, bool skip_dw, Workspace& ws, cudaStream_t st);
 int launch_gemm(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int lda, int ldb, int ldc,
                 int ta, int tb, cudaStream_t st);
 int launch_mean_f(const float* x, float* y, long long rows, int F, cudaStream_t st);

@@ -37,6 +37,7 @@ struct BwdParams {
   float* dw_part;  // [grid][K][chunks][256]
   float* db_part;  // [grid][FoP] per-filter bias-gradient partials (nullable)
   int B, Fin, Fout, K, p, log2p, relu;
+  int skip_dw;     // the weight/bias gradients come from the saved basis (stack_dw.cu): only dx is computed here
   int dy_is_mean;  // dy is [B][M/p]: the gradient of the mean over filters (every filter gets dy/Fout)
   TileGeom g;      // FP/KS/RS describe the X slabs
   int FoP, RSz;    // padded Fout, dZ slab stride
@@ -71,7 +72,7 @@ __global__ void __launch_bounds__(896, 1) k_cheb_bwd_fused(const BwdParams P) {
   constexpr int NCH = MT * NT / 2;
 
   // ---- once per CTA ---------------------------------------------------------------------------------------
-  build_operator(P.rowptr, P.col, P.val, G.M, G.Mpad, P.nnz, RS, opL);
+  if (!P.skip_dw) build_operator(P.rowptr, P.col, P.val, G.M, G.Mpad, P.nnz, RS, opL);
   if (need_dx && P.K > 1) build_operator(P.rowptr_t, P.col_t, P.val_t, G.M, G.Mpad, P.nnz, RS, opT);
   if (need_dx) {
     // B fragments of W_k^T (k8 = filters o, n8 = input features f), TF32 hi/lo
@@ -105,7 +106,7 @@ __global__ void __launch_bounds__(896, 1) k_cheb_bwd_fused(const BwdParams P) {
     const int b0 = tile * G.S;
     __syncthreads();
     // ---- x -> slab A;  dZ slab from (dy, y, arg-max) ---------------------------------------------------------
-    for (int s = 0; s < G.S; ++s) {
+    for (int s = 0; s < (P.skip_dw ? 0 : G.S); ++s) {
       const int b = b0 + s;
       const float* xb = P.x + (long long)b * per_sample;
       for (int m = warp * rows_per_instr + lrow; m < G.Mpad; m += nwarps * rows_per_instr) {
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(896, 1) k_cheb_bwd_fused(const BwdParams P) {
     __syncthreads();
 
     // ---- phase A: X_k order by order, dW_k += X_k^T dZ ---------------------------------------------------------
-    for (int k = 0; k < P.K; ++k) {
+    for (int k = 0; k < (P.skip_dw ? 0 : P.K); ++k) {
       unsigned char* cur = (k & 1) ? slabB : slabA;
       if (k > 0) {
         const unsigned char* src = (k & 1) ? slabA : slabB;
@@ -299,6 +300,7 @@ __global__ void __launch_bounds__(896, 1) k_cheb_bwd_fused(const BwdParams P) {
     }
   }
   __syncthreads();
+  if (P.skip_dw) return;
   float* out = P.dw_part + (size_t)blockIdx.x * P.K * NCH * 256;
   for (int i = tid; i < P.K * NCH * 256; i += blockDim.x) out[i] = dWs[i];
   if (P.db_part != nullptr) {  // per-filter bias gradient of this CTA: threads -> filters in fixed order
@@ -536,7 +538,8 @@ static int launch_bwd(const BwdParams& P, const BwdPlan& pl, int grid, cudaStrea
 
 int fused_cheb_bwd(const float* x, const int32_t* perm, int M_in, const float* y, const uint8_t* argmax, const float* dy,
                    const gcnb_csr& L, const gcnb_csr* Lt, const float* W, float* dx, float* dW, float* db,
-                   const LayerShape& s, int bias_mode, int relu, int dy_is_mean, Workspace& ws, cudaStream_t st) {
+                   const LayerShape& s, int bias_mode, int relu, int dy_is_mean, bool skip_dw, Workspace& ws,
+                   cudaStream_t st) {
   const bool need_dx = dx != nullptr;
   const BwdPlan pl = plan_bwd(s, need_dx);
   if (!pl.ok) {
@@ -561,6 +564,7 @@ int fused_cheb_bwd(const float* x, const int32_t* perm, int M_in, const float* y
   const bool db_fused = bias_mode == GCNB_BIAS_PER_FILTER && db != nullptr;
   P.W = W; P.dx = dx; P.dw_part = part; P.db_part = db_fused ? dbf : nullptr;
   P.B = s.B; P.Fin = s.Fin; P.Fout = s.Fout; P.K = s.K; P.p = s.p; P.relu = relu; P.dy_is_mean = dy_is_mean;
+  P.skip_dw = skip_dw ? 1 : 0;
   P.log2p = 0;
   while ((1 << P.log2p) < s.p) ++P.log2p;
   P.g = pl.g; P.FoP = pl.FoP; P.RSz = pl.RSz; P.ntiles = ntiles; P.nchunks = pl.nchunks;
@@ -579,6 +583,7 @@ int fused_cheb_bwd(const float* x, const int32_t* perm, int M_in, const float* y
     if (rc == GCNB_ERR_INVALID) set_error("fused backward: no kernel instance for MT=%d NT=%d SLOTS=%d", pl.MT, pl.NT, pl.SLOTS);
     return rc;
   }
+  if (skip_dw) return GCNB_OK;
   rc = launch_dw_from_partials(part, dW, grid, s.K, pl.MT, pl.NT, s.Fin, s.Fout, P.db_part, db, pl.FoP, st);
   if (rc) return rc;
   if (bias_mode == GCNB_BIAS_PER_VERTEX && db != nullptr) return launch_db_vertex(dy, y, argmax, db, s, relu, dy_is_mean, ws, st);

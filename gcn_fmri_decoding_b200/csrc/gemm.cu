@@ -133,9 +133,108 @@ __global__ void __launch_bounds__(128) k_gemm_3xtf32(const GemmArgs g) {
     }
 }
 
+// ---- small / skinny problems (the FC layers at B = 512): 32x32x32 tiles so that even a 512x256 output gives 128 CTAs,
+// and a 3-stage cp.async pipeline (4-byte copies: any alignment, any transpose, zero-fill out of range) so that the
+// serial walk over K is not exposed to global-memory latency.
+constexpr int SBM = 32, SBN = 32, SBK = 32, SST = 3;
+constexpr int SAS = SBK + 4;  // 36: A-fragment rows on distinct banks
+constexpr int SBS = SBN + 8;  // 40: 8t + g distinct
+
+__device__ __forceinline__ void cp_async4(float* dst, const float* src, bool ok) {
+  const int n = ok ? 4 : 0;  // src-size 0 => the 4 bytes are zero-filled
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(n) : "memory");
+}
+
+__global__ void __launch_bounds__(128) k_gemm_small_3xtf32(const GemmArgs g) {
+  __shared__ float As[SST][SBM * SAS];
+  __shared__ float Bs[SST][SBK * SBS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gq = lane >> 2, t = lane & 3;
+  const int wm = (warp >> 1) * 16, wn = (warp & 1) * 16;
+  const int m0 = blockIdx.y * SBM, n0 = blockIdx.x * SBN;
+  float acc[2][4];
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[j][c] = 0.f;
+
+  auto issue = [&](int kt, int st) {
+    const int k0 = kt * SBK;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int idx = tid + i * 128;  // 0..1023
+      int m, k;
+      if (g.ta) { k = idx >> 5; m = idx & 31; } else { m = idx >> 5; k = idx & 31; }
+      const bool oka = (m0 + m) < g.M && (k0 + k) < g.K;
+      const float* pa = g.ta ? g.A + (long long)(k0 + k) * g.lda + m0 + m : g.A + (long long)(m0 + m) * g.lda + k0 + k;
+      cp_async4(&As[st][m * SAS + k], oka ? pa : g.A, oka);
+      int kb, n;
+      if (g.tb) { n = idx >> 5; kb = idx & 31; } else { kb = idx >> 5; n = idx & 31; }
+      const bool okb = (k0 + kb) < g.K && (n0 + n) < g.N;
+      const float* pb = g.tb ? g.B + (long long)(n0 + n) * g.ldb + k0 + kb : g.B + (long long)(k0 + kb) * g.ldb + n0 + n;
+      cp_async4(&Bs[st][kb * SBS + n], okb ? pb : g.B, okb);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  const int nk = (g.K + SBK - 1) / SBK;
+  for (int s = 0; s < SST - 1; ++s) {
+    if (s < nk) issue(s, s);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  for (int kt = 0; kt < nk; ++kt) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(SST - 2) : "memory");
+    __syncthreads();  // tile kt landed for everyone; tile kt-1's buffer is free for the prefetch below
+    if (kt + SST - 1 < nk) issue(kt + SST - 1, (kt + SST - 1) % SST);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+    const float* as = As[kt % SST];
+    const float* bs = Bs[kt % SST];
+#pragma unroll
+    for (int ks = 0; ks < SBK; ks += 8) {
+      uint32_t ah[4], al[4];
+      const float* p = as + (wm + gq) * SAS + ks + t;
+      split_trunc(p[0], ah[0], al[0]);
+      split_trunc(p[8 * SAS], ah[1], al[1]);
+      split_trunc(p[4], ah[2], al[2]);
+      split_trunc(p[8 * SAS + 4], ah[3], al[3]);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const float* q = bs + (ks + t) * SBS + wn + j * 8 + gq;
+        uint32_t bh0, bl0, bh1, bl1;
+        split_trunc(q[0], bh0, bl0);
+        split_trunc(q[4 * SBS], bh1, bl1);
+        mma_3xtf32(acc[j], ah, al, bh0, bh1, bl0, bl1);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int n = n0 + wn + j * 8 + 2 * t;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int m = m0 + wm + gq + 8 * h;
+      if (m >= g.M) continue;
+      float v0 = acc[j][2 * h], v1 = acc[j][2 * h + 1];
+      if (g.bias != nullptr) {
+        if (n < g.N) v0 += __ldg(g.bias + n);
+        if (n + 1 < g.N) v1 += __ldg(g.bias + n + 1);
+      }
+      float* c = g.C + (long long)m * g.ldc + n;
+      if (n < g.N) c[0] = v0;
+      if (n + 1 < g.N) c[1] = v1;
+    }
+  }
+}
+
 int launch_gemm(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int lda, int ldb, int ldc,
                 int ta, int tb, cudaStream_t st) {
   GemmArgs g{A, B, C, bias, M, N, K, lda, ldb, ldc, ta, tb};
+  if ((long long)ceil_div(N, GBN) * ceil_div(M, GBM) < 2 * 148) {  // not enough 64x64 tiles to fill the chip
+    dim3 grid((unsigned)ceil_div(N, SBN), (unsigned)ceil_div(M, SBM));
+    k_gemm_small_3xtf32<<<grid, 128, 0, st>>>(g);
+    GCNB_LAUNCH_CHECK("k_gemm_small_3xtf32");
+    return GCNB_OK;
+  }
   dim3 grid((unsigned)ceil_div(N, GBN), (unsigned)ceil_div(M, GBM));
   k_gemm_3xtf32<<<grid, 128, 0, st>>>(g);
   GCNB_LAUNCH_CHECK("k_gemm_3xtf32");

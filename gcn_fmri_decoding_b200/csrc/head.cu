@@ -30,7 +30,18 @@ __global__ void k_softmax_xent(const float* __restrict__ logits, const long long
   if (lane == 0) loss_rows[row] = lse - z[lab];
 }
 
-__global__ void k_mean_rows(const float* __restrict__ v, float* __restrict__ out, int n) {
+// state[0] = beta1^t, state[1] = beta2^t, state[2] = lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t), state[3] = t
+__device__ __forceinline__ void adam_tick(float* state, float lr, float b1, float b2) {
+  const float p1 = state[0] * b1, p2 = state[1] * b2;
+  state[0] = p1;
+  state[1] = p2;
+  state[2] = lr * sqrtf(1.f - p2) / (1.f - p1);
+  state[3] += 1.f;
+}
+
+
+__global__ void k_mean_rows(const float* __restrict__ v, float* __restrict__ out, int n, float* adam_state, float lr,
+                            float b1, float b2) {
   __shared__ float red[256];
   float s = 0.f;
   for (int i = threadIdx.x; i < n; i += 256) s += v[i];
@@ -40,16 +51,10 @@ __global__ void k_mean_rows(const float* __restrict__ v, float* __restrict__ out
     if ((int)threadIdx.x < d) red[threadIdx.x] += red[threadIdx.x + d];
     __syncthreads();
   }
-  if (threadIdx.x == 0) out[0] = red[0] / (float)n;
-}
-
-// state[0] = beta1^t, state[1] = beta2^t, state[2] = lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t), state[3] = t
-__device__ __forceinline__ void adam_tick(float* state, float lr, float b1, float b2) {
-  const float p1 = state[0] * b1, p2 = state[1] * b2;
-  state[0] = p1;
-  state[1] = p2;
-  state[2] = lr * sqrtf(1.f - p2) / (1.f - p1);
-  state[3] += 1.f;
+  if (threadIdx.x == 0) {
+    out[0] = red[0] / (float)n;
+    if (adam_state != nullptr) adam_tick(adam_state, lr, b1, b2);
+  }
 }
 
 __global__ void k_adam_tick(float* state, float lr, float b1, float b2) { adam_tick(state, lr, b1, b2); }
@@ -130,23 +135,32 @@ struct ColsumArgs {
   int block_begin[5];  // blocks of 32 columns, prefix over the matrices
 };
 
-// block = (matrix, 32-column chunk): 8 row groups x 32 lanes, fixed-order combine
-__global__ void __launch_bounds__(256) k_colsum_multi(ColsumArgs a) {
-  __shared__ float red[256];
+// block = (matrix, 32-column chunk): 32 row groups x 32 lanes, four independent chains per thread, fixed-order combine
+__global__ void __launch_bounds__(1024) k_colsum_multi(ColsumArgs a) {
+  __shared__ float red[1024];
   int mi = 0;
   while (mi < 3 && (int)blockIdx.x >= a.block_begin[mi + 1]) ++mi;
   const int c0 = ((int)blockIdx.x - a.block_begin[mi]) * 32;
   const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
   const int c = c0 + lane, R = a.rows[mi], Cn = a.cols[mi];
-  float s = 0.f;
-  if (c < Cn)
-    for (int r = grp; r < R; r += 8) s += a.m[mi][(long long)r * Cn + c];
-  red[threadIdx.x] = s;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (c < Cn) {
+    const float* p = a.m[mi] + c;
+    int r = grp;
+    for (; r + 96 < R; r += 128) {
+      s0 += p[(long long)r * Cn];
+      s1 += p[(long long)(r + 32) * Cn];
+      s2 += p[(long long)(r + 64) * Cn];
+      s3 += p[(long long)(r + 96) * Cn];
+    }
+    for (; r < R; r += 32) s0 += p[(long long)r * Cn];
+  }
+  red[threadIdx.x] = (s0 + s1) + (s2 + s3);
   __syncthreads();
   if (grp == 0 && c < Cn) {
     float t = 0.f;
 #pragma unroll
-    for (int g2 = 0; g2 < 8; ++g2) t += red[g2 * 32 + lane];
+    for (int g2 = 0; g2 < 32; ++g2) t += red[g2 * 32 + lane];
     a.out[mi][c] = t;
   }
 }
@@ -178,20 +192,16 @@ int gcnb_softmax_xent_f32(const float* logits, const int64_t* labels, float* los
                           int B, int C, float* adam_state, float lr, float beta1, float beta2, gcnb_stream_t stream) {
   GCNB_REQUIRE(logits && labels && loss && loss_rows && B >= 1 && C >= 1, "gcnb_softmax_xent_f32: bad arguments");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (B <= 8192) {
+  if (B <= 64) {  // tiny batches: one CTA does everything (one launch)
     k_softmax_xent_1cta<<<1, 1024, 0, st>>>(logits, reinterpret_cast<const long long*>(labels), loss, dlogits, B, C,
                                             1.f / (float)B, adam_state, lr, beta1, beta2);
     GCNB_LAUNCH_CHECK("k_softmax_xent_1cta");
     return GCNB_OK;
   }
-  if (adam_state != nullptr) {
-    k_adam_tick<<<1, 1, 0, st>>>(adam_state, lr, beta1, beta2);
-    GCNB_LAUNCH_CHECK("k_adam_tick");
-  }
   k_softmax_xent<<<ceil_div(B * 32, 256), 256, 0, st>>>(logits, reinterpret_cast<const long long*>(labels), loss_rows,
                                                        dlogits, B, C, 1.f / (float)B);
   GCNB_LAUNCH_CHECK("k_softmax_xent");
-  k_mean_rows<<<1, 256, 0, st>>>(loss_rows, loss, B);
+  k_mean_rows<<<1, 256, 0, st>>>(loss_rows, loss, B, adam_state, lr, beta1, beta2);  // fixed-order mean + clock tick
   GCNB_LAUNCH_CHECK("k_mean_rows");
   return GCNB_OK;
 }
@@ -228,7 +238,7 @@ int gcnb_colsum_multi_f32(const float* const* mats, float* const* outs, const in
     a.cols[i] = on ? cols[i] : 0;
     a.block_begin[i + 1] = a.block_begin[i] + (on ? ceil_div(cols[i], 32) : 0);
   }
-  k_colsum_multi<<<a.block_begin[4], 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  k_colsum_multi<<<a.block_begin[4], 1024, 0, static_cast<cudaStream_t>(stream)>>>(a);
   GCNB_LAUNCH_CHECK("k_colsum_multi");
   return GCNB_OK;
 }

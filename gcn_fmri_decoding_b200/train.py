@@ -234,10 +234,10 @@ class FusedTrainer:
             last = i == nconv - 1
             if cheb:
                 pl = m._plan(m.L[i])
-                # first layer: keep the Chebyshev basis (its backward needs no dx, so dW becomes one streamed GEMM);
-                # last layer: also emit the mean over the filters
+                # keep the Chebyshev basis: the weight gradient becomes one streamed GEMM and the backward kernel only runs
+                # the adjoint recursion for dx (none at all for the first layer); last layer: also emit the mean over filters
                 y, am, hm, stack = ops.cheb_fwd_mean(h, perm, pl.rowptr, pl.col, pl.val, m.conv_weights[i], m.conv_bias[i],
-                                                     m.K[i], m.p[i], mode, True, m.algo, i == 0 and self.save_basis)
+                                                     m.K[i], m.p[i], mode, True, m.algo, self.save_basis)
                 if last:
                     h0 = hm
                 saved.append((h, perm, y, am, pl, stack if stack.numel() else None))

@@ -417,7 +417,7 @@ def test_saved_basis_weight_gradient(dev, graph_l4, lvl, B, Fin, Fout, K, p, bre
     dy = rng.randn(B, M // p, Fout).astype(np.float32)
     pr = [dict(W=W, b=b, K=K, p=p)]
     y64, tr = O.conv_stack(x, [L], pr, brelu=brelu, dtype=np.float64, keep=True)
-    _, g64 = O.conv_stack_bwd(tr, [L], pr, dy, brelu=brelu, dtype=np.float64)
+    dx64, g64 = O.conv_stack_bwd(tr, [L], pr, dy, brelu=brelu, dtype=np.float64, first_needs_dx=True)
     pl = GraphPlan(L, dev)
     mode = ops.BIAS_PER_FILTER if brelu == "b1relu" else ops.BIAS_PER_VERTEX
     xt, Wt, bt = T(x, dev), T(W, dev), T(b, dev)
@@ -437,6 +437,11 @@ def test_saved_basis_weight_gradient(dev, graph_l4, lvl, B, Fin, Fout, K, p, bre
     gW3, gb3 = torch.empty_like(Wt), torch.empty(b.size, device=dev)
     ops.cheb_bwd_into(xt, None, y, am, T(dy, dev), False, *pl.tensors(), Wt, gW3, gb3, K, p, mode, True, False, ops.ALGO_FUSED, stack)
     assert torch.equal(gW, gW3) and torch.equal(gb, gb3)  # deterministic
+    # a layer that also needs dx: dW/db from the saved basis, dx from the adjoint recursion alone
+    gW4, gb4 = torch.empty_like(Wt), torch.empty(b.size, device=dev)
+    dx = ops.cheb_bwd_into(xt, None, y, am, T(dy, dev), False, *pl.tensors(), Wt, gW4, gb4, K, p, mode, True, True, ops.ALGO_AUTO, stack)
+    assert rel_inf(dx.cpu().numpy(), dx64) <= TOL
+    assert rel_inf(gW4.cpu().numpy(), g64[0]["dW"]) <= TOL and rel_inf(gb4.cpu().numpy().reshape(b.shape), g64[0]["db"]) <= TOL
 
 
 def test_head_pieces(dev, graph_l4):
