@@ -25,6 +25,7 @@ struct StackDwParams {
   long long R;     // B*M rows
   int B, M, Mo, Fout, FoP, FP, p, log2p, relu, dy_is_mean;
   int CR, SX, SZ, nchunks;
+  int NS;  // TMA stages for the X tiles
 };
 
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
@@ -42,10 +43,16 @@ __global__ void __launch_bounds__(256, (K * MT * NT > 20) ? 1 : 2) k_dw_from_sta
   extern __shared__ __align__(16) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const int CR = P.CR, SX = P.SX, SZ = P.SZ, FP = P.FP;
-  const size_t xbytes = (size_t)K * CR * SX * 4, zbytes = (size_t)CR * SZ * 4;
-  float* Xs[2] = {reinterpret_cast<float*>(smem), reinterpret_cast<float*>(smem + xbytes + zbytes)};
-  float* Zs[2] = {reinterpret_cast<float*>(smem + xbytes), reinterpret_cast<float*>(smem + 2 * xbytes + zbytes)};
+  const int CR = P.CR, SX = P.SX, SZ = P.SZ, FP = P.FP, NS = P.NS;
+  // smem: NS stages of K dense X tiles [CR][FP] (filled by TMA bulk copies), two dZ tiles [CR][SZ], NS mbarriers
+  // stage = K dense X tiles [CR][FP] + the raw pooled rows of the chunk (dy, y, arg-max), all filled by TMA bulk copies
+  const int cpr = CR >> P.log2p;  // pooled rows per chunk
+  const size_t xbytes = (size_t)K * CR * SX * 4;
+  const size_t rawf = (size_t)cpr * P.Fout * 4;                      // dy / y tile (dy: cpr floats in mean form)
+  const size_t rawa = ((size_t)cpr * P.Fout + 15) / 16 * 16;         // arg-max tile
+  const size_t sbytes = xbytes + 2 * rawf + rawa;                    // multiple of 16
+  float* Zs = reinterpret_cast<float*>(smem + NS * sbytes);          // expanded dZ tile [CR][SZ]
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + NS * sbytes + (size_t)CR * SZ * 4);
   constexpr int NCH = MT * NT / 2;
 
   float acc[K][MT][NT][4];
@@ -59,73 +66,83 @@ __global__ void __launch_bounds__(256, (K * MT * NT > 20) ? 1 : 2) k_dw_from_sta
         for (int c = 0; c < 4; ++c) acc[k][m][n][c] = 0.f;
   float dbacc = 0.f;  // column o = tid % FoP of dZ (FoP divides 256)
 
-  const int q4 = FP >> 2;
-  auto issue_x = [&](int chunk, int buf) {  // K tiles of CR rows x FP floats, dense in HBM, padded rows in smem
-    const long long r0 = (long long)chunk * CR;
-    const int q_shift = FP == 8 ? 1 : (FP == 16 ? 2 : 3), r_shift = CR == 128 ? 7 : (CR == 64 ? 6 : 5);
-    for (int idx = tid; idx < K * CR * q4; idx += 256) {
-      const int q = idx & (q4 - 1), r = (idx >> q_shift) & (CR - 1), k = idx >> (q_shift + r_shift);
-      float* dst = Xs[buf] + ((size_t)k * CR + r) * SX + 4 * q;
-      if (r0 + r < P.R) cp_async16(dst, P.xstack + ((size_t)k * P.R + r0 + r) * FP + 4 * q);
-      else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    cp_async_commit();
-  };
-  // dZ rows of a chunk from the pooled tensors, split in two halves so that the global loads of the NEXT chunk are
-  // in flight while the tensor cores work on the current one.  M % p == 0 and CR % p == 0, so a pooling window never
-  // straddles a chunk and the flat pooled row is simply row >> log2p: no divisions, every pooled element is loaded
-  // once, and the (up to) 4 x 3 loads of a thread are independent.
-  const int fo_shift = P.FoP == 16 ? 4 : 5;
-  const int zo = tid & (P.FoP - 1);
-  const int rows_per_pass = 256 >> fo_shift, cpr = CR >> P.log2p;
+  if (tid == 0)
+    for (int s = 0; s < NS; ++s) mbar_init(mbar + s, 1);
+  __syncthreads();
+
   const long long npr = P.R >> P.log2p;
-  float gv[4];
-  int am[4];
-  auto load_z = [&](int chunk) {  // requires cpr <= 4 * rows_per_pass (checked on the host)
-    const long long pr0 = ((long long)chunk * CR) >> P.log2p;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int j = (tid >> fo_shift) + u * rows_per_pass;
-      const long long pr = pr0 + j;
-      gv[u] = 0.f;
-      am[u] = 0;
-      if (j < cpr && pr < npr && zo < P.Fout) {
-        const long long gi = pr * P.Fout + zo;
-        if (P.argmax != nullptr && P.p > 1) am[u] = __ldg(P.argmax + gi);
-        gv[u] = P.dy_is_mean ? __ldg(P.dy + pr) / (float)P.Fout : __ldg(P.dy + gi);
-        if (P.relu && !(__ldg(P.y + gi) > 0.f)) gv[u] = 0.f;
+  const bool has_am = P.argmax != nullptr && P.p > 1;
+  // bulk copies per chunk: for every order k the rows of a chunk are contiguous in HBM, and so are its pooled rows
+  auto issue = [&](int chunk, int stage) {
+    const long long r0 = (long long)chunk * CR;
+    const int rows = (int)min((long long)CR, P.R - r0);
+    unsigned char* st = smem + (size_t)stage * sbytes;
+    float* xs = reinterpret_cast<float*>(st);
+    if (rows < CR)  // tail chunk: rows past the end must read as zero (their dZ rows are zero, but 0 * garbage may be NaN)
+      for (int i = tid; i < K * (CR - rows) * FP; i += 256) {
+        const int k = i / ((CR - rows) * FP), rem = i - k * (CR - rows) * FP;
+        xs[(size_t)k * CR * FP + rows * FP + rem] = 0.f;
       }
-    }
-  };
-  auto store_z = [&](int buf) {
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int j = (tid >> fo_shift) + u * rows_per_pass;
-      if (j >= cpr) continue;
-      dbacc += gv[u];
-      float* dst = Zs[buf] + (size_t)(j << P.log2p) * SZ + zo;
-      for (int i = 0; i < P.p; ++i) dst[(size_t)i * SZ] = (i == am[u]) ? gv[u] : 0.f;
+    const long long pr0 = r0 >> P.log2p;
+    const int prs = (int)min((long long)cpr, npr - pr0);
+    const uint32_t xb = (uint32_t)rows * FP * 4u;
+    const uint32_t fb = (uint32_t)prs * P.Fout * 4u, db = P.dy_is_mean ? (uint32_t)prs * 4u : fb;
+    const uint32_t ab = has_am ? (uint32_t)prs * P.Fout : 0u;
+    const float* dsrc = P.dy + (P.dy_is_mean ? pr0 : pr0 * P.Fout);
+    // pieces whose size is not a multiple of 16 bytes (only possible in the last chunk) are copied by the threads
+    const bool d_bulk = (db & 15u) == 0, f_bulk = (fb & 15u) == 0, a_bulk = (ab & 15u) == 0;
+    if (!d_bulk)
+      for (int i = tid; i < (int)(db >> 2); i += 256) reinterpret_cast<float*>(st + xbytes)[i] = __ldg(dsrc + i);
+    if (P.relu && !f_bulk)
+      for (int i = tid; i < (int)(fb >> 2); i += 256) reinterpret_cast<float*>(st + xbytes + rawf)[i] = __ldg(P.y + pr0 * P.Fout + i);
+    if (has_am && !a_bulk)
+      for (int i = tid; i < (int)ab; i += 256) (st + xbytes + 2 * rawf)[i] = __ldg(P.argmax + pr0 * P.Fout + i);
+    if (tid == 0) {
+      mbar_expect_tx(mbar + stage, xb * K + (d_bulk ? db : 0u) + ((P.relu && f_bulk) ? fb : 0u) + ((has_am && a_bulk) ? ab : 0u));
+      for (int k = 0; k < K; ++k) bulk_g2s(xs + (size_t)k * CR * FP, P.xstack + ((size_t)k * P.R + r0) * FP, xb, mbar + stage);
+      if (d_bulk && db) bulk_g2s(st + xbytes, dsrc, db, mbar + stage);
+      if (P.relu && f_bulk && fb) bulk_g2s(st + xbytes + rawf, P.y + pr0 * P.Fout, fb, mbar + stage);
+      if (has_am && a_bulk && ab) bulk_g2s(st + xbytes + 2 * rawf, P.argmax + pr0 * P.Fout, ab, mbar + stage);
     }
   };
 
-  int chunk = blockIdx.x, buf = 0;
-  if (chunk < P.nchunks) {
-    issue_x(chunk, 0);
-    load_z(chunk);
-    store_z(0);
-  }
-  for (; chunk < P.nchunks; chunk += gridDim.x, buf ^= 1) {
-    const int next = chunk + gridDim.x;
-    if (next < P.nchunks) {
-      issue_x(next, buf ^ 1);
-      load_z(next);
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
+  // dZ tile of the chunk from its raw pooled rows (shared -> shared): MaxPoolGrad o ReluGrad of dy
+  const int fo_shift = P.FoP == 16 ? 4 : 5;
+  const int zo = tid & (P.FoP - 1);
+  auto expand_z = [&](int chunk, int stage) {
+    const unsigned char* st = smem + (size_t)stage * sbytes;
+    const float* rdy = reinterpret_cast<const float*>(st + xbytes);
+    const float* ry = reinterpret_cast<const float*>(st + xbytes + rawf);
+    const unsigned char* ram = st + xbytes + 2 * rawf;
+    const long long pr0 = ((long long)chunk * CR) >> P.log2p;
+    for (int j = tid >> fo_shift; j < cpr; j += 256 >> fo_shift) {
+      float v = 0.f;
+      int am = 0;
+      if (pr0 + j < npr && zo < P.Fout) {
+        const int gi = j * P.Fout + zo;
+        v = P.dy_is_mean ? rdy[j] / (float)P.Fout : rdy[gi];
+        if (P.relu && !(ry[gi] > 0.f)) v = 0.f;
+        if (has_am) am = ram[gi];
+      }
+      dbacc += v;
+      float* dst = Zs + (size_t)(j << P.log2p) * SZ + zo;
+      for (int i = 0; i < P.p; ++i) dst[(size_t)i * SZ] = (i == am) ? v : 0.f;
     }
+  };
+
+  const int stride = gridDim.x;
+  int chunk = blockIdx.x;
+  for (int s = 0; s < NS - 1; ++s)
+    if (chunk + s * stride < P.nchunks) issue(chunk + s * stride, s);
+  for (int it = 0; chunk < P.nchunks; chunk += stride, ++it) {
+    const int stage = it % NS;
+    const int pre = chunk + (NS - 1) * stride;  // refills the stage consumed one iteration ago (barrier at the end)
+    if (pre < P.nchunks) issue(pre, (it + NS - 1) % NS);
+    mbar_wait(mbar + stage, (uint32_t)((it / NS) & 1));
+    expand_z(chunk, stage);
     __syncthreads();
-    const float* xs = Xs[buf];
-    const float* zs = Zs[buf];
+    const float* zs = Zs;
+    const float* xs = reinterpret_cast<const float*>(smem + (size_t)stage * sbytes);
     for (int step = warp; step < CR / 8; step += 8) {
       const int r8 = step * 8;
       uint32_t bh[NT][2], bl[NT][2];
@@ -151,8 +168,7 @@ __global__ void __launch_bounds__(256, (K * MT * NT > 20) ? 1 : 2) k_dw_from_sta
         }
       }
     }
-    if (next < P.nchunks) store_z(buf ^ 1);  // Zs[buf^1] was last read one iteration ago (barrier below)
-    __syncthreads();  // everyone done with `buf` before it is refilled two iterations later
+    __syncthreads();  // everyone done with this stage and the dZ tile before they are refilled
   }
 
   // ---- warps -> CTA (fixed order), CTA partial in the chunk layout k_dw_from_partials expects -----------------
@@ -190,7 +206,7 @@ __global__ void __launch_bounds__(256, (K * MT * NT > 20) ? 1 : 2) k_dw_from_sta
 
 struct StackPlan {
   bool ok;
-  int FP, FoP, MT, NT, CR, SX, SZ, ctas_per_sm;
+  int FP, FoP, MT, NT, CR, SX, SZ, NS, ctas_per_sm;
   size_t smem;
 };
 
@@ -205,21 +221,26 @@ static StackPlan plan_stack(const LayerShape& s) {
   pl.FoP = s.Fout <= 16 ? 16 : 32;
   pl.MT = pl.FP <= 16 ? 1 : 2;
   pl.NT = pl.FoP / 8;
-  pl.SX = pl.FP == 8 ? 24 : pl.FP + 8;
+  pl.SX = pl.FP;  // dense rows: the tiles arrive by TMA bulk copies (2-way bank conflicts on the A fragments)
   pl.SZ = pl.FoP + 8;
   const size_t red = (size_t)8 * s.K * (pl.MT * pl.NT / 2) * 256 * 4;
   const bool light = s.K * pl.MT * pl.NT <= 20;
   for (int pass = light ? 0 : 1; pass < 2; ++pass) {  // pass 0: two CTAs per SM (<= 110 KB each); pass 1: one
     const size_t budget = pass == 0 ? 110 * 1024 : 220 * 1024;
     for (int cr : {128, 64, 32}) {
-      const size_t need = 2 * ((size_t)s.K * cr * pl.SX * 4 + (size_t)cr * pl.SZ * 4);
-      if (cr / s.p > 4 * 256 / pl.FoP) continue;  // pooled rows of a chunk must fit the 4 register slots per thread
-      if (std::max(need, red) <= budget) {
-        pl.CR = cr;
-        pl.smem = std::max(need, red);
-        pl.ctas_per_sm = pass == 0 ? 2 : 1;
-        pl.ok = true;
-        return pl;
+      if ((cr / s.p) * s.Fout % 16 != 0 || (cr / s.p) % 4 != 0) continue;  // pooled tiles start 16-byte aligned
+      for (int ns : {3, 2}) {
+        const size_t cprh = (size_t)cr / s.p;
+        const size_t stage = (size_t)s.K * cr * pl.SX * 4 + 2 * cprh * s.Fout * 4 + (cprh * s.Fout + 15) / 16 * 16;
+        const size_t need = ns * stage + (size_t)cr * pl.SZ * 4 + 64;
+        if (std::max(need, red) <= budget) {
+          pl.CR = cr;
+          pl.NS = ns;
+          pl.smem = std::max(need, red);
+          pl.ctas_per_sm = pass == 0 ? 2 : 1;
+          pl.ok = true;
+          return pl;
+        }
       }
     }
   }
@@ -259,7 +280,7 @@ int stack_dw(const float* xstack, const float* y, const uint8_t* argmax, const f
   P.p = s.p; P.log2p = 0;
   while ((1 << P.log2p) < s.p) ++P.log2p;
   P.relu = relu; P.dy_is_mean = dy_is_mean;
-  P.CR = pl.CR; P.SX = pl.SX; P.SZ = pl.SZ;
+  P.CR = pl.CR; P.SX = pl.SX; P.SZ = pl.SZ; P.NS = pl.NS;
   P.nchunks = (int)ceil_div_ll(P.R, pl.CR);
   const int grid = std::min(P.nchunks, std::min(di.sm_count * pl.ctas_per_sm, 296));
   const int nch = pl.MT * pl.NT / 2;
