@@ -349,12 +349,20 @@ def main():
         mode = ops.BIAS_PER_FILTER
         n1 = 25
         with torch.no_grad():
-            ys1 = [ops.cheb_fwd(ring_x[i], model.perm, *pl1.tensors(), W1, b1, 5, 4, mode, True, True, args.algo) for i in range(n1)]
+            # the same launches the training step issues (train.FusedTrainer): forward keeps the Chebyshev basis,
+            # backward = streamed dW GEMM from the basis (+ the adjoint recursion for dx in layer 2)
+            f1 = lambda i: ops.cheb_fwd_mean(ring_x[i], model.perm, pl1.rowptr, pl1.col, pl1.val, W1, b1, 5, 4, mode, True,
+                                             args.algo, True)
+            ys1 = [f1(i) for i in range(n1)]
             n2 = 40
             y1s = [ys1[i % n1][0] + 0.0 * i for i in range(n2)]
-            ys2 = [ops.cheb_fwd(y1s[i], None, *pl2.tensors(), W2, b2, 5, 4, mode, True, True, args.algo) for i in range(n2)]
-            dy2 = [torch.randn_like(ys2[i][0]) for i in range(n2)]
+            f2 = lambda i: ops.cheb_fwd_mean(y1s[i], None, pl2.rowptr, pl2.col, pl2.val, W2, b2, 5, 4, mode, True, args.algo,
+                                             True)
+            ys2 = [f2(i) for i in range(n2)]
+            dm2 = [torch.randn_like(ys2[i][2]) for i in range(n2)]   # gradient of the mean over filters
             dy1 = [torch.randn_like(ys1[i][0]) for i in range(n1)]
+            gW1, gb1 = torch.empty_like(W1), torch.empty(32, device=dev)
+            gW2, gb2 = torch.empty_like(W2), torch.empty(32, device=dev)
 
             def timed(fn, n, reps=3):
                 """GPU seconds per call: the n calls (one per ring slot) are captured into a CUDA graph and the
@@ -383,30 +391,37 @@ def main():
                 return a.elapsed_time(b) * 1e-3 / (reps * n), per_call
 
             specs = [
-                ("conv1 fwd (gather+cheb K=5 15->32+b1relu+mpool4, M=400)", n1,
-                 lambda i: ops.cheb_fwd(ring_x[i], model.perm, *pl1.tensors(), W1, b1, 5, 4, mode, True, True, args.algo),
+                ("conv1 fwd: k_cheb_fwd_fused (gather+cheb K=5 15->32+b1relu+mpool4, M=400, keeps basis)", n1, f1,
                  layer_bytes(BATCH, 360, 400, 15, 32, 5, 4, pl1.nnz, 32, False, False)),
-                ("conv2 fwd (cheb K=5 32->32+b1relu+mpool4, M=100)", n2,
-                 lambda i: ops.cheb_fwd(y1s[i], None, *pl2.tensors(), W2, b2, 5, 4, mode, True, True, args.algo),
+                ("conv2 fwd: k_cheb_fwd_fused (cheb K=5 32->32+b1relu+mpool4+mean, M=100, keeps basis)", n2, f2,
                  layer_bytes(BATCH, 100, 100, 32, 32, 5, 4, pl2.nnz, 32, False, False)),
-                ("conv2 bwd (dW,db,dx)", n2,
-                 lambda i: torch.ops.gcn_b200.cheb_bwd(y1s[i], None, ys2[i][0], ys2[i][1], dy2[i], *pl2.tensors(), W2, 5, 4,
-                                                       mode, True, True, args.algo),
+                ("conv2 bwd: k_dw_from_stack + k_cheb_bwd_fused (dW,db from basis; dx by adjoint recursion)", n2,
+                 lambda i: ops.cheb_bwd_into(y1s[i], None, ys2[i][0], ys2[i][1], dm2[i], True, *pl2.tensors(), W2, gW2, gb2, 5,
+                                             4, mode, True, True, args.algo, ys2[i][3]),
                  layer_bytes(BATCH, 100, 100, 32, 32, 5, 4, pl2.nnz, 32, True, True)),
-                ("conv1 bwd (dW,db)", n1,
-                 lambda i: torch.ops.gcn_b200.cheb_bwd(ring_x[i], model.perm, ys1[i][0], ys1[i][1], dy1[i], *pl1.tensors(),
-                                                       W1, 5, 4, mode, True, False, args.algo),
+                ("conv1 bwd: k_dw_from_stack (dW,db from basis)", n1,
+                 lambda i: ops.cheb_bwd_into(ring_x[i], model.perm, ys1[i][0], ys1[i][1], dy1[i], False, *pl1.tensors(), W1,
+                                             gW1, gb1, 5, 4, mode, True, False, args.algo, ys1[i][3]),
                  layer_bytes(BATCH, 360, 400, 15, 32, 5, 4, pl1.nnz, 32, True, False)),
             ]
+            traffic = {}
+            tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+            if os.path.isfile(tpath):
+                with open(tpath) as f:
+                    traffic = json.load(f)
             for name, n, fn, nbytes in specs:
                 sec, per_call = timed(fn, n)
+                key = name.split(":")[0]
                 kernels.append({"op": name, "launches_per_op": per_call, "us": sec * 1e6, "algorithmic_bytes": nbytes,
-                                "achieved_gbs": nbytes / sec * 1e-9, "frac": nbytes / sec * 1e-9 / peak})
+                                "achieved_gbs": nbytes / sec * 1e-9, "frac": nbytes / sec * 1e-9 / peak,
+                                "traffic": traffic.get(key)})
         top = max(kernels, key=lambda k: k["us"])
         total_bytes = sum(k["algorithmic_bytes"] for k in kernels)
         total_us = sum(k["us"] for k in kernels)
         roofline = {"bound": "hbm", "kernel": top["op"], "achieved": top["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                    "frac": top["frac"], "traffic": None, "peak_source": peak_src,
+                    "frac": top["frac"], "traffic": top["traffic"], "peak_source": peak_src,
+                    "note": "algorithmic bytes per SURVEY 8d (no basis stack); the training path also writes/reads the "
+                            "K-order basis (65.5 MB conv1, 32.8 MB conv2) -- see traffic and DESIGN.md section 3",
                     "conv_stack_fwd_bwd": {"algorithmic_bytes": total_bytes, "us": total_us,
                                            "achieved": total_bytes / total_us * 1e-3,
                                            "frac": total_bytes / total_us * 1e-3 / peak},
