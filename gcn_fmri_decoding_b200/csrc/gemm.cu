@@ -134,9 +134,9 @@ __global__ void __launch_bounds__(128) k_gemm_3xtf32(const GemmArgs g) {
 }
 
 // ---- small / skinny problems (the FC layers at B = 512): 32x32x32 tiles so that even a 512x256 output gives 128 CTAs,
-// and a 3-stage cp.async pipeline (4-byte copies: any alignment, any transpose, zero-fill out of range) so that the
+// and a 5-stage cp.async pipeline (4-byte copies: any alignment, any transpose, zero-fill out of range) so that the
 // serial walk over K is not exposed to global-memory latency.
-constexpr int SBM = 32, SBN = 32, SBK = 32, SST = 3;
+constexpr int SBM = 32, SBN = 32, SBK = 32, SST = 5;  // 5 stages: 48.6 KB static smem, covers L2 latency on the serial walk over K
 constexpr int SAS = SBK + 4;  // 36: A-fragment rows on distinct banks
 constexpr int SBS = SBN + 8;  // 40: 8t + g distinct
 
