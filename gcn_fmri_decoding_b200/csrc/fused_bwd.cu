@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(896, 1) k_cheb_bwd_fused(const BwdParams P) {
                          __float_as_uint(w.w));
           }
         }
-        __syncthreads();  // sparse step complete for every row
+        group_barrier(sg, G.RW * 32);  // sparse step complete for every row of this sample group's columns
         float* curf = reinterpret_cast<float*>(cur);
 #pragma unroll
         for (int a = 0; a < SLOTS; ++a) {
@@ -286,8 +286,9 @@ __global__ void __launch_bounds__(896, 1) k_cheb_bwd_fused(const BwdParams P) {
             }
           }
         }
-        __syncthreads();
+        group_barrier(sg, G.RW * 32);
       }
+      __syncthreads();
       // dx rows of the tile: the slab that received b_0
       const float* fin = reinterpret_cast<const float*>(((P.K - 1) & 1) ? slabB : slabA);
       for (int s = 0; s < G.S; ++s) {

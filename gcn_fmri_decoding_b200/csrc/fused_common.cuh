@@ -60,6 +60,13 @@ __device__ __forceinline__ void split_trunc(float v, uint32_t& hi, uint32_t& lo)
   lo = __float_as_uint(v - __uint_as_float(hi));
 }
 
+// Barrier over the warps of one sample group only (named barrier 1 + sg).  The slab columns of different sample
+// groups are disjoint, so inside the recursion the groups need not wait for each other: they drift apart and the
+// sparse phase of one overlaps the tensor-core phase of another.
+__device__ __forceinline__ void group_barrier(int sg, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(1 + sg), "r"(nthreads) : "memory");
+}
+
 // ---- mbarrier + TMA bulk copy (global -> shared), used to prefetch the next tile of windows ------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

@@ -172,13 +172,14 @@ __global__ void __launch_bounds__((SLOTS * NT > 8) ? 512 : 896, 1) k_cheb_fwd_fu
 
     // Optional: keep the basis for the backward pass.  X_k sits untouched in its slab during step k+1, so each warp
     // streams its share of rows out at the start of that step (no extra barrier).
-    auto spill = [&](int k, const unsigned char* slab) {
+    auto spill = [&](int k, const unsigned char* slab) {  // each sample group streams out its own columns
       if (P.xstack == nullptr) return;
       const int q4 = FP >> 2;  // float4 per (row, sample)
-      const int per_row = G.S * q4;
-      for (int idx = tid; idx < G.M * per_row; idx += blockDim.x) {
+      const int per_row = G.WS * q4;
+      const int gthreads = G.RW * 32, gtid = tid - sg * gthreads;
+      for (int idx = gtid; idx < G.M * per_row; idx += gthreads) {
         const int m = idx / per_row, rem = idx - m * per_row;
-        const int s = rem / q4, q = rem - s * q4;
+        const int s = sg * G.WS + rem / q4, q = rem % q4;
         const int b = b0 + s;
         if (b >= P.B) continue;
         const float4 v = *reinterpret_cast<const float4*>(slab + ((size_t)m * RS + s * FP + 4 * q) * 4);
@@ -196,7 +197,7 @@ __global__ void __launch_bounds__((SLOTS * NT > 8) ? 512 : 896, 1) k_cheb_fwd_fu
       if (warp & 1) contract(k - 1, prev);
       if (!(P.debug & 1)) spmm_dispatch(G.LPR, op, prev, cur, G.Mpad, col_byte, rw, G.RW, k == 1 ? 1.f : 2.f, k > 1);
       if (!(warp & 1)) contract(k - 1, prev);
-      __syncthreads();
+      group_barrier(sg, G.RW * 32);  // X_k complete for this sample group's columns
     }
     spill(P.K - 1, ((P.K - 1) & 1) ? slabB : slabA);
     contract(P.K - 1, ((P.K - 1) & 1) ? slabB : slabA);
