@@ -40,7 +40,7 @@ void count_launch();  // diagnostic counter behind gcnb_launch_count()
     }                                                                           \
   } while (0)
 
-static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+__host__ __device__ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
 
@@ -86,9 +86,28 @@ int launch_to_node_major(const float* x, const int32_t* perm, float* X0, int B, 
 int launch_from_node_major(const float* Xn, float* x, int B, int M, int F, cudaStream_t st);
 int launch_epilogue(const float* Zn, const float* bias, float* y, uint8_t* argmax, int B, int M, int F, int p,
                     int bias_mode, int relu, cudaStream_t st);
-int launch_dz(const float* dy, const float* y, const uint8_t* argmax, float* dZn, int B, int M, int F, int p,
+// dZn rows (m*B + b) have a stride of ldz floats (>= F; padded for the tensor-core kernels of the general path)
+int launch_dz(const float* dy, const float* y, const uint8_t* argmax, float* dZn, int ldz, int B, int M, int F, int p,
               int relu, cudaStream_t st);
-int launch_db(const float* dZn, float* db, float* scratch_MF, int B, int M, int F, int bias_mode, cudaStream_t st);
+size_t db_scratch_floats(int M, int F);
+int launch_db(const float* dZn, int ldz, float* db, float* scratch, int B, int M, int F, int bias_mode, cudaStream_t st);
+
+// ---- tensor-core contractions of the general path, general_mma.cu ---------------------------------
+int node_mma_ldz(int Fout);
+bool node_contract_supported(const LayerShape& s);
+int node_contract(const float* Xs, long long slab, const float* W, const float* bias, float* out, const LayerShape& s,
+                  int bias_mode, int relu, int direct, cudaStream_t st);
+bool node_dw_supported(const LayerShape& s);
+int node_dw_blocks(const LayerShape& s);
+int node_dw(const float* Xs, long long slab, const float* dZ, float* part, const LayerShape& s, cudaStream_t st);
+bool node_dz_wt_supported(const LayerShape& s);
+int node_dz_wt(const float* dZ, const float* W, float* Gs, long long slab, const LayerShape& s, cudaStream_t st);
+
+// ---- TMA-staged sparse recursion step for HBM-resident state, spmm_tma.cu -------------------------
+bool spmm_tma_supported(const gcnb_csr& L, long long C, const float* src, const float* add, const float* add2,
+                        const float* out);
+int spmm_tma(const gcnb_csr& L, const float* src, const float* add, const float* add2, float* out, long long C,
+             float alpha, float beta, float beta2, cudaStream_t st);
 
 // ---- fused (shared-memory resident) path, fused_fwd.cu / fused_bwd.cu ------------------------
 bool fused_fwd_supported(const LayerShape& s);

@@ -102,6 +102,16 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                : "memory");
 }
 
+// Same copy without the proxy fence, for full/empty mbarrier rings: the stage being overwritten was only READ through
+// the generic proxy, and those reads are ordered before the copy by the consumers' arrive on the empty barrier and
+// the producer's wait on it (no generic write to the destination to make visible to the async proxy).
+__device__ __forceinline__ void bulk_g2s_ring(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // Geometry shared by host (launch configuration) and device.
 struct TileGeom {
   int M, Mpad, RT;  // vertices, padded to 16, row tiles of 16

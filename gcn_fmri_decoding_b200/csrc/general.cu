@@ -65,16 +65,16 @@ int launch_from_node_major(const float* Xn, float* x, int B, int M, int F, cudaS
 }
 
 // ------------------------------------------------------------------------------------------------
-// sparse recursion step:  out[m][:] = alpha * sum_j val_j * src[col_j][:] + beta * add[m][:]
-//   forward  X_k     = 2 L~ X_{k-1} - X_{k-2}      (alpha=2 (1 for k=1), beta=-1 (0))
-//   adjoint  g_{k-1} = 2 L~^T g_k + g_{k-1}        (add aliases out)
+// sparse recursion step:  out[m][:] = alpha * sum_j val_j * src[col_j][:] + beta * add[m][:] + beta2 * add2[m][:]
+//   forward  X_k = 2 L~ X_{k-1} - X_{k-2}                 (alpha=2 (1 for k=1), beta=-1, no add2)
+//   adjoint  b_k = G_k + 2 L~^T b_{k+1} - b_{k+2}         (Clenshaw; add = G_k aliases out, add2 = b_{k+2})
 // One block row per vertex, threads along the B*F columns, VEC floats per thread.
 // ------------------------------------------------------------------------------------------------
 template <int VEC>
 __global__ void __launch_bounds__(128) k_spmm_step(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                                                    const float* __restrict__ val, const float* __restrict__ src,
-                                                   const float* add, float* out, int M, long long C, float alpha,
-                                                   float beta) {
+                                                   const float* add, const float* add2, float* out, int M,
+                                                   long long C, float alpha, float beta, float beta2) {
   const long long CV = C / VEC;
   for (int m = blockIdx.y; m < M; m += gridDim.y) {
     const int beg = rowptr[m], end = rowptr[m + 1];
@@ -105,34 +105,37 @@ __global__ void __launch_bounds__(128) k_spmm_step(const int32_t* __restrict__ r
           r.z = fmaf(beta, a.z, r.z);
           r.w = fmaf(beta, a.w, r.w);
         }
+        if (add2 != nullptr) {
+          const float4 a = *reinterpret_cast<const float4*>(add2 + o);
+          r.x = fmaf(beta2, a.x, r.x);
+          r.y = fmaf(beta2, a.y, r.y);
+          r.z = fmaf(beta2, a.z, r.z);
+          r.w = fmaf(beta2, a.w, r.w);
+        }
         *reinterpret_cast<float4*>(out + o) = r;
       } else {
         float r = alpha * acc[0];
         if (add != nullptr) r = fmaf(beta, add[o], r);
+        if (add2 != nullptr) r = fmaf(beta2, add2[o], r);
         out[o] = r;
       }
     }
   }
 }
 
-static int launch_spmm_step(const gcnb_csr& L, const float* src, const float* add, float* out, long long C,
-                            float alpha, float beta, cudaStream_t st) {
+static int launch_spmm_step(const gcnb_csr& L, const float* src, const float* add, const float* add2, float* out,
+                            long long C, float alpha, float beta, float beta2, cudaStream_t st) {
+  if (spmm_tma_supported(L, C, src, add, add2, out)) return spmm_tma(L, src, add, add2, out, C, alpha, beta, beta2, st);
   const bool vec = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(out) |
-                                     reinterpret_cast<uintptr_t>(add)) % 16 == 0);
+                                     reinterpret_cast<uintptr_t>(add) | reinterpret_cast<uintptr_t>(add2)) % 16 == 0);
   const long long CV = vec ? C / 4 : C;
   dim3 grid((unsigned)std::min<long long>(ceil_div_ll(CV, 128), 4096), (unsigned)std::min(L.M, 65535));
   if (vec)
-    k_spmm_step<4><<<grid, 128, 0, st>>>(L.rowptr, L.col, L.val, src, add, out, L.M, C, alpha, beta);
+    k_spmm_step<4><<<grid, 128, 0, st>>>(L.rowptr, L.col, L.val, src, add, add2, out, L.M, C, alpha, beta, beta2);
   else
-    k_spmm_step<1><<<grid, 128, 0, st>>>(L.rowptr, L.col, L.val, src, add, out, L.M, C, alpha, beta);
+    k_spmm_step<1><<<grid, 128, 0, st>>>(L.rowptr, L.col, L.val, src, add, add2, out, L.M, C, alpha, beta, beta2);
   GCNB_LAUNCH_CHECK("k_spmm_step");
   return GCNB_OK;
-}
-
-// out[i] -= src[i]
-__global__ void k_sub_inplace(float* out, const float* __restrict__ src, long long n) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    out[i] -= src[i];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -221,8 +224,8 @@ static int launch_rowgemm(const RowGemm& g, int nz, cudaStream_t st) {
 // then dW[f*K+k][o] = sum_chunk part  (two-stage, deterministic -- no float atomics)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_dw_partial(const float* __restrict__ Xs, long long slab,
-                                                    const float* __restrict__ dZ, float* __restrict__ part, long long R,
-                                                    int Fin, int Fout, int rows_per_chunk, int nchunks) {
+                                                    const float* __restrict__ dZ, int ldz, float* __restrict__ part,
+                                                    long long R, int Fin, int Fout, int rows_per_chunk, int nchunks) {
   __shared__ __align__(16) float Xt[32][36];
   __shared__ float Dt[32][33];
   const int tid = threadIdx.x, lane = tid & 31, ty = tid >> 5;
@@ -238,7 +241,7 @@ __global__ void __launch_bounds__(256) k_dw_partial(const float* __restrict__ Xs
       const int rr = idx >> 5, j = idx & 31;
       const long long r = r0 + rr;
       Xt[rr][j] = (r < rend && f0 + j < Fin) ? __ldg(Xk + r * Fin + f0 + j) : 0.f;
-      Dt[rr][j] = (r < rend && o0 + j < Fout) ? __ldg(dZ + r * Fout + o0 + j) : 0.f;
+      Dt[rr][j] = (r < rend && o0 + j < Fout) ? __ldg(dZ + r * ldz + o0 + j) : 0.f;
     }
     __syncthreads();
 #pragma unroll 8
@@ -312,7 +315,7 @@ int launch_epilogue(const float* Zn, const float* bias, float* y, uint8_t* argma
 
 // adjoint of the epilogue: dZn[m][b*F+o] = (m is the window's arg-max) ? dy * [y>0] : 0
 __global__ void k_dz(const float* __restrict__ dy, const float* __restrict__ y, const uint8_t* __restrict__ argmax,
-                     float* __restrict__ dZn, int B, int M, int F, int p, int relu) {
+                     float* __restrict__ dZn, int ldz, int B, int M, int F, int p, int relu) {
   const int Mo = (M + p - 1) / p;
   const int before = (Mo * p - M) / 2;
   const long long total = (long long)B * Mo * F;
@@ -326,31 +329,32 @@ __global__ void k_dz(const float* __restrict__ dy, const float* __restrict__ y, 
     for (int w = 0; w < p; ++w) {
       const int m = j * p - before + w;
       if (m < 0 || m >= M) continue;
-      dZn[((long long)m * B + b) * F + o] = (w == am) ? g : 0.f;
+      dZn[((long long)m * B + b) * ldz + o] = (w == am) ? g : 0.f;
     }
   }
 }
 
-int launch_dz(const float* dy, const float* y, const uint8_t* argmax, float* dZn, int B, int M, int F, int p,
+int launch_dz(const float* dy, const float* y, const uint8_t* argmax, float* dZn, int ldz, int B, int M, int F, int p,
               int relu, cudaStream_t st) {
   const long long total = (long long)B * ceil_div(M, p) * F;
-  k_dz<<<(unsigned)std::min<long long>(ceil_div_ll(total, 256), 1 << 20), 256, 0, st>>>(dy, y, argmax, dZn, B, M, F, p,
-                                                                                      relu);
+  k_dz<<<(unsigned)std::min<long long>(ceil_div_ll(total, 256), 1 << 20), 256, 0, st>>>(dy, y, argmax, dZn, ldz, B, M,
+                                                                                      F, p, relu);
   GCNB_LAUNCH_CHECK("k_dz");
   return GCNB_OK;
 }
 
-// db2[m][o] = sum_b dZn[m][b*F+o]   (one block per vertex; fixed summation order)
-__global__ void __launch_bounds__(256) k_db_vertex(const float* __restrict__ dZn, float* __restrict__ db2, int B, int F) {
+// db2[m][o] = sum_b dZn[m][b*ldz+o]   (one block per vertex; fixed summation order)
+__global__ void __launch_bounds__(256) k_db_vertex(const float* __restrict__ dZn, int ldz, float* __restrict__ db2, int B,
+                                                   int F) {
   __shared__ float red[256];
   const int m = blockIdx.x;
-  const float* row = dZn + (long long)m * B * F;
+  const float* row = dZn + (long long)m * B * ldz;
   for (int o0 = 0; o0 < F; o0 += 32) {
     // 8 groups of 32 lanes stride over b, then a fixed-order tree over the 8 groups
     const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
     float s = 0.f;
     if (o0 + lane < F)
-      for (int b = grp; b < B; b += 8) s += row[(long long)b * F + o0 + lane];
+      for (int b = grp; b < B; b += 8) s += row[(long long)b * ldz + o0 + lane];
     red[threadIdx.x] = s;
     __syncthreads();
     if (grp == 0 && o0 + lane < F) {
@@ -363,32 +367,51 @@ __global__ void __launch_bounds__(256) k_db_vertex(const float* __restrict__ dZn
   }
 }
 
-// db[o] = sum_m db2[m][o]
-__global__ void __launch_bounds__(256) k_db_filter(const float* __restrict__ db2, float* __restrict__ db, int M, int F) {
+// db[o] = sum_m db2[m][o] in two fixed-order stages: kDbFilterChunks partial sums over vertex ranges, then their sum
+constexpr int kDbFilterChunks = 64;
+
+__global__ void __launch_bounds__(256) k_db_filter_partial(const float* __restrict__ db2, float* __restrict__ part, int M,
+                                                           int F) {
   __shared__ float red[256];
   const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
   const int o = blockIdx.x * 32 + lane;
+  const int per = (M + kDbFilterChunks - 1) / kDbFilterChunks;
+  const int m0 = blockIdx.y * per, m1 = min(M, m0 + per);
   float s = 0.f;
   if (o < F)
-    for (int m = grp; m < M; m += 8) s += db2[(long long)m * F + o];
+    for (int m = m0 + grp; m < m1; m += 8) s += db2[(long long)m * F + o];
   red[threadIdx.x] = s;
   __syncthreads();
   if (grp == 0 && o < F) {
     float t = 0.f;
 #pragma unroll
     for (int g2 = 0; g2 < 8; ++g2) t += red[g2 * 32 + lane];
-    db[o] = t;
+    part[blockIdx.y * F + o] = t;
   }
 }
 
-int launch_db(const float* dZn, float* db, float* scratch_MF, int B, int M, int F, int bias_mode, cudaStream_t st) {
+__global__ void k_db_filter_final(const float* __restrict__ part, float* __restrict__ db, int F) {
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= F) return;
+  float t = 0.f;
+  for (int c = 0; c < kDbFilterChunks; ++c) t += part[c * F + o];
+  db[o] = t;
+}
+
+// scratch: M*F floats (per-vertex sums) followed by kDbFilterChunks*F floats
+size_t db_scratch_floats(int M, int F) { return (size_t)M * F + (size_t)kDbFilterChunks * F; }
+
+int launch_db(const float* dZn, int ldz, float* db, float* scratch, int B, int M, int F, int bias_mode, cudaStream_t st) {
   if (bias_mode == GCNB_BIAS_NONE || db == nullptr) return GCNB_OK;
-  float* db2 = bias_mode == GCNB_BIAS_PER_VERTEX ? db : scratch_MF;
-  k_db_vertex<<<M, 256, 0, st>>>(dZn, db2, B, F);
+  float* db2 = bias_mode == GCNB_BIAS_PER_VERTEX ? db : scratch;
+  k_db_vertex<<<M, 256, 0, st>>>(dZn, ldz, db2, B, F);
   GCNB_LAUNCH_CHECK("k_db_vertex");
   if (bias_mode == GCNB_BIAS_PER_FILTER) {
-    k_db_filter<<<ceil_div(F, 32), 256, 0, st>>>(db2, db, M, F);
-    GCNB_LAUNCH_CHECK("k_db_filter");
+    float* part = scratch + (size_t)M * F;
+    k_db_filter_partial<<<dim3(ceil_div(F, 32), kDbFilterChunks), 256, 0, st>>>(db2, part, M, F);
+    GCNB_LAUNCH_CHECK("k_db_filter_partial");
+    k_db_filter_final<<<ceil_div(F, 128), 128, 0, st>>>(part, db, F);
+    GCNB_LAUNCH_CHECK("k_db_filter_final");
   }
   return GCNB_OK;
 }
@@ -405,28 +428,26 @@ static int dw_chunking(long long R, int* rows_per_chunk) {
 
 size_t general_cheb_workspace(const LayerShape& s, bool backward, bool need_dx) {
   const size_t slab = (size_t)s.M * s.B * s.Fin;
-  const size_t zn = (size_t)s.M * s.B * s.Fout;
+  const size_t zn = (size_t)s.M * s.B * node_mma_ldz(s.Fout);  // dZn rows may be padded for the tensor-core kernels
   size_t n = 0;
   auto add = [&](size_t floats) { n = align_up(n, 256) + floats * sizeof(float); };
   add(slab * s.K);  // X stack (forward) / recomputed stack (backward)
   add(zn);          // Zn or dZn
   if (backward) {
     int rpc;
-    const int nch = dw_chunking((long long)s.M * s.B, &rpc);
+    const int nch = std::max(dw_chunking((long long)s.M * s.B, &rpc), node_dw_blocks(s));
     add((size_t)s.K * nch * s.Fin * s.Fout);  // dW partials
-    add((size_t)s.M * s.Fout);                // db scratch
+    add(db_scratch_floats(s.M, s.Fout));      // db scratch
     if (need_dx) add(slab * s.K);             // G stack
   }
   return align_up(n, 256) + 256;
 }
 
-static int build_stack(const float* X0, float* Xs, const gcnb_csr& L, long long slab, long long C, int K,
-                       cudaStream_t st) {
-  (void)X0;
+static int build_stack(float* Xs, const gcnb_csr& L, long long slab, long long C, int K, cudaStream_t st) {
   for (int k = 1; k < K; ++k) {
     const float* prev = Xs + (long long)(k - 1) * slab;
     const float* prev2 = k >= 2 ? Xs + (long long)(k - 2) * slab : nullptr;
-    int rc = launch_spmm_step(L, prev, prev2, Xs + (long long)k * slab, C, k == 1 ? 1.f : 2.f, -1.f, st);
+    int rc = launch_spmm_step(L, prev, prev2, nullptr, Xs + (long long)k * slab, C, k == 1 ? 1.f : 2.f, -1.f, 0.f, st);
     if (rc) return rc;
   }
   return GCNB_OK;
@@ -438,15 +459,28 @@ int general_cheb_fwd(const float* x, const int32_t* perm, int M_in, const gcnb_c
   const long long C = (long long)s.B * s.Fin;
   const long long slab = (long long)s.M * C;
   float* Xs = ws.take<float>((size_t)slab * s.K);
-  float* Zn = ws.take<float>((size_t)s.M * s.B * s.Fout);
+  float* Zn = ws.take<float>((size_t)s.M * s.B * node_mma_ldz(s.Fout));
   if (!Xs || !Zn) {
     set_error("workspace too small for the general forward path");
     return GCNB_ERR_WORKSPACE;
   }
   int rc = launch_to_node_major(x, perm, Xs, s.B, s.M, M_in, s.Fin, st);
   if (rc) return rc;
-  rc = build_stack(Xs, Xs, L, slab, C, s.K, st);
+  rc = build_stack(Xs, L, slab, C, s.K, st);
   if (rc) return rc;
+  if (node_contract_supported(s)) {
+    // tensor-core contraction streaming the stack through TMA; without pooling the bias/ReLU epilogue is fused
+    // and y is written once, straight in the caller's [B, M, Fout] layout
+    if (s.p == 1) {
+      rc = node_contract(Xs, slab, W, bias, y, s, bias_mode, relu, 1, st);
+      if (rc) return rc;
+      if (argmax) GCNB_CUDA(cudaMemsetAsync(argmax, 0, (size_t)s.B * s.M * s.Fout, st));
+      return GCNB_OK;
+    }
+    rc = node_contract(Xs, slab, W, nullptr, Zn, s, GCNB_BIAS_NONE, 0, 0, st);
+    if (rc) return rc;
+    return launch_epilogue(Zn, bias, y, argmax, s.B, s.M, s.Fout, s.p, bias_mode, relu, st);
+  }
   RowGemm g;
   g.A = Xs; g.a_q = slab; g.lda = s.Fin;
   g.Bm = W; g.b_z = 0; g.b_q = s.Fout; g.sbk = (long long)s.K * s.Fout; g.sbn = 1;
@@ -463,30 +497,38 @@ int general_cheb_bwd(const float* x, const int32_t* perm, int M_in, const float*
   const long long C = (long long)s.B * s.Fin;
   const long long slab = (long long)s.M * C;
   const long long R = (long long)s.M * s.B;
+  const bool mma_dw = node_dw_supported(s);
+  const bool mma_g = dx != nullptr && node_dz_wt_supported(s);
+  const int ldz = (mma_dw || mma_g) ? node_mma_ldz(s.Fout) : s.Fout;
   int rpc;
-  const int nch = dw_chunking(R, &rpc);
+  const int nch = mma_dw ? node_dw_blocks(s) : dw_chunking(R, &rpc);
   float* Xs = ws.take<float>((size_t)slab * s.K);
-  float* dZn = ws.take<float>((size_t)R * s.Fout);
-  float* part = ws.take<float>((size_t)s.K * nch * s.Fin * s.Fout);
-  float* dbs = ws.take<float>((size_t)s.M * s.Fout);
+  float* dZn = ws.take<float>((size_t)R * node_mma_ldz(s.Fout));
+  float* part = ws.take<float>((size_t)s.K * std::max(nch, node_dw_blocks(s)) * s.Fin * s.Fout);
+  float* dbs = ws.take<float>(db_scratch_floats(s.M, s.Fout));
   float* Gs = dx ? ws.take<float>((size_t)slab * s.K) : nullptr;
   if (!Xs || !dZn || !part || !dbs || (dx && !Gs)) {
     set_error("workspace too small for the general backward path");
     return GCNB_ERR_WORKSPACE;
   }
-  int rc = launch_dz(dy, y, argmax, dZn, s.B, s.M, s.Fout, s.p, relu, st);
+  int rc = launch_dz(dy, y, argmax, dZn, ldz, s.B, s.M, s.Fout, s.p, relu, st);
   if (rc) return rc;
-  rc = launch_db(dZn, db, dbs, s.B, s.M, s.Fout, bias_mode, st);
+  rc = launch_db(dZn, ldz, db, dbs, s.B, s.M, s.Fout, bias_mode, st);
   if (rc) return rc;
   // recompute the Chebyshev stack from x (nothing but x, y and argmax is kept from the forward)
   rc = launch_to_node_major(x, perm, Xs, s.B, s.M, M_in, s.Fin, st);
   if (rc) return rc;
-  rc = build_stack(Xs, Xs, L, slab, C, s.K, st);
+  rc = build_stack(Xs, L, slab, C, s.K, st);
   if (rc) return rc;
-  {
+  if (mma_dw) {
+    rc = node_dw(Xs, slab, dZn, part, s, st);
+    if (rc) return rc;
+  } else {
     dim3 grid((unsigned)nch, (unsigned)s.K, (unsigned)(ceil_div(s.Fin, 32) * ceil_div(s.Fout, 32)));
-    k_dw_partial<<<grid, 256, 0, st>>>(Xs, slab, dZn, part, R, s.Fin, s.Fout, rpc, nch);
+    k_dw_partial<<<grid, 256, 0, st>>>(Xs, slab, dZn, ldz, part, R, s.Fin, s.Fout, rpc, nch);
     GCNB_LAUNCH_CHECK("k_dw_partial");
+  }
+  {
     const int total = s.K * s.Fin * s.Fout;
     k_dw_reduce<<<ceil_div(total, 256), 256, 0, st>>>(part, dW, s.K, s.Fin, s.Fout, nch);
     GCNB_LAUNCH_CHECK("k_dw_reduce");
@@ -496,25 +538,25 @@ int general_cheb_bwd(const float* x, const int32_t* perm, int M_in, const float*
     set_error("dx requested but the transposed operator Lt is NULL");
     return GCNB_ERR_INVALID;
   }
-  // G_k = dZ W_k^T for every k, then the adjoint recursion down to g_0
-  RowGemm g;
-  g.A = dZn; g.a_q = 0; g.lda = s.Fout;
-  g.Bm = W; g.b_z = s.Fout; g.b_q = 0; g.sbk = 1; g.sbn = (long long)s.K * s.Fout;
-  g.C = Gs; g.c_z = slab; g.ldc = s.Fin;
-  g.R = R; g.N = s.Fin; g.Kd = s.Fout; g.nq = 1;
-  rc = launch_rowgemm(g, s.K, st);
-  if (rc) return rc;
-  for (int k = s.K - 1; k >= 2; --k) {
-    float* gk = Gs + (long long)k * slab;
-    float* gk1 = Gs + (long long)(k - 1) * slab;
-    float* gk2 = Gs + (long long)(k - 2) * slab;
-    rc = launch_spmm_step(*Lt, gk, gk1, gk1, C, 2.f, 1.f, st);
+  // seeds G_k = dZ W_k^T for every k, then the Clenshaw form of the adjoint recursion, in place on the seeds:
+  //   b_k = G_k + 2 L~^T b_{k+1} - b_{k+2}  (k = K-2 .. 1, b_{K-1} = G_{K-1}),   dx = G_0 + L~^T b_1 - b_2
+  if (mma_g) {
+    rc = node_dz_wt(dZn, W, Gs, slab, s, st);
     if (rc) return rc;
-    k_sub_inplace<<<(unsigned)std::min<long long>(ceil_div_ll(slab, 256), 1 << 16), 256, 0, st>>>(gk2, gk, slab);
-    GCNB_LAUNCH_CHECK("k_sub_inplace");
+  } else {
+    RowGemm g;
+    g.A = dZn; g.a_q = 0; g.lda = ldz;
+    g.Bm = W; g.b_z = s.Fout; g.b_q = 0; g.sbk = 1; g.sbn = (long long)s.K * s.Fout;
+    g.C = Gs; g.c_z = slab; g.ldc = s.Fin;
+    g.R = R; g.N = s.Fin; g.Kd = s.Fout; g.nq = 1;
+    rc = launch_rowgemm(g, s.K, st);
+    if (rc) return rc;
   }
-  if (s.K > 1) {
-    rc = launch_spmm_step(*Lt, Gs + slab, Gs, Gs, C, 1.f, 1.f, st);
+  for (int k = s.K - 2; k >= 0; --k) {
+    float* bk = Gs + (long long)k * slab;
+    const float* bk1 = Gs + (long long)(k + 1) * slab;
+    const float* bk2 = k + 2 <= s.K - 1 ? Gs + (long long)(k + 2) * slab : nullptr;
+    rc = launch_spmm_step(*Lt, bk1, bk, bk2, bk, C, k == 0 ? 1.f : 2.f, 1.f, -1.f, st);
     if (rc) return rc;
   }
   return launch_from_node_major(Gs, dx, s.B, s.M, s.Fin, st);

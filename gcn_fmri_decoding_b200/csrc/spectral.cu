@@ -135,7 +135,7 @@ size_t gcnb_spectral_workspace_bytes(int B, int M, int Fin, int Fout, int p, int
   (void)p;
   const size_t a = (size_t)M * B * Fin * sizeof(float), c = (size_t)M * B * Fout * sizeof(float);
   size_t n = 2 * align_up(a, 256) + 2 * align_up(c, 256);
-  if (backward) n += align_up((size_t)M * Fout * sizeof(float), 256);
+  if (backward) n += align_up(db_scratch_floats(M, Fout) * sizeof(float), 256);
   return n + 256;
 }
 
@@ -189,13 +189,13 @@ int gcnb_spectral_bwd_f32(const float* x, const float* y, const uint8_t* argmax,
   float* bufB = ws.take<float>(na);  // Xh, later dXn
   float* dZn = ws.take<float>(nc);
   float* dYh = ws.take<float>(nc);
-  float* dbs = ws.take<float>((size_t)M * Fout);
+  float* dbs = ws.take<float>(db_scratch_floats(M, Fout));
   if (!bufA || !bufB || !dZn || !dYh || !dbs) {
     set_error("gcnb_spectral_bwd_f32: workspace too small");
     return GCNB_ERR_WORKSPACE;
   }
-  if ((rc = launch_dz(dy, y, argmax, dZn, B, M, Fout, p, relu, st))) return rc;
-  if ((rc = launch_db(dZn, db, dbs, B, M, Fout, bias_mode, st))) return rc;
+  if ((rc = launch_dz(dy, y, argmax, dZn, Fout, B, M, Fout, p, relu, st))) return rc;
+  if ((rc = launch_db(dZn, Fout, db, dbs, B, M, Fout, bias_mode, st))) return rc;
   if ((rc = launch_to_node_major(x, nullptr, bufA, B, M, M, Fin, st))) return rc;
   if ((rc = launch_sgemm(false, Ut, bufA, bufB, M, (long long)B * Fin, M, M, st))) return rc;   // xh
   if ((rc = launch_sgemm(false, Ut, dZn, dYh, M, (long long)B * Fout, M, M, st))) return rc;    // dyh = Ut dz

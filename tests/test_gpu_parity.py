@@ -138,6 +138,8 @@ SWEEP = [
     (2, 1, 1, 1, 3, 1, "b1relu"),     # degenerate widths
     (2, 2, 33, 40, 3, 2, "b1relu"),   # widths that are not multiples of 8
     (1, 2, 64, 64, 3, 8, "b1relu"),
+    (3, 40, 32, 32, 3, 2, "b1relu"),  # vertex-major rows wider than one TMA column chunk (B*Fin = 1280 floats)
+    (1, 8, 16, 32, 12, 1, "b2relu"),  # general path: TMA SpMM + all three tensor-core contractions, K=12
 ]
 
 
@@ -566,20 +568,30 @@ def test_full_size_properties(dev, graph_l4):
             assert float((other - ys[0]).abs().max()) <= 1e-4 * float(ys[0].abs().max())
 
 
-def test_large_graph_general_path(dev):
-    """Vertex-level graph (config 5 family, scaled down): HBM-resident operator, K=25."""
+@pytest.mark.parametrize("B", [3, 4])
+def test_large_graph_general_path(dev, B):
+    """Vertex-level graph (config 5 family, scaled down): HBM-resident operator, K=25.  B=4 makes the vertex-major
+    rows 16-byte multiples (TMA-staged SpMM) and leaves ragged last tiles in the tensor-core contractions."""
     from gcn_fmri_decoding_b200 import synth
 
     L = synth.fibonacci_sphere_graph(3000, 6)
     rng = np.random.RandomState(9)
-    x = rng.randn(3, 3000, 15).astype(np.float32)
+    x = rng.randn(B, 3000, 15).astype(np.float32)
     W = (rng.randn(15 * 25, 32) * 0.05).astype(np.float32)
     b = np.full(32, 0.2, np.float32)
-    dy = rng.randn(3, 3000, 32).astype(np.float32)
+    dy = rng.randn(B, 3000, 32).astype(np.float32)
     pr = [dict(W=W, b=b, K=25, p=1)]
     y64, tr = O.conv_stack(x, [L], pr, dtype=np.float64, keep=True)
+    # A pre-activation within fp32 rounding of zero makes the ReLU mask (hence the gradient routed through that one
+    # element) a coin toss between fp32 and the fp64 oracle: take those elements out of dy.  (With this seed there
+    # is exactly such an element.)
+    pre = tr[0]["z"] + b
+    dy[np.abs(pre) < 1e-5 * np.abs(pre).max()] = 0.0
     dx64, g64 = O.conv_stack_bwd(tr, [L], pr, dy, dtype=np.float64, first_needs_dx=True)
-    r = run_layer(dev, L, x, W, b, 25, 1, "b1relu", 0, dy=dy)
+    from gcn_fmri_decoding_b200 import _lib
+
+    r = run_layer(dev, L, x, W, b, 25, 1, "b1relu", _lib.ALGO_GENERAL, dy=dy)
     assert rel_inf(r["y"], y64) <= TOL
     assert rel_inf(r["dW"], g64[0]["dW"]) <= TOL
+    assert rel_inf(r["db"], g64[0]["db"]) <= TOL
     assert rel_inf(r["dx"], dx64) <= TOL
