@@ -193,9 +193,17 @@ const char* gcnb_last_error_string(void) { return g_err; }
 
 unsigned long long gcnb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+// Layout of the saved Chebyshev stack: 1 = fused kernels' [K][B][M][FP], 2 = general path's vertex-major
+// [K][M][B][Fin] (graphs the fused kernels cannot hold), 0 = this shape keeps no stack.
+static int stack_layout(const LayerShape& s) {
+  if (fused_fwd_supported(s)) return stack_dw_supported(s) ? 1 : 0;
+  return 2;
+}
+
 int gcnb_cheb_stack_width(int B, int M, int nnz, int Fin, int Fout, int K, int p) {
   LayerShape s{B, M, nnz, Fin, Fout, K, p};
-  return (fused_fwd_supported(s) && stack_dw_supported(s)) ? fused_feature_pad(Fin) : 0;
+  const int layout = stack_layout(s);
+  return layout == 1 ? fused_feature_pad(Fin) : layout == 2 ? Fin : 0;
 }
 
 int gcnb_cheb_fused_supported(int B, int M, int nnz, int Fin, int Fout, int K, int p, int backward, int need_dx) {
@@ -239,8 +247,9 @@ int gcnb_cheb_fwd_f32(const float* x, const int32_t* perm, int M_in, const gcnb_
     if (rc == GCNB_OK && y_mean != nullptr && Fout > 32) rc = launch_mean_f(y, y_mean, pooled_rows, Fout, st);
     return rc;
   }
-  GCNB_REQUIRE(xstack == nullptr, "gcnb_cheb_fwd_f32: xstack is only produced by the fused kernels (see gcnb_cheb_fused_supported)");
-  rc = general_cheb_fwd(x, perm, M_in, *L, W, bias, y, argmax, s, bias_mode, relu, ws, st);
+  GCNB_REQUIRE(xstack == nullptr || stack_layout(s) == 2,
+               "gcnb_cheb_fwd_f32: the general path cannot produce the stack layout gcnb_cheb_stack_width() announced");
+  rc = general_cheb_fwd(x, perm, M_in, *L, W, bias, y, argmax, xstack, s, bias_mode, relu, ws, st);
   if (rc == GCNB_OK && y_mean != nullptr) rc = launch_mean_f(y, y_mean, pooled_rows, Fout, st);
   return rc;
 }
@@ -262,10 +271,12 @@ int gcnb_cheb_bwd_f32(const float* x, const int32_t* perm, int M_in, const float
   LayerShape s{B, L->M, L->nnz, Fin, Fout, K, p};
   Workspace ws(workspace, workspace_bytes);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (xstack != nullptr && dx == nullptr && algo != GCNB_ALGO_GENERAL && stack_dw_supported(s))
+  const int layout = xstack ? stack_layout(s) : 0;
+  GCNB_REQUIRE(xstack == nullptr || layout != 0, "gcnb_cheb_bwd_f32: no stack layout exists for this shape");
+  if (layout == 1 && dx == nullptr && algo != GCNB_ALGO_GENERAL)
     return stack_dw(xstack, y, argmax, dy, dy_is_mean, dW, db, s, bias_mode, relu, ws, st);
-  const bool fused_ok = fused_bwd_supported(s, dx != nullptr);
-  if (xstack != nullptr && dx != nullptr && algo != GCNB_ALGO_GENERAL && fused_ok && stack_dw_supported(s)) {
+  const bool fused_ok = layout != 2 && fused_bwd_supported(s, dx != nullptr);
+  if (layout == 1 && dx != nullptr && algo != GCNB_ALGO_GENERAL && fused_ok) {
     // saved basis: the weight gradient is one streamed GEMM; the fused kernel only runs the adjoint recursion for dx
     rc = stack_dw(xstack, y, argmax, dy, dy_is_mean, dW, db, s, bias_mode, relu, ws, st);
     if (rc) return rc;
@@ -290,7 +301,8 @@ int gcnb_cheb_bwd_f32(const float* x, const int32_t* perm, int M_in, const float
     if (rc) return rc;
     dy = full;
   }
-  return general_cheb_bwd(x, perm, M_in, y, argmax, dy, *L, Lt, W, dx, dW, db, s, bias_mode, relu, ws, st);
+  return general_cheb_bwd(x, perm, M_in, y, argmax, dy, *L, Lt, W, dx, dW, db, layout == 2 ? xstack : nullptr, s,
+                          bias_mode, relu, ws, st);
 }
 
 int gcnb_brelu_fwd_f32(const float* x, const float* bias, float* y, int B, int M, int F, int bias_mode,

@@ -74,11 +74,11 @@ int device_info(DeviceInfo* out);
 // ---- general (HBM-resident) path, general.cu ------------------------------------------------
 size_t general_cheb_workspace(const LayerShape& s, bool backward, bool need_dx);
 int general_cheb_fwd(const float* x, const int32_t* perm, int M_in, const gcnb_csr& L, const float* W,
-                     const float* bias, float* y, uint8_t* argmax, const LayerShape& s, int bias_mode, int relu,
-                     Workspace& ws, cudaStream_t st);
+                     const float* bias, float* y, uint8_t* argmax, float* xstack, const LayerShape& s, int bias_mode,
+                     int relu, Workspace& ws, cudaStream_t st);
 int general_cheb_bwd(const float* x, const int32_t* perm, int M_in, const float* y, const uint8_t* argmax, const float* dy, const gcnb_csr& L,
-                     const gcnb_csr* Lt, const float* W, float* dx, float* dW, float* db, const LayerShape& s,
-                     int bias_mode, int relu, Workspace& ws, cudaStream_t st);
+                     const gcnb_csr* Lt, const float* W, float* dx, float* dW, float* db, const float* xstack,
+                     const LayerShape& s, int bias_mode, int relu, Workspace& ws, cudaStream_t st);
 
 // pieces shared with the spectral path
 int launch_to_node_major(const float* x, const int32_t* perm, float* X0, int B, int M, int M_in, int F,

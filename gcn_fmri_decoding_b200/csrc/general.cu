@@ -47,8 +47,81 @@ __global__ void k_from_node_major(const float* __restrict__ Xn, float* __restric
   }
 }
 
+// Tiled versions of the two layout changes (and of the p == 1 epilogue adjoint): a CTA moves a tile of kTileM
+// vertices x TB samples through shared memory so that BOTH sides are read / written in long contiguous runs
+// (TM*F floats per sample on the sample-major side, TB*F floats per vertex on the vertex-major side) instead of
+// F-float snippets on one of them.
+//   MODE 0: Xn[m][b*ld + f] = x[b][perm ? perm[m] : m][f]      (0 for fake vertices)
+//   MODE 1: x[b][m][f]      = Xn[m][b*ld + f]
+//   MODE 2: dZn[m][b*ld + o] = relu ? (y[b][m][o] > 0 ? dy[b][m][o] : 0) : dy[b][m][o]        (p == 1)
+constexpr int kTileM = 16;
+
+template <int MODE>
+__global__ void __launch_bounds__(256) k_tile_swap(const float* __restrict__ src, const float* __restrict__ src2,
+                                                   const int32_t* __restrict__ perm, float* __restrict__ dst, int B, int M,
+                                                   int M_in, int F, int ld, int TB, int relu) {
+  extern __shared__ float tile[];  // [kTileM][TB*F]
+  const int m0 = blockIdx.x * kTileM, b0 = blockIdx.y * TB;
+  const int tm = min(kTileM, M - m0), tb = min(TB, B - b0);
+  const int row = TB * F;
+  if (MODE == 1) {
+    // vertex-major in: per vertex a run of tb*F floats (rows are ld apart per sample; ld == F here)
+    for (int i = threadIdx.x; i < tm * tb * F; i += 256) {
+      const int m = i / (tb * F), c = i - m * (tb * F);
+      tile[m * row + c] = src[((long long)(m0 + m) * B + b0) * ld + c];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < tb * tm * F; i += 256) {
+      const int b = i / (tm * F), j = i - b * (tm * F);
+      const int m = j / F, f = j - m * F;
+      dst[((long long)(b0 + b) * M + m0) * F + j] = tile[m * row + b * F + f];
+    }
+  } else {
+    for (int i = threadIdx.x; i < tb * tm * F; i += 256) {
+      const int b = i / (tm * F), j = i - b * (tm * F);
+      const int m = j / F, f = j - m * F;
+      float v;
+      if (MODE == 0) {
+        const int sm = perm ? perm[m0 + m] : m0 + m;
+        v = sm < M_in ? src[((long long)(b0 + b) * M_in + sm) * F + f] : 0.f;
+      } else {
+        const long long o = ((long long)(b0 + b) * M + m0) * F + j;
+        v = src[o];
+        if (relu && !(src2[o] > 0.f)) v = 0.f;
+      }
+      tile[m * row + b * F + f] = v;
+    }
+    __syncthreads();
+    if (ld == F) {
+      for (int i = threadIdx.x; i < tm * tb * F; i += 256) {
+        const int m = i / (tb * F), c = i - m * (tb * F);
+        dst[((long long)(m0 + m) * B + b0) * F + c] = tile[m * row + c];
+      }
+    } else {
+      for (int i = threadIdx.x; i < tm * tb * F; i += 256) {
+        const int m = i / (tb * F), c = i - m * (tb * F);
+        const int b = c / F, f = c - b * F;
+        dst[((long long)(m0 + m) * B + b0 + b) * ld + f] = tile[m * row + c];
+      }
+    }
+  }
+}
+
+// samples per tile so that the tile fits the 48 KB static shared-memory window; 0 = use the untiled kernels
+static int tile_samples(int B, int F) {
+  const int cap = 48 * 1024 / (kTileM * F * 4);
+  return cap >= 4 ? std::min(std::min(B, 32), cap) : 0;
+}
+
 int launch_to_node_major(const float* x, const int32_t* perm, float* X0, int B, int M, int M_in, int F,
                          cudaStream_t st) {
+  const int TB = tile_samples(B, F);
+  if (TB > 0) {
+    dim3 grid((unsigned)ceil_div(M, kTileM), (unsigned)ceil_div(B, TB));
+    k_tile_swap<0><<<grid, 256, (size_t)kTileM * TB * F * 4, st>>>(x, nullptr, perm, X0, B, M, M_in, F, F, TB, 0);
+    GCNB_LAUNCH_CHECK("k_tile_swap<0>");
+    return GCNB_OK;
+  }
   long long C = (long long)B * F;
   dim3 grid((unsigned)std::min<long long>(ceil_div_ll(C, 256), 1024), (unsigned)std::min(M, 65535));
   k_to_node_major<<<grid, 256, 0, st>>>(x, perm, X0, B, M, M_in, F);
@@ -57,6 +130,13 @@ int launch_to_node_major(const float* x, const int32_t* perm, float* X0, int B, 
 }
 
 int launch_from_node_major(const float* Xn, float* x, int B, int M, int F, cudaStream_t st) {
+  const int TB = tile_samples(B, F);
+  if (TB > 0) {
+    dim3 grid((unsigned)ceil_div(M, kTileM), (unsigned)ceil_div(B, TB));
+    k_tile_swap<1><<<grid, 256, (size_t)kTileM * TB * F * 4, st>>>(Xn, nullptr, nullptr, x, B, M, M, F, F, TB, 0);
+    GCNB_LAUNCH_CHECK("k_tile_swap<1>");
+    return GCNB_OK;
+  }
   long long C = (long long)B * F;
   dim3 grid((unsigned)std::min<long long>(ceil_div_ll(C, 256), 1024), (unsigned)std::min(M, 65535));
   k_from_node_major<<<grid, 256, 0, st>>>(Xn, x, B, M, F);
@@ -336,6 +416,13 @@ __global__ void k_dz(const float* __restrict__ dy, const float* __restrict__ y, 
 
 int launch_dz(const float* dy, const float* y, const uint8_t* argmax, float* dZn, int ldz, int B, int M, int F, int p,
               int relu, cudaStream_t st) {
+  const int TB = tile_samples(B, F);
+  if (p == 1 && TB > 0 && M <= 65535 * kTileM) {
+    dim3 grid((unsigned)ceil_div(M, kTileM), (unsigned)ceil_div(B, TB));
+    k_tile_swap<2><<<grid, 256, (size_t)kTileM * TB * F * 4, st>>>(dy, y, nullptr, dZn, B, M, M, F, ldz, TB, relu);
+    GCNB_LAUNCH_CHECK("k_tile_swap<2>");
+    return GCNB_OK;
+  }
   const long long total = (long long)B * ceil_div(M, p) * F;
   k_dz<<<(unsigned)std::min<long long>(ceil_div_ll(total, 256), 1 << 20), 256, 0, st>>>(dy, y, argmax, dZn, ldz, B, M,
                                                                                       F, p, relu);
@@ -454,11 +541,12 @@ static int build_stack(float* Xs, const gcnb_csr& L, long long slab, long long C
 }
 
 int general_cheb_fwd(const float* x, const int32_t* perm, int M_in, const gcnb_csr& L, const float* W,
-                     const float* bias, float* y, uint8_t* argmax, const LayerShape& s, int bias_mode, int relu,
-                     Workspace& ws, cudaStream_t st) {
+                     const float* bias, float* y, uint8_t* argmax, float* xstack, const LayerShape& s, int bias_mode,
+                     int relu, Workspace& ws, cudaStream_t st) {
   const long long C = (long long)s.B * s.Fin;
   const long long slab = (long long)s.M * C;
-  float* Xs = ws.take<float>((size_t)slab * s.K);
+  // the Chebyshev stack is built in the caller's buffer when it wants to keep it for the backward pass
+  float* Xs = xstack ? xstack : ws.take<float>((size_t)slab * s.K);
   float* Zn = ws.take<float>((size_t)s.M * s.B * node_mma_ldz(s.Fout));
   if (!Xs || !Zn) {
     set_error("workspace too small for the general forward path");
@@ -492,8 +580,8 @@ int general_cheb_fwd(const float* x, const int32_t* perm, int M_in, const gcnb_c
 }
 
 int general_cheb_bwd(const float* x, const int32_t* perm, int M_in, const float* y, const uint8_t* argmax, const float* dy, const gcnb_csr& L,
-                     const gcnb_csr* Lt, const float* W, float* dx, float* dW, float* db, const LayerShape& s,
-                     int bias_mode, int relu, Workspace& ws, cudaStream_t st) {
+                     const gcnb_csr* Lt, const float* W, float* dx, float* dW, float* db, const float* xstack,
+                     const LayerShape& s, int bias_mode, int relu, Workspace& ws, cudaStream_t st) {
   const long long C = (long long)s.B * s.Fin;
   const long long slab = (long long)s.M * C;
   const long long R = (long long)s.M * s.B;
@@ -502,7 +590,8 @@ int general_cheb_bwd(const float* x, const int32_t* perm, int M_in, const float*
   const int ldz = (mma_dw || mma_g) ? node_mma_ldz(s.Fout) : s.Fout;
   int rpc;
   const int nch = mma_dw ? node_dw_blocks(s) : dw_chunking(R, &rpc);
-  float* Xs = ws.take<float>((size_t)slab * s.K);
+  float* Xw = xstack ? nullptr : ws.take<float>((size_t)slab * s.K);
+  const float* Xs = xstack ? xstack : Xw;
   float* dZn = ws.take<float>((size_t)R * node_mma_ldz(s.Fout));
   float* part = ws.take<float>((size_t)s.K * std::max(nch, node_dw_blocks(s)) * s.Fin * s.Fout);
   float* dbs = ws.take<float>(db_scratch_floats(s.M, s.Fout));
@@ -515,11 +604,13 @@ int general_cheb_bwd(const float* x, const int32_t* perm, int M_in, const float*
   if (rc) return rc;
   rc = launch_db(dZn, ldz, db, dbs, s.B, s.M, s.Fout, bias_mode, st);
   if (rc) return rc;
-  // recompute the Chebyshev stack from x (nothing but x, y and argmax is kept from the forward)
-  rc = launch_to_node_major(x, perm, Xs, s.B, s.M, M_in, s.Fin, st);
-  if (rc) return rc;
-  rc = build_stack(Xs, L, slab, C, s.K, st);
-  if (rc) return rc;
+  if (xstack == nullptr) {
+    // recompute the Chebyshev stack from x (nothing but x, y and argmax was kept from the forward)
+    rc = launch_to_node_major(x, perm, Xw, s.B, s.M, M_in, s.Fin, st);
+    if (rc) return rc;
+    rc = build_stack(Xw, L, slab, C, s.K, st);
+    if (rc) return rc;
+  }
   if (mma_dw) {
     rc = node_dw(Xs, slab, dZn, part, s, st);
     if (rc) return rc;

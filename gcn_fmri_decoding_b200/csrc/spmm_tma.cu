@@ -24,7 +24,7 @@ namespace {
 constexpr int kSlots = 8;
 constexpr int kChunkMax = 1024;  // floats per column chunk = 256 consumer threads x float4
 constexpr int kConsWarps = 8;
-constexpr int kProdWarps = 2;    // one warp cannot issue ~7 copies per row fast enough (it is instruction bound)
+constexpr int kProdWarps = 4;    // one warp cannot issue ~7 copies per row fast enough (it is instruction bound)
 constexpr int kSpmmThreads = (kConsWarps + kProdWarps) * 32;
 constexpr int kSpmmMaxStages = 8;
 constexpr int kHdrBytes = 64;
@@ -36,6 +36,7 @@ struct StageHdr {
   float val[kSlots];
   int pad2[4];
 };
+static_assert((kProdWarps & (kProdWarps - 1)) == 0 && kSpmmMaxStages % kProdWarps == 0, "stage ownership");
 static_assert(sizeof(StageHdr) == kHdrBytes, "stage header is 64 bytes");
 
 struct SpmmArgs {
@@ -75,15 +76,17 @@ __global__ void __launch_bounds__(kSpmmThreads, 1) k_spmm_tma(SpmmArgs a) {
   const int G = gridDim.x;
 
   if (warp >= kConsWarps) {
-    // ---- producer warps.  Items of this CTA are q = blockIdx.x + i*G, i = 0, 1, ...; producer p issues the items
-    // with i % kProdWarps == p.  A row of more than kSlots entries takes several stages, so the ring position of an
-    // item is the running sum of the stage counts of all earlier items: both producers scan the degrees of a batch
-    // of 32 items (one per lane) and agree on it without talking to each other.
+    // ---- producer warps.  The items of this CTA are q = blockIdx.x + i*G, i = 0, 1, ...; a row of more than kSlots
+    // entries takes several stages, so the ring position `it` of a stage use is the running sum of the stage counts
+    // of all earlier items: every producer scans the degrees of a batch of 32 items (one per lane) and they agree
+    // on it without talking to each other.  Producer p fills the uses with it % kProdWarps == p.  NS is a multiple of
+    // kProdWarps, so a given stage is always filled -- and its release always awaited -- by the same producer, one
+    // phase after the other: exactly the single-producer ring discipline an mbarrier parity wait needs.
     const int p = warp - kConsWarps;
     int* pcol = reinterpret_cast<int*>(smem + 2 * kSpmmMaxStages * 8) + p * 32 * kSlots * 2;
     float* pval = reinterpret_cast<float*>(pcol + 32 * kSlots);
     const bool has_add = a.add != nullptr, has_add2 = a.add2 != nullptr;
-    long long it_base = 0;
+    int it_base = 0;
     for (long long i0 = 0; blockIdx.x + i0 * G < total; i0 += 32) {
       const long long q = blockIdx.x + (i0 + lane) * G;
       int beg = 0, end = 0, m = 0, cc = 0;
@@ -100,9 +103,11 @@ __global__ void __launch_bounds__(kSpmmThreads, 1) k_spmm_tma(SpmmArgs a) {
         const int t = __shfl_up_sync(0xffffffffu, incl, d);
         if (lane >= d) incl += t;
       }
-      const long long it_first = it_base + incl - passes;
-      it_base += __shfl_sync(0xffffffffu, incl, 31);
-      if ((lane % kProdWarps) == p) {
+      const int it_first = it_base + incl - passes;
+      const int batch_uses = __shfl_sync(0xffffffffu, incl, 31);
+      const int nvalid = __popc(__ballot_sync(0xffffffffu, q < total));
+      const bool simple = batch_uses == nvalid;  // every row of the batch fits one stage: use i0 + l <-> item l
+      if (simple && lane < nvalid && ((it_base + lane) & (kProdWarps - 1)) == p) {
 #pragma unroll
         for (int e = 0; e < kSlots; ++e)
           if (beg + e < end) {
@@ -111,58 +116,66 @@ __global__ void __launch_bounds__(kSpmmThreads, 1) k_spmm_tma(SpmmArgs a) {
           }
       }
       __syncwarp();
-      for (int ii = p; ii < 32; ii += kProdWarps) {
+
+      // fill stage use `it` with pass `pass` (of npass) of item ii; executed by the whole warp
+      auto fill = [&](int ii, int pass, int npass, int it) {
         const int ibeg = __shfl_sync(0xffffffffu, beg, ii), iend = __shfl_sync(0xffffffffu, end, ii);
-        const int npass = __shfl_sync(0xffffffffu, passes, ii);
-        if (npass == 0) break;
         const int im = __shfl_sync(0xffffffffu, m, ii);
-        long long it = __shfl_sync(0xffffffffu, it_first, ii);
         long long c0 = 0;
         uint32_t wbytes = (uint32_t)a.C * 4;
         if (!kOne) {
           c0 = (long long)__shfl_sync(0xffffffffu, cc, ii) * a.CW;
           wbytes = (uint32_t)((a.C - c0 < a.CW ? a.C - c0 : a.CW) * 4);
         }
-        const float* addrow = has_add ? a.add + (long long)im * a.C + c0 : nullptr;
-        const float* add2row = has_add2 ? a.add2 + (long long)im * a.C + c0 : nullptr;
-        for (int j0 = ibeg, pass = 0; pass < npass; ++pass, ++it, j0 += kSlots) {
-          const int n = iend - j0 < kSlots ? iend - j0 : kSlots;
-          const bool last = pass == npass - 1;
-          const int s = (int)(it % NS);
-          if (it >= NS) mbar_wait(empty + s, (uint32_t)((it / NS - 1) & 1));
-          unsigned char* st = stages + (size_t)s * a.stage_bytes;
-          StageHdr* h = reinterpret_cast<StageHdr*>(st);
-          float* seg = reinterpret_cast<float*>(st + kHdrBytes);
-          // lanes [0, n): neighbour rows; lane n / n+1: the add rows (last stage of the row only)
-          const int ncopy = n + (last ? (int)has_add + (int)has_add2 : 0);
-          const float* from = nullptr;
-          float* to = seg + (size_t)lane * a.CW;
-          if (lane < n) {
-            int cj;
-            float v;
-            if (pass == 0) {
-              cj = pcol[ii * kSlots + lane];
-              v = pval[ii * kSlots + lane];
-            } else {
-              cj = __ldg(a.col + j0 + lane);
-              v = __ldg(a.val + j0 + lane);
-            }
-            h->val[lane] = v;
-            from = a.src + (long long)cj * a.C + c0;
-          } else if (lane == n) {
-            from = addrow;
-            to = seg + (size_t)kSlots * a.CW;
-          } else if (lane == n + 1) {
-            from = add2row;
-            to = seg + (size_t)(kSlots + 1) * a.CW;
+        const int j0 = ibeg + pass * kSlots;
+        const int n = iend - j0 < kSlots ? iend - j0 : kSlots;
+        const bool last = pass == npass - 1;
+        const int s = it % NS, u = it / NS;
+        if (u > 0) mbar_wait(empty + s, (uint32_t)((u - 1) & 1));
+        unsigned char* st = stages + (size_t)s * a.stage_bytes;
+        StageHdr* h = reinterpret_cast<StageHdr*>(st);
+        float* seg = reinterpret_cast<float*>(st + kHdrBytes);
+        // lanes [0, n): neighbour rows; lane n / n+1: the add rows (last stage of the row only)
+        const int ncopy = n + (last ? (int)has_add + (int)has_add2 : 0);
+        const float* from = nullptr;
+        float* to = seg + (size_t)lane * a.CW;
+        if (lane < n) {
+          int cj;
+          float v;
+          if (simple) {
+            cj = pcol[ii * kSlots + lane];
+            v = pval[ii * kSlots + lane];
+          } else {
+            cj = __ldg(a.col + j0 + lane);
+            v = __ldg(a.val + j0 + lane);
           }
-          if (lane == 0) h->nflags = n | (pass == 0 ? 256 : 0) | (last ? 512 : 0);
-          __syncwarp();  // header complete before the (releasing) arrive
-          if (lane == 0) mbar_expect_tx(full + s, (uint32_t)ncopy * wbytes);
-          __syncwarp();
-          if (lane < ncopy) bulk_g2s_ring(to, from, wbytes, full + s);
+          h->val[lane] = v;
+          from = a.src + (long long)cj * a.C + c0;
+        } else if (lane == n) {
+          from = has_add ? a.add + (long long)im * a.C + c0 : nullptr;
+          to = seg + (size_t)kSlots * a.CW;
+        } else if (lane == n + 1) {
+          from = has_add2 ? a.add2 + (long long)im * a.C + c0 : nullptr;
+          to = seg + (size_t)(kSlots + 1) * a.CW;
+        }
+        if (lane == 0) h->nflags = n | (pass == 0 ? 256 : 0) | (last ? 512 : 0);
+        __syncwarp();  // header complete before the (releasing) arrive
+        if (lane == 0) mbar_expect_tx(full + s, (uint32_t)ncopy * wbytes);
+        __syncwarp();
+        if (lane < ncopy) bulk_g2s_ring(to, from, wbytes, full + s);
+      };
+
+      if (simple) {
+        for (int ii = (p - it_base) & (kProdWarps - 1); ii < nvalid; ii += kProdWarps) fill(ii, 0, 1, it_base + ii);
+      } else {
+        for (int ii = 0; ii < nvalid; ++ii) {
+          const int npass = __shfl_sync(0xffffffffu, passes, ii);
+          const int itf = __shfl_sync(0xffffffffu, it_first, ii);
+          for (int pass = 0; pass < npass; ++pass)
+            if (((itf + pass) & (kProdWarps - 1)) == p) fill(ii, pass, npass, itf + pass);
         }
       }
+      it_base += batch_uses;
       __syncwarp();
     }
     return;
@@ -235,7 +248,9 @@ bool plan_spmm(long long C, int* CW, int* nchunk, int* NS, uint32_t* stage_bytes
   if (device_info(&di) != GCNB_OK) return false;
   const size_t fixed = align_up((size_t)kFixedBytes, 128);
   if ((size_t)di.smem_optin < fixed + 2 * (size_t)*stage_bytes) return false;
+  if ((size_t)di.smem_optin < fixed + (size_t)kProdWarps * *stage_bytes) return false;
   *NS = (int)std::min<size_t>(kSpmmMaxStages, ((size_t)di.smem_optin - fixed) / *stage_bytes);
+  *NS = *NS / kProdWarps * kProdWarps;  // each stage belongs to one producer warp
   *smem = fixed + (size_t)*NS * *stage_bytes;
   return true;
 }

@@ -73,8 +73,9 @@ GCNB_API unsigned long long gcnb_launch_count(void);
 /* 1 if the fused shared-memory kernels can take this layer shape, else 0. */
 GCNB_API int gcnb_cheb_fused_supported(int B, int M, int nnz, int Fin, int Fout, int K, int p, int backward, int need_dx);
 
-/* Padded feature width FP of the saved-basis buffer (`xstack`, [K][B][M][FP] floats) for this layer shape, or 0 when
- * the forward cannot emit it / the backward cannot consume it. */
+/* Feature width FP of the saved-basis buffer `xstack` (K*B*M*FP floats, layout private to the library: [K][B][M][FP]
+ * with padded FP for graphs the fused kernels hold in shared memory, vertex-major [K][M][B][Fin] for vertex-level
+ * graphs on the general path), or 0 when this shape keeps no basis. */
 GCNB_API int gcnb_cheb_stack_width(int B, int M, int nnz, int Fin, int Fout, int K, int p);
 
 /* Bytes of workspace gcnb_cheb_{fwd,bwd}_f32 need for this shape (256-byte aligned pointer). */
@@ -98,8 +99,8 @@ GCNB_API size_t gcnb_cheb_workspace_bytes(int B, int M, int nnz, int Fin, int Fo
  * bias (nullable iff bias_mode == NONE); argmax (nullable: not written); p >= 1, power of 2.
  * y_mean (nullable): also write mean_o y[b,j,o] as [B][M/p] -- tf.reduce_mean(x, -1) of the last conv layer
  *   (models_gcn.py:673) fused into the epilogue.
- * xstack (nullable, training): also keep the Chebyshev basis X_k, k < K, as [K][B][M][FP] (FP from
- *   gcnb_cheb_stack_width) so that the backward pass of a first layer (no dx) can skip the recursion.
+ * xstack (nullable, training): also keep the Chebyshev basis X_k, k < K, in a caller buffer of K*B*M*FP floats (FP
+ *   from gcnb_cheb_stack_width) so that the backward pass can skip recomputing the recursion.
  */
 GCNB_API int gcnb_cheb_fwd_f32(const float* x, const int32_t* perm, int M_in, const gcnb_csr* L, const float* W,
                       const float* bias, float* y, uint8_t* argmax, float* y_mean, float* xstack, int B, int Fin,
@@ -117,7 +118,8 @@ GCNB_API int gcnb_cheb_fwd_f32(const float* x, const int32_t* perm, int M_in, co
  * dW / db are overwritten (not accumulated).  db may be NULL when bias_mode == NONE.
  * dy_is_mean != 0: dy is [B][M/p], the gradient of the mean over filters (every filter receives dy/Fout);
  *   the adjoint of y_mean above.
- * xstack (nullable): the basis saved by the forward; used when dx == NULL (dW becomes one streamed tall-skinny GEMM).
+ * xstack (nullable): the basis saved by the forward (dW becomes one streamed tall-skinny GEMM; only the adjoint
+ *   recursion for dx is left).
  */
 GCNB_API int gcnb_cheb_bwd_f32(const float* x, const int32_t* perm, int M_in, const float* y, const uint8_t* argmax,
                       const float* dy, int dy_is_mean, const float* xstack, const gcnb_csr* L,

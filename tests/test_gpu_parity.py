@@ -446,6 +446,41 @@ def test_saved_basis_weight_gradient(dev, graph_l4, lvl, B, Fin, Fout, K, p, bre
     assert rel_inf(gW4.cpu().numpy(), g64[0]["dW"]) <= TOL and rel_inf(gb4.cpu().numpy().reshape(b.shape), g64[0]["db"]) <= TOL
 
 
+def test_saved_basis_vertex_level_graph(dev):
+    """Graphs the fused kernels cannot hold keep the basis in the general path's vertex-major layout: the backward
+    then skips the K-1 sparse steps and must give exactly what the recompute path gives."""
+    from gcn_fmri_decoding_b200 import _lib, ops, synth
+    from gcn_fmri_decoding_b200.plan import GraphPlan
+
+    M, B, Fin, Fout, K = 3000, 4, 15, 32, 9
+    L = synth.fibonacci_sphere_graph(M, 6)
+    pl = GraphPlan(L, dev)
+    if _lib.lib().gcnb_cheb_fused_supported(B, M, pl.nnz, Fin, Fout, K, 1, 0, 0):
+        pytest.skip("this shape fits the fused kernels")
+    assert _lib.lib().gcnb_cheb_stack_width(B, M, pl.nnz, Fin, Fout, K, 1) == Fin
+    rng = np.random.RandomState(5)
+    x = rng.randn(B, M, Fin).astype(np.float32)
+    W = (rng.randn(Fin * K, Fout) * 0.1).astype(np.float32)
+    b = np.full(Fout, 0.2, np.float32)
+    dy = rng.randn(B, M, Fout).astype(np.float32)
+    xt, Wt, bt, dyt = T(x, dev), T(W, dev), T(b, dev), T(dy, dev)
+    y, am, ymean, stack = ops.cheb_fwd_mean(xt, None, pl.rowptr, pl.col, pl.val, Wt, bt, K, 1, ops.BIAS_PER_FILTER, True,
+                                            ops.ALGO_AUTO, True)
+    assert tuple(stack.shape) == (K, B, M, Fin)
+    basis = O.chebyshev_stack(x, L, K, np.float64).reshape(B, M, Fin, K)           # [b, m, f, k]
+    got = stack.cpu().numpy().reshape(K, M, B, Fin).transpose(2, 1, 3, 0)            # [k,m,b,f] -> [b,m,f,k]
+    assert rel_inf(got, basis) <= 1e-5
+    assert rel_inf(ymean.cpu().numpy(), y.cpu().numpy().mean(-1)) <= 1e-6
+    out = []
+    for st in (stack, None):
+        gW, gb = torch.empty_like(Wt), torch.empty(Fout, device=dev)
+        dx = ops.cheb_bwd_into(xt, None, y, am, dyt, False, *pl.tensors(), Wt, gW, gb, K, 1, ops.BIAS_PER_FILTER, True, True,
+                               ops.ALGO_AUTO, st)
+        out.append((dx, gW, gb))
+    for a, c in zip(*out):
+        assert torch.equal(a, c)
+
+
 def test_head_pieces(dev, graph_l4):
     """Fused mean over filters (forward) / mean-form dy (backward), ReLU+dropout, column sums, xent -- against NumPy."""
     import ctypes as C

@@ -37,8 +37,20 @@ with torch.no_grad():
         return torch.ops.gcn_b200.cheb_bwd(x, None, y, am, dy, *pl.tensors(), W, K, 1, ops.BIAS_PER_FILTER, True, True, 0)
 
     bwd()
+    gW, gb = torch.empty_like(W), torch.empty(32, device=dev)
+
+    def fwd_keep():
+        return ops.cheb_fwd_mean(x, None, pl.rowptr, pl.col, pl.val, W, bias, K, 1, ops.BIAS_PER_FILTER, True, 0, True)
+
+    stack = fwd_keep()[3]
+
+    def bwd_saved():
+        return ops.cheb_bwd_into(x, None, y, am, dy, False, *pl.tensors(), W, gW, gb, K, 1, ops.BIAS_PER_FILTER, True, True,
+                                 0, stack)
+
+    bwd_saved()
     if not once:
-        for name, fn in (("fwd", fwd), ("bwd", bwd)):
+        for name, fn in (("fwd", fwd), ("bwd", bwd), ("fwd_keep_basis", fwd_keep), ("bwd_saved_basis", bwd_saved)):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             torch.cuda.synchronize()
             a.record()
