@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libgcnb200.so")
 GCNB_OK = 0
 BIAS_NONE, BIAS_PER_FILTER, BIAS_PER_VERTEX = 0, 1, 2
 ALGO_AUTO, ALGO_GENERAL, ALGO_FUSED = 0, 1, 2
+EPI_NONE, EPI_RELU_DROPOUT, EPI_MASK = 0, 1, 2
 
 
 class GcnbCsr(C.Structure):
@@ -51,6 +52,8 @@ SIGNATURES = {
     "gcnb_relu_dropout_bwd_f32": (_i, [_p, _p, C.c_longlong, _i, _i, _i, C.c_float, _p]),
     "gcnb_colsum_multi_f32": (_i, [_p, _p, _p, _p, _i, _p]),
     "gcnb_gemm_f32": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "gcnb_gemm_epilogue_f32": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, C.c_float, C.c_uint, _p,
+                                    _p]),
     "gcnb_adam_tf_f32": (_i, [_p, _p, _p, _p, _p, _p, C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_float,
                               C.c_float, C.c_float, _i, _p]),
 }

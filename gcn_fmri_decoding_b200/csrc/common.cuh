@@ -132,6 +132,31 @@ int fused_cheb_bwd(const float* x, const int32_t* perm, int M_in, const float* y
                    int bias_mode, int relu, int dy_is_mean, bool skip_dw, Workspace& ws, cudaStream_t st);
 int launch_gemm(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int lda, int ldb, int ldc,
                 int ta, int tb, cudaStream_t st);
+// GEMM with a fused element-wise epilogue (gemm.cu): GCNB_EPI_RELU_DROPOUT / GCNB_EPI_MASK, see gcnb_gemm_epilogue_f32
+int launch_gemm_epi(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int lda, int ldb,
+                    int ldc, int ta, int tb, int epilogue, const float* aux, int ld_aux, float keep, unsigned seed,
+                    const float* step, cudaStream_t st);
+
+// ---- counter-based dropout mask shared by k_relu_dropout_fwd (head.cu) and the GEMM epilogue (gemm.cu) ----------
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {  // murmur3 finaliser
+  x ^= x >> 16;
+  x *= 0x85ebca6bu;
+  x ^= x >> 13;
+  x *= 0xc2b2ae35u;
+  x ^= x >> 16;
+  return x;
+}
+// key of one (layer seed, optimiser step) pair; step = the Adam state vector (element 3 = step count) or NULL
+__device__ __forceinline__ uint32_t dropout_key(uint32_t seed, const float* step) {
+  return mix32(seed ^ mix32((uint32_t)(step ? step[3] : 0.f) + 0x9e3779b9u));
+}
+__device__ __forceinline__ uint32_t dropout_threshold(float keep) {
+  return keep >= 1.f ? 0xffffffffu : (uint32_t)(keep * 4294967296.0);
+}
+// element i (row-major index within the activation matrix) survives iff this is true
+__device__ __forceinline__ bool dropout_keeps(uint32_t i, uint32_t key, uint32_t thresh) {
+  return mix32(i * 0x9e3779b1u + key) < thresh;
+}
 int launch_mean_f(const float* x, float* y, long long rows, int F, cudaStream_t st);
 int launch_mean_f_bwd(const float* dy, float* dx, long long rows, int F, cudaStream_t st);
 

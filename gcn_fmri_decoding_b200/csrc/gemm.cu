@@ -22,6 +22,33 @@ struct GemmArgs {
   float* C;
   const float* bias;
   int M, N, K, lda, ldb, ldc, ta, tb;
+  // fused epilogue (after the bias): GCNB_EPI_RELU_DROPOUT: v = dropout(relu(v)) with the mask of k_relu_dropout_fwd;
+  // GCNB_EPI_MASK: v = aux[m][n] > 0 ? v / keep : 0  (the adjoint of the former, aux = the forward activation)
+  int epi;
+  const float* aux;
+  int ld_aux;
+  float keep, inv_keep;
+  unsigned seed;
+  const float* step;
+};
+
+struct Epilogue {
+  uint32_t key, thresh;
+  __device__ __forceinline__ explicit Epilogue(const GemmArgs& g) : key(0), thresh(0) {
+    if (g.epi == GCNB_EPI_RELU_DROPOUT) {
+      key = dropout_key(g.seed, g.step);
+      thresh = dropout_threshold(g.keep);
+    }
+  }
+  __device__ __forceinline__ float operator()(const GemmArgs& g, float v, int m, int n) const {
+    if (g.epi == GCNB_EPI_RELU_DROPOUT) {
+      v = fmaxf(v, 0.f);
+      if (g.keep < 1.f) v = dropout_keeps((uint32_t)((long long)m * g.N + n), key, thresh) ? v * g.inv_keep : 0.f;
+    } else if (g.epi == GCNB_EPI_MASK) {
+      v = __ldg(g.aux + (long long)m * g.ld_aux + n) > 0.f ? v * g.inv_keep : 0.f;
+    }
+    return v;
+  }
 };
 
 __device__ __forceinline__ float gemm_a(const GemmArgs& g, int m, int k) {
@@ -112,6 +139,7 @@ __global__ void __launch_bounds__(128) k_gemm_3xtf32(const GemmArgs g) {
     __syncthreads();
   }
 
+  const Epilogue epi(g);
 #pragma unroll
   for (int i = 0; i < 2; ++i)
 #pragma unroll
@@ -127,8 +155,8 @@ __global__ void __launch_bounds__(128) k_gemm_3xtf32(const GemmArgs g) {
           if (n + 1 < g.N) v1 += __ldg(g.bias + n + 1);
         }
         float* c = g.C + (long long)m * g.ldc + n;
-        if (n < g.N) c[0] = v0;
-        if (n + 1 < g.N) c[1] = v1;
+        if (n < g.N) c[0] = epi(g, v0, m, n);
+        if (n + 1 < g.N) c[1] = epi(g, v1, m, n + 1);
       }
     }
 }
@@ -207,6 +235,7 @@ __global__ void __launch_bounds__(128) k_gemm_small_3xtf32(const GemmArgs g) {
       }
     }
   }
+  const Epilogue epi(g);
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
     const int n = n0 + wn + j * 8 + 2 * t;
@@ -220,15 +249,22 @@ __global__ void __launch_bounds__(128) k_gemm_small_3xtf32(const GemmArgs g) {
         if (n + 1 < g.N) v1 += __ldg(g.bias + n + 1);
       }
       float* c = g.C + (long long)m * g.ldc + n;
-      if (n < g.N) c[0] = v0;
-      if (n + 1 < g.N) c[1] = v1;
+      if (n < g.N) c[0] = epi(g, v0, m, n);
+      if (n + 1 < g.N) c[1] = epi(g, v1, m, n + 1);
     }
   }
 }
 
 int launch_gemm(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int lda, int ldb, int ldc,
                 int ta, int tb, cudaStream_t st) {
-  GemmArgs g{A, B, C, bias, M, N, K, lda, ldb, ldc, ta, tb};
+  return launch_gemm_epi(A, B, C, bias, M, N, K, lda, ldb, ldc, ta, tb, GCNB_EPI_NONE, nullptr, 0, 1.f, 0u, nullptr, st);
+}
+
+int launch_gemm_epi(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int lda, int ldb,
+                    int ldc, int ta, int tb, int epilogue, const float* aux, int ld_aux, float keep, unsigned seed,
+                    const float* step, cudaStream_t st) {
+  GemmArgs g{A, B, C, bias, M, N, K, lda, ldb, ldc, ta, tb, epilogue, aux, ld_aux, keep, keep >= 1.f ? 1.f : 1.f / keep,
+             seed, step};
   if ((long long)ceil_div(N, GBN) * ceil_div(M, GBM) < 2 * 148) {  // not enough 64x64 tiles to fill the chip
     dim3 grid((unsigned)ceil_div(N, SBN), (unsigned)ceil_div(M, SBM));
     k_gemm_small_3xtf32<<<grid, 128, 0, st>>>(g);
@@ -248,4 +284,17 @@ extern "C" int gcnb_gemm_f32(const float* A, const float* B, float* C, const flo
   GCNB_REQUIRE(A && B && C && M >= 1 && N >= 1 && K >= 1, "gcnb_gemm_f32: bad arguments");
   GCNB_REQUIRE(lda >= (transA ? M : K) && ldb >= (transB ? K : N) && ldc >= N, "gcnb_gemm_f32: leading dimension too small");
   return gcnb::launch_gemm(A, B, C, bias, M, N, K, lda, ldb, ldc, transA, transB, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int gcnb_gemm_epilogue_f32(const float* A, const float* B, float* C, const float* bias, int M, int N, int K,
+                                      int lda, int ldb, int ldc, int transA, int transB, int epilogue, const float* aux,
+                                      int ld_aux, float keep, unsigned seed, const float* step, gcnb_stream_t stream) {
+  GCNB_REQUIRE(A && B && C && M >= 1 && N >= 1 && K >= 1, "gcnb_gemm_epilogue_f32: bad arguments");
+  GCNB_REQUIRE(lda >= (transA ? M : K) && ldb >= (transB ? K : N) && ldc >= N,
+               "gcnb_gemm_epilogue_f32: leading dimension too small");
+  GCNB_REQUIRE(epilogue >= GCNB_EPI_NONE && epilogue <= GCNB_EPI_MASK, "gcnb_gemm_epilogue_f32: bad epilogue %d", epilogue);
+  GCNB_REQUIRE(keep > 0.f && keep <= 1.f, "gcnb_gemm_epilogue_f32: keep must be in (0, 1]");
+  GCNB_REQUIRE(epilogue != GCNB_EPI_MASK || (aux != nullptr && ld_aux >= N), "gcnb_gemm_epilogue_f32: the mask epilogue needs aux");
+  return gcnb::launch_gemm_epi(A, B, C, bias, M, N, K, lda, ldb, ldc, transA, transB, epilogue, aux, ld_aux, keep, seed, step,
+                               static_cast<cudaStream_t>(stream));
 }

@@ -95,25 +95,16 @@ __global__ void __launch_bounds__(1024) k_softmax_xent_1cta(const float* __restr
   }
 }
 
-__device__ __forceinline__ uint32_t mix32(uint32_t x) {  // murmur3 finaliser
-  x ^= x >> 16;
-  x *= 0x85ebca6bu;
-  x ^= x >> 13;
-  x *= 0xc2b2ae35u;
-  x ^= x >> 16;
-  return x;
-}
-
 __global__ void k_relu_dropout_fwd(float* __restrict__ x, long long rows, int cols, int ld, float keep, float inv_keep,
                                    uint32_t seed, const float* __restrict__ step) {
   const long long total = rows * cols;
-  const uint32_t key = mix32(seed ^ mix32((uint32_t)(step ? step[3] : 0.f) + 0x9e3779b9u));
-  const uint32_t thresh = keep >= 1.f ? 0xffffffffu : (uint32_t)(keep * 4294967296.0);
+  const uint32_t key = dropout_key(seed, step);
+  const uint32_t thresh = dropout_threshold(keep);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / cols;
     const int c = (int)(i - r * cols);
     float v = fmaxf(x[r * ld + c], 0.f);
-    if (keep < 1.f) v = (mix32((uint32_t)i * 0x9e3779b1u + key) < thresh) ? v * inv_keep : 0.f;
+    if (keep < 1.f) v = dropout_keeps((uint32_t)i, key, thresh) ? v * inv_keep : 0.f;
     x[r * ld + c] = v;
   }
 }

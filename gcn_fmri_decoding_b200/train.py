@@ -261,21 +261,34 @@ class FusedTrainer:
         # bound; the in-house 3xTF32 kernel (`gemm`, used by the spectral layer) pays off only for large operands.
         use_own_gemm = self.own_gemm
 
-        def fc_fwd(i, a_in):
+        def gemm_epi(A, Bm, out, bias, M_, N_, K_, ta, tb, epi, aux, seed):
+            rc = lib.gcnb_gemm_epilogue_f32(vp(A), vp(Bm), vp(out), None if bias is None else vp(bias), M_, N_, K_,
+                                            A.shape[1], Bm.shape[1], out.shape[1], ta, tb, epi,
+                                            None if aux is None else vp(aux), 0 if aux is None else aux.shape[1],
+                                            self.keep, seed, vp(self.state), stream)
+            self._lib.check(rc, "gcnb_gemm_epilogue_f32")
+            return out
+
+        def fc_fwd(i, a_in, hidden):
+            """FC layer i; hidden layers apply ReLU + dropout (fused into the GEMM store on the in-house path)."""
             W = m.fc_weights[i]
             if not use_own_gemm:
-                return torch.addmm(m.fc_bias[i], a_in, W)
+                a = torch.addmm(m.fc_bias[i], a_in, W)
+                if hidden:
+                    rc = lib.gcnb_relu_dropout_fwd_f32(vp(a), a.shape[0], a.shape[1], a.shape[1], self.keep, 0x5eed + i,
+                                                       vp(self.state), stream)
+                    self._lib.check(rc, "gcnb_relu_dropout_fwd_f32")
+                return a
             out = torch.empty((a_in.shape[0], W.shape[1]), dtype=torch.float32, device=x.device)
+            if hidden:
+                return gemm_epi(a_in, W, out, m.fc_bias[i], a_in.shape[0], W.shape[1], W.shape[0], 0, 0,
+                                self._lib.EPI_RELU_DROPOUT, None, 0x5eed + i)
             return gemm(a_in, W, out, m.fc_bias[i], a_in.shape[0], W.shape[1], W.shape[0], 0, 0)
 
         acts = [h0]
         for i in range(nfc - 1):
-            a = fc_fwd(i, acts[-1])
-            rc = lib.gcnb_relu_dropout_fwd_f32(vp(a), a.shape[0], a.shape[1], a.shape[1], self.keep, 0x5eed + i,
-                                               vp(self.state), stream)
-            self._lib.check(rc, "gcnb_relu_dropout_fwd_f32")
-            acts.append(a)
-        logits = fc_fwd(nfc - 1, acts[-1])
+            acts.append(fc_fwd(i, acts[-1], True))
+        logits = fc_fwd(nfc - 1, acts[-1], False)
         B, ncls = logits.shape
         d = torch.empty_like(logits)
         rows = torch.empty(B, dtype=torch.float32, device=x.device)
@@ -291,14 +304,17 @@ class FusedTrainer:
             if use_own_gemm:
                 gemm(acts[i], d, self.gview[id(W)], None, W.shape[0], W.shape[1], d.shape[0], 1, 0)   # dW = a^T d
                 dn = torch.empty((d.shape[0], W.shape[0]), dtype=torch.float32, device=x.device)
-                d = gemm(d, W, dn, None, d.shape[0], W.shape[0], W.shape[1], 0, 1)                    # dx = d W^T
+                if i > 0:  # dx = d W^T through the ReLU/dropout mask of the activation it feeds, in the same launch
+                    d = gemm_epi(d, W, dn, None, d.shape[0], W.shape[0], W.shape[1], 0, 1, self._lib.EPI_MASK, acts[i], 0)
+                else:
+                    d = gemm(d, W, dn, None, d.shape[0], W.shape[0], W.shape[1], 0, 1)
             else:
                 torch.mm(acts[i].t(), d, out=self.gview[id(W)])
                 d = torch.mm(d, W.t())
-            if i > 0:
-                rc = lib.gcnb_relu_dropout_bwd_f32(vp(d), vp(acts[i]), d.shape[0], d.shape[1], d.shape[1], d.shape[1],
-                                                   self.keep, stream)
-                self._lib.check(rc, "gcnb_relu_dropout_bwd_f32")
+                if i > 0:
+                    rc = lib.gcnb_relu_dropout_bwd_f32(vp(d), vp(acts[i]), d.shape[0], d.shape[1], d.shape[1], d.shape[1],
+                                                       self.keep, stream)
+                    self._lib.check(rc, "gcnb_relu_dropout_bwd_f32")
         for lo in range(0, nfc, 4):
             grp = list(range(lo, min(nfc, lo + 4)))
             n = len(grp)

@@ -176,6 +176,16 @@ GCNB_API int gcnb_softmax_xent_f32(const float* logits, const int64_t* labels, f
 GCNB_API int gcnb_gemm_f32(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int lda,
                   int ldb, int ldc, int transA, int transB, gcnb_stream_t stream);
 
+/* The same GEMM with the FC layer's element-wise step fused into the store (one launch less per layer and pass):
+ *   GCNB_EPI_RELU_DROPOUT: C = dropout(relu(op(A) op(B) + bias)) -- cgcnn.fc, models_gcn.py:650-656 + tf.nn.dropout :677;
+ *     the mask is the one gcnb_relu_dropout_fwd_f32 draws for the same (keep, seed, *step) on a [M x N] matrix;
+ *   GCNB_EPI_MASK: C = aux[m][n] > 0 ? (op(A) op(B)) / keep : 0 -- its adjoint applied to dx = d W^T, aux = the
+ *     forward activation (what gcnb_relu_dropout_bwd_f32 does in a separate pass). */
+enum { GCNB_EPI_NONE = 0, GCNB_EPI_RELU_DROPOUT = 1, GCNB_EPI_MASK = 2 };
+GCNB_API int gcnb_gemm_epilogue_f32(const float* A, const float* B, float* C, const float* bias, int M, int N, int K,
+                                    int lda, int ldb, int ldc, int transA, int transB, int epilogue, const float* aux,
+                                    int ld_aux, float keep, unsigned seed, const float* step, gcnb_stream_t stream);
+
 /* y = dropout(relu(x)) in place on x[rows][ld] (first `cols` columns): keep-probability `keep`, kept values scaled by
  * 1/keep (tf.nn.relu + tf.nn.dropout, models_gcn.py:655,677).  Counter-based generator keyed by (seed, *step, index);
  * step is a device counter so that CUDA-graph replays draw fresh masks.  keep >= 1 is a plain ReLU. */

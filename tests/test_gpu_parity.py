@@ -549,6 +549,30 @@ def test_head_pieces(dev, graph_l4):
         assert rc == 0
         ref = (A.double().t() if ta else A.double()) @ (Bm.double().t() if tb else Bm.double()) + bias.double()
         assert float((Cc.double() - ref).abs().max()) <= 1e-5 * float(ref.abs().max()), (Mg, Ng, Kg, ta, tb)
+    # fused FC epilogues: bit-identical to the GEMM followed by the stand-alone ReLU/dropout kernels (same mask, same step)
+    for (Mg, Ng, Kg) in ((512, 512, 25), (512, 256, 512), (70, 45, 33), (512, 4096, 64)):
+        A = T(rng.randn(Mg, Kg).astype(np.float32), dev)
+        Bm = T(rng.randn(Kg, Ng).astype(np.float32), dev)
+        bias = T(rng.randn(Ng).astype(np.float32), dev)
+        stp = torch.tensor([0.0, 0.0, 0.0, 5.0], device=dev)
+        for keep in (0.5, 1.0):
+            two, one = torch.empty(Mg, Ng, device=dev), torch.empty(Mg, Ng, device=dev)
+            assert lib.gcnb_gemm_f32(vp(A), vp(Bm), vp(two), vp(bias), Mg, Ng, Kg, Kg, Ng, Ng, 0, 0, stream) == 0
+            assert lib.gcnb_relu_dropout_fwd_f32(vp(two), Mg, Ng, Ng, keep, 11, vp(stp), stream) == 0
+            assert lib.gcnb_gemm_epilogue_f32(vp(A), vp(Bm), vp(one), vp(bias), Mg, Ng, Kg, Kg, Ng, Ng, 0, 0, _lib.EPI_RELU_DROPOUT,
+                                              None, 0, keep, 11, vp(stp), stream) == 0
+            assert torch.equal(one, two), (Mg, Ng, Kg, keep)
+            # adjoint: d W^T masked by the activation
+            dd = T(rng.randn(Mg, Ng).astype(np.float32), dev)
+            Wt_ = T(rng.randn(Kg, Ng).astype(np.float32), dev)           # dx[Mg x Kg] = dd[Mg x Ng] Wt_^T
+            act = T(np.maximum(rng.randn(Mg, Kg), 0).astype(np.float32), dev)
+            two, one = torch.empty(Mg, Kg, device=dev), torch.empty(Mg, Kg, device=dev)
+            assert lib.gcnb_gemm_f32(vp(dd), vp(Wt_), vp(two), None, Mg, Kg, Ng, Ng, Ng, Kg, 0, 1, stream) == 0
+            assert lib.gcnb_relu_dropout_bwd_f32(vp(two), vp(act), Mg, Kg, Kg, Kg, keep, stream) == 0
+            assert lib.gcnb_gemm_epilogue_f32(vp(dd), vp(Wt_), vp(one), None, Mg, Kg, Ng, Ng, Ng, Kg, 0, 1, _lib.EPI_MASK, vp(act), Kg,
+                                              keep, 0, None, stream) == 0
+            assert torch.equal(one, two), (Mg, Ng, Kg, keep)
+    assert lib.gcnb_gemm_epilogue_f32(vp(A), vp(Bm), vp(one), None, 4, 4, 4, 4, 4, 4, 0, 0, _lib.EPI_MASK, None, 0, 0.5, 0, None, stream) != 0
     # cross-entropy forward+backward and the optimiser clock
     lg = T(rng.randn(512, 22).astype(np.float32) * 3, dev)
     lab = T(rng.randint(0, 21, 512), dev, torch.long)
