@@ -8,6 +8,8 @@
 // memory filled with guarded loads (any M, N, K, any alignment, either operand transposed).
 #include <algorithm>
 
+#include <cooperative_groups.h>
+
 #include "fused_common.cuh"
 
 namespace gcnb {
@@ -30,6 +32,7 @@ struct GemmArgs {
   float keep, inv_keep;
   unsigned seed;
   const float* step;
+  int splits;  // small kernel: K is split over a thread-block cluster of this many CTAs (1 = no split)
 };
 
 struct Epilogue {
@@ -186,8 +189,13 @@ __global__ void __launch_bounds__(128) k_gemm_small_3xtf32(const GemmArgs g) {
 #pragma unroll
     for (int c = 0; c < 4; ++c) acc[j][c] = 0.f;
 
+  // split-K over the CTAs of a cluster (blockIdx.z = rank): each takes a contiguous range of k-tiles
+  const int nk_all = (g.K + SBK - 1) / SBK;
+  const int per = (nk_all + g.splits - 1) / g.splits;
+  const int kt0 = (int)blockIdx.z * per;
+  const int nk = max(0, min(nk_all, kt0 + per) - kt0);
   auto issue = [&](int kt, int st) {
-    const int k0 = kt * SBK;
+    const int k0 = (kt0 + kt) * SBK;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int idx = tid + i * 128;  // 0..1023
@@ -205,7 +213,6 @@ __global__ void __launch_bounds__(128) k_gemm_small_3xtf32(const GemmArgs g) {
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
-  const int nk = (g.K + SBK - 1) / SBK;
   for (int s = 0; s < SST - 1; ++s) {
     if (s < nk) issue(s, s);
     else asm volatile("cp.async.commit_group;" ::: "memory");
@@ -234,6 +241,34 @@ __global__ void __launch_bounds__(128) k_gemm_small_3xtf32(const GemmArgs g) {
         mma_3xtf32(acc[j], ah, al, bh0, bh1, bl0, bl1);
       }
     }
+  }
+  if (g.splits > 1) {
+    // Deterministic split-K reduction through distributed shared memory: every rank but 0 parks its partial tile in
+    // its own shared memory, rank 0 adds them in rank order and runs the epilogue.
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();  // the pipeline buffers are dead: reuse the first one for the partial tile
+    float* part = &As[0][0];
+    const unsigned rank = cluster.block_rank();
+    if (rank != 0) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) part[(j * 4 + c) * 128 + tid] = acc[j][c];
+    }
+    cluster.sync();
+    if (rank == 0) {
+      for (unsigned r = 1; r < cluster.num_blocks(); ++r) {
+        const float* rp = cluster.map_shared_rank(part, r);
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc[j][c] += rp[(j * 4 + c) * 128 + tid];
+      }
+    }
+    cluster.sync();  // the partials must stay alive until rank 0 has read them
+    if (rank != 0) return;
   }
   const Epilogue epi(g);
 #pragma unroll
@@ -264,9 +299,34 @@ int launch_gemm_epi(const float* A, const float* B, float* C, const float* bias,
                     int ldc, int ta, int tb, int epilogue, const float* aux, int ld_aux, float keep, unsigned seed,
                     const float* step, cudaStream_t st) {
   GemmArgs g{A, B, C, bias, M, N, K, lda, ldb, ldc, ta, tb, epilogue, aux, ld_aux, keep, keep >= 1.f ? 1.f : 1.f / keep,
-             seed, step};
+             seed, step, 1};
+  g.splits = 1;
   if ((long long)ceil_div(N, GBN) * ceil_div(M, GBM) < 2 * 148) {  // not enough 64x64 tiles to fill the chip
     dim3 grid((unsigned)ceil_div(N, SBN), (unsigned)ceil_div(M, SBM));
+    // A handful of output tiles with a long K (weight gradients of the FC layers: [25 x 512], [256 x 22] over K = 512)
+    // leaves most SMs idle behind a serial walk over K: split K over a cluster of up to 8 CTAs.
+    const int ctas = (int)(grid.x * grid.y), nk = ceil_div(K, SBK);
+    int splits = 1;
+    while (splits < 8 && splits * 2 <= nk / 2 && ctas * splits * 2 <= 148) splits *= 2;
+    if (splits > 1) {
+      g.splits = splits;
+      grid.z = splits;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = grid;
+      cfg.blockDim = dim3(128);
+      cfg.dynamicSmemBytes = 0;
+      cfg.stream = st;
+      cudaLaunchAttribute attr;
+      attr.id = cudaLaunchAttributeClusterDimension;
+      attr.val.clusterDim.x = 1;
+      attr.val.clusterDim.y = 1;
+      attr.val.clusterDim.z = splits;
+      cfg.attrs = &attr;
+      cfg.numAttrs = 1;
+      GCNB_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_small_3xtf32, g));
+      GCNB_LAUNCH_CHECK("k_gemm_small_3xtf32 (cluster split-K)");
+      return GCNB_OK;
+    }
     k_gemm_small_3xtf32<<<grid, 128, 0, st>>>(g);
     GCNB_LAUNCH_CHECK("k_gemm_small_3xtf32");
     return GCNB_OK;

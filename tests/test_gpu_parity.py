@@ -392,12 +392,14 @@ def test_fused_trainer_matches_autograd_trainer(dev, graph_l4):
         g_fused = tb.flat_g + 5e-4 * p0 * tb.decay              # the update kernel adds the L2 term itself
         scale = float(g_auto.abs().max())
         assert float((g_auto - g_fused).abs().max()) <= 1e-4 * scale, (graph, own)
+        big = g_auto.abs() > 1e-3 * scale
         for _ in range(2):
             ta.step(x, y)
             tb.step(x, y)
+            big &= ta.flat_grad.abs() > 1e-3 * scale            # ... at every one of the steps
         torch.cuda.synchronize()
         pa = torch.cat([p.detach().reshape(-1) for p in a.parameters()])
-        big = g_auto.abs() > 1e-3 * scale
+        assert int(big.sum()) > 1000
         assert float((pa - tb.flat_p)[big].abs().max()) <= 2e-4, (graph, own)  # three steps of size 1e-3
 
 
