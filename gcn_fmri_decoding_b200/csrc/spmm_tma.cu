@@ -3,11 +3,13 @@
 //   out[m][:] = alpha * sum_j val_j * src[col_j][:] + beta * add[m][:] + beta2 * add2[m][:]
 //
 // The state is vertex-major, one contiguous row of C = B*Fin floats per vertex, so the neighbour rows an output
-// row needs are whole contiguous spans: the producer warp of a persistent CTA turns every CSR entry into one
+// row needs are whole contiguous spans: the four producer warps of a persistent CTA turn every CSR entry into one
 // cp.async.bulk copy (global -> shared, mbarrier complete_tx) into a ring of stages -- up to 8 neighbour rows
 // plus the two "add" rows per stage -- and the eight consumer warps reduce a stage with conflict-free LDS.128
 // and write the result with coalesced 16-byte stores.  No register staging, NS stages (~30 KB each) in flight
 // per SM.  Rows longer than 8 entries take several stages; the partial sum stays in registers in between.
+// (One producer warp is instruction bound at ~1800 cycles per row -- measured 211 us per order against 104 us
+// for the register path; four of them, each owning its own stages, reach 99.7 us.)
 // Work items (row, column chunk of <= 1024 floats) are dealt round-robin so that concurrently running CTAs
 // work on neighbouring rows and share their neighbour rows in L2.
 //
