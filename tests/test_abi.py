@@ -32,6 +32,17 @@ def test_workspace_queries_are_pure_host_calls():
     assert fwd >= 4 * (5 * 400 * 512 * 15 + 400 * 512 * 32)
     assert bwd > fwd
     assert lib.gcnb_spectral_workspace_bytes(8, 100, 8, 16, 4, 1) > lib.gcnb_spectral_workspace_bytes(8, 100, 8, 16, 4, 0)
+    # vertex-level graph (BASELINE config 5): the general path needs the whole K-order stack (+ the G stack for dx)
+    B, M, nnz, Fin, Fout, K = 64, 32492, 196396, 15, 32, 25
+    slab = 4 * B * M * Fin
+    fwd5 = lib.gcnb_cheb_workspace_bytes(B, M, nnz, Fin, Fout, K, 1, 0, 0, _lib.ALGO_AUTO)
+    bwd5 = lib.gcnb_cheb_workspace_bytes(B, M, nnz, Fin, Fout, K, 1, 1, 1, _lib.ALGO_AUTO)
+    assert K * slab < fwd5 < K * slab + 8 * B * M * (Fout + 8)
+    assert 2 * K * slab < bwd5 < 2 * K * slab + 16 * B * M * (Fout + 8)
+    # saved-basis width: padded feature count for graphs the fused kernels hold, Fin (vertex-major stack) otherwise
+    assert lib.gcnb_cheb_stack_width(512, 400, 3684, 15, 32, 5, 4) == 16
+    assert lib.gcnb_cheb_stack_width(B, M, nnz, Fin, Fout, K, 1) == Fin
+    assert lib.gcnb_cheb_fused_supported(B, M, nnz, Fin, Fout, K, 1, 0, 0) == 0
 
 
 def test_missing_library_fails_loudly(monkeypatch):
