@@ -67,9 +67,16 @@ def cpu_network(seed=7):
     return perm, Ls, params, fcs
 
 
-def cpu_step_rate(n_windows, reps, warm, cores):
-    """windows/s of the oracle's training step (fwd+loss+bwd; fp32 as the reference runs) on `cores` threads."""
+def cpu_step_rate(n_windows, reps, warm, cores, mode=None):
+    """Seconds per oracle training step (fwd+loss+bwd; fp32 as the reference runs) on `cores` host threads.
+
+    SciPy's CSR x dense product is single-threaded, so the step is parallelised over 32-window chunks by a thread
+    pool; BLAS is pinned to ONE thread inside the pool (cores x cores oversubscription made the round-1 number 5x
+    too slow).  mode "pool" = that; "blas" = no pool, BLAS on all cores; None = time both once, keep the faster.
+    Returns (times, mode)."""
     from concurrent.futures import ThreadPoolExecutor
+
+    from threadpoolctl import threadpool_limits
 
     from gcn_fmri_decoding_b200 import graclus, synth
     from oracle import layers_np as O
@@ -79,18 +86,34 @@ def cpu_step_rate(n_windows, reps, warm, cores):
     lab = synth.labels(n_windows)
     chunks = [c for c in np.array_split(np.arange(n_windows), max(1, n_windows // 32)) if len(c)]
 
-    def one():
-        with ThreadPoolExecutor(cores) as ex:
-            list(ex.map(lambda c: O.network_step(x[c], lab[c], Ls, params, fcs, REG, dtype=np.float32), chunks))
+    def step(c):
+        O.network_step(x[c], lab[c], Ls, params, fcs, REG, dtype=np.float32)
 
+    def one_pool():
+        with threadpool_limits(limits=1):
+            with ThreadPoolExecutor(cores) as ex:
+                list(ex.map(step, chunks))
+
+    def one_blas():
+        with threadpool_limits(limits=cores):
+            step(np.arange(n_windows))
+
+    def clock(fn):
+        t = time.perf_counter()
+        fn()
+        return time.perf_counter() - t
+
+    if mode is None:
+        one_pool(), one_blas()
+        mode = "pool" if clock(one_pool) <= clock(one_blas) else "blas"
+    one = one_pool if mode == "pool" else one_blas
     for _ in range(warm):
         one()
-    times = []
-    for _ in range(reps):
-        t = time.perf_counter()
-        one()
-        times.append(time.perf_counter() - t)
-    return times
+    return [clock(one) for _ in range(reps)], mode
+
+
+CPU_MODE_TEXT = {"pool": "thread pool over 32-window chunks, BLAS pinned to 1 thread per worker",
+                 "blas": "one chunk, BLAS on all cores"}
 
 
 def run_reference(args):
@@ -99,11 +122,11 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    probe = cpu_step_rate(64, 1, 1, cores)[0]
-    rate = 64 / probe
+    probe, mode = cpu_step_rate(256, 1, 0, cores)
+    rate = 256 / probe[0]
     budget = 120.0 / max(1, args.steps + args.warmup)
     n = int(min(BATCH, max(32, (rate * budget) // 32 * 32)))
-    times = cpu_step_rate(n, args.steps, args.warmup, cores)
+    times, mode = cpu_step_rate(n, args.steps, args.warmup, cores, mode)
     total = float(np.sum(times))
     value = n * args.steps / total
     line = {
@@ -112,8 +135,8 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": "%d windows per step" % n},
         "cpu_baseline": {"value": value, "unit": "windows/s", "cores": cores, "kind": "port",
-                         "sample": "%d-window training step (fwd+loss+bwd) of the NumPy/SciPy oracle, %d steps, "
-                                   "thread pool over 32-window chunks + BLAS" % (n, args.steps)},
+                         "sample": "%d-window training step (fwd+loss+bwd, no optimiser update) of the NumPy/SciPy "
+                                   "oracle, %d steps, %s" % (n, args.steps, CPU_MODE_TEXT[mode])},
         "e2e": {"value": value, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -430,10 +453,10 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        times = cpu_step_rate(BATCH, 5, 2, cores)
+        times, mode = cpu_step_rate(BATCH, 5, 2, cores)
         cpu = {"value": BATCH / float(np.median(times)), "unit": "windows/s", "cores": cores, "kind": "port",
-               "sample": "512-window training step (fwd+loss+bwd) of the NumPy/SciPy oracle, median of 5 after 2 warm-ups, "
-                         "thread pool over 32-window chunks + BLAS"}
+               "sample": "512-window training step (fwd+loss+bwd, no optimiser update) of the NumPy/SciPy oracle, median "
+                         "of 5 after 2 warm-ups, " + CPU_MODE_TEXT[mode]}
 
     if rank == 0:
         line = {

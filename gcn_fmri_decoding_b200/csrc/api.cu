@@ -243,6 +243,9 @@ int gcnb_cheb_fwd_f32(const float* x, const int32_t* perm, int M_in, const gcnb_
   }
   const long long pooled_rows = (long long)B * ceil_div(s.M, p);
   if (algo == GCNB_ALGO_FUSED || (algo == GCNB_ALGO_AUTO && fused_ok)) {
+    // tensor-core (tcgen05/TMEM) kernel when the shape fits it; it writes the same xstack layout as the mma.sync one
+    if (umma_fwd_supported(s) && (xstack == nullptr || stack_layout(s) == 1))
+      return umma_cheb_fwd(x, perm, M_in, *L, W, bias, y, argmax, y_mean, xstack, s, bias_mode, relu, st);
     rc = fused_cheb_fwd(x, perm, M_in, *L, W, bias, y, argmax, y_mean, xstack, s, bias_mode, relu, ws, st);
     if (rc == GCNB_OK && y_mean != nullptr && Fout > 32) rc = launch_mean_f(y, y_mean, pooled_rows, Fout, st);
     return rc;

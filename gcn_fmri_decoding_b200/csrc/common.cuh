@@ -109,6 +109,12 @@ bool spmm_tma_supported(const gcnb_csr& L, long long C, const float* src, const 
 int spmm_tma(const gcnb_csr& L, const float* src, const float* add, const float* add2, float* out, long long C,
              float alpha, float beta, float beta2, cudaStream_t st);
 
+// ---- tcgen05 / TMEM forward for shared-memory resident graphs, cheb_fwd_umma.cu -------------------------
+bool umma_fwd_supported(const LayerShape& s);
+int umma_cheb_fwd(const float* x, const int32_t* perm, int M_in, const gcnb_csr& L, const float* W, const float* bias,
+                  float* y, uint8_t* argmax, float* y_mean, float* xstack, const LayerShape& s, int bias_mode, int relu,
+                  cudaStream_t st);
+
 // ---- fused (shared-memory resident) path, fused_fwd.cu / fused_bwd.cu ------------------------
 bool fused_fwd_supported(const LayerShape& s);
 bool fused_bwd_supported(const LayerShape& s, bool need_dx);
