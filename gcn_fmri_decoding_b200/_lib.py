@@ -34,6 +34,7 @@ SIGNATURES = {
     "gcnb_launch_count": (C.c_ulonglong, []),
     "gcnb_cheb_fused_supported": (_i, [_i] * 9),
     "gcnb_cheb_workspace_bytes": (_z, [_i] * 10),
+    "gcnb_cheb_fwd_describe": (_i, [_i] * 7 + [C.c_char_p, _z]),
     "gcnb_cheb_stack_width": (_i, [_i] * 7),
     "gcnb_cheb_fwd_f32": (_i, [_p, _p, _i, _CSRP, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _z, _p]),
     "gcnb_cheb_bwd_f32": (_i, [_p, _p, _i, _p, _p, _p, _i, _p, _CSRP, _CSRP, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _z, _p]),
@@ -81,6 +82,13 @@ def lib():
             fn.argtypes = args
         _lib = handle
     return _lib
+
+
+def describe_fwd(B, M, nnz, Fin, Fout, K, p):
+    """Which forward kernel AUTO dispatch picks for this layer shape, and its tile geometry."""
+    buf = C.create_string_buffer(512)
+    check(lib().gcnb_cheb_fwd_describe(B, M, nnz, Fin, Fout, K, p, buf, 512), "gcnb_cheb_fwd_describe")
+    return buf.value.decode()
 
 
 def last_error():

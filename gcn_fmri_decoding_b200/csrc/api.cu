@@ -206,6 +206,15 @@ int gcnb_cheb_stack_width(int B, int M, int nnz, int Fin, int Fout, int K, int p
   return layout == 1 ? fused_feature_pad(Fin) : layout == 2 ? Fin : 0;
 }
 
+int gcnb_cheb_fwd_describe(int B, int M, int nnz, int Fin, int Fout, int K, int p, char* out, size_t n) {
+  if (!out || n == 0) return GCNB_ERR_INVALID;
+  LayerShape s{B, M, nnz, Fin, Fout, K, p};
+  if (umma_fwd_describe(s, out, n) > 0) return GCNB_OK;
+  snprintf(out, n, "%s", fused_fwd_supported(s) ? "k_cheb_fwd_fused: mma.sync, shared-memory resident"
+                                                  : "general path: HBM-resident state (k_spmm_tma + k_stack_contract)");
+  return GCNB_OK;
+}
+
 int gcnb_cheb_fused_supported(int B, int M, int nnz, int Fin, int Fout, int K, int p, int backward, int need_dx) {
   LayerShape s{B, M, nnz, Fin, Fout, K, p};
   return backward ? (fused_bwd_supported(s, need_dx != 0) ? 1 : 0) : (fused_fwd_supported(s) ? 1 : 0);

@@ -15,8 +15,10 @@
 //     (the hardware truncation of kind::tf32 IS the "hi" part of X; only the bf16 remainder is stored separately).
 //     Accumulators stay in TMEM across all K orders, double-buffered across tiles.
 //   * 4 epilogue warps drain the finished tile of the PREVIOUS iteration from TMEM while the sparse warps already
-//     work on the next one: tcgen05.ld (thread = vertex, 32 filters), bias, ReLU, max over p consecutive vertices
-//     with the first-maximum rule of MaxPoolGrad, y / arg-max / mean-over-filters stores.
+//     work on the next one.  State rows are kept SIBLING-MAJOR: vertex v = p*j + i of window-slab s lives in row
+//     i*BQ + s*Q + j, so the p members of a pooling window sit in the SAME TMEM lane of p different accumulator
+//     blocks and mpool1 is a thread-local running maximum (first-maximum rule of MaxPoolGrad) -- no shuffles, no
+//     shared-memory transpose; thread = pooled vertex, 32 filters: bias, ReLU, y / arg-max / mean-over-filters.
 // x is read from HBM once, y written once; the K-stack only goes to HBM when the caller asks for it (training).
 #include <algorithm>
 #include <cstdlib>
@@ -33,6 +35,17 @@ static constexpr int kMmaWarp = 4;    // warp 4
 static constexpr int kThreads = (kSparseWarps + kEpiWarps + 1) * 32;
 static constexpr int kBarOrder = 1;   // named barrier: sparse warps + MMA warp, once per Chebyshev order
 
+#ifdef GCNB_TRACE
+// debug builds only (-DGCNB_TRACE): clock64 stamps of CTA 0's roles, read back by gcnb_debug_read_trace
+__device__ long long g_trace[4][512];
+#define TRACE(region, cond)                                                        \
+  do {                                                                             \
+    if (blockIdx.x == 0 && lane == 0 && (cond) && tr_n < 512) g_trace[region][tr_n++] = clock64(); \
+  } while (0)
+#else
+#define TRACE(region, cond) do { } while (0)
+#endif
+
 struct UmmaFwdParams {
   const float* x;
   const int32_t* perm;
@@ -48,46 +61,61 @@ struct UmmaFwdParams {
   float* y_mean;
   float* xstack;
   int B, M, Fin, Fout, K, p, log2p, bias_mode, relu;
-  int NS;        // slabs per tile
+  int NS;        // window-slabs per tile (each holds G windows side by side in its rows)
   int S;         // windows per tile = NS * G
-  int MT;        // 128-row MMA tiles per slab
+  int Q;         // rows of one window-slab inside a sibling block = M/p rounded up to 8
+  int BQ;        // rows of one sibling block = NS * Q
+  int T;         // 128-row MMA tiles per sibling block
   int NG;        // groups of 4 rows
   int ntiles;
   int nlo;       // lo buffers per slab (2, or 1 when shared memory is short)
   int nacc;      // TMEM accumulator buffers (2, or 1)
-  int acc_cols;  // TMEM columns of one accumulator buffer = S * MT * 32
+  int acc_cols;  // TMEM columns of one accumulator buffer = G * p * T * 32
   int tmem_cols; // allocated columns (power of two)
-  int slab_rows; // rows of one slab incl. the zero row (multiple of 8)
+  int slab_rows; // rows of one state buffer incl. the zero row (multiple of 8)
+  int debug;     // GCNB_TRACE builds only: bit0 skip the gathers, bit1 skip the tcgen05.mma issue
   // byte offsets into dynamic shared memory
-  int off_lo, off_wh, off_wl, off_wb, off_ent, off_grow, off_gslot, off_glen, off_src, off_rlen, off_sorted, off_bias,
-      off_bar;
+  int off_lo, off_wh, off_wl, off_wb, off_ent, off_grow, off_grho, off_gslot, off_glen, off_src, off_rlen, off_sorted, off_bias,
+      off_bar, off_rp;
 };
 
 // ---------------------------------------------------------------------------------------------------------------
-template <int FP>
+template <int FP, int MAXI>
 __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdParams P) {
   extern __shared__ __align__(1024) unsigned char smem[];
   constexpr int G = 32 / FP;    // windows per 128-byte row
   constexpr int CPW = FP / 4;   // 16-byte chunks per window
   const uint32_t sb = smem_u32(smem);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int M = P.M, K = P.K, NS = P.NS;
-  const uint32_t slab_bytes = (uint32_t)P.slab_rows * 128u, lo_bytes = (uint32_t)P.slab_rows * 64u;
-  // slab (buffer u, slab s) at sb + (u*NS + s)*slab_bytes ; lo (buffer u, slab s) at sb + off_lo + (u*NS + s)*lo_bytes
-  int* grow = reinterpret_cast<int*>(smem + P.off_grow);       // [NG*4] row of (group, slot), -1 = none
+  const int M = P.M, K = P.K, NS = P.NS, Q = P.Q, BQ = P.BQ;
+  const int pm1 = P.p - 1, log2p = P.log2p;
+  const uint32_t buf_bytes = (uint32_t)P.slab_rows * 128u, lo_bytes = (uint32_t)P.slab_rows * 64u;
+  // state buffer u at sb + u*buf_bytes ; remainder (lo) buffer u at sb + off_lo + u*lo_bytes
+  int* grow = reinterpret_cast<int*>(smem + P.off_grow);       // [NG*4] vertex of (group, slot), -1 = none
+  int* grho = reinterpret_cast<int*>(smem + P.off_grho);       // [NG*4] its state row inside window-slab 0
   int2* gslot = reinterpret_cast<int2*>(smem + P.off_gslot);   // [NG*4] (first entry pair, row length)
   int* glen = reinterpret_cast<int*>(smem + P.off_glen);       // [NG] entry pairs of the longest row of the group
   int* src_row = reinterpret_cast<int*>(smem + P.off_src);     // [M] source row of the raw window, -1 = zero
   int* rlen = reinterpret_cast<int*>(smem + P.off_rlen);       // [NG*4]
   int* sorted = reinterpret_cast<int*>(smem + P.off_sorted);   // [NG*4]
+  int* rp = reinterpret_cast<int*>(smem + P.off_rp);           // [M+1] row pointers
   float* bias_s = reinterpret_cast<float*>(smem + P.off_bias); // [32]
   const uint32_t bar0 = sb + P.off_bar;
   auto bar_mma = [bar0](uint32_t i) { return bar0 + i * 8u; };          // tcgen05.mma of order n done (n & 1)
   auto bar_full = [bar0](uint32_t i) { return bar0 + 16u + i * 8u; };   // accumulator buffer i complete
   auto bar_empty = [bar0](uint32_t i) { return bar0 + 32u + i * 8u; };  // accumulator buffer i drained
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + P.off_bar + 48);
+  // state row of vertex v inside window-slab 0 (sibling-major)
+  auto rho = [=](int v) { return (v & pm1) * BQ + (v >> log2p); };
 
   // ---- prologue (all warps) ---------------------------------------------------------------------------------
+#ifdef GCNB_TRACE
+  int tr_p = 0;
+#define TRACEP() do { if (blockIdx.x == 0 && tid == 160) g_trace[1][tr_p++] = clock64(); } while (0)
+#else
+#define TRACEP() do { } while (0)
+#endif
+  TRACEP();
   if ((sb & 1023u) != 0) __trap();  // the swizzled operand layouts need a 1 KB aligned base
   if (tid == 0) {
     mbar_init(bar_mma(0), 1); mbar_init(bar_mma(1), 1);
@@ -96,8 +124,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
     mbar_init_fence();
   }
   if (warp == kMmaWarp) tmem_alloc(sb + P.off_bar + 48, (uint32_t)P.tmem_cols);
-  // zero the state (slabs + lo): the zero row behind every slab and the rows an MMA tile reads past M stay zero
-  for (uint32_t a = tid * 16u; a < (uint32_t)P.off_wh; a += kThreads * 16u) sts128(sb + a, make_float4(0.f, 0.f, 0.f, 0.f));
+  // zero the state buffers: the zero row behind every buffer and the padding rows of the blocks stay zero (the
+  // remainder buffers need no initialisation -- garbage there only reaches accumulator rows nobody reads -- and
+  // host the prologue's scratch tables rlen / sorted / rp until the first order overwrites them)
+  for (uint32_t a = tid * 16u; a < (uint32_t)P.off_lo; a += kThreads * 16u) sts128(sb + a, make_float4(0.f, 0.f, 0.f, 0.f));
   // taps: tf32 hi / lo and bf16 images, contraction index kk = k*FP + f  (W row = f*K + k, models_gcn.py:611-615)
   for (int idx = tid; idx < K * FP * 32; idx += kThreads) {
     const int o = idx & 31, kk = idx >> 5, k = kk / FP, f = kk - k * FP;
@@ -111,7 +141,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
   // operator image: rows sorted by decreasing length; entries re-encoded as (gather code, value) in CSR order,
   // every row starting on an even entry so that one LDS.128 fetches two entries
   const int M4 = P.NG * 4;
-  for (int r = tid; r < M4; r += kThreads) rlen[r] = r < M ? __ldg(P.rowptr + r + 1) - __ldg(P.rowptr + r) : -1;
+  for (int r = tid; r <= M; r += kThreads) rp[r] = __ldg(P.rowptr + r);
   for (int r = tid; r < M; r += kThreads) {
     int s = r;
     if (P.perm) { s = __ldg(P.perm + r); if (s < 0 || s >= P.M_in) s = -1; }
@@ -120,47 +150,95 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
   if (tid < 32) bias_s[tid] = (P.bias_mode == GCNB_BIAS_PER_FILTER && tid < P.Fout) ? __ldg(P.bias + tid) : 0.f;
   {
     const int npairs = (P.nnz + M + 2) >> 1;  // zero entries everywhere (padding entry of odd rows: zero row, 0.0)
-    const uint32_t zc = gather_code(M);
+    const uint32_t zc = gather_code(P.p * BQ);
     int4* e4 = reinterpret_cast<int4*>(smem + P.off_ent);
     for (int i = tid; i < npairs; i += kThreads) e4[i] = make_int4((int)zc, 0, (int)zc, 0);
   }
+  TRACEP();
   __syncthreads();
-  for (int r = tid; r < M4; r += kThreads) {
-    const int l = rlen[r];
-    int rank = 0;
-    for (int o = 0; o < M4; ++o) {
-      const int lo = rlen[o];
-      rank += (lo > l || (lo == l && o < r)) ? 1 : 0;
-    }
-    sorted[rank] = r;
-  }
+  TRACEP();
+  for (int r = tid; r < M4; r += kThreads) rlen[r] = r < M ? rp[r + 1] - rp[r] : -1;
   {
+    // one thread per entry (loads of a batch of four issued before any is used); its row by bisection of rp
     int2* ent = reinterpret_cast<int2*>(smem + P.off_ent);
-    for (int r = warp; r < M; r += kThreads / 32) {
-      const int beg = __ldg(P.rowptr + r), len = rlen[r];
-      const int es = (beg + r + 1) & ~1;
-      for (int j = lane; j < len; j += 32)
-        ent[es + j] = make_int2((int)gather_code(__ldg(P.col + beg + j)), __float_as_int(__ldg(P.val + beg + j)));
+    for (int e0 = 0; e0 < P.nnz; e0 += kThreads * 4) {
+      int cc[4];
+      float vv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * kThreads + tid;
+        cc[u] = e < P.nnz ? __ldg(P.col + e) : 0;
+        vv[u] = e < P.nnz ? __ldg(P.val + e) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * kThreads + tid;
+        if (e < P.nnz) {
+          int lo = 0, hi = M;  // largest r with rp[r] <= e
+          while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (rp[mid] <= e) lo = mid; else hi = mid;
+          }
+          ent[((rp[lo] + lo + 1) & ~1) + (e - rp[lo])] = make_int2((int)gather_code(rho(cc[u])), __float_as_int(vv[u]));
+        }
+      }
     }
   }
+  TRACEP();
+  __syncthreads();
+  TRACEP();
+  {
+    // counting sort of the rows by decreasing length (bins live in the entry-free tail of the scratch area); the
+    // order inside a bin is whatever the atomics give -- it only decides which rows share a warp step, never a sum
+    int* bins = sorted + M4;  // [M + 2]: bin b holds rows of length (M - b); the padding rows (length -1) come last
+    for (int i = tid; i < M + 2; i += kThreads) bins[i] = 0;
+    __syncthreads();
+    for (int r = tid; r < M4; r += kThreads) atomicAdd(&bins[M - rlen[r]], 1);
+    __syncthreads();
+    if (warp == 0) {  // exclusive prefix over the bins, one warp
+      int carry = 0;
+      for (int b0 = 0; b0 < M + 2; b0 += 32) {
+        const int i = b0 + lane;
+        const int v = i < M + 2 ? bins[i] : 0;
+        int x = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int y = __shfl_up_sync(0xffffffffu, x, d);
+          if (lane >= d) x += y;
+        }
+        if (i < M + 2) bins[i] = carry + x - v;
+        carry += __shfl_sync(0xffffffffu, x, 31);
+      }
+    }
+    __syncthreads();
+    for (int r = tid; r < M4; r += kThreads) sorted[atomicAdd(&bins[M - rlen[r]], 1)] = r;
+  }
+  TRACEP();
   __syncthreads();
   for (int i = tid; i < M4; i += kThreads) {
     const int r = sorted[i];
     if (r < M) {
       grow[i] = r;
-      gslot[i] = make_int2(((__ldg(P.rowptr + r) + r + 1) & ~1) >> 1, rlen[r]);
+      grho[i] = rho(r);
+      gslot[i] = make_int2(((rp[r] + r + 1) & ~1) >> 1, rlen[r]);
     } else {
       grow[i] = -1;
+      grho[i] = 0;
       gslot[i] = make_int2(0, 0);
     }
     if ((i & 3) == 0) glen[i >> 2] = r < M ? (rlen[r] + 1) >> 1 : 0;
   }
+  TRACEP();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  TRACEP();
 
-  const int NI = P.NG * NS;  // work items (row group, slab) of one order
+#ifdef GCNB_TRACE
+  int tr_n = 0;
+#endif
+  const int NI = P.NG * NS;  // work items (row group, window-slab) of one order
   const int nsync = (kSparseWarps + 1) * 32;
 
   if (warp > kMmaWarp) {
@@ -169,55 +247,67 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
     const int q = lane >> 3, c = lane & 7;
     const uint32_t c16 = (uint32_t)c << 4;
     const int gw = c / CPW, fc = c - gw * CPW;  // window inside the row, feature chunk inside the window
-    const uint32_t ent_base = sb + P.off_ent;
+    // The rows a lane works on never change: keep what the order loop needs of each of its (up to MAXI) items in
+    // registers -- state offset of its 16-byte chunk, address of its entry list, lengths, vertex id.
+    uint32_t it_off[MAXI], it_ent[MAXI], it_pk[MAXI];  // pk: own pairs | group pairs << 8 | window-in-tile << 16
+    int it_row[MAXI];                                   // vertex (-1: no work), for the global addresses
+#pragma unroll
+    for (int u = 0; u < MAXI; ++u) {
+      const int ii = u * kSparseWarps + ((u & 1) ? kSparseWarps - 1 - sw : sw);  // snake deal of the sorted groups
+      it_row[u] = -1;
+      it_off[u] = 0; it_ent[u] = sb + P.off_ent; it_pk[u] = 0;
+      if (ii < NI) {
+        const int g = ii / NS, s = ii - g * NS;
+        const int2 meta = gslot[g * 4 + q];
+        const int rr = grho[g * 4 + q] + s * Q;
+        it_row[u] = grow[g * 4 + q];
+        it_off[u] = slab_off(rr, c);
+        it_ent[u] = sb + P.off_ent + (uint32_t)meta.x * 16u;
+        it_pk[u] = (uint32_t)((meta.y + 1) >> 1) | ((uint32_t)glen[g] << 8) | ((uint32_t)(s * G + gw) << 16) |
+                   ((uint32_t)s << 24);
+      }
+    }
+    // lo offset of the same chunk (64-byte rows, SWIZZLE_64B), from the state offset
+    auto lo_of = [c](uint32_t off) {
+      const uint32_t rr = off >> 7;
+      return rr * 64u + ((((uint32_t)(c >> 1) ^ ((rr >> 1) & 3u)) << 4) | ((uint32_t)(c & 1) << 3));
+    };
     uint32_t n = 0;  // orders issued so far (all tiles)
     int base = 0;
+    TRACE(0, sw == 0);
     for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
       // ---- order 0: the (gathered, zero padded) raw windows -----------------------------------------------
       {
         const uint32_t lo_u = P.nlo == 2 ? (n & 1u) : 0u;
         if (P.nlo == 1 && n > 0) mbar_wait(bar_mma((n - 1) & 1), ((n - 1) >> 1) & 1);
-        for (int r0 = 0; r0 * kSparseWarps < NI; r0 += 4) {
-          float4 v[4];
-          int rows[4], slabs[4];
+        const uint32_t dst = sb + (uint32_t)base * buf_bytes, dlo = sb + P.off_lo + lo_u * lo_bytes;
+        float4 v[MAXI];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int r = r0 + u;
-            const int ii = r * kSparseWarps + ((r & 1) ? kSparseWarps - 1 - sw : sw);
-            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            rows[u] = -1;
-            slabs[u] = 0;
-            if (ii < NI) {
-              const int g = ii / NS, s = ii - g * NS;
-              const int row = grow[g * 4 + q];
-              rows[u] = row;
-              slabs[u] = s;
-              const int b = tile * P.S + s * G + gw;
-              if (row >= 0 && b < P.B) {
-                const int src = src_row[row];
-                if (src >= 0) {
-                  const float* xp = P.x + ((long long)b * P.M_in + src) * P.Fin + fc * 4;
-                  const int nf = P.Fin - fc * 4;
-                  if (nf > 0) v[u].x = __ldg(xp);
-                  if (nf > 1) v[u].y = __ldg(xp + 1);
-                  if (nf > 2) v[u].z = __ldg(xp + 2);
-                  if (nf > 3) v[u].w = __ldg(xp + 3);
-                }
-              }
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            if (rows[u] >= 0) {
-              const int s = slabs[u], row = rows[u];
-              store_state(sb + (uint32_t)(base * NS + s) * slab_bytes, sb + P.off_lo + (lo_u * NS + s) * lo_bytes, row, c,
-                          v[u]);
-              const int b = tile * P.S + s * G + gw;
-              if (P.xstack && b < P.B)
-                *reinterpret_cast<float4*>(P.xstack + ((long long)b * M + row) * FP + fc * 4) = v[u];
+        for (int u = 0; u < MAXI; ++u) {
+          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          const int b = tile * P.S + (int)((it_pk[u] >> 16) & 0xff);
+          if (it_row[u] >= 0 && b < P.B) {
+            const int src = src_row[it_row[u]];
+            if (src >= 0) {
+              const float* xp = P.x + ((long long)b * P.M_in + src) * P.Fin + fc * 4;
+              const int nf = P.Fin - fc * 4;
+              if (nf > 0) v[u].x = __ldg(xp);
+              if (nf > 1) v[u].y = __ldg(xp + 1);
+              if (nf > 2) v[u].z = __ldg(xp + 2);
+              if (nf > 3) v[u].w = __ldg(xp + 3);
             }
           }
         }
+#pragma unroll
+        for (int u = 0; u < MAXI; ++u) {
+          if (it_row[u] >= 0) {
+            store_state_at(dst + it_off[u], dlo + lo_of(it_off[u]), v[u]);
+            const int b = tile * P.S + (int)((it_pk[u] >> 16) & 0xff);
+            if (P.xstack && b < P.B)
+              *reinterpret_cast<float4*>(P.xstack + ((long long)b * M + it_row[u]) * FP + fc * 4) = v[u];
+          }
+        }
+        TRACE(0, sw == 0);
         fence_async_smem();
         named_bar_sync(kBarOrder, nsync);
         ++n;
@@ -228,41 +318,72 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
         const uint32_t lo_u = P.nlo == 2 ? (n & 1u) : 0u;
         if (P.nlo == 1) mbar_wait(bar_mma((n - 1) & 1), ((n - 1) >> 1) & 1);
         float* spill = P.xstack ? P.xstack + (long long)k * P.B * M * FP : nullptr;
-        for (int r = 0;; ++r) {
-          const int ii = r * kSparseWarps + ((r & 1) ? kSparseWarps - 1 - sw : sw);
-          if (ii >= NI) break;
-          const int g = ii / NS, s = ii - g * NS;
-          const int row = grow[g * 4 + q];
-          const int2 meta = gslot[g * 4 + q];
-          const int len2 = glen[g];
-          const uint32_t src = sb + (uint32_t)((cur ^ 1) * NS + s) * slab_bytes;
-          const uint32_t dst = sb + (uint32_t)(cur * NS + s) * slab_bytes;
-          const uint32_t ea = ent_base + (uint32_t)meta.x * 16u;
-          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 2
-          for (int j = 0; j < len2; ++j) {
-            if (2 * j < meta.y) {
-              const int4 e = lds128i(ea + (uint32_t)j * 16u);
-              const float4 v0 = lds128(src + ((uint32_t)e.x ^ c16));
-              const float4 v1 = lds128(src + ((uint32_t)e.z ^ c16));
-              const float w0 = __int_as_float(e.y), w1 = __int_as_float(e.w);
-              a0 = fmaf(w0, v0.x, a0); a1 = fmaf(w0, v0.y, a1); a2 = fmaf(w0, v0.z, a2); a3 = fmaf(w0, v0.w, a3);
-              a0 = fmaf(w1, v1.x, a0); a1 = fmaf(w1, v1.y, a1); a2 = fmaf(w1, v1.z, a2); a3 = fmaf(w1, v1.w, a3);
+        const uint32_t dlo = sb + P.off_lo + lo_u * lo_bytes;
+        const uint32_t srcb = sb + (uint32_t)(cur ^ 1) * buf_bytes, dst = sb + (uint32_t)cur * buf_bytes;
+        if (k == K - 1 && tile + (int)gridDim.x < P.ntiles) {
+          // pull the next tile's raw windows into L2 while this order computes
+#pragma unroll
+          for (int u = 0; u < MAXI; ++u) {
+            const int b = (tile + (int)gridDim.x) * P.S + (int)((it_pk[u] >> 16) & 0xff);
+            if (it_row[u] >= 0 && b < P.B && fc * 4 < P.Fin) {
+              const int src = src_row[it_row[u]];
+              if (src >= 0)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(P.x + ((long long)b * P.M_in + src) * P.Fin + fc * 4));
             }
           }
+        }
+        // Two work items at a time (the snake deal makes neighbours in the list near-equal in length): twice the
+        // independent shared-memory loads in flight per warp.
+        auto finish = [&](int row, uint32_t off, uint32_t pk, float a0, float a1, float a2, float a3) {
           if (row >= 0) {
             float4 o;
             if (k == 1) {
               o = make_float4(a0, a1, a2, a3);
             } else {
-              const float4 own = lds128(dst + slab_off(row, c));
+              const float4 own = lds128(dst + off);
               o = make_float4(fmaf(2.f, a0, -own.x), fmaf(2.f, a1, -own.y), fmaf(2.f, a2, -own.z), fmaf(2.f, a3, -own.w));
             }
-            store_state(dst, sb + P.off_lo + (lo_u * NS + s) * lo_bytes, row, c, o);
-            const int b = tile * P.S + s * G + gw;
+            store_state_at(dst + off, dlo + lo_of(off), o);
+            const int b = tile * P.S + (int)((pk >> 16) & 0xff);
             if (spill && b < P.B) *reinterpret_cast<float4*>(spill + ((long long)b * M + row) * FP + fc * 4) = o;
           }
+        };
+#pragma unroll
+        for (int u = 0; u < MAXI; u += 2) {
+          const bool two = u + 1 < MAXI;
+          const int u1 = two ? u + 1 : u;
+          const uint32_t pka = it_pk[u], pkb = two ? it_pk[u1] : 0u;
+          const int owna = (int)(pka & 0xff), ownb = (int)(pkb & 0xff);
+          int lim = max((int)((pka >> 8) & 0xff), (int)((pkb >> 8) & 0xff));
+#ifdef GCNB_TRACE
+          if (P.debug & 1) lim = 0;
+#endif
+          const uint32_t srca = srcb + ((pka >> 24) * (uint32_t)Q << 7);  // window-slab offset keeps the swizzle phase
+          const uint32_t srcq = srcb + ((pkb >> 24) * (uint32_t)Q << 7);
+          const uint32_t ea = it_ent[u], eb = it_ent[u1];
+          const int lasta = max(owna - 1, 0), lastb = max(ownb - 1, 0);
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+          // Branch-free over the longest row of the two groups: a lane whose own row is shorter re-reads its last
+          // entry pair with zero weights.
+          for (int j = 0; j < lim; ++j) {
+            const int4 e = lds128i(ea + (uint32_t)min(j, lasta) * 16u);
+            const int4 f = lds128i(eb + (uint32_t)min(j, lastb) * 16u);
+            const float4 v0 = lds128(srca + ((uint32_t)e.x ^ c16));
+            const float4 v1 = lds128(srca + ((uint32_t)e.z ^ c16));
+            const float4 x0 = lds128(srcq + ((uint32_t)f.x ^ c16));
+            const float4 x1 = lds128(srcq + ((uint32_t)f.z ^ c16));
+            const bool la = j < owna, lb = two && j < ownb;
+            const float w0 = la ? __int_as_float(e.y) : 0.f, w1 = la ? __int_as_float(e.w) : 0.f;
+            const float z0 = lb ? __int_as_float(f.y) : 0.f, z1 = lb ? __int_as_float(f.w) : 0.f;
+            a0 = fmaf(w0, v0.x, a0); a1 = fmaf(w0, v0.y, a1); a2 = fmaf(w0, v0.z, a2); a3 = fmaf(w0, v0.w, a3);
+            b0 = fmaf(z0, x0.x, b0); b1 = fmaf(z0, x0.y, b1); b2 = fmaf(z0, x0.z, b2); b3 = fmaf(z0, x0.w, b3);
+            a0 = fmaf(w1, v1.x, a0); a1 = fmaf(w1, v1.y, a1); a2 = fmaf(w1, v1.z, a2); a3 = fmaf(w1, v1.w, a3);
+            b0 = fmaf(z1, x1.x, b0); b1 = fmaf(z1, x1.y, b1); b2 = fmaf(z1, x1.z, b2); b3 = fmaf(z1, x1.w, b3);
+          }
+          finish(it_row[u], it_off[u], pka, a0, a1, a2, a3);
+          if (two) finish(it_row[u1], it_off[u1], pkb, b0, b1, b2, b3);
         }
+        TRACE(0, sw == 0);
         fence_async_smem();
         named_bar_sync(kBarOrder, nsync);
         ++n;
@@ -279,6 +400,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
       if (use > 0) mbar_wait(bar_empty(buf), (uint32_t)(use - 1) & 1u);
       for (int k = 0; k < K; ++k) {
         named_bar_sync(kBarOrder, nsync);  // X_k (and its remainder) is complete in shared memory
+        TRACE(2, true);
         tc_fence_after();
         if (lane == 0) {
           const int cur = (base + k) & 1;
@@ -286,15 +408,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
           const uint32_t wh = sb + P.off_wh + (uint32_t)(k * (FP / 4) * 4) * 128u;
           const uint32_t wl = sb + P.off_wl + (uint32_t)(k * (FP / 4) * 4) * 128u;
           const uint32_t wb = sb + P.off_wb + (uint32_t)(k * (FP / 8) * 4) * 128u;
-          for (int s = 0; s < NS; ++s) {
-            const uint32_t slab = sb + (uint32_t)(cur * NS + s) * slab_bytes;
-            const uint32_t lo = sb + P.off_lo + (lo_u * NS + s) * lo_bytes;
+          const uint32_t sbuf = sb + (uint32_t)cur * buf_bytes, lbuf = sb + P.off_lo + lo_u * lo_bytes;
+#ifdef GCNB_TRACE
+          if (!(P.debug & 2))
+#endif
 #pragma unroll
-            for (int g = 0; g < G; ++g) {
-              for (int i = 0; i < P.MT; ++i) {
-                const uint32_t d = tmem + (uint32_t)(buf * P.acc_cols + ((s * G + g) * P.MT + i) * 32);
-                const uint32_t a = slab + (uint32_t)i * 16384u + (uint32_t)(g * FP * 4);
-                const uint32_t l = lo + (uint32_t)i * 8192u + (uint32_t)(g * FP * 2);
+          for (int g = 0; g < G; ++g) {
+            for (int i = 0; i < P.p; ++i) {
+              for (int t = 0; t < P.T; ++t) {
+                const uint32_t d = tmem + (uint32_t)(buf * P.acc_cols + ((g * P.p + i) * P.T + t) * 32);
+                const uint32_t row0 = (uint32_t)(i * BQ + t * 128);
+                const uint32_t a = sbuf + row0 * 128u + (uint32_t)(g * FP * 4);
+                const uint32_t l = lbuf + row0 * 64u + (uint32_t)(g * FP * 2);
 #pragma unroll
                 for (int j = 0; j < FP / 8; ++j)
                   mma_tf32(d, smem_desc(kDescSlab, a + j * 32), smem_desc(kDescTaps, wh + j * 1024), kIdescTf32,
@@ -312,9 +437,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
           if (k == K - 1) mma_commit(bar_full(buf));
         }
         __syncwarp();
-        // X_k's slab and remainder may be overwritten two orders from now: only pass the next barrier once the
+        TRACE(2, true);
+        // X_k's buffer and remainder may be overwritten two orders from now: only pass the next barrier once the
         // tensor cores have finished reading them
         mbar_wait(bar_mma(n & 1), (n >> 1) & 1);
+        TRACE(2, true);
         ++n;
       }
       base = (base + K) & 1;
@@ -322,81 +449,104 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
   } else {
     // =========================================== epilogue warps =================================================
     const int e = warp;  // TMEM lane quarter
-    const int p = P.p, log2p = P.log2p;
+    const int p = P.p;
     const int Mo = M >> log2p;
-    const int il = lane & (p - 1);  // position inside the pooling window
+    const bool pool_relu_fix = P.relu && p > 1;
     int it = 0;
     for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x, ++it) {
       const int buf = P.nacc == 2 ? (it & 1) : 0;
       const int use = P.nacc == 2 ? (it >> 1) : it;
       mbar_wait(bar_full(buf), (uint32_t)use & 1u);
+      TRACE(3, e == 0);
       tc_fence_after();
-      for (int w = 0; w < P.S; ++w) {
-        const int b = tile * P.S + w;
-        for (int i = 0; i < P.MT; ++i) {
-          const int row0 = i * 128 + e * 32;
-          if (row0 >= M) continue;
-          float a[32];
-          tmem_ld32(tmem + ((uint32_t)(e * 32) << 16) + (uint32_t)(buf * P.acc_cols + (w * P.MT + i) * 32), a);
-          const int row = row0 + lane;
-          const bool valid = row < M && b < P.B;
-          if (P.bias_mode == GCNB_BIAS_PER_FILTER) {
 #pragma unroll
-            for (int c4 = 0; c4 < 8; ++c4) {
-              const float4 bv = *reinterpret_cast<const float4*>(bias_s + c4 * 4);
-              a[c4 * 4] += bv.x; a[c4 * 4 + 1] += bv.y; a[c4 * 4 + 2] += bv.z; a[c4 * 4 + 3] += bv.w;
-            }
-          } else if (P.bias_mode == GCNB_BIAS_PER_VERTEX) {
-            if (valid) {
-              const float* bp = P.bias + (long long)row * P.Fout;
+      for (int g = 0; g < G; ++g) {
+        for (int t = 0; t < P.T; ++t) {
+          const int rb0 = t * 128 + e * 32;
+          if (rb0 >= BQ) continue;
+          const int rb = rb0 + lane;             // row inside a sibling block = (window-slab, pooled vertex)
+          const int s = rb / Q, j = rb - s * Q;
+          const int b = tile * P.S + s * G + g;
+          const bool valid = rb < BQ && j < Mo && b < P.B;
+          const long long orow = (long long)b * Mo + j;
+          const uint32_t tbase = tmem + ((uint32_t)(e * 32) << 16) + (uint32_t)(buf * P.acc_cols + (g * p * P.T + t) * 32);
+          float msum = 0.f;
 #pragma unroll
-              for (int c4 = 0; c4 < 8; ++c4) {
-                if (c4 * 4 < P.Fout) {
+          for (int h = 0; h < 2; ++h) {
+            float m[16];
+            int idx[16];
+            tmem_ld16(tbase + h * 16, m);
+            if (P.bias_mode == GCNB_BIAS_PER_VERTEX && valid) {
+              const float* bp = P.bias + (long long)(j << log2p) * P.Fout + h * 16;
+#pragma unroll
+              for (int c4 = 0; c4 < 4; ++c4) {
+                if (h * 16 + c4 * 4 < P.Fout) {
                   const float4 bv = __ldg(reinterpret_cast<const float4*>(bp + c4 * 4));
-                  a[c4 * 4] += bv.x; a[c4 * 4 + 1] += bv.y; a[c4 * 4 + 2] += bv.z; a[c4 * 4 + 3] += bv.w;
+                  m[c4 * 4] += bv.x; m[c4 * 4 + 1] += bv.y; m[c4 * 4 + 2] += bv.z; m[c4 * 4 + 3] += bv.w;
                 }
               }
             }
-          }
-          if (P.relu) {
 #pragma unroll
-            for (int o = 0; o < 32; ++o) a[o] = fmaxf(a[o], 0.f);
-          }
-          uint32_t am[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-          if (p > 1) {
-            const uint32_t gmask = (1u << p) - 1u;
-            const int gshift = lane & ~(p - 1);
+            for (int o = 0; o < 16; ++o) idx[o] = 0;
+            for (int i = 1; i < p; ++i) {
+              float a[16];
+              tmem_ld16(tbase + (uint32_t)(i * P.T * 32) + h * 16, a);
+              if (P.bias_mode == GCNB_BIAS_PER_VERTEX && valid) {
+                const float* bp = P.bias + (long long)((j << log2p) + i) * P.Fout + h * 16;
 #pragma unroll
-            for (int o = 0; o < 32; ++o) {
-              float m = a[o];
-              for (int d = 1; d < p; d <<= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
-              const uint32_t hit = (__ballot_sync(0xffffffffu, a[o] == m) >> gshift) & gmask;
-              const uint32_t first = hit ? (uint32_t)(__ffs((int)hit) - 1) : 0u;  // first maximum (MaxPoolGrad)
-              a[o] = m;
-              am[o >> 2] |= first << ((o & 3) * 8);
-            }
-          }
-          if (valid) {
-            const long long orow = (long long)b * Mo + (row >> log2p);
-            float* yp = P.y + orow * P.Fout;
-            uint8_t* ap = (P.argmax && p > 1) ? P.argmax + orow * P.Fout : nullptr;
+                for (int c4 = 0; c4 < 4; ++c4) {
+                  if (h * 16 + c4 * 4 < P.Fout) {
+                    const float4 bv = __ldg(reinterpret_cast<const float4*>(bp + c4 * 4));
+                    a[c4 * 4] += bv.x; a[c4 * 4 + 1] += bv.y; a[c4 * 4 + 2] += bv.z; a[c4 * 4 + 3] += bv.w;
+                  }
+                }
+              }
 #pragma unroll
-            for (int c4 = 0; c4 < 8; ++c4) {
-              if (c4 * 4 < P.Fout && (c4 >> (3 - log2p)) == il) {
-                *reinterpret_cast<float4*>(yp + c4 * 4) = make_float4(a[c4 * 4], a[c4 * 4 + 1], a[c4 * 4 + 2], a[c4 * 4 + 3]);
-                if (ap) *reinterpret_cast<uint32_t*>(ap + c4 * 4) = am[c4];
+              for (int o = 0; o < 16; ++o) {
+                const bool gt = a[o] > m[o];  // strict: the first maximum wins (MaxPoolGrad)
+                m[o] = gt ? a[o] : m[o];
+                idx[o] = gt ? i : idx[o];
               }
             }
-            if (P.y_mean && il == 0) {
-              float sm = 0.f;
+            if (P.bias_mode == GCNB_BIAS_PER_FILTER) {
 #pragma unroll
-              for (int o = 0; o < 32; ++o)
-                if (o < P.Fout) sm += a[o];
-              P.y_mean[orow] = sm / (float)P.Fout;
+              for (int c4 = 0; c4 < 4; ++c4) {
+                const float4 bv = *reinterpret_cast<const float4*>(bias_s + h * 16 + c4 * 4);
+                m[c4 * 4] += bv.x; m[c4 * 4 + 1] += bv.y; m[c4 * 4 + 2] += bv.z; m[c4 * 4 + 3] += bv.w;
+              }
             }
+            if (P.relu) {
+#pragma unroll
+              for (int o = 0; o < 16; ++o) {
+                // a window whose maximum is clipped is a tie of zeros after the ReLU: the first vertex is the arg-max
+                if (pool_relu_fix && !(m[o] > 0.f)) idx[o] = 0;
+                m[o] = fmaxf(m[o], 0.f);
+              }
+            }
+            if (valid) {
+              float* yp = P.y + orow * P.Fout + h * 16;
+#pragma unroll
+              for (int c4 = 0; c4 < 4; ++c4)
+                if (h * 16 + c4 * 4 < P.Fout)
+                  *reinterpret_cast<float4*>(yp + c4 * 4) = make_float4(m[c4 * 4], m[c4 * 4 + 1], m[c4 * 4 + 2], m[c4 * 4 + 3]);
+              if (P.argmax && p > 1) {
+                uint8_t* ap = P.argmax + orow * P.Fout + h * 16;
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4)
+                  if (h * 16 + c4 * 4 < P.Fout)
+                    *reinterpret_cast<uint32_t*>(ap + c4 * 4) = (uint32_t)idx[c4 * 4] | ((uint32_t)idx[c4 * 4 + 1] << 8) |
+                                                                ((uint32_t)idx[c4 * 4 + 2] << 16) |
+                                                                ((uint32_t)idx[c4 * 4 + 3] << 24);
+              }
+            }
+#pragma unroll
+            for (int o = 0; o < 16; ++o)
+              if (h * 16 + o < P.Fout) msum += m[o];
           }
+          if (P.y_mean && valid) P.y_mean[orow] = msum / (float)P.Fout;
         }
       }
+      TRACE(3, e == 0);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_empty(buf));
@@ -417,10 +567,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
 // ---------------------------------------------------------------------------------------------------------------
 struct UmmaFwdPlan {
   bool ok;
-  int FP, G, NS, MT, NG, nlo, nacc, acc_cols, tmem_cols, slab_rows;
+  int FP, G, NS, Q, BQ, T, NG, nlo, nacc, acc_cols, tmem_cols, slab_rows, MAXI;
   size_t smem;
-  int off_lo, off_wh, off_wl, off_wb, off_ent, off_grow, off_gslot, off_glen, off_src, off_rlen, off_sorted, off_bias,
-      off_bar;
+  int off_lo, off_wh, off_wl, off_wb, off_ent, off_grow, off_grho, off_gslot, off_glen, off_src, off_rlen, off_sorted,
+      off_bias, off_bar, off_rp;
 };
 
 static bool umma_enabled() {
@@ -437,60 +587,63 @@ static UmmaFwdPlan plan_umma_fwd(const LayerShape& s, int sm_count, int smem_opt
   if (!umma_enabled()) return pl;
   if (s.Fin <= 8 || s.Fin > 32 || s.Fout < 4 || s.Fout > 32 || (s.Fout & 3)) return pl;
   if (s.p != 1 && s.p != 2 && s.p != 4 && s.p != 8) return pl;
-  if (s.M % s.p != 0 || s.M < 1 || s.M > 512 || s.K < 1 || s.B < 1) return pl;
+  if (s.M % s.p != 0 || s.M < 1 || s.M > 2048 || s.K < 1 || s.B < 1) return pl;
   pl.FP = s.Fin <= 16 ? 16 : 32;
   pl.G = 32 / pl.FP;
-  pl.MT = ceil_div(s.M, 128);
   pl.NG = ceil_div(s.M, 4);
-  pl.slab_rows = (int)align_up((size_t)s.M + 1, 8);
-  const size_t slab = (size_t)pl.slab_rows * 128, lo = (size_t)pl.slab_rows * 64;
+  pl.Q = (int)align_up((size_t)(s.M / s.p), 8);
   const size_t taps = (size_t)s.K * pl.FP * 32 * 4;  // one tf32 image
   const size_t ent = align_up(((size_t)s.nnz + s.M + 2) * 8, 16);
-  const size_t tables = (size_t)pl.NG * 4 * 4 /*grow*/ + (size_t)pl.NG * 4 * 8 /*gslot*/ + align_up((size_t)pl.NG * 4, 16) +
-                        align_up((size_t)s.M * 4, 16) /*src*/ + 2 * (size_t)pl.NG * 4 * 4 /*rlen, sorted*/ + 128 /*bias*/ +
-                        64 /*barriers*/;
+  const size_t tables = 2 * (size_t)pl.NG * 16 /*grow, grho*/ + (size_t)pl.NG * 32 /*gslot*/ + align_up((size_t)pl.NG * 4, 16) +
+                        align_up((size_t)s.M * 4, 16) /*src*/ + 128 /*bias*/ + 64 /*barriers*/;
+  // prologue-only scratch (rlen, sorted, rp) lives in the first remainder buffer
+  const size_t scratch = 2 * (size_t)pl.NG * 16 + align_up((size_t)(s.M + 2) * 4, 16) + align_up((size_t)(s.M + 1) * 4, 16);
   const size_t budget = std::min<size_t>((size_t)smem_optin, 227 * 1024);
   double best = 1e30;
-  for (int ns = 1; ns <= 4; ++ns) {
-    const int S = ns * pl.G;
-    const int acc_cols = S * pl.MT * 32;
+  for (int ns = 1; ns <= 8; ++ns) {
+    const int BQ = ns * pl.Q, T = ceil_div(BQ, 128);
+    const int acc_cols = pl.G * s.p * T * 32;
     if (acc_cols > 512) continue;
+    const int rows = (int)align_up((size_t)s.p * BQ + 1, 8);
+    if ((size_t)rows * 128 >= (1u << 18)) continue;  // descriptors address 256 KB
+    if (pl.NG * ns > 5 * kSparseWarps) continue;      // a lane keeps at most 5 work items in registers
     for (int nlo = 2; nlo >= 1; --nlo) {
-      const size_t need = 2 * ns * slab + (size_t)nlo * ns * lo + 2 * taps + taps / 2 + ent + tables;
-      // the last MMA tile of a slab reads up to row MT*128: those bytes must exist inside the allocation
-      const size_t overrun = (size_t)(pl.MT * 128 - pl.slab_rows) * 128;
-      if (need > budget || 2 * ns * slab + overrun > need) continue;
-      const int tiles = ceil_div(s.B, S);
-      const double cost = std::ceil((double)tiles / sm_count) * ns * (nlo == 2 ? 1.0 : 1.05) - 0.001 * ns;
+      const size_t need = 2 * (size_t)rows * 128 + (size_t)nlo * rows * 64 + 2 * taps + taps / 2 + ent + tables;
+      // the last MMA tile of the last block reads up to row (p-1)*BQ + T*128: those bytes must exist in the allocation
+      const long long over = ((long long)(s.p - 1) * BQ + T * 128 - rows) * 128;
+      if (need > budget || 2 * (size_t)rows * 128 + (over > 0 ? (size_t)over : 0) > need || scratch > (size_t)rows * 64) continue;
+      const int tiles = ceil_div(s.B, ns * pl.G);
+      // rounds of tiles over the SMs x work per tile; MMA rows wasted by a nearly empty last tile of a block count a little
+      const double cost = std::ceil((double)tiles / sm_count) * ns * (nlo == 2 ? 1.0 : 1.08) + 0.02 * T * 128.0 / BQ - 0.001 * ns;
       if (cost < best) {
         best = cost;
-        pl.NS = ns;
-        pl.nlo = nlo;
-        pl.acc_cols = acc_cols;
-        pl.smem = need;
+        pl.NS = ns; pl.BQ = BQ; pl.T = T; pl.nlo = nlo; pl.acc_cols = acc_cols; pl.slab_rows = rows; pl.smem = need;
       }
       break;
     }
   }
   if (best > 1e29) return pl;
   pl.nacc = 2 * pl.acc_cols <= 512 ? 2 : 1;
+  pl.MAXI = ceil_div(pl.NG * pl.NS, kSparseWarps) <= 3 ? 3 : 5;
   int cols = 32;
   while (cols < pl.nacc * pl.acc_cols) cols *= 2;
   pl.tmem_cols = cols;
-  size_t off = 2 * (size_t)pl.NS * slab;
-  pl.off_lo = (int)off; off += (size_t)pl.nlo * pl.NS * lo;
+  size_t off = 2 * (size_t)pl.slab_rows * 128;
+  pl.off_lo = (int)off; off += (size_t)pl.nlo * pl.slab_rows * 64;
   pl.off_wh = (int)off; off += taps;
   pl.off_wl = (int)off; off += taps;
   pl.off_wb = (int)off; off += taps / 2;
   pl.off_ent = (int)off; off += ent;
   pl.off_grow = (int)off; off += (size_t)pl.NG * 16;
+  pl.off_grho = (int)off; off += (size_t)pl.NG * 16;
   pl.off_gslot = (int)off; off += (size_t)pl.NG * 32;
   pl.off_glen = (int)off; off += align_up((size_t)pl.NG * 4, 16);
   pl.off_src = (int)off; off += align_up((size_t)s.M * 4, 16);
-  pl.off_rlen = (int)off; off += (size_t)pl.NG * 16;
-  pl.off_sorted = (int)off; off += (size_t)pl.NG * 16;
   pl.off_bias = (int)off; off += 128;
   pl.off_bar = (int)off; off += 64;
+  pl.off_rlen = pl.off_lo;
+  pl.off_sorted = pl.off_rlen + pl.NG * 16;
+  pl.off_rp = pl.off_sorted + pl.NG * 16 + (int)align_up((size_t)(s.M + 2) * 4, 16);  // bins sit between sorted and rp
   if (off > pl.smem) return pl;
   pl.ok = true;
   return pl;
@@ -503,6 +656,21 @@ bool umma_fwd_supported(const LayerShape& s) {
     di.smem_optin = 227 * 1024;
   }
   return plan_umma_fwd(s, di.sm_count, di.smem_optin).ok;
+}
+
+int umma_fwd_describe(const LayerShape& s, char* out, size_t n) {
+  DeviceInfo di;
+  if (device_info(&di) != GCNB_OK) {
+    di.sm_count = 148;
+    di.smem_optin = 227 * 1024;
+  }
+  const UmmaFwdPlan pl = plan_umma_fwd(s, di.sm_count, di.smem_optin);
+  if (!pl.ok) return 0;
+  return snprintf(out, n,
+                  "k_cheb_fwd_umma<FP=%d>: tcgen05/TMEM, %d windows/tile (%d slabs x %d), sibling block %d rows (Q=%d), "
+                  "%d MMA tiles/block, %d remainder buffers, %d accumulator buffers x %d TMEM columns, %zu B smem, %d tiles",
+                  pl.FP, pl.NS * pl.G, pl.NS, pl.G, pl.BQ, pl.Q, pl.T, pl.nlo, pl.nacc, pl.acc_cols, pl.smem,
+                  ceil_div(s.B, pl.NS * pl.G));
 }
 
 int umma_cheb_fwd(const float* x, const int32_t* perm, int M_in, const gcnb_csr& L, const float* W, const float* bias,
@@ -523,22 +691,32 @@ int umma_cheb_fwd(const float* x, const int32_t* perm, int M_in, const gcnb_csr&
   P.B = s.B; P.M = s.M; P.Fin = s.Fin; P.Fout = s.Fout; P.K = s.K; P.p = s.p; P.bias_mode = bias_mode; P.relu = relu;
   P.log2p = 0;
   while ((1 << P.log2p) < s.p) ++P.log2p;
-  P.NS = pl.NS; P.S = pl.NS * pl.G; P.MT = pl.MT; P.NG = pl.NG; P.nlo = pl.nlo; P.nacc = pl.nacc;
+  P.NS = pl.NS; P.S = pl.NS * pl.G; P.Q = pl.Q; P.BQ = pl.BQ; P.T = pl.T; P.NG = pl.NG; P.nlo = pl.nlo; P.nacc = pl.nacc;
   P.acc_cols = pl.acc_cols; P.tmem_cols = pl.tmem_cols; P.slab_rows = pl.slab_rows;
   P.ntiles = ceil_div(s.B, P.S);
   P.off_lo = pl.off_lo; P.off_wh = pl.off_wh; P.off_wl = pl.off_wl; P.off_wb = pl.off_wb; P.off_ent = pl.off_ent;
-  P.off_grow = pl.off_grow; P.off_gslot = pl.off_gslot; P.off_glen = pl.off_glen; P.off_src = pl.off_src;
-  P.off_rlen = pl.off_rlen; P.off_sorted = pl.off_sorted; P.off_bias = pl.off_bias; P.off_bar = pl.off_bar;
+  P.off_grow = pl.off_grow; P.off_grho = pl.off_grho; P.off_gslot = pl.off_gslot; P.off_glen = pl.off_glen;
+  P.off_src = pl.off_src; P.off_rlen = pl.off_rlen; P.off_sorted = pl.off_sorted; P.off_bias = pl.off_bias;
+  P.off_bar = pl.off_bar; P.off_rp = pl.off_rp;
+#ifdef GCNB_TRACE
+  P.debug = std::getenv("GCNB_UMMA_DEBUG") ? std::atoi(std::getenv("GCNB_UMMA_DEBUG")) : 0;
+#endif
   const int grid = std::min(P.ntiles, di.sm_count);
-  if (pl.FP == 16) {
-    GCNB_CUDA(cudaFuncSetAttribute(k_cheb_fwd_umma<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    k_cheb_fwd_umma<16><<<grid, kThreads, pl.smem, st>>>(P);
-  } else {
-    GCNB_CUDA(cudaFuncSetAttribute(k_cheb_fwd_umma<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    k_cheb_fwd_umma<32><<<grid, kThreads, pl.smem, st>>>(P);
+#define GCNB_UMMA_CASE(fp, mi)                                                                                      \
+  if (pl.FP == fp && pl.MAXI == mi) {                                                                               \
+    GCNB_CUDA(cudaFuncSetAttribute(k_cheb_fwd_umma<fp, mi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem)); \
+    k_cheb_fwd_umma<fp, mi><<<grid, kThreads, pl.smem, st>>>(P);                                                    \
   }
+  GCNB_UMMA_CASE(16, 3) GCNB_UMMA_CASE(16, 5) GCNB_UMMA_CASE(32, 3) GCNB_UMMA_CASE(32, 5)
+#undef GCNB_UMMA_CASE
   GCNB_LAUNCH_CHECK("k_cheb_fwd_umma");
   return GCNB_OK;
 }
 
 }  // namespace gcnb
+
+#ifdef GCNB_TRACE
+extern "C" __attribute__((visibility("default"))) int gcnb_debug_read_trace(long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, gcnb::g_trace, sizeof(long long) * 4 * 512);
+}
+#endif

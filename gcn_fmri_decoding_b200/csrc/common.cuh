@@ -111,6 +111,7 @@ int spmm_tma(const gcnb_csr& L, const float* src, const float* add, const float*
 
 // ---- tcgen05 / TMEM forward for shared-memory resident graphs, cheb_fwd_umma.cu -------------------------
 bool umma_fwd_supported(const LayerShape& s);
+int umma_fwd_describe(const LayerShape& s, char* out, size_t n);  // 0 when the shape is not supported
 int umma_cheb_fwd(const float* x, const int32_t* perm, int M_in, const gcnb_csr& L, const float* W, const float* bias,
                   float* y, uint8_t* argmax, float* y_mean, float* xstack, const LayerShape& s, int bias_mode, int relu,
                   cudaStream_t st);

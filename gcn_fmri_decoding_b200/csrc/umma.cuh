@@ -126,6 +126,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 32 lanes x 16 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // ---- shared-memory access by 32-bit shared address ------------------------------------------------------------
 __device__ __forceinline__ float4 lds128(uint32_t a) {
   float4 v;
@@ -181,6 +196,14 @@ __device__ __forceinline__ void store_state(uint32_t slab, uint32_t lo, int row,
   const float rx = v.x - tf32_trunc(v.x), ry = v.y - tf32_trunc(v.y);
   const float rz = v.z - tf32_trunc(v.z), rw = v.w - tf32_trunc(v.w);
   sts64(lo + lo_off(row, c), pack_bf16(rx, ry), pack_bf16(rz, rw));
+}
+
+// the same with both byte addresses already resolved
+__device__ __forceinline__ void store_state_at(uint32_t slab_addr, uint32_t lo_addr, float4 v) {
+  sts128(slab_addr, v);
+  const float rx = v.x - tf32_trunc(v.x), ry = v.y - tf32_trunc(v.y);
+  const float rz = v.z - tf32_trunc(v.z), rw = v.w - tf32_trunc(v.w);
+  sts64(lo_addr, pack_bf16(rx, ry), pack_bf16(rz, rw));
 }
 
 }  // namespace um

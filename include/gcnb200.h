@@ -73,6 +73,9 @@ GCNB_API unsigned long long gcnb_launch_count(void);
 /* 1 if the fused shared-memory kernels can take this layer shape, else 0. */
 GCNB_API int gcnb_cheb_fused_supported(int B, int M, int nnz, int Fin, int Fout, int K, int p, int backward, int need_dx);
 
+/* Human-readable description of the forward kernel AUTO dispatch picks for this shape (diagnostics, bench records). */
+GCNB_API int gcnb_cheb_fwd_describe(int B, int M, int nnz, int Fin, int Fout, int K, int p, char* out, size_t n);
+
 /* Feature width FP of the saved-basis buffer `xstack` (K*B*M*FP floats, layout private to the library: [K][B][M][FP]
  * with padded FP for graphs the fused kernels hold in shared memory, vertex-major [K][M][B][Fin] for vertex-level
  * graphs on the general path), or 0 when this shape keeps no basis. */

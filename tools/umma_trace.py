@@ -1,0 +1,42 @@
+"""Debug (build with GCNB_NVCC_EXTRA=-DGCNB_TRACE): timeline of CTA 0 of k_cheb_fwd_umma for the conv1 / conv2 shapes."""
+import ctypes as C
+import os
+import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from gcn_fmri_decoding_b200 import _lib, ops, synth
+from gcn_fmri_decoding_b200.plan import GraphPlan
+
+dev = torch.device("cuda:0")
+A, gs, perm, L = synth.brain_graph(4)
+which = sys.argv[1] if len(sys.argv) > 1 else "f1"
+if which == "f1":
+    pl = GraphPlan(L[0], dev)
+    x = torch.randn(512, 360, 15, device=dev)
+    W = torch.randn(75, 32, device=dev) * .2
+    pt = torch.as_tensor(perm, dtype=torch.int32, device=dev)
+else:
+    pl = GraphPlan(L[2], dev)
+    x = torch.randn(512, 100, 32, device=dev)
+    W = torch.randn(160, 32, device=dev) * .2
+    pt = None
+b = torch.full((32,), .2, device=dev)
+for _ in range(3):
+    ops.cheb_fwd(x, pt, *pl.tensors(), W, b, 5, 4, 1, True, True, 0)
+torch.cuda.synchronize()
+lib = _lib.lib()
+lib._handle if False else None
+h = C.CDLL(_lib.LIB_PATH)
+buf = (C.c_longlong * (4 * 512))()
+rc = h.gcnb_debug_read_trace(buf)
+t = np.array(buf[:]).reshape(4, 512)
+t0 = t[t > 0].min()
+names = ["sparse0", "items", "mma", "epi0"]
+for r in range(4):
+    if r == 1:
+        v = t[1][t[1] > 0] - t0
+        print("prologue", " ".join(str(int(a)) for a in v[:16]))
+        continue
+    v = t[r][t[r] > 0] - t0
+    print(names[r], len(v), " ".join(str(int(a)) for a in v[:64]))
