@@ -49,6 +49,9 @@ SIGNATURES = {
     "gcnb_mean_f_fwd_f32": (_i, [_p, _p, _i, _i, _p]),
     "gcnb_mean_f_bwd_f32": (_i, [_p, _p, _i, _i, _p]),
     "gcnb_softmax_xent_f32": (_i, [_p, _p, _p, _p, _p, _i, _i, _p, C.c_float, C.c_float, C.c_float, _p]),
+    "gcnb_head_step_workspace_bytes": (_z, [_i] * 5),
+    "gcnb_head_step_f32": (_i, [_p] * 17 + [_i] * 5 + [C.c_float, C.c_uint, C.c_uint, _p, C.c_float, C.c_float, C.c_float,
+                                 _i, _p, _z, _p]),
     "gcnb_relu_dropout_fwd_f32": (_i, [_p, C.c_longlong, _i, _i, C.c_float, C.c_uint, _p, _p]),
     "gcnb_relu_dropout_bwd_f32": (_i, [_p, _p, C.c_longlong, _i, _i, _i, C.c_float, _p]),
     "gcnb_colsum_multi_f32": (_i, [_p, _p, _p, _p, _i, _p]),

@@ -164,6 +164,27 @@ __device__ __forceinline__ uint32_t dropout_threshold(float keep) {
 __device__ __forceinline__ bool dropout_keeps(uint32_t i, uint32_t key, uint32_t thresh) {
   return mix32(i * 0x9e3779b1u + key) < thresh;
 }
+// ---- the classifier head as one persistent cooperative kernel, head_fused.cu ---------------------------------------
+struct HeadParams {
+  const float* a0;
+  const long long* labels;
+  const float *W1, *b1, *W2, *b2, *W3, *b3;
+  float *logits, *loss;
+  float *gW1, *gb1, *gW2, *gb2, *gW3, *gb3, *d0;
+  // scratch
+  float *h1, *h2, *d1, *d2, *d3, *part2, *partW2, *loss_rows;
+  int B, n0, n1, n2, C;  // widths: a0 [B x n0], h1 [B x n1], h2 [B x n2], logits [B x C]
+  float keep, inv_keep;
+  unsigned seed1, seed2;
+  float* state;  // optimiser clock {b1^t, b2^t, lr_t, t} (nullable); element 3 keys the dropout masks
+  float lr, beta1, beta2;
+  int tick;
+};
+
+bool head_step_supported(int B, int n0, int n1, int n2, int C);
+size_t head_step_workspace(int B, int n0, int n1, int n2, int C);
+int head_step(const HeadParams& P, Workspace& ws, cudaStream_t st);
+
 int launch_mean_f(const float* x, float* y, long long rows, int F, cudaStream_t st);
 int launch_mean_f_bwd(const float* dy, float* dx, long long rows, int F, cudaStream_t st);
 

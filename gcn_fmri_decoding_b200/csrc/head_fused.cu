@@ -1,0 +1,511 @@
+// The classifier head of the training step as ONE persistent cooperative kernel:
+//   forward  (models_gcn.py:650-656, :674-681, :253-259)
+//     h1 = dropout(relu(a0 W1 + b1)) ; h2 = dropout(relu(h1 W2 + b2)) ; logits = h2 W3 + b3
+//     loss = mean_b (logsumexp(logits_b) - logits_b[label_b]) ; d3 = (softmax - onehot) / B
+//   backward (what tf.gradients builds, :298-303)
+//     gW3 = h2^T d3, gb3 = colsum d3, d2 = (d3 W3^T) . mask2
+//     gW2 = h1^T d2, gb2 = colsum d2, d1 = (d2 W2^T) . mask1
+//     gW1 = a0^T d1, gb1 = colsum d1, d0 = d1 W1^T          (d0 = gradient of the mean over filters, fed to conv2 bwd)
+// a0 [B x d0] is the mean over the filters of the last conv layer (models_gcn.py:673), written by its epilogue.
+//
+// The head is ~0.6 GFLOP in seven dependent GEMM stages: at B = 512 it is launch- and latency-bound, not
+// throughput-bound (round 1: 13 launches, 97 us).  Here one CTA per SM stays resident and walks six phases separated
+// by grid barriers; every phase deals its 64x64 output tiles (K split where a phase has too few tiles) over all
+// CTAs.  Plain fp32 FFMA (4x4 register tiles out of shared memory): exact fp32 products, no split passes, and the
+// whole head needs ~8 us of FFMA issue.  All reductions run in a fixed order: results are bit-reproducible.
+#include <cooperative_groups.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace gcnb {
+
+constexpr int HT = 256;         // threads per CTA
+constexpr int TM = 64, TN = 64, TK = 32;
+constexpr int TS = TM + 4;      // shared tile row stride (floats): keeps 16-byte alignment of the float4 reads
+constexpr int SK2 = 4;          // K split of h1 W2 (too few output tiles otherwise)
+constexpr int SKW = 2;          // K (= batch) split of h1^T d2
+constexpr int SKC = 128;        // k chunk of the narrow products
+
+__host__ __device__ static inline int ceil_div_d(int a, int b) { return (a + b - 1) / b; }
+
+struct TileSmem {
+  float a[TK][TS];
+  float b[TK][TS];
+};
+
+// Strided 2-D view of an operand in global memory: element (i, j) = p[i * si + j * sj].
+struct View {
+  const float* p;
+  long long si, sj;
+  __device__ __forceinline__ float at(int i, int j) const { return p[i * si + j * sj]; }
+};
+
+enum { EPI_H1 = 0, EPI_PART2 = 1, EPI_PARTW2 = 2, EPI_D1 = 3 };
+
+// One family of 64x64 output tiles C = A[M x K] B[K x N], K split `splits` ways; unit u = (tile, split).
+// ONE copy of this code serves all four GEMM stages of the head (the kernel executes every instruction only a few
+// times per launch, so instruction-cache misses are what a larger, fully specialised body costs).
+__device__ __noinline__ void gemm_units(const HeadParams& P, float* smem_f, View A, bool a_kfast, View Bv, bool b_kfast,
+                                        int M, int N, int K, int splits, int epi, int ubase, int ucount, uint32_t key,
+                                        uint32_t thresh) {
+  TileSmem& sm = *reinterpret_cast<TileSmem*>(smem_f);
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int tn = ceil_div_d(N, TN);
+  const int kper = ceil_div_d(ceil_div_d(K, splits), TK) * TK;
+  for (int u = (int)blockIdx.x - ubase; u < ucount; u += (int)gridDim.x) {
+    if (u < 0) continue;
+    const int sp = u % splits, t = u / splits;
+    const int m0 = (t / tn) * TM, c0 = (t % tn) * TN;
+    const int k0 = sp * kper, k1 = min(K, k0 + kper);
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    float ra[8], rb[8];
+    auto fetch = [&](int kc) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int e = i * HT + tid;
+        const int ak = a_kfast ? (e & 31) : (e >> 6), am = a_kfast ? (e >> 5) : (e & 63);
+        ra[i] = (m0 + am < M && kc + ak < k1) ? A.at(m0 + am, kc + ak) : 0.f;
+        const int bk = b_kfast ? (e & 31) : (e >> 6), bn = b_kfast ? (e >> 5) : (e & 63);
+        rb[i] = (c0 + bn < N && kc + bk < k1) ? Bv.at(kc + bk, c0 + bn) : 0.f;
+      }
+    };
+    fetch(k0);
+    for (int kc = k0; kc < k1; kc += TK) {
+      __syncthreads();  // the previous chunk has been consumed
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int e = i * HT + tid;
+        const int ak = a_kfast ? (e & 31) : (e >> 6), am = a_kfast ? (e >> 5) : (e & 63);
+        sm.a[ak][am] = ra[i];
+        const int bk = b_kfast ? (e & 31) : (e >> 6), bn = b_kfast ? (e >> 5) : (e & 63);
+        sm.b[bk][bn] = rb[i];
+      }
+      __syncthreads();
+      if (kc + TK < k1) fetch(kc + TK);  // in flight while this chunk is multiplied
+#pragma unroll 8
+      for (int k = 0; k < TK; ++k) {
+        const float4 av = *reinterpret_cast<const float4*>(&sm.a[k][ty * 4]);
+        const float4 bv = *reinterpret_cast<const float4*>(&sm.b[k][tx * 4]);
+        const float a4[4] = {av.x, av.y, av.z, av.w}, b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a4[i], b4[j], acc[i][j]);
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = m0 + ty * 4 + i;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = c0 + tx * 4 + j;
+        if (m < M && n < N) {
+          const long long o = (long long)m * N + n;
+          float v = acc[i][j];
+          if (epi == EPI_H1) {
+            v = fmaxf(v + __ldg(P.b1 + n), 0.f);
+            if (P.keep < 1.f) v = dropout_keeps((uint32_t)o, key, thresh) ? v * P.inv_keep : 0.f;
+            P.h1[o] = v;
+          } else if (epi == EPI_PART2) {
+            P.part2[(long long)sp * M * N + o] = v;
+          } else if (epi == EPI_PARTW2) {
+            P.partW2[(long long)sp * M * N + o] = v;
+          } else {
+            P.d1[o] = P.h1[o] > 0.f ? v * P.inv_keep : 0.f;
+          }
+        }
+      }
+    }
+  }
+}
+
+// Narrow products: out[j * soj + c * soc] = sum_k X(k, j) * Y(k, c) for j < Jv <= 16 and c < CY <= 32, k < Kd.
+// Both operands are staged through shared memory in chunks of SKC k (cooperative loads, next chunk in flight while
+// the current one is multiplied); thread (jl, cg) owns out(jl, cg) and out(jl, cg + 16) and walks k in order, so
+// there is no cross-thread reduction and the result is bit-reproducible.  kfast: k is the contiguous index of both
+// operands in memory (loads then run along k), else j / c are.  One copy of the code for its three users.
+__device__ __noinline__ void skinny16(float* sm /* >= SKC*17 + SKC*33 floats */, View X, int Jv, View Y, int CY, int Kd,
+                                      bool kfast, float* out, long long soj, long long soc) {
+  float(*xs)[17] = reinterpret_cast<float(*)[17]>(sm);
+  float(*ys)[33] = reinterpret_cast<float(*)[33]>(sm + SKC * 17);
+  const int tid = threadIdx.x, jl = tid & 15, cg = tid >> 4;
+  constexpr int NX = SKC * 16 / HT, NY = SKC * 32 / HT;
+  float rx[NX], ry[NY];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      const int e = i * HT + tid;
+      const int kk = kfast ? (e & (SKC - 1)) : (e >> 4), j = kfast ? (e / SKC) : (e & 15);
+      rx[i] = (k0 + kk < Kd && j < Jv) ? X.at(k0 + kk, j) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < NY; ++i) {
+      const int e = i * HT + tid;
+      const int kk = kfast ? (e & (SKC - 1)) : (e >> 5), c = kfast ? (e / SKC) : (e & 31);
+      ry[i] = (k0 + kk < Kd && c < CY) ? Y.at(k0 + kk, c) : 0.f;
+    }
+  };
+  float acc0 = 0.f, acc1 = 0.f;
+  fetch(0);
+  for (int k0 = 0; k0 < Kd; k0 += SKC) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      const int e = i * HT + tid;
+      const int kk = kfast ? (e & (SKC - 1)) : (e >> 4), j = kfast ? (e / SKC) : (e & 15);
+      xs[kk][j] = rx[i];
+    }
+#pragma unroll
+    for (int i = 0; i < NY; ++i) {
+      const int e = i * HT + tid;
+      const int kk = kfast ? (e & (SKC - 1)) : (e >> 5), c = kfast ? (e / SKC) : (e & 31);
+      ys[kk][c] = ry[i];
+    }
+    __syncthreads();
+    if (k0 + SKC < Kd) fetch(k0 + SKC);
+#pragma unroll 8
+    for (int k = 0; k < SKC; ++k) {
+      const float x = xs[k][jl];
+      acc0 = fmaf(x, ys[k][cg], acc0);
+      acc1 = fmaf(x, ys[k][cg + 16], acc1);
+    }
+  }
+  __syncthreads();
+  if (jl < Jv && cg < CY) out[jl * soj + cg * soc] = acc0;
+  if (jl < Jv && cg + 16 < CY) out[jl * soj + (cg + 16) * soc] = acc1;
+}
+
+// out[c] = sum_r X[r][c] for 32 columns c0..c0+31: 8 row slices x 32 columns, fixed-order combine.
+__device__ __noinline__ void colsum32(float* red /* [8][32] */, const float* X, int ld, int cols, int c0, int R,
+                                      float* __restrict__ out) {
+  const int tid = threadIdx.x, cl = tid & 31, rs = tid >> 5;
+  const int c = c0 + cl;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (c < cols) {
+    int r = rs;
+    for (; r + 24 < R; r += 32) {
+      s0 += X[(long long)r * ld + c];
+      s1 += X[(long long)(r + 8) * ld + c];
+      s2 += X[(long long)(r + 16) * ld + c];
+      s3 += X[(long long)(r + 24) * ld + c];
+    }
+    for (; r < R; r += 8) s0 += X[(long long)r * ld + c];
+  }
+  __syncthreads();
+  red[rs * 32 + cl] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (tid < 32 && c < cols) {
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s += red[q * 32 + cl];
+    out[c] = s;
+  }
+  __syncthreads();
+}
+
+#ifdef GCNB_TRACE
+__device__ long long g_head_trace[32];
+#define HTRACE(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_head_trace[i] = clock64(); } while (0)
+#else
+#define HTRACE(i) do { } while (0)
+#endif
+
+__global__ void __launch_bounds__(HT, 1) k_head_step(const HeadParams P) {
+  cg::grid_group grid = cg::this_grid();
+  HTRACE(0);
+  // one shared buffer, three views: the GEMM tiles, the staging of the narrow products, rows of h2 (+ W3)
+  __shared__ __align__(16) float smem_f[16 * 16 * 33];
+  static_assert(sizeof(TileSmem) <= sizeof(float) * 16 * 16 * 33, "tile view must fit");
+  static_assert(SKC * 17 + SKC * 33 <= 16 * 16 * 33, "narrow-product staging must fit");
+  float* red = smem_f;
+  const int tid = threadIdx.x;
+  const int nb = gridDim.x, bid = blockIdx.x;
+  const int B = P.B, n0 = P.n0, n1 = P.n1, n2 = P.n2, C = P.C;
+  const uint32_t key1 = dropout_key(P.seed1, P.state), key2 = dropout_key(P.seed2, P.state);
+  const uint32_t thresh = dropout_threshold(P.keep);
+  const int tmB = ceil_div_d(B, TM), tn1 = ceil_div_d(n1, TN), tn2 = ceil_div_d(n2, TN), tm1 = ceil_div_d(n1, TM);
+
+  // ---- F1: h1 = dropout(relu(a0 W1 + b1)) ---------------------------------------------------------------------
+  gemm_units(P, smem_f, View{P.a0, n0, 1}, true, View{P.W1, n1, 1}, false, B, n1, n0, 1, EPI_H1, 0, tmB * tn1, key1, thresh);
+  HTRACE(1);
+  grid.sync();
+  HTRACE(2);
+
+  // ---- F2: partial sums of h1 W2, K split SK2 ways ---------------------------------------------------------------
+  gemm_units(P, smem_f, View{P.h1, n1, 1}, true, View{P.W2, n2, 1}, false, B, n2, n1, SK2, EPI_PART2, 0, tmB * tn2 * SK2, 0, 0);
+  HTRACE(3);
+  grid.sync();
+  HTRACE(4);
+
+  // ---- F3: per row: h2 = dropout(relu(sum of partials + b2)), logits, cross-entropy, d3 ------------------------
+  {
+    const int warp = tid >> 5, lane = tid & 31;
+    // Four rows at a time, two warps per row: hidden units summed from the partials, logits, cross-entropy.
+    // Shared memory: four row buffers [hidden units | logits], then the logits weights when they fit (22 KB at 256 x 22).
+    const int o_lg = (n2 + 31) & ~31;
+    float* w3s = smem_f + 4 * (o_lg + 32);
+    const bool w3_smem = (size_t)4 * (o_lg + 32) + (size_t)n2 * C <= (size_t)(16 * 16 * 33);
+    const int q = warp >> 1, half = warp & 1, t64 = half * 32 + lane;  // row slot, thread index inside the warp pair
+    if (w3_smem && bid * 4 < B) {
+      for (int i0 = 0; i0 < n2 * C; i0 += HT * 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = i0 + u * HT + tid < n2 * C ? __ldg(P.W3 + i0 + u * HT + tid) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (i0 + u * HT + tid < n2 * C) w3s[i0 + u * HT + tid] = v[u];
+      }
+    }
+    __syncthreads();
+    for (int rb = bid * 4; rb < B; rb += nb * 4) {
+      const int r = rb + q;
+      float* hr = smem_f + q * (o_lg + 32);
+      float* lgr = hr + o_lg;
+      if (r < B) {
+        for (int n = t64; n < n2; n += 64) {
+          float v = __ldg(P.b2 + n);
+#pragma unroll
+          for (int sp = 0; sp < SK2; ++sp) v += P.part2[((long long)sp * B + r) * n2 + n];
+          v = fmaxf(v, 0.f);
+          if (P.keep < 1.f) v = dropout_keeps((uint32_t)((long long)r * n2 + n), key2, thresh) ? v * P.inv_keep : 0.f;
+          hr[n] = v;
+          P.h2[(long long)r * n2 + n] = v;
+        }
+      }
+      __syncthreads();
+      if (r < B) {
+        for (int c = half; c < C; c += 2) {
+          float sacc = 0.f;
+          if (w3_smem) {
+            for (int k = lane; k < n2; k += 32) sacc = fmaf(hr[k], w3s[k * C + c], sacc);
+          } else {
+            for (int k = lane; k < n2; k += 32) sacc = fmaf(hr[k], __ldg(P.W3 + (long long)k * C + c), sacc);
+          }
+#pragma unroll
+          for (int d = 16; d > 0; d >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, d);
+          if (lane == 0) {
+            sacc += __ldg(P.b3 + c);
+            lgr[c] = sacc;
+            P.logits[(long long)r * C + c] = sacc;
+          }
+        }
+      }
+      __syncthreads();
+      if (r < B && half == 0) {
+        float mx = -INFINITY;
+        for (int c = lane; c < C; c += 32) mx = fmaxf(mx, lgr[c]);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+        float se = 0.f;
+        for (int c = lane; c < C; c += 32) se += expf(lgr[c] - mx);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) se += __shfl_xor_sync(0xffffffffu, se, d);
+        const float lse = mx + logf(se);
+        const long long lab = P.labels[r];
+        const bool ok = lab >= 0 && lab < C;  // a label outside [0, C) contributes no loss and no gradient
+        const float scale = 1.f / (float)B;
+        for (int c = lane; c < C; c += 32)
+          P.d3[(long long)r * C + c] = ok ? (expf(lgr[c] - lse) - (c == (int)lab ? 1.f : 0.f)) * scale : 0.f;
+        if (lane == 0) P.loss_rows[r] = ok ? lse - lgr[(int)lab] : 0.f;
+      }
+      __syncthreads();
+    }
+  }
+  HTRACE(5);
+  grid.sync();
+  HTRACE(6);
+
+  // ---- B1: gW3, gb3, d2 = (d3 W3^T) . mask2 ; mean loss ----------------------------------------------------------
+  {
+    const int uW3 = ceil_div_d(n2, 16), uD2 = ceil_div_d(B * n2, HT * 4);
+    for (int u = bid; u < uW3 + 1 + uD2; u += nb) {
+      if (u < uW3) {
+        const int j0 = u * 16;  // gW3[j][c] = sum_r h2[r][j] d3[r][c]
+        skinny16(red, View{P.h2 + j0, n2, 1}, min(16, n2 - j0), View{P.d3, C, 1}, C, B, false, P.gW3 + (long long)j0 * C, C, 1);
+      } else if (u == uW3) {
+        colsum32(red, P.d3, C, C, 0, B, P.gb3);
+        float s = 0.f;  // mean loss, fixed order
+        for (int i = tid; i < B; i += HT) s += P.loss_rows[i];
+        __syncthreads();
+        red[tid] = s;
+        __syncthreads();
+        for (int d = HT / 2; d > 0; d >>= 1) {
+          if (tid < d) red[tid] += red[tid + d];
+          __syncthreads();
+        }
+        if (tid == 0) P.loss[0] = red[0] / (float)B;
+        __syncthreads();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int o = ((u - uW3 - 1) * 4 + i) * HT + tid;
+          if (o < B * n2) {
+            const int r = o / n2, n = o - r * n2;
+            float s = 0.f;
+            if (P.h2[o] > 0.f) {
+              const float* dr = P.d3 + (long long)r * C;
+              const float* wr = P.W3 + (long long)n * C;
+              for (int c = 0; c < C; ++c) s = fmaf(dr[c], __ldg(wr + c), s);
+              s *= P.inv_keep;
+            }
+            P.d2[o] = s;
+          }
+        }
+      }
+    }
+  }
+  HTRACE(7);
+  grid.sync();
+  HTRACE(8);
+  if (bid == 0 && tid == 0 && P.state != nullptr && P.tick) {
+    const float p1 = P.state[0] * P.beta1, p2 = P.state[1] * P.beta2;
+    P.state[0] = p1;
+    P.state[1] = p2;
+    P.state[2] = P.lr * sqrtf(1.f - p2) / (1.f - p1);
+    P.state[3] += 1.f;
+  }
+
+  // ---- B2: partial gW2 = h1^T d2 (batch split SKW ways), d1 = (d2 W2^T) . mask1, gb2 -----------------------------
+  {
+    const int uW = tm1 * tn2 * SKW, uD = tmB * tn1, uB = ceil_div_d(n2, 32);
+    gemm_units(P, smem_f, View{P.h1, 1, n1}, false, View{P.d2, n2, 1}, false, n1, n2, B, SKW, EPI_PARTW2, 0, uW, 0, 0);
+    gemm_units(P, smem_f, View{P.d2, n2, 1}, true, View{P.W2, 1, n2}, true, B, n1, n2, 1, EPI_D1, uW % nb, uD, 0, 0);
+    for (int u = bid - (uW + uD) % nb; u < uB; u += nb)
+      if (u >= 0) colsum32(red, P.d2, n2, n2, u * 32, B, P.gb2);
+  }
+  HTRACE(9);
+  grid.sync();
+  HTRACE(10);
+
+  // ---- B3: gW2 = sum of partials, gW1 = a0^T d1, gb1, d0 = d1 W1^T ------------------------------------------------
+  {
+    const int uS = ceil_div_d(n1 * n2, HT * 8), uW1 = ceil_div_d(n1, 16), uB1 = ceil_div_d(n1, 32), uD0 = ceil_div_d(B, 16);
+    for (int u = bid; u < uS + uW1 + uB1 + uD0; u += nb) {
+      if (u < uS) {
+        float v[8][SKW];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const long long o = ((long long)u * 8 + i) * HT + tid;
+#pragma unroll
+          for (int q = 0; q < SKW; ++q) v[i][q] = o < (long long)n1 * n2 ? P.partW2[(long long)q * n1 * n2 + o] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const long long o = ((long long)u * 8 + i) * HT + tid;
+          float sacc = v[i][0];
+#pragma unroll
+          for (int q = 1; q < SKW; ++q) sacc += v[i][q];
+          if (o < (long long)n1 * n2) P.gW2[o] = sacc;
+        }
+      } else if (u < uS + uW1) {
+        const int j0 = (u - uS) * 16;  // gW1[m][n] = sum_r a0[r][m] d1[r][n] for 16 columns n
+        skinny16(red, View{P.d1 + j0, n1, 1}, min(16, n1 - j0), View{P.a0, n0, 1}, n0, B, false, P.gW1 + j0, 1, n1);
+      } else if (u < uS + uW1 + uB1) {
+        colsum32(red, P.d1, n1, n1, (u - uS - uW1) * 32, B, P.gb1);
+      } else {
+        const int r0 = (u - uS - uW1 - uB1) * 16;  // d0[r][m] = sum_k d1[r][k] W1[m][k] for 16 rows r
+        skinny16(red, View{P.d1 + (long long)r0 * n1, 1, n1}, min(16, B - r0), View{P.W1, 1, n1}, n0, n1, true,
+                 P.d0 + (long long)r0 * n0, n0, 1);
+      }
+    }
+  }
+  HTRACE(11);
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+size_t head_step_workspace(int B, int n0, int n1, int n2, int C) {
+  (void)n0;
+  size_t f = (size_t)B * n1 * 2 /*h1, d1*/ + (size_t)B * n2 * 2 /*h2, d2*/ + (size_t)B * C /*d3*/ +
+             (size_t)SK2 * B * n2 /*part2*/ + (size_t)SKW * n1 * n2 /*partW2*/ + (size_t)B /*loss rows*/;
+  return f * sizeof(float) + 16 * 256;
+}
+
+bool head_step_supported(int B, int n0, int n1, int n2, int C) {
+  return B >= 1 && n0 >= 1 && n0 <= 32 && C >= 1 && C <= 32 && n1 >= 1 && n2 >= 1 && n2 <= 2048;
+}
+
+int head_step(const HeadParams& P0, Workspace& ws, cudaStream_t st) {
+  HeadParams P = P0;
+  const int B = P.B, n1 = P.n1, n2 = P.n2, C = P.C;
+  P.h1 = ws.take<float>((size_t)B * n1);
+  P.d1 = ws.take<float>((size_t)B * n1);
+  P.h2 = ws.take<float>((size_t)B * n2);
+  P.d2 = ws.take<float>((size_t)B * n2);
+  P.d3 = ws.take<float>((size_t)B * C);
+  P.part2 = ws.take<float>((size_t)SK2 * B * n2);
+  P.partW2 = ws.take<float>((size_t)SKW * n1 * n2);
+  P.loss_rows = ws.take<float>((size_t)B);
+  if (!P.loss_rows) {
+    set_error("gcnb_head_step_f32: workspace too small");
+    return GCNB_ERR_WORKSPACE;
+  }
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  int per_sm = 0;
+  GCNB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_head_step, HT, 0));
+  if (per_sm < 1) {
+    set_error("gcnb_head_step_f32: the kernel does not fit on an SM");
+    return GCNB_ERR_CUDA;
+  }
+  // one CTA per SM: every phase has at most ~150 work units, and two units on one SM while another SM idles lose
+  // more than the extra warps hide (measured: 83 us with two CTAs per SM, 67 us with one)
+  const int grid = di.sm_count;
+  void* args[] = {(void*)&P};
+  GCNB_CUDA(cudaLaunchCooperativeKernel((const void*)k_head_step, dim3(grid), dim3(HT), args, 0, st));
+  GCNB_LAUNCH_CHECK("k_head_step");
+  return GCNB_OK;
+}
+
+}  // namespace gcnb
+
+using namespace gcnb;
+
+extern "C" {
+
+size_t gcnb_head_step_workspace_bytes(int B, int n0, int n1, int n2, int C) {
+  return head_step_supported(B, n0, n1, n2, C) ? head_step_workspace(B, n0, n1, n2, C) : 0;
+}
+
+int gcnb_head_step_f32(const float* a0, const int64_t* labels, const float* W1, const float* b1, const float* W2,
+                       const float* b2, const float* W3, const float* b3, float* logits, float* loss, float* gW1,
+                       float* gb1, float* gW2, float* gb2, float* gW3, float* gb3, float* d0, int B, int n0, int n1,
+                       int n2, int C, float keep, unsigned seed1, unsigned seed2, float* adam_state, float lr,
+                       float beta1, float beta2, int tick, void* workspace, size_t workspace_bytes,
+                       gcnb_stream_t stream) {
+  GCNB_REQUIRE(head_step_supported(B, n0, n1, n2, C),
+               "gcnb_head_step_f32: unsupported sizes B=%d widths %d-%d-%d-%d (needs n0 <= 32, C <= 32, n2 <= 2048)", B, n0,
+               n1, n2, C);
+  GCNB_REQUIRE(a0 && labels && W1 && b1 && W2 && b2 && W3 && b3 && logits && loss && gW1 && gb1 && gW2 && gb2 && gW3 &&
+                   gb3 && d0,
+               "gcnb_head_step_f32: NULL argument");
+  GCNB_REQUIRE(keep > 0.f && keep <= 1.f, "gcnb_head_step_f32: keep probability must be in (0, 1] (got %g)", (double)keep);
+  HeadParams P{};
+  P.a0 = a0; P.labels = reinterpret_cast<const long long*>(labels);
+  P.W1 = W1; P.b1 = b1; P.W2 = W2; P.b2 = b2; P.W3 = W3; P.b3 = b3;
+  P.logits = logits; P.loss = loss;
+  P.gW1 = gW1; P.gb1 = gb1; P.gW2 = gW2; P.gb2 = gb2; P.gW3 = gW3; P.gb3 = gb3; P.d0 = d0;
+  P.B = B; P.n0 = n0; P.n1 = n1; P.n2 = n2; P.C = C;
+  P.keep = keep; P.inv_keep = 1.f / keep; P.seed1 = seed1; P.seed2 = seed2;
+  P.state = adam_state; P.lr = lr; P.beta1 = beta1; P.beta2 = beta2; P.tick = tick;
+  Workspace ws(workspace, workspace_bytes);
+  return head_step(P, ws, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"
+
+#ifdef GCNB_TRACE
+extern "C" __attribute__((visibility("default"))) int gcnb_debug_read_head_trace(long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, gcnb::g_head_trace, sizeof(long long) * 32);
+}
+#endif

@@ -176,16 +176,21 @@ class FusedTrainer:
     buffer.  Gradients equal those of ``Trainer`` (autograd) -- see ``tests/test_gpu_parity.py``.
     """
 
-    def __init__(self, model, lr=1e-3, distributed=None, use_cuda_graph=True, dropout=1.0, beta1=0.9, beta2=0.999,
-                 eps=1e-8, own_gemm=False, save_basis=True):
+    def __init__(self, model, lr=1e-3, distributed=None, use_cuda_graph=True, dropout=None, beta1=0.9, beta2=0.999,
+                 eps=1e-8, own_gemm=True, save_basis=True, fused_head=True):
         import ctypes as C
 
         from . import _lib, ops
 
         self.model, self.lr, self.b1, self.b2, self.eps = model, lr, beta1, beta2, eps
         self.C, self._lib, self.ops = C, _lib, ops
+        # keep-probability of the FC dropout: the model's own (what Trainer and the reference use, models_gcn.py:145,677)
+        # unless the caller overrides it; it is baked into the captured graph.
+        if dropout is None:
+            dropout = getattr(model, "dropout", 1.0)
         self.keep = float(dropout) if dropout else 1.0
         self.own_gemm = own_gemm
+        self.fused_head = fused_head
         self.save_basis = save_basis
         self.distributed = dist.is_available() and dist.is_initialized() if distributed is None else distributed
         self.world = dist.get_world_size() if self.distributed else 1
@@ -285,6 +290,58 @@ class FusedTrainer:
                                 self._lib.EPI_RELU_DROPOUT, None, 0x5eed + i)
             return gemm(a_in, W, out, m.fc_bias[i], a_in.shape[0], W.shape[1], W.shape[0], 0, 0)
 
+        B = h0.shape[0]
+        widths = [h0.shape[1]] + [w.shape[1] for w in m.fc_weights]
+        head_ws = lib.gcnb_head_step_workspace_bytes(B, *widths) if (self.fused_head and nfc == 3) else 0
+        if head_ws:
+            # the whole head -- three FC layers, cross-entropy, their backward pass, the optimiser clock -- in ONE launch
+            logits = torch.empty((B, widths[3]), dtype=torch.float32, device=x.device)
+            d = torch.empty((B, widths[0]), dtype=torch.float32, device=x.device)
+            ws = torch.empty(head_ws, dtype=torch.uint8, device=x.device)
+            g = lambda t: vp(self.gview[id(t)])
+            W1, W2, W3 = m.fc_weights
+            b1, b2, b3 = m.fc_bias
+            rc = lib.gcnb_head_step_f32(vp(h0), vp(labels), vp(W1), vp(b1), vp(W2), vp(b2), vp(W3), vp(b3), vp(logits),
+                                        vp(self._loss), g(W1), g(b1), g(W2), g(b2), g(W3), g(b3), vp(d), B, *widths,
+                                        self.keep, 0x5eed, 0x5eed + 1, vp(self.state), self.lr, self.b1, self.b2, 1,
+                                        vp(ws), ws.numel(), stream)
+            self._lib.check(rc, "gcnb_head_step_f32")
+        else:
+            logits, d = self._head_by_layers(h0, labels, gemm, gemm_epi, fc_fwd, lib, vp, stream)
+        # ---- backward: conv stack (d is the gradient of the mean over filters of the last layer) ----
+        dy, dy_is_mean = d, True
+        if not cheb:
+            dy, dy_is_mean = torch.ops.gcn_b200.mean_f_bwd(d, h.shape[-1]), False
+        for i in range(nconv - 1, -1, -1):
+            hin, perm, y, am, pl, stack = saved[i]
+            need_dx = i > 0
+            gW, gb = self.gview[id(m.conv_weights[i])], self.gview[id(m.conv_bias[i])]
+            if cheb:
+                dx = ops.cheb_bwd_into(hin, perm, y, am, dy, dy_is_mean, *pl.tensors(), m.conv_weights[i], gW, gb, m.K[i],
+                                       m.p[i], mode, True, need_dx, m.algo, stack)
+            else:
+                dx, dW, db = torch.ops.gcn_b200.spectral_bwd(hin, y, am, dy, pl.Ut, m.conv_weights[i], m.p[i], mode, True,
+                                                             need_dx)
+                gW.copy_(dW)
+                gb.copy_(db.view_as(gb))
+            dy, dy_is_mean = dx, False
+        # ---- update ----
+        if self.world > 1:
+            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM)
+        rc = lib.gcnb_adam_tf_f32(vp(self.flat_p), vp(self.flat_g), vp(self.flat_m), vp(self.flat_v), vp(self.decay),
+                                  vp(self.state), self.n, self.lr, self.b1, self.b2, self.eps,
+                                  float(m.regularization or 0.0), 1.0 / self.world, 0, stream)
+        self._lib.check(rc, "gcnb_adam_tf_f32")
+        return self._loss, logits
+
+
+    def _head_by_layers(self, h0, labels, gemm, gemm_epi, fc_fwd, lib, vp, stream):
+        """The head launch by launch (any number of FC layers): GEMM + fused ReLU/dropout per layer, cross-entropy,
+        two GEMMs per layer backward, one multi-matrix column sum for the bias gradients."""
+        m, C = self.model, self.C
+        nfc = len(m.M)
+        x = h0
+        use_own_gemm = self.own_gemm
         acts = [h0]
         for i in range(nfc - 1):
             acts.append(fc_fwd(i, acts[-1], True))
@@ -324,31 +381,7 @@ class FusedTrainer:
             cls = (C.c_int * n)(*[ds[i].shape[1] for i in grp])
             rc = lib.gcnb_colsum_multi_f32(mats, outs, rws, cls, n, stream)
             self._lib.check(rc, "gcnb_colsum_multi_f32")
-        # ---- backward: conv stack (d is the gradient of the mean over filters of the last layer) ----
-        dy, dy_is_mean = d, True
-        if not cheb:
-            dy, dy_is_mean = torch.ops.gcn_b200.mean_f_bwd(d, h.shape[-1]), False
-        for i in range(nconv - 1, -1, -1):
-            hin, perm, y, am, pl, stack = saved[i]
-            need_dx = i > 0
-            gW, gb = self.gview[id(m.conv_weights[i])], self.gview[id(m.conv_bias[i])]
-            if cheb:
-                dx = ops.cheb_bwd_into(hin, perm, y, am, dy, dy_is_mean, *pl.tensors(), m.conv_weights[i], gW, gb, m.K[i],
-                                       m.p[i], mode, True, need_dx, m.algo, stack)
-            else:
-                dx, dW, db = torch.ops.gcn_b200.spectral_bwd(hin, y, am, dy, pl.Ut, m.conv_weights[i], m.p[i], mode, True,
-                                                             need_dx)
-                gW.copy_(dW)
-                gb.copy_(db.view_as(gb))
-            dy, dy_is_mean = dx, False
-        # ---- update ----
-        if self.world > 1:
-            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM)
-        rc = lib.gcnb_adam_tf_f32(vp(self.flat_p), vp(self.flat_g), vp(self.flat_m), vp(self.flat_v), vp(self.decay),
-                                  vp(self.state), self.n, self.lr, self.b1, self.b2, self.eps,
-                                  float(m.regularization or 0.0), 1.0 / self.world, 0, stream)
-        self._lib.check(rc, "gcnb_adam_tf_f32")
-        return self._loss, logits
+        return logits, d
 
     def regularization_term(self):
         """``regularization * sum_v ||v||^2 / 2`` over the regularised tensors (reported with the loss, not needed by the step)."""
@@ -356,7 +389,14 @@ class FusedTrainer:
             return float(self.model.regularization or 0.0) * 0.5 * float((self.flat_p * self.flat_p * self.decay).sum())
 
     def step(self, x, labels, dropout=None):
-        """One optimisation step on the local shard; returns (cross-entropy loss tensor, logits).  ``labels`` int64."""
+        """One optimisation step on the local shard; returns (cross-entropy loss tensor, logits).  ``labels`` int64.
+
+        The returned loss is the mean cross-entropy; ``regularization_term()`` gives the L2 term the reference adds to
+        the reported loss (models_gcn.py:260-262) -- the update itself always includes it.  ``dropout`` must be None or
+        the keep-probability this trainer was built with (it is part of the captured graph)."""
+        if dropout is not None and abs(float(dropout if dropout else 1.0) - self.keep) > 1e-12:
+            raise ValueError("FusedTrainer was built with dropout keep-probability %g; step(dropout=%g) would be ignored "
+                             "-- construct the trainer with the value you want" % (self.keep, float(dropout)))
         if not self.use_cuda_graph:
             return self._step_impl(x, labels)
         if self._graph is None:

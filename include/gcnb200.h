@@ -174,6 +174,27 @@ GCNB_API int gcnb_softmax_xent_f32(const float* logits, const int64_t* labels, f
                           float* loss_rows, int B, int C, float* adam_state, float lr, float beta1, float beta2,
                           gcnb_stream_t stream);
 
+/*
+ * The classifier head of one training step in ONE launch (a persistent cooperative kernel, grid barriers between the
+ * six dependent stages): cgcnn.fc x2 with ReLU + dropout (models_gcn.py:650-656, :674-677), the logits layer (:680-681),
+ * the mean sparse-softmax cross-entropy (:253-259) and the whole backward pass tf.gradients builds for them (:298-303).
+ *   h1 = dropout(relu(a0 W1 + b1)), h2 = dropout(relu(h1 W2 + b2)), logits = h2 W3 + b3, loss = mean CE(logits, labels)
+ *   gW*, gb* = gradients of the loss (overwritten); d0 [B][n0] = gradient w.r.t. a0 (the mean over the filters of the
+ *   last conv layer, i.e. the dy of gcnb_cheb_bwd_f32 with dy_is_mean = 1).
+ * a0 [B][n0], W1 [n0][n1], W2 [n1][n2], W3 [n2][C], logits [B][C], loss [1]; n0 <= 32, C <= 32, n2 <= 2048.
+ * Dropout: keep-probability `keep` (1 = none), counter-based masks keyed by (seed1 | seed2, adam_state[3]) -- the masks
+ * gcnb_relu_dropout_fwd_f32 draws -- so CUDA-graph replays draw fresh masks.  tick != 0 advances the optimiser clock
+ * {b1^t, b2^t, lr_t, t} in adam_state (as gcnb_softmax_xent_f32 does) after the masks of this step have been drawn.
+ * A label outside [0, C) contributes neither loss nor gradient.  fp32 FFMA throughout; fixed-order reductions.
+ */
+GCNB_API size_t gcnb_head_step_workspace_bytes(int B, int n0, int n1, int n2, int C); /* 0: sizes not supported */
+GCNB_API int gcnb_head_step_f32(const float* a0, const int64_t* labels, const float* W1, const float* b1, const float* W2,
+                                const float* b2, const float* W3, const float* b3, float* logits, float* loss,
+                                float* gW1, float* gb1, float* gW2, float* gb2, float* gW3, float* gb3, float* d0, int B,
+                                int n0, int n1, int n2, int C, float keep, unsigned seed1, unsigned seed2,
+                                float* adam_state, float lr, float beta1, float beta2, int tick, void* workspace,
+                                size_t workspace_bytes, gcnb_stream_t stream);
+
 /* C[M x N] = op(A) op(B) (+ bias[N]); row-major, fp32 in/out, tensor cores with a 3-pass TF32 split (fp32-level
  * accuracy).  The dense transforms of the spectral layer and the FC layers of the training step use it. */
 GCNB_API int gcnb_gemm_f32(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int lda,

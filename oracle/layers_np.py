@@ -322,10 +322,35 @@ def conv_stack_bwd(trace, Ls, params, dy, filter="chebyshev5", brelu="b1relu", d
 
 
 # ----------------------------------------------------------------------------- whole training step (CPU baseline)
-def network_step(x, labels, Ls, params, fcs, regularization, filter="chebyshev5", brelu="b1relu", dtype=np.float32):
+def counter_dropout_mask(rows, cols, keep, seed, step):
+    """The 0/1 mask the CUDA path draws for a ``[rows, cols]`` activation (``dropout_keeps`` in ``csrc/common.cuh``:
+    murmur3-finaliser hash of the element index, keyed by a layer seed and the optimiser step count).  Exists so that the
+    oracle can be run with the SAME mask as the device when ``tf.nn.dropout`` (models_gcn.py:677) is active."""
+    def mix32(x):
+        x = np.asarray(x, np.uint64) & 0xFFFFFFFF
+        x ^= x >> 16
+        x = (x * 0x85EBCA6B) & 0xFFFFFFFF
+        x ^= x >> 13
+        x = (x * 0xC2B2AE35) & 0xFFFFFFFF
+        x ^= x >> 16
+        return x
+
+    if keep >= 1.0:
+        return np.ones((rows, cols), np.float64)
+    key = mix32(np.uint64(seed) ^ mix32((np.uint64(int(step)) + 0x9E3779B9) & 0xFFFFFFFF))
+    thresh = np.uint64(int(np.float32(keep) * 4294967296.0))
+    idx = np.arange(rows * cols, dtype=np.uint64)
+    h = mix32((idx * 0x9E3779B1 + key) & 0xFFFFFFFF)
+    return (h < thresh).astype(np.float64).reshape(rows, cols)
+
+
+def network_step(x, labels, Ls, params, fcs, regularization, filter="chebyshev5", brelu="b1relu", dtype=np.float32,
+                 dropout_masks=None, keep=1.0):
     """Forward + loss + backward of the whole network (conv stack, mean over F, FC head, CE + L2).
 
     What one ``sess.run([op_train, ...])`` computes up to the optimiser update (models_gcn.py:146, :298-303).
+    ``dropout_masks`` (one 0/1 array per hidden FC layer) with keep-probability ``keep`` reproduces ``tf.nn.dropout``
+    (models_gcn.py:677: kept activations scaled by 1/keep) for a GIVEN mask.
     Returns ``(loss, conv_grads, fc_grads)``.  Used as the CPU baseline and by the gradient parity test.
     """
     h, trace = conv_stack(x, Ls, params, filter=filter, brelu=brelu, dtype=dtype, keep=True)
@@ -333,7 +358,11 @@ def network_step(x, labels, Ls, params, fcs, regularization, filter="chebyshev5"
     acts = [h.mean(axis=-1, dtype=dtype)]
     for i, (W, b) in enumerate(fcs):
         z = acts[-1] @ np.asarray(W, dtype) + np.asarray(b, dtype)
-        acts.append(np.maximum(z, 0) if i < len(fcs) - 1 else z)
+        if i < len(fcs) - 1:
+            z = np.maximum(z, 0)
+            if dropout_masks is not None:
+                z = (z * np.asarray(dropout_masks[i], dtype) / dtype(keep)).astype(dtype)
+        acts.append(z)
     logits = acts[-1]
     regs = [np.asarray(p["W"]) for p in params if filter != "chebyshev2"] + [v for Wb in fcs for v in Wb]
     value = loss(logits.astype(np.float64), labels, regs, regularization)
@@ -347,6 +376,8 @@ def network_step(x, labels, Ls, params, fcs, regularization, filter="chebyshev5"
         W, b = fcs[i]
         if i < len(fcs) - 1:
             d = d * (acts[i + 1] > 0)
+            if dropout_masks is not None:
+                d = (d / dtype(keep)).astype(dtype)  # acts > 0 already implies "kept"
         fc_grads[i] = (acts[i].T @ d + regularization * np.asarray(W, dtype), d.sum(0) + regularization * np.asarray(b, dtype))
         d = d @ np.asarray(W, dtype).T
     dh = np.repeat(d[:, :, None], F_last, axis=2) / dtype(F_last)

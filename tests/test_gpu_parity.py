@@ -661,3 +661,152 @@ def test_large_graph_general_path(dev, B):
     assert rel_inf(r["dW"], g64[0]["dW"]) <= TOL
     assert rel_inf(r["db"], g64[0]["db"]) <= TOL
     assert rel_inf(r["dx"], dx64) <= TOL
+
+
+# ------------------------------------------------------------------------------------------ round 2
+def _head_oracle(a0, labels, Ws, bs, masks, keep):
+    """fp64 head forward + backward for given dropout masks (models_gcn.py:650-656, :674-681, :253-259, :298-303)."""
+    a0 = a0.astype(np.float64)
+    h1 = np.maximum(a0 @ Ws[0] + bs[0], 0) * masks[0] / keep
+    h2 = np.maximum(h1 @ Ws[1] + bs[1], 0) * masks[1] / keep
+    lg = h2 @ Ws[2] + bs[2]
+    z = lg - lg.max(1, keepdims=True)
+    logp = z - np.log(np.exp(z).sum(1, keepdims=True))
+    B = len(labels)
+    loss = -logp[np.arange(B), labels].mean()
+    d3 = np.exp(logp)
+    d3[np.arange(B), labels] -= 1
+    d3 /= B
+    d2 = (d3 @ Ws[2].T) * (h2 > 0) / keep
+    d1 = (d2 @ Ws[1].T) * (h1 > 0) / keep
+    return dict(logits=lg, loss=loss, gW=[a0.T @ d1, h1.T @ d2, h2.T @ d3], gb=[d1.sum(0), d2.sum(0), d3.sum(0)],
+                d0=d1 @ Ws[0].T)
+
+
+@pytest.mark.parametrize("B,widths,keep", [(512, (25, 512, 256, 22), 1.0), (512, (25, 512, 256, 22), 0.5),
+                                           (37, (25, 512, 256, 22), 0.5), (130, (7, 100, 50, 5), 0.75),
+                                           (64, (32, 129, 67, 32), 1.0)])
+def test_head_step_kernel_matches_oracle(dev, B, widths, keep):
+    """gcnb_head_step_f32 (one cooperative launch: FC x3, cross-entropy, full backward) against the fp64 oracle run with
+    the SAME dropout masks (the counter-based mask is mirrored in oracle.counter_dropout_mask)."""
+    import ctypes as C
+
+    from gcn_fmri_decoding_b200 import _lib
+
+    lib = _lib.lib()
+    rng = np.random.RandomState(B + widths[1])
+    n0, n1, n2, nc = widths
+    a0 = np.abs(rng.randn(B, n0)).astype(np.float32)
+    labels = rng.randint(0, nc, size=B).astype(np.int64)
+    Ws = [(rng.randn(a, b) * 0.2).astype(np.float32) for a, b in ((n0, n1), (n1, n2), (n2, nc))]
+    bs = [(rng.randn(b) * 0.1 + 0.1).astype(np.float32) for b in (n1, n2, nc)]
+    step = 3.0
+    state = T(np.array([0.9 ** 3, 0.999 ** 3, 0.0, step], np.float32), dev)
+    masks = [O.counter_dropout_mask(B, n1, keep, 0x5eed, step), O.counter_dropout_mask(B, n2, keep, 0x5eed + 1, step)]
+    ref = _head_oracle(a0, labels, [w.astype(np.float64) for w in Ws], [b.astype(np.float64) for b in bs], masks, keep)
+    ta0, tl = T(a0, dev), T(labels, dev, torch.long)
+    tW, tb = [T(w, dev) for w in Ws], [T(b, dev) for b in bs]
+    gW, gb = [torch.empty_like(w) for w in tW], [torch.empty_like(b) for b in tb]
+    logits = torch.empty(B, nc, device=dev)
+    loss = torch.zeros((), device=dev)
+    d0 = torch.empty(B, n0, device=dev)
+    nbytes = lib.gcnb_head_step_workspace_bytes(B, n0, n1, n2, nc)
+    assert nbytes > 0
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    outs = []
+    for rep in range(2):  # twice: bit-reproducible
+        state.copy_(T(np.array([0.9 ** 3, 0.999 ** 3, 0.0, step], np.float32), dev))
+        rc = lib.gcnb_head_step_f32(vp(ta0), vp(tl), vp(tW[0]), vp(tb[0]), vp(tW[1]), vp(tb[1]), vp(tW[2]), vp(tb[2]),
+                                    vp(logits), vp(loss), vp(gW[0]), vp(gb[0]), vp(gW[1]), vp(gb[1]), vp(gW[2]), vp(gb[2]),
+                                    vp(d0), B, n0, n1, n2, nc, keep, 0x5eed, 0x5eed + 1, vp(state), 1e-3, 0.9, 0.999, 1,
+                                    vp(ws), ws.numel(), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        _lib.check(rc, "gcnb_head_step_f32")
+        torch.cuda.synchronize()
+        outs.append([t.clone() for t in (logits, loss, d0, *gW, *gb)])
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    assert float(state[3]) == step + 1  # the optimiser clock advanced once
+    assert rel_inf(logits.cpu().numpy(), ref["logits"]) <= TOL
+    assert np.array_equal(logits.cpu().numpy().argmax(1), ref["logits"].argmax(1))
+    assert abs(float(loss) - ref["loss"]) <= TOL * abs(ref["loss"])
+    assert rel_inf(d0.cpu().numpy(), ref["d0"]) <= TOL
+    for i in range(3):
+        assert rel_inf(gW[i].cpu().numpy(), ref["gW"][i]) <= TOL, i
+        assert rel_inf(gb[i].cpu().numpy(), ref["gb"][i]) <= TOL, i
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_fused_trainer_with_dropout_matches_oracle(dev, graph_l4, graph):
+    """The benched configuration -- FusedTrainer(dropout=0.5, own_gemm=True), fused head, tcgen05 forward, saved basis --
+    against oracle.network_step run with the device's dropout masks: every gradient of the step."""
+    from gcn_fmri_decoding_b200 import graclus, synth
+    from gcn_fmri_decoding_b200.train import FusedTrainer
+
+    g = graph_l4
+    # A small batch: every pooled window / ReLU whose fp64 decision margin is below fp32 rounding is a coin toss that
+    # reroutes one gradient element (see test_large_graph_general_path); with 16 windows this seed has none.
+    B = 16
+    xraw = synth.bold_windows(B, seed=31)
+    labels = synth.labels(B, seed=31)
+    model = build_model(g, [32, 32], [5, 5], [4, 4], [512, 256, 22], "chebyshev5", "b1relu", dev, perm=g["perm"])
+    tr = FusedTrainer(model, distributed=False, use_cuda_graph=graph, dropout=0.5, own_gemm=True)
+    sd = {k: v.astype(np.float64) for k, v in model.state_dict_tf().items()}
+    p0 = tr.flat_p.clone()
+    loss, logits = tr.step(T(xraw, dev), T(labels, dev, torch.long))
+    torch.cuda.synchronize()
+    # the first step draws its masks with the optimiser step count 0
+    masks = [O.counter_dropout_mask(B, 512, 0.5, 0x5eed, 0), O.counter_dropout_mask(B, 256, 0.5, 0x5eed + 1, 0)]
+    xperm = graclus.perm_data_3d(xraw, g["perm"])
+    params = [dict(W=sd["conv%d/weights" % i], b=sd["conv%d/bias" % i].reshape(32), K=5, p=4) for i in (1, 2)]
+    fcs = [(sd[s + "/weights"], sd[s + "/bias"]) for s in ("fc1", "fc2", "logits")]
+    ref_loss, conv_g, fc_g = O.network_step(xperm, labels, model.L, params, fcs, 0.0, dtype=np.float64,
+                                            dropout_masks=masks, keep=0.5)
+    assert abs(float(loss) - ref_loss) <= TOL * abs(ref_loss)       # CE only (regularization=0 in the oracle call)
+    for i in range(2):
+        assert rel_inf(tr.gview[id(model.conv_weights[i])].cpu().numpy(), conv_g[i]["dW"]) <= TOL, i
+        assert rel_inf(tr.gview[id(model.conv_bias[i])].cpu().numpy().reshape(32), conv_g[i]["db"]) <= TOL, i
+    for i in range(3):
+        assert rel_inf(tr.gview[id(model.fc_weights[i])].cpu().numpy(), fc_g[i][0]) <= TOL, i
+        assert rel_inf(tr.gview[id(model.fc_bias[i])].cpu().numpy(), fc_g[i][1]) <= TOL, i
+    # one TF-Adam step from p0 with g + reg * p on the regularised tensors (models_gcn.py:260-262, :294)
+    gfull = tr.flat_g + 5e-4 * p0 * tr.decay
+    m = 0.1 * gfull
+    v = 0.001 * gfull * gfull
+    lr_t = 1e-3 * np.sqrt(1 - 0.999) / (1 - 0.9)
+    expect = p0 - lr_t * m / (v.sqrt() + 1e-8)
+    assert float((expect - tr.flat_p).abs().max()) <= 1e-6
+
+
+def test_benched_shapes_run_on_tcgen05(dev):
+    """The forward kernel AUTO dispatch picks for the BASELINE config shapes is the tcgen05/TMEM one."""
+    from gcn_fmri_decoding_b200 import _lib
+
+    for shape in ((512, 400, 3684, 15, 32, 5, 4), (512, 100, 898, 32, 32, 5, 4), (128, 372, 3684, 32, 32, 5, 1)):
+        assert "tcgen05" in _lib.describe_fwd(*shape), shape
+
+
+@pytest.mark.parametrize("lvl,Fin,p,brelu", [(0, 15, 4, "b1relu"), (2, 32, 4, "b1relu"), (1, 15, 2, "b2relu"), (0, 32, 8, "b2relu")])
+def test_fused_argmax_bit_exact_against_own_activations(dev, graph_l4, lvl, Fin, p, brelu):
+    """mpool1 inside the fused kernel is bit-exact: the pooled values and the arg-max bytes equal the first-maximum
+    pooling (MaxPoolGrad's rule, ties included) of the SAME kernel's un-pooled activations (p = 1 launch)."""
+    from gcn_fmri_decoding_b200 import ops
+    from gcn_fmri_decoding_b200.plan import GraphPlan
+
+    L = graph_l4["L"][lvl]
+    M = L.shape[0]
+    assert M % p == 0
+    pl = GraphPlan(L, dev)
+    torch.manual_seed(lvl * 10 + p)
+    B = 33
+    x = torch.randn(B, M, Fin, device=dev)
+    W = torch.randn(Fin * 5, 32, device=dev) * 0.2
+    mode = ops.BIAS_PER_FILTER if brelu == "b1relu" else ops.BIAS_PER_VERTEX
+    b = torch.randn(32 if brelu == "b1relu" else M * 32, device=dev) * 0.3
+    y, am = ops.cheb_fwd(x, None, *pl.tensors(), W, b, 5, p, mode, True, True, ops.ALGO_FUSED)
+    a, _ = ops.cheb_fwd(x, None, *pl.tensors(), W, b, 5, 1, mode, True, False, ops.ALGO_FUSED)
+    win = a.view(B, M // p, p, 32)
+    mx = win.max(2, keepdim=True).values
+    first = torch.where(win == mx, torch.arange(p, device=dev).view(1, 1, p, 1), torch.full((), p, device=dev)).min(2).values
+    assert torch.equal(mx.squeeze(2), y)
+    assert torch.equal(first.to(torch.uint8), am)
