@@ -129,18 +129,31 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
   // host the prologue's scratch tables rlen / sorted / rp until the first order overwrites them)
   for (uint32_t a = tid * 16u; a < (uint32_t)P.off_lo; a += kThreads * 16u) sts128(sb + a, make_float4(0.f, 0.f, 0.f, 0.f));
   // taps: tf32 hi / lo and bf16 images, contraction index kk = k*FP + f  (W row = f*K + k, models_gcn.py:611-615)
-  for (int idx = tid; idx < K * FP * 32; idx += kThreads) {
-    const int o = idx & 31, kk = idx >> 5, k = kk / FP, f = kk - k * FP;
-    float w = 0.f;
-    if (f < P.Fin && o < P.Fout) w = __ldg(P.W + ((long long)f * K + k) * P.Fout + o);
-    const float hi = tf32_rna(w), lo = tf32_rna(w - hi);
-    *reinterpret_cast<float*>(smem + P.off_wh + tap_off_tf32(kk, o)) = hi;
-    *reinterpret_cast<float*>(smem + P.off_wl + tap_off_tf32(kk, o)) = lo;
-    *reinterpret_cast<__nv_bfloat16*>(smem + P.off_wb + tap_off_bf16(kk, o)) = __float2bfloat16_rn(w);
+  for (int i0 = 0; i0 < K * FP * 32; i0 += kThreads * 4) {
+    float wv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {  // all four loads in flight before the first conversion
+      const int idx = i0 + u * kThreads + tid;
+      const int o = idx & 31, kk = idx >> 5, k = kk / FP, f = kk - k * FP;
+      wv[u] = (idx < K * FP * 32 && f < P.Fin && o < P.Fout) ? __ldg(P.W + ((long long)f * K + k) * P.Fout + o) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int idx = i0 + u * kThreads + tid;
+      if (idx < K * FP * 32) {
+        const int o = idx & 31, kk = idx >> 5;
+        const float w = wv[u], hi = tf32_rna(w), lo = tf32_rna(w - hi);
+        *reinterpret_cast<float*>(smem + P.off_wh + tap_off_tf32(kk, o)) = hi;
+        *reinterpret_cast<float*>(smem + P.off_wl + tap_off_tf32(kk, o)) = lo;
+        *reinterpret_cast<__nv_bfloat16*>(smem + P.off_wb + tap_off_bf16(kk, o)) = __float2bfloat16_rn(w);
+      }
+    }
   }
   // operator image: rows sorted by decreasing length; entries re-encoded as (gather code, value) in CSR order,
   // every row starting on an even entry so that one LDS.128 fetches two entries
   const int M4 = P.NG * 4;
+  int* bins = sorted;  // [M + 3]: bin b counts rows of length (M - b); the padding rows (length -1) come last;
+                       // bins[M + 2] = longest row.  (`sorted` itself is no longer materialised.)
   for (int r = tid; r <= M; r += kThreads) rp[r] = __ldg(P.rowptr + r);
   for (int r = tid; r < M; r += kThreads) {
     int s = r;
@@ -148,6 +161,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
     src_row[r] = s;
   }
   if (tid < 32) bias_s[tid] = (P.bias_mode == GCNB_BIAS_PER_FILTER && tid < P.Fout) ? __ldg(P.bias + tid) : 0.f;
+  for (int i = tid; i < M + 3; i += kThreads) bins[i] = 0;
   {
     const int npairs = (P.nnz + M + 2) >> 1;  // zero entries everywhere (padding entry of odd rows: zero row, 0.0)
     const uint32_t zc = gather_code(P.p * BQ);
@@ -157,29 +171,39 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
   TRACEP();
   __syncthreads();
   TRACEP();
-  for (int r = tid; r < M4; r += kThreads) rlen[r] = r < M ? rp[r + 1] - rp[r] : -1;
+  for (int r = tid; r < M4; r += kThreads) {
+    const int l = r < M ? rp[r + 1] - rp[r] : -1;
+    rlen[r] = l;
+    atomicAdd(&bins[M - l], 1);
+    if (l > 0) atomicMax(&bins[M + 2], l);
+  }
   {
-    // one thread per entry (loads of a batch of four issued before any is used); its row by bisection of rp
+    // one thread per entry, eight at a time: all loads issued first, then eight independent bisections of rp
     int2* ent = reinterpret_cast<int2*>(smem + P.off_ent);
-    for (int e0 = 0; e0 < P.nnz; e0 += kThreads * 4) {
-      int cc[4];
-      float vv[4];
+    for (int e0 = 0; e0 < P.nnz; e0 += kThreads * 8) {
+      int cc[8], lo[8];
+      float vv[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 8; ++u) {
         const int e = e0 + u * kThreads + tid;
         cc[u] = e < P.nnz ? __ldg(P.col + e) : 0;
         vv[u] = e < P.nnz ? __ldg(P.val + e) : 0.f;
+        lo[u] = 0;
+      }
+      // largest r with rp[r] <= e: fixed-trip bisection over [0, 2^s) so that the eight chains interleave
+      for (int step = 1 << (31 - __clz(max(M, 1))); step > 0; step >>= 1) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int cand = lo[u] + step;
+          if (cand <= M && rp[min(cand, M)] <= e0 + u * kThreads + tid) lo[u] = cand;
+        }
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 8; ++u) {
         const int e = e0 + u * kThreads + tid;
         if (e < P.nnz) {
-          int lo = 0, hi = M;  // largest r with rp[r] <= e
-          while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (rp[mid] <= e) lo = mid; else hi = mid;
-          }
-          ent[((rp[lo] + lo + 1) & ~1) + (e - rp[lo])] = make_int2((int)gather_code(rho(cc[u])), __float_as_int(vv[u]));
+          const int r = min(lo[u], M - 1);
+          ent[((rp[r] + r + 1) & ~1) + (e - rp[r])] = make_int2((int)gather_code(rho(cc[u])), __float_as_int(vv[u]));
         }
       }
     }
@@ -187,47 +211,41 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
   TRACEP();
   __syncthreads();
   TRACEP();
-  {
-    // counting sort of the rows by decreasing length (bins live in the entry-free tail of the scratch area); the
-    // order inside a bin is whatever the atomics give -- it only decides which rows share a warp step, never a sum
-    int* bins = sorted + M4;  // [M + 2]: bin b holds rows of length (M - b); the padding rows (length -1) come last
-    for (int i = tid; i < M + 2; i += kThreads) bins[i] = 0;
-    __syncthreads();
-    for (int r = tid; r < M4; r += kThreads) atomicAdd(&bins[M - rlen[r]], 1);
-    __syncthreads();
-    if (warp == 0) {  // exclusive prefix over the bins, one warp
-      int carry = 0;
-      for (int b0 = 0; b0 < M + 2; b0 += 32) {
-        const int i = b0 + lane;
-        const int v = i < M + 2 ? bins[i] : 0;
-        int x = v;
+  if (warp == 0) {
+    // exclusive prefix over the occupied bins [M - longest, M + 1] (rows sorted by decreasing length), one warp
+    const int first = M - bins[M + 2];
+    int carry = 0;
+    for (int b0 = first; b0 < M + 2; b0 += 32) {
+      const int i = b0 + lane;
+      const int v = i < M + 2 ? bins[i] : 0;
+      int x = v;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const int y = __shfl_up_sync(0xffffffffu, x, d);
-          if (lane >= d) x += y;
-        }
-        if (i < M + 2) bins[i] = carry + x - v;
-        carry += __shfl_sync(0xffffffffu, x, 31);
+      for (int d = 1; d < 32; d <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, d);
+        if (lane >= d) x += y;
       }
+      if (i < M + 2) bins[i] = carry + x - v;
+      carry += __shfl_sync(0xffffffffu, x, 31);
     }
-    __syncthreads();
-    for (int r = tid; r < M4; r += kThreads) sorted[atomicAdd(&bins[M - rlen[r]], 1)] = r;
   }
-  TRACEP();
   __syncthreads();
-  for (int i = tid; i < M4; i += kThreads) {
-    const int r = sorted[i];
+  // every row takes its place in the sorted order (the order inside a bin is whatever the atomics give: it only
+  // decides which rows share a warp step, never a sum) and fills the group tables there
+  for (int r = tid; r < M4; r += kThreads) {
+    const int l = rlen[r];
+    const int i = atomicAdd(&bins[M - l], 1);
     if (r < M) {
       grow[i] = r;
       grho[i] = rho(r);
-      gslot[i] = make_int2(((rp[r] + r + 1) & ~1) >> 1, rlen[r]);
+      gslot[i] = make_int2(((rp[r] + r + 1) & ~1) >> 1, l);
     } else {
       grow[i] = -1;
       grho[i] = 0;
       gslot[i] = make_int2(0, 0);
     }
-    if ((i & 3) == 0) glen[i >> 2] = r < M ? (rlen[r] + 1) >> 1 : 0;
   }
+  __syncthreads();
+  for (int g = tid; g < P.NG; g += kThreads) glen[g] = (gslot[g * 4].y + 1) >> 1;  // slot 0 holds the group's longest row
   TRACEP();
   tc_fence_before();
   __syncthreads();
@@ -597,7 +615,7 @@ static UmmaFwdPlan plan_umma_fwd(const LayerShape& s, int sm_count, int smem_opt
   const size_t tables = 2 * (size_t)pl.NG * 16 /*grow, grho*/ + (size_t)pl.NG * 32 /*gslot*/ + align_up((size_t)pl.NG * 4, 16) +
                         align_up((size_t)s.M * 4, 16) /*src*/ + 128 /*bias*/ + 64 /*barriers*/;
   // prologue-only scratch (rlen, sorted, rp) lives in the first remainder buffer
-  const size_t scratch = 2 * (size_t)pl.NG * 16 + align_up((size_t)(s.M + 2) * 4, 16) + align_up((size_t)(s.M + 1) * 4, 16);
+  const size_t scratch = 2 * (size_t)pl.NG * 16 + align_up((size_t)(s.M + 3) * 4, 16) + align_up((size_t)(s.M + 1) * 4, 16);
   const size_t budget = std::min<size_t>((size_t)smem_optin, 227 * 1024);
   double best = 1e30;
   for (int ns = 1; ns <= 8; ++ns) {
@@ -643,7 +661,7 @@ static UmmaFwdPlan plan_umma_fwd(const LayerShape& s, int sm_count, int smem_opt
   pl.off_bar = (int)off; off += 64;
   pl.off_rlen = pl.off_lo;
   pl.off_sorted = pl.off_rlen + pl.NG * 16;
-  pl.off_rp = pl.off_sorted + pl.NG * 16 + (int)align_up((size_t)(s.M + 2) * 4, 16);  // bins sit between sorted and rp
+  pl.off_rp = pl.off_sorted + pl.NG * 16 + (int)align_up((size_t)(s.M + 3) * 4, 16);  // sorted doubles as the bins
   if (off > pl.smem) return pl;
   pl.ok = true;
   return pl;

@@ -786,12 +786,15 @@ def test_benched_shapes_run_on_tcgen05(dev):
         assert "tcgen05" in _lib.describe_fwd(*shape), shape
 
 
-@pytest.mark.parametrize("lvl,Fin,p,brelu", [(0, 15, 4, "b1relu"), (2, 32, 4, "b1relu"), (1, 15, 2, "b2relu"), (0, 32, 8, "b2relu")])
+@pytest.mark.parametrize("lvl,Fin,p,brelu", [(0, 15, 4, "b1relu"), (2, 32, 4, "b1relu"), (1, 15, 2, "b2relu"), (2, 32, 2, "b2relu"),
+                                             (1, 15, 8, "b1relu")])
 def test_fused_argmax_bit_exact_against_own_activations(dev, graph_l4, lvl, Fin, p, brelu):
     """mpool1 inside the fused kernel is bit-exact: the pooled values and the arg-max bytes equal the first-maximum
     pooling (MaxPoolGrad's rule, ties included) of the SAME kernel's un-pooled activations (p = 1 launch)."""
     from gcn_fmri_decoding_b200 import ops
     from gcn_fmri_decoding_b200.plan import GraphPlan
+
+    from gcn_fmri_decoding_b200 import _lib
 
     L = graph_l4["L"][lvl]
     M = L.shape[0]
@@ -799,6 +802,8 @@ def test_fused_argmax_bit_exact_against_own_activations(dev, graph_l4, lvl, Fin,
     pl = GraphPlan(L, dev)
     torch.manual_seed(lvl * 10 + p)
     B = 33
+    # both launches must run the same kernel family for the bit-for-bit comparison to mean anything
+    assert "tcgen05" in _lib.describe_fwd(B, M, pl.nnz, Fin, 32, 5, p) and "tcgen05" in _lib.describe_fwd(B, M, pl.nnz, Fin, 32, 5, 1)
     x = torch.randn(B, M, Fin, device=dev)
     W = torch.randn(Fin * 5, 32, device=dev) * 0.2
     mode = ops.BIAS_PER_FILTER if brelu == "b1relu" else ops.BIAS_PER_VERTEX
