@@ -177,7 +177,7 @@ class FusedTrainer:
     """
 
     def __init__(self, model, lr=1e-3, distributed=None, use_cuda_graph=True, dropout=None, beta1=0.9, beta2=0.999,
-                 eps=1e-8, own_gemm=True, save_basis=True, fused_head=True):
+                 eps=1e-8, own_gemm=True, save_basis=True, fused_head=True, peer_allreduce=True):
         import ctypes as C
 
         from . import _lib, ops
@@ -217,9 +217,37 @@ class FusedTrainer:
                 off += n
         if self.distributed:
             dist.broadcast(self.flat_p, src=0)
+        # world > 1: the gradient average is fused into the optimiser kernel over peer-mapped staging buffers
+        # (gcnb_adam_tf_allreduce_f32); falls back to one NCCL all-reduce when symmetric memory is not available.
+        self.allreduce_kind = "none"
+        self._peer = None
+        if self.world > 1:
+            self.allreduce_kind = "nccl"
+            if peer_allreduce and dev.type == "cuda":
+                try:
+                    self._peer = self._setup_peer_staging(dev)
+                    self.allreduce_kind = "peer-memory (fused into the Adam kernel)"
+                except Exception as e:  # no NVLink peer access / symmetric memory unsupported: NCCL it is
+                    self._peer_error = repr(e)
         self.use_cuda_graph = use_cuda_graph
         self._graph = None
         self._loss = torch.zeros((), dtype=torch.float32, device=dev)
+
+    def _setup_peer_staging(self, dev):
+        """Symmetric (peer-mapped) staging buffer of every rank: 2*n floats + 64 flags, zeroed, pointers exchanged."""
+        import torch.distributed._symmetric_memory as symm
+
+        lib = self._lib.lib()
+        nbytes = int(lib.gcnb_adam_allreduce_stage_bytes(self.n))
+        buf = symm.empty(nbytes // 4, dtype=torch.float32, device=dev)
+        buf.zero_()
+        hdl = symm.rendezvous(buf, dist.group.WORLD)
+        ptrs = [int(p) for p in hdl.buffer_ptrs]
+        if len(ptrs) != self.world or any(p == 0 for p in ptrs):
+            raise RuntimeError("symmetric memory rendezvous returned %d pointers for %d ranks" % (len(ptrs), self.world))
+        torch.cuda.synchronize()
+        dist.barrier()  # every rank's buffer is zero before anybody can raise a flag
+        return {"buf": buf, "hdl": hdl, "ptrs": (self.C.c_void_p * self.world)(*ptrs), "rank": dist.get_rank()}
 
     # -- one step, eagerly ---------------------------------------------------------------------------------------
     @torch.no_grad()
@@ -326,6 +354,13 @@ class FusedTrainer:
                 gb.copy_(db.view_as(gb))
             dy, dy_is_mean = dx, False
         # ---- update ----
+        if self._peer is not None:
+            rc = lib.gcnb_adam_tf_allreduce_f32(vp(self.flat_p), vp(self.flat_g), vp(self.flat_m), vp(self.flat_v),
+                                                vp(self.decay), vp(self.state), self.n, self.b1, self.b2, self.eps,
+                                                float(m.regularization or 0.0), self._peer["ptrs"], self._peer["rank"],
+                                                self.world, stream)
+            self._lib.check(rc, "gcnb_adam_tf_allreduce_f32")
+            return self._loss, logits
         if self.world > 1:
             dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM)
         rc = lib.gcnb_adam_tf_f32(vp(self.flat_p), vp(self.flat_g), vp(self.flat_m), vp(self.flat_v), vp(self.decay),

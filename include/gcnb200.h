@@ -234,6 +234,20 @@ GCNB_API int gcnb_adam_tf_f32(float* p, const float* g, float* m, float* v, cons
                      long long n, float lr, float beta1, float beta2, float eps, float reg, float gscale, int tick,
                      gcnb_stream_t stream);
 
+/*
+ * Data-parallel training: the gradient all-reduce FUSED into the optimiser update (one cooperative launch; replaces
+ * ncclAllReduce + gcnb_adam_tf_f32 on the step's critical path).  Every rank stages its flat gradient in a peer-mapped
+ * buffer, exchanges one flag per peer over NVLink, reads all ranks' gradients straight from peer memory, sums them in
+ * rank order (bit-identical on every rank, so replicas never drift) and applies the Adam step above with
+ * gscale = 1 / world.  `state` must already hold this step's clock (gcnb_head_step_f32 / gcnb_softmax_xent_f32 tick).
+ * peer_stage[q] (HOST array of `world` DEVICE pointers): rank q's staging area of gcnb_adam_allreduce_stage_bytes(n)
+ * bytes, mapped into this process (e.g. torch symmetric memory, CUDA IPC), zero-filled before the first step.
+ */
+GCNB_API size_t gcnb_adam_allreduce_stage_bytes(long long n);
+GCNB_API int gcnb_adam_tf_allreduce_f32(float* p, const float* g, float* m, float* v, const uint8_t* decay,
+                                        const float* state, long long n, float beta1, float beta2, float eps, float reg,
+                                        void* const* peer_stage, int rank, int world, gcnb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
