@@ -315,7 +315,7 @@ class TrainWorkload:
                            regularization=REG, batch_size=B, perm=perm, n_input_vertices=360, algo=args.algo)
         # dropout keep-probability 0.5 on the FC layers, as the reference trains (model.py:169, models_gcn.py:145)
         self.trainer = FusedTrainer(self.model, use_cuda_graph=not args.no_graph, dropout=0.5, own_gemm=not args.cublas_fc,
-                                    fused_head=not args.no_fused_head)
+                                    fused_head=not args.no_fused_head, peer_allreduce=not args.nccl_allreduce)
         # ring of distinct resident batches: more than 2 x 126 MB of raw windows
         per = B * 360 * 15 * 4
         self.R = R = max(4, int(np.ceil(276e6 / per)))
@@ -348,7 +348,7 @@ class TrainWorkload:
     def result_ok(self):
         v = float(self.last)
         assert np.isfinite(v), "training diverged"
-        return {"final_loss": v}
+        return {"final_loss": v, "allreduce": self.trainer.allreduce_kind}
 
     def e2e_setup(self):
         torch, B, dev = self.torch, self.batch, self.dev
@@ -653,6 +653,8 @@ def main():
     ap.add_argument("--algo", type=int, default=0, help="0 auto, 1 general (HBM) kernels, 2 fused kernels")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fused-head", action="store_true", help="head launch by launch instead of k_head_step")
+    ap.add_argument("--nccl-allreduce", action="store_true", help="N>1: plain NCCL all-reduce instead of the peer-memory "
+                    "reduction fused into the Adam kernel")
     ap.add_argument("--cublas-fc", action="store_true", help="(with --no-fused-head) FC GEMMs through cuBLAS fp32")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]

@@ -58,9 +58,9 @@ SIGNATURES = {
     "gcnb_gemm_f32": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "gcnb_gemm_epilogue_f32": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, C.c_float, C.c_uint, _p,
                                     _p]),
-    "gcnb_adam_allreduce_stage_bytes": (_z, [C.c_longlong]),
-    "gcnb_adam_tf_allreduce_f32": (_i, [_p, _p, _p, _p, _p, _p, C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_float,
-                                        _p, _i, _i, _p]),
+    "gcnb_adam_allreduce_flag_bytes": (_z, []),
+    "gcnb_adam_tf_allreduce_f32": (_i, [_p, _p, _p, _p, _p, C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_float,
+                                        _p, _p, _i, _i, _p]),
     "gcnb_adam_tf_f32": (_i, [_p, _p, _p, _p, _p, _p, C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_float,
                               C.c_float, C.c_float, _i, _p]),
 }

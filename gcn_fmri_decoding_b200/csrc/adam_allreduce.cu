@@ -1,26 +1,23 @@
-// Data-parallel gradient averaging FUSED into the optimiser update: one cooperative kernel per step that
-//   (A) publishes this rank's flat gradient in a peer-mapped staging buffer (double-buffered by step parity),
-//   (B) exchanges one flag per peer over NVLink (release store into every peer's flag array, acquire spin on its own),
-//   (C) reads every rank's staged gradient straight from peer memory (P2P loads through NVLink / NVSwitch), sums them in
-//       RANK ORDER -- so every rank computes bit-identical averages and the replicas never drift -- and applies the
-//       TF-1.x Adam step (models_gcn.py:294) in the same pass.
+// Data-parallel gradient averaging FUSED into the optimiser update: one ordinary (non-cooperative) kernel per step.
+// Every rank's flat gradient buffer lives in peer-mapped memory (torch symmetric memory / CUDA IPC), so the backward
+// kernels write the gradients where the peers can read them -- there is no staging copy.  The kernel
+//   (1) raises one flag per peer over NVLink (system-scope release store into every peer's flag array),
+//   (2) has every CTA wait for all peers' flags of this exchange (acquire spin on its OWN flag array: local reads),
+//   (3) reads every rank's gradient straight from peer memory (P2P loads through NVLink / NVSwitch), sums them in RANK
+//       ORDER -- every rank computes bit-identical averages, the replicas never drift -- and applies the TF-1.x Adam
+//       step (models_gcn.py:294) in the same pass.
 // It replaces `ncclAllReduce` + `k_adam_tf`: the all-reduce of this path is 632 KB once per ~0.3 ms step, i.e. pure
-// latency (round 1 measured +30..50 us per step for the NCCL call at 2..8 GPUs), and a one-shot read of 7 x 632 KB per
-// GPU is ~6 us of NVLink time.  The reference has no distributed code at all; the collective exists
-// only because SURVEY.md 8(e) shards the batch.
+// latency (+26 us per step measured for the NCCL call inside the CUDA graph at 2 GPUs).  The reference has no
+// distributed code at all; the collective exists only because SURVEY.md 8(e) shards the batch.
 //
-// Memory the caller provides (host side: gcn_fmri_decoding_b200/train.py allocates it as torch symmetric memory and
-// passes the peer pointers): per rank a staging area of 2*n floats followed by a flag array of 64 uint32, zeroed
-// before the first step.  Flags carry the optimiser step number, which only grows: no reset, no second barrier --
-// the parity slot a peer may still be reading is only rewritten two steps later, after that peer has signalled
-// the step in between.
-#include <cooperative_groups.h>
-
+// Reuse of the gradient buffer: the caller alternates between TWO gradient buffers (even / odd steps; train.py keeps
+// one CUDA graph per parity).  A buffer a peer may still be reading is only rewritten two steps later, and by then that
+// peer has raised its flag for the step in between, which it does after finishing its reads: no second handshake.
+// Flags carry an exchange counter of their own (slot 63 of the rank's flag array) that only grows -- the optimiser
+// state may be rewound (warm-up steps before a graph capture), the flags may not.
 #include <algorithm>
 
 #include "common.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace gcnb {
 
@@ -28,14 +25,13 @@ constexpr int kMaxRanks = 16;
 
 struct AdamArParams {
   float* p;
-  const float* g;
   float *m, *v;
   const uint8_t* decay;
-  const float* state;            // {b1^t, b2^t, lr_t, t}: t (already advanced for this step) keys parity and flags
+  const float* state;            // {b1^t, b2^t, lr_t, t}, already advanced for this step
   long long n;
   float b1, b2, eps, reg;
-  float* stage[kMaxRanks];       // stage[q] = rank q's staging area (2*n floats), peer-mapped
-  uint32_t* flags[kMaxRanks];    // flags[q] = rank q's flag array (one uint32 per source rank)
+  const float* grad[kMaxRanks];  // grad[q] = rank q's flat gradient of this step (peer-mapped); grad[rank] is local
+  uint32_t* flags[kMaxRanks];    // flags[q] = rank q's flag array: [0, world) one per source rank, 62 CTA counter, 63 exchange
   int rank, world;
 };
 
@@ -47,43 +43,79 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ float4 ld_cv4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.cv.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ void adam_one(const AdamArParams& P, long long i, float gsum, float gscale, float lr_t) {
+  const float pi = P.p[i];
+  float gi = gsum * gscale;
+  if (P.decay != nullptr && P.decay[i]) gi = fmaf(P.reg, pi, gi);
+  const float mi = fmaf(1.f - P.b1, gi - P.m[i], P.m[i]);
+  const float vi = fmaf(1.f - P.b2, gi * gi - P.v[i], P.v[i]);
+  P.m[i] = mi;
+  P.v[i] = vi;
+  P.p[i] = pi - lr_t * mi / (sqrtf(vi) + P.eps);
+}
 
 __global__ void __launch_bounds__(256) k_adam_tf_allreduce(const AdamArParams P) {
-  cg::grid_group grid = cg::this_grid();
-  const uint32_t step = (uint32_t)P.state[3];
-  const long long par = (long long)(step & 1u) * P.n;
-  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
-  // (A) publish the local gradient
-  float* mine = P.stage[P.rank] + par;
-  for (long long i = tid; i < P.n; i += nth) mine[i] = P.g[i];
-  __threadfence_system();
-  grid.sync();
-  // (B) one flag per peer, then wait for every peer's flag of this step
-  if (blockIdx.x == 0) {
-    if ((int)threadIdx.x < P.world) st_release_sys(P.flags[threadIdx.x] + P.rank, step);
-    if ((int)threadIdx.x < P.world) {
-      const uint32_t* f = P.flags[P.rank] + threadIdx.x;
-      const long long t0 = clock64();
-      while ((int32_t)(ld_acquire_sys(f) - step) < 0) {
-        if (clock64() - t0 > 20000000000ll) __trap();  // a missing peer must not hang the GPU forever
-      }
+  uint32_t* myflags = P.flags[P.rank];
+  __shared__ uint32_t s_seq;
+  if (threadIdx.x == 0) s_seq = *reinterpret_cast<volatile uint32_t*>(myflags + 63) + 1u;  // bumped by the LAST CTA only
+  __syncthreads();
+  const uint32_t seq = s_seq;
+  // (1) the gradients of this rank were written by earlier kernels of this stream: publish them system-wide, raise flags
+  if (blockIdx.x == 0 && (int)threadIdx.x < P.world) {
+    __threadfence_system();
+    st_release_sys(P.flags[threadIdx.x] + P.rank, seq);
+  }
+  // (2) every CTA waits for every peer (local acquire loads; the flags arrive over NVLink)
+  if ((int)threadIdx.x < P.world) {
+    const uint32_t* f = myflags + threadIdx.x;
+    const long long t0 = clock64();
+    while ((int32_t)(ld_acquire_sys(f) - seq) < 0) {
+      if (clock64() - t0 > 20000000000ll) __trap();  // a missing peer must not hang the GPU forever
     }
   }
-  grid.sync();
-  // (C) sum the ranks in rank order straight from peer memory, then Adam
+  __syncthreads();
+  // (3) sum the ranks in rank order straight from peer memory (all peer loads of an element group in flight before the
+  // first add), then Adam
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  const long long n4 = P.n >> 2;
   const float lr_t = P.state[2];
   const float gscale = 1.f / (float)P.world;
-  for (long long i = tid; i < P.n; i += nth) {
+  for (long long i = tid; i < n4; i += nth) {
+    float4 gs = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q0 = 0; q0 < P.world; q0 += 8) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (q0 + u < P.world) v[u] = ld_cv4(P.grad[q0 + u] + (i << 2));  // .cv: never a stale cached line
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (q0 + u < P.world) { gs.x += v[u].x; gs.y += v[u].y; gs.z += v[u].z; gs.w += v[u].w; }
+    }
+    adam_one(P, (i << 2) + 0, gs.x, gscale, lr_t);
+    adam_one(P, (i << 2) + 1, gs.y, gscale, lr_t);
+    adam_one(P, (i << 2) + 2, gs.z, gscale, lr_t);
+    adam_one(P, (i << 2) + 3, gs.w, gscale, lr_t);
+  }
+  for (long long i = (n4 << 2) + tid; i < P.n; i += nth) {
     float gs = 0.f;
-    for (int q = 0; q < P.world; ++q) gs += __ldcv(P.stage[q] + par + i);  // volatile-class load: never a stale line
-    const float pi = P.p[i];
-    float gi = gs * gscale;
-    if (P.decay != nullptr && P.decay[i]) gi = fmaf(P.reg, pi, gi);
-    const float mi = fmaf(1.f - P.b1, gi - P.m[i], P.m[i]);
-    const float vi = fmaf(1.f - P.b2, gi * gi - P.v[i], P.v[i]);
-    P.m[i] = mi;
-    P.v[i] = vi;
-    P.p[i] = pi - lr_t * mi / (sqrtf(vi) + P.eps);
+    for (int q = 0; q < P.world; ++q) gs += __ldcv(P.grad[q] + i);
+    adam_one(P, i, gs, gscale, lr_t);
+  }
+  // the last CTA to finish closes the exchange: only then may the next launch see the new counter
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(myflags + 62, 1u) == gridDim.x - 1) {
+      myflags[62] = 0;
+      __threadfence();
+      *reinterpret_cast<volatile uint32_t*>(myflags + 63) = seq;
+    }
   }
 }
 
@@ -93,29 +125,30 @@ using namespace gcnb;
 
 extern "C" {
 
-size_t gcnb_adam_allreduce_stage_bytes(long long n) { return (size_t)(2 * n) * sizeof(float) + 64 * sizeof(uint32_t); }
+size_t gcnb_adam_allreduce_flag_bytes(void) { return 64 * sizeof(uint32_t); }
 
-int gcnb_adam_tf_allreduce_f32(float* p, const float* g, float* m, float* v, const uint8_t* decay, const float* state,
-                               long long n, float beta1, float beta2, float eps, float reg, void* const* peer_stage,
-                               int rank, int world, gcnb_stream_t stream) {
-  GCNB_REQUIRE(p && g && m && v && state && n >= 1 && peer_stage, "gcnb_adam_tf_allreduce_f32: bad arguments");
+int gcnb_adam_tf_allreduce_f32(float* p, float* m, float* v, const uint8_t* decay, const float* state, long long n,
+                               float beta1, float beta2, float eps, float reg, const void* const* peer_grad,
+                               void* const* peer_flags, int rank, int world, gcnb_stream_t stream) {
+  GCNB_REQUIRE(p && m && v && state && n >= 1 && peer_grad && peer_flags, "gcnb_adam_tf_allreduce_f32: bad arguments");
   GCNB_REQUIRE(world >= 1 && world <= kMaxRanks && rank >= 0 && rank < world,
                "gcnb_adam_tf_allreduce_f32: rank %d / world %d out of range (at most %d ranks)", rank, world, kMaxRanks);
   AdamArParams P{};
-  P.p = p; P.g = g; P.m = m; P.v = v; P.decay = decay; P.state = state; P.n = n;
+  P.p = p; P.m = m; P.v = v; P.decay = decay; P.state = state; P.n = n;
   P.b1 = beta1; P.b2 = beta2; P.eps = eps; P.reg = reg; P.rank = rank; P.world = world;
   for (int q = 0; q < world; ++q) {
-    GCNB_REQUIRE(peer_stage[q] != nullptr, "gcnb_adam_tf_allreduce_f32: peer pointer %d is NULL", q);
-    P.stage[q] = static_cast<float*>(peer_stage[q]);
-    P.flags[q] = reinterpret_cast<uint32_t*>(static_cast<float*>(peer_stage[q]) + 2 * n);
+    GCNB_REQUIRE(peer_grad[q] != nullptr && peer_flags[q] != nullptr, "gcnb_adam_tf_allreduce_f32: peer pointer %d is NULL", q);
+    GCNB_REQUIRE((reinterpret_cast<uintptr_t>(peer_grad[q]) & 15) == 0,
+                 "gcnb_adam_tf_allreduce_f32: gradient buffers must be 16-byte aligned");
+    P.grad[q] = static_cast<const float*>(peer_grad[q]);
+    P.flags[q] = static_cast<uint32_t*>(peer_flags[q]);
   }
   DeviceInfo di;
   int rc = device_info(&di);
   if (rc) return rc;
+  // at most one CTA per SM: every CTA spins on the flags, so all of them must be resident together with CTA 0
   const int grid = (int)std::max<long long>(1, std::min<long long>(ceil_div_ll(n, 256 * 4), di.sm_count));
-  void* args[] = {(void*)&P};
-  GCNB_CUDA(cudaLaunchCooperativeKernel((const void*)k_adam_tf_allreduce, dim3(grid), dim3(256), args, 0,
-                                        static_cast<cudaStream_t>(stream)));
+  k_adam_tf_allreduce<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(P);
   GCNB_LAUNCH_CHECK("k_adam_tf_allreduce");
   return GCNB_OK;
 }

@@ -199,47 +199,60 @@ class FusedTrainer:
         sizes = [p.numel() for p in self.params]
         self.n = sum(sizes)
         self.flat_p = torch.empty(self.n, dtype=torch.float32, device=dev)
-        self.flat_g = torch.zeros(self.n, dtype=torch.float32, device=dev)
         self.flat_m = torch.zeros(self.n, dtype=torch.float32, device=dev)
         self.flat_v = torch.zeros(self.n, dtype=torch.float32, device=dev)
         self.decay = torch.zeros(self.n, dtype=torch.uint8, device=dev)
         self.state = torch.tensor([1.0, 1.0, 0.0, 0.0], dtype=torch.float32, device=dev)  # b1^t, b2^t, lr_t, t
+        # world > 1: the gradient average is fused into the optimiser kernel (gcnb_adam_tf_allreduce_f32): the flat
+        # gradient buffers then live in peer-mapped symmetric memory, two of them used on alternate steps (a peer may
+        # still be reading the previous one).  Falls back to one NCCL all-reduce when symmetric memory is unavailable.
+        import os
+        self.allreduce_kind = "none"
+        self._peer = None
+        # diagnostic only (timing the step without its collective; the replicas then drift apart)
+        self._skip_allreduce = os.environ.get("GCNB_DP_SKIP_ALLREDUCE") == "1"
+        gbufs = None
+        if self.world > 1 and not self._skip_allreduce:
+            self.allreduce_kind = "nccl"
+            if peer_allreduce and dev.type == "cuda":
+                try:
+                    self._peer, gbufs = self._setup_peer_buffers(dev)
+                    self.allreduce_kind = "peer-memory (fused into the Adam kernel)"
+                except Exception as e:  # no NVLink peer access / symmetric memory unsupported: NCCL it is
+                    self._peer_error = repr(e)
+        if gbufs is None:
+            gbufs = [torch.zeros(self.n, dtype=torch.float32, device=dev)]
+        self._gbufs = gbufs
         regularized = {id(p) for p in model._regularized}
-        self.gview = {}
+        self._gviews = [dict() for _ in gbufs]
         off = 0
         with torch.no_grad():
             for p, n in zip(self.params, sizes):
                 self.flat_p[off:off + n].copy_(p.detach().reshape(-1))
                 p.data = self.flat_p[off:off + n].view_as(p)
-                self.gview[id(p)] = self.flat_g[off:off + n].view_as(p)
+                for gv, gb in zip(self._gviews, gbufs):
+                    gv[id(p)] = gb[off:off + n].view_as(p)
                 if id(p) in regularized:
                     self.decay[off:off + n] = 1
                 off += n
+        self._par = self._cur_par = 0
+        self.flat_g, self.gview = self._gbufs[0], self._gviews[0]   # the buffers of the step in flight / last run
         if self.distributed:
             dist.broadcast(self.flat_p, src=0)
-        # world > 1: the gradient average is fused into the optimiser kernel over peer-mapped staging buffers
-        # (gcnb_adam_tf_allreduce_f32); falls back to one NCCL all-reduce when symmetric memory is not available.
-        self.allreduce_kind = "none"
-        self._peer = None
-        if self.world > 1:
-            self.allreduce_kind = "nccl"
-            if peer_allreduce and dev.type == "cuda":
-                try:
-                    self._peer = self._setup_peer_staging(dev)
-                    self.allreduce_kind = "peer-memory (fused into the Adam kernel)"
-                except Exception as e:  # no NVLink peer access / symmetric memory unsupported: NCCL it is
-                    self._peer_error = repr(e)
         self.use_cuda_graph = use_cuda_graph
-        self._graph = None
+        self._graphs = {}
         self._loss = torch.zeros((), dtype=torch.float32, device=dev)
 
-    def _setup_peer_staging(self, dev):
-        """Symmetric (peer-mapped) staging buffer of every rank: 2*n floats + 64 flags, zeroed, pointers exchanged."""
+    def _setup_peer_buffers(self, dev):
+        """Symmetric (peer-mapped) memory of every rank: two flat gradient buffers + the flag array, zeroed; returns the
+        per-parity pointer tables for the kernel and the two local gradient tensors."""
         import torch.distributed._symmetric_memory as symm
 
+        C = self.C
         lib = self._lib.lib()
-        nbytes = int(lib.gcnb_adam_allreduce_stage_bytes(self.n))
-        buf = symm.empty(nbytes // 4, dtype=torch.float32, device=dev)
+        stride = (self.n + 3) & ~3                      # parity buffers start 16-byte aligned
+        nflag = int(lib.gcnb_adam_allreduce_flag_bytes()) // 4
+        buf = symm.empty(2 * stride + nflag, dtype=torch.float32, device=dev)
         buf.zero_()
         hdl = symm.rendezvous(buf, dist.group.WORLD)
         ptrs = [int(p) for p in hdl.buffer_ptrs]
@@ -247,7 +260,10 @@ class FusedTrainer:
             raise RuntimeError("symmetric memory rendezvous returned %d pointers for %d ranks" % (len(ptrs), self.world))
         torch.cuda.synchronize()
         dist.barrier()  # every rank's buffer is zero before anybody can raise a flag
-        return {"buf": buf, "hdl": hdl, "ptrs": (self.C.c_void_p * self.world)(*ptrs), "rank": dist.get_rank()}
+        grads = [(C.c_void_p * self.world)(*[p + par * stride * 4 for p in ptrs]) for par in (0, 1)]
+        flags = (C.c_void_p * self.world)(*[p + 2 * stride * 4 for p in ptrs])
+        peer = {"buf": buf, "hdl": hdl, "grads": grads, "flags": flags, "rank": dist.get_rank()}
+        return peer, [buf[0:self.n], buf[stride:stride + self.n]]
 
     # -- one step, eagerly ---------------------------------------------------------------------------------------
     @torch.no_grad()
@@ -355,13 +371,13 @@ class FusedTrainer:
             dy, dy_is_mean = dx, False
         # ---- update ----
         if self._peer is not None:
-            rc = lib.gcnb_adam_tf_allreduce_f32(vp(self.flat_p), vp(self.flat_g), vp(self.flat_m), vp(self.flat_v),
-                                                vp(self.decay), vp(self.state), self.n, self.b1, self.b2, self.eps,
-                                                float(m.regularization or 0.0), self._peer["ptrs"], self._peer["rank"],
-                                                self.world, stream)
+            rc = lib.gcnb_adam_tf_allreduce_f32(vp(self.flat_p), vp(self.flat_m), vp(self.flat_v), vp(self.decay),
+                                                vp(self.state), self.n, self.b1, self.b2, self.eps,
+                                                float(m.regularization or 0.0), self._peer["grads"][self._cur_par],
+                                                self._peer["flags"], self._peer["rank"], self.world, stream)
             self._lib.check(rc, "gcnb_adam_tf_allreduce_f32")
             return self._loss, logits
-        if self.world > 1:
+        if self.world > 1 and not self._skip_allreduce:
             dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM)
         rc = lib.gcnb_adam_tf_f32(vp(self.flat_p), vp(self.flat_g), vp(self.flat_m), vp(self.flat_v), vp(self.decay),
                                   vp(self.state), self.n, self.lr, self.b1, self.b2, self.eps,
@@ -432,10 +448,15 @@ class FusedTrainer:
         if dropout is not None and abs(float(dropout if dropout else 1.0) - self.keep) > 1e-12:
             raise ValueError("FusedTrainer was built with dropout keep-probability %g; step(dropout=%g) would be ignored "
                              "-- construct the trainer with the value you want" % (self.keep, float(dropout)))
+        par = self._cur_par = self._par
+        self.flat_g, self.gview = self._gbufs[par], self._gviews[par]
+        if len(self._gbufs) > 1:
+            self._par ^= 1                      # the next step writes the other gradient buffer
         if not self.use_cuda_graph:
             return self._step_impl(x, labels)
-        if self._graph is None:
-            self._sx, self._sl = torch.empty_like(x), torch.empty_like(labels)
+        if par not in self._graphs:
+            if not self._graphs:
+                self._sx, self._sl = torch.empty_like(x), torch.empty_like(labels)
             self._sx.copy_(x)
             self._sl.copy_(labels)
             snap = [t.clone() for t in (self.flat_p, self.flat_m, self.flat_v, self.state)]
@@ -444,14 +465,23 @@ class FusedTrainer:
             with torch.cuda.stream(side):
                 for _ in range(3):
                     self._step_impl(self._sx, self._sl)
+                    if self._peer is not None:
+                        # warm-up steps reuse ONE gradient buffer back to back: let every peer finish reading it
+                        torch.cuda.synchronize()
+                        dist.barrier()
             torch.cuda.current_stream().wait_stream(side)
-            self._graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self._graph):
-                self._out = self._step_impl(self._sx, self._sl)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self._step_impl(self._sx, self._sl)
+            self._graphs[par] = (graph, out)
             with torch.no_grad():
                 for t, s in zip((self.flat_p, self.flat_m, self.flat_v, self.state), snap):
                     t.copy_(s)
+            if self._peer is not None:
+                torch.cuda.synchronize()
+                dist.barrier()
         self._sx.copy_(x, non_blocking=True)
         self._sl.copy_(labels, non_blocking=True)
-        self._graph.replay()
-        return self._out
+        graph, out = self._graphs[par]
+        graph.replay()
+        return out

@@ -235,18 +235,21 @@ GCNB_API int gcnb_adam_tf_f32(float* p, const float* g, float* m, float* v, cons
                      gcnb_stream_t stream);
 
 /*
- * Data-parallel training: the gradient all-reduce FUSED into the optimiser update (one cooperative launch; replaces
- * ncclAllReduce + gcnb_adam_tf_f32 on the step's critical path).  Every rank stages its flat gradient in a peer-mapped
- * buffer, exchanges one flag per peer over NVLink, reads all ranks' gradients straight from peer memory, sums them in
- * rank order (bit-identical on every rank, so replicas never drift) and applies the Adam step above with
- * gscale = 1 / world.  `state` must already hold this step's clock (gcnb_head_step_f32 / gcnb_softmax_xent_f32 tick).
- * peer_stage[q] (HOST array of `world` DEVICE pointers): rank q's staging area of gcnb_adam_allreduce_stage_bytes(n)
- * bytes, mapped into this process (e.g. torch symmetric memory, CUDA IPC), zero-filled before the first step.
+ * Data-parallel training: the gradient all-reduce FUSED into the optimiser update (one ordinary launch; replaces
+ * ncclAllReduce + gcnb_adam_tf_f32 on the step's critical path).  Every rank's flat gradient buffer is peer-mapped;
+ * the kernel raises one flag per peer over NVLink, waits for all peers' flags, reads all ranks' gradients straight from
+ * peer memory, sums them in rank order (bit-identical on every rank, so replicas never drift) and applies the Adam
+ * step above with gscale = 1 / world.  `state` must already hold this step's clock.
+ * peer_grad[q] / peer_flags[q] (HOST arrays of `world` DEVICE pointers, mapped into this process, e.g. torch symmetric
+ * memory or CUDA IPC): rank q's flat gradient of THIS step and its flag array of gcnb_adam_allreduce_flag_bytes() bytes
+ * (zero-filled once).  The caller must alternate between two gradient buffers on successive steps (a peer may still
+ * be reading the previous one); the flag arrays stay the same.
  */
-GCNB_API size_t gcnb_adam_allreduce_stage_bytes(long long n);
-GCNB_API int gcnb_adam_tf_allreduce_f32(float* p, const float* g, float* m, float* v, const uint8_t* decay,
-                                        const float* state, long long n, float beta1, float beta2, float eps, float reg,
-                                        void* const* peer_stage, int rank, int world, gcnb_stream_t stream);
+GCNB_API size_t gcnb_adam_allreduce_flag_bytes(void);
+GCNB_API int gcnb_adam_tf_allreduce_f32(float* p, float* m, float* v, const uint8_t* decay, const float* state,
+                                        long long n, float beta1, float beta2, float eps, float reg,
+                                        const void* const* peer_grad, void* const* peer_flags, int rank, int world,
+                                        gcnb_stream_t stream);
 
 #ifdef __cplusplus
 }
