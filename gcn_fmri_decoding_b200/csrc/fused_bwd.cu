@@ -13,6 +13,7 @@
 // atomics: warps -> CTA through a shared-memory scratch (fixed order), CTAs -> a small second kernel.
 // The bias gradient is a separate two-stage column sum over the pooled tensors (also fixed order).
 #include <algorithm>
+#include <mutex>
 #include <cmath>
 #include <cstdlib>
 
@@ -405,9 +406,19 @@ struct BwdPlan {
   int off_opT, off_wfragT, off_dws, off_scratch, off_dz, off_slab;
 };
 
+// Tuning / debugging knobs: each environment variable is read ONCE per process (first use) and cached.
 static int env_int_b(const char* name, int dflt) {
+  struct Slot { const char* name; int value; };
+  static Slot cache[16];
+  static int used = 0;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  for (int i = 0; i < used; ++i)
+    if (cache[i].name == name) return cache[i].value;  // string literals: pointer identity is enough
   const char* v = std::getenv(name);
-  return v ? std::atoi(v) : dflt;
+  const int val = v ? std::atoi(v) : dflt;
+  if (used < 16) cache[used++] = Slot{name, val};
+  return val;
 }
 
 static BwdPlan plan_bwd(const LayerShape& s, bool need_dx) {
@@ -446,7 +457,9 @@ static BwdPlan plan_bwd(const LayerShape& s, bool need_dx) {
       if (slots > 4) continue;
       const int SL = slots <= 1 ? 1 : (slots <= 2 ? 2 : 4);
       // registers: phase A holds MT*NT accumulators, phase B SLOTS*MT*2; keep both <= 8 fragments
-      if (pl.MT * pl.NT > 8 || (need_dx && SL * pl.MT * 2 > 8)) continue;
+      // the instance table below has no <MT=2, *, SLOTS=4> kernel: reject it whether or not dx is wanted, so that
+      // fused_bwd_supported() implies an existing instance
+      if (pl.MT * pl.NT > 8 || SL * pl.MT * 2 > 8) continue;
       const int nw = rwn * sgn;
       // slab strides: RS/8 odd keeps the transposed fragment loads of the dW contraction conflict free
       int RS = S * g.FP + 8;

@@ -4,6 +4,7 @@
 // layout transposes and the pre-pool activation of the reference (models_gcn.py:598-617, 619-639)
 // never exist in memory.  See fused_common.cuh for the CTA layout.
 #include <algorithm>
+#include <mutex>
 #include <cmath>
 #include <cstdlib>
 
@@ -275,9 +276,19 @@ struct FwdPlan {
   bool staged;
 };
 
+// Tuning / debugging knobs: each environment variable is read ONCE per process (first use) and cached.
 static int env_int(const char* name, int dflt) {
+  struct Slot { const char* name; int value; };
+  static Slot cache[16];
+  static int used = 0;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  for (int i = 0; i < used; ++i)
+    if (cache[i].name == name) return cache[i].value;  // string literals: pointer identity is enough
   const char* v = std::getenv(name);
-  return v ? std::atoi(v) : dflt;
+  const int val = v ? std::atoi(v) : dflt;
+  if (used < 16) cache[used++] = Slot{name, val};
+  return val;
 }
 
 // M_in: vertices of the raw input (differs from M when the permutation gather is fused in).

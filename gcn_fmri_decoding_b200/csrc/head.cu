@@ -24,10 +24,13 @@ __global__ void k_softmax_xent(const float* __restrict__ logits, const long long
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) se += __shfl_xor_sync(0xffffffffu, se, d);
   const float lse = mx + logf(se);
-  const int lab = (int)labels[row];
+  const long long lab64 = labels[row];
+  const bool ok = lab64 >= 0 && lab64 < C;  // a label outside [0, C) contributes neither loss nor gradient
+  const int lab = ok ? (int)lab64 : 0;
   if (dlogits != nullptr)
-    for (int c = lane; c < C; c += 32) dlogits[(long long)row * C + c] = (expf(z[c] - lse) - (c == lab ? 1.f : 0.f)) * scale;
-  if (lane == 0) loss_rows[row] = lse - z[lab];
+    for (int c = lane; c < C; c += 32)
+      dlogits[(long long)row * C + c] = ok ? (expf(z[c] - lse) - (c == lab ? 1.f : 0.f)) * scale : 0.f;
+  if (lane == 0) loss_rows[row] = ok ? lse - z[lab] : 0.f;
 }
 
 // state[0] = beta1^t, state[1] = beta2^t, state[2] = lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t), state[3] = t
@@ -79,11 +82,13 @@ __global__ void __launch_bounds__(1024) k_softmax_xent_1cta(const float* __restr
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) se += __shfl_xor_sync(0xffffffffu, se, d);
     const float lse = mx + logf(se);
-    const int lab = (int)labels[row];
+    const long long lab64 = labels[row];
+    const bool ok = lab64 >= 0 && lab64 < C;
+    const int lab = ok ? (int)lab64 : 0;
     if (dlogits != nullptr)
       for (int c = lane; c < C; c += 32)
-        dlogits[(long long)row * C + c] = (expf(z[c] - lse) - (c == lab ? 1.f : 0.f)) * scale;
-    mine += lse - z[lab];
+        dlogits[(long long)row * C + c] = ok ? (expf(z[c] - lse) - (c == lab ? 1.f : 0.f)) * scale : 0.f;
+    if (ok) mine += lse - z[lab];
   }
   if (lane == 0) red[warp] = mine;
   __syncthreads();

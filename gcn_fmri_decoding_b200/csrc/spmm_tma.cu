@@ -289,12 +289,9 @@ int spmm_tma(const gcnb_csr& L, const float* src, const float* add, const float*
   a.C = C; a.M = L.M; a.alpha = alpha; a.beta = beta; a.beta2 = beta2;
   DeviceInfo di;
   if (device_info(&di) != GCNB_OK) return GCNB_ERR_CUDA;
-  static bool attr_set = false;
-  if (!attr_set) {
-    GCNB_CUDA(cudaFuncSetAttribute(k_spmm_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, di.smem_optin));
-    GCNB_CUDA(cudaFuncSetAttribute(k_spmm_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, di.smem_optin));
-    attr_set = true;
-  }
+  // per device / context, so set on every launch like the other kernels (a process may drive several GPUs)
+  GCNB_CUDA(cudaFuncSetAttribute(k_spmm_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, di.smem_optin));
+  GCNB_CUDA(cudaFuncSetAttribute(k_spmm_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, di.smem_optin));
   const long long total = (long long)L.M * a.nchunk;
   const int grid = (int)std::min<long long>(total, di.sm_count);
   if (a.nchunk == 1)

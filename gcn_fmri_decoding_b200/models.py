@@ -95,6 +95,7 @@ class cgcnn(nn.Module):
         self.n_input_vertices = n_input_vertices if n_input_vertices is not None else M_0
 
         # ---- parameters (shapes/initialisers of models_gcn.py:330-355) ------------------------------
+        self.seed = int(seed)
         rng = np.random.RandomState(seed)
         self.conv_weights, self.conv_bias = nn.ParameterList(), nn.ParameterList()
         self._regularized = []
@@ -114,7 +115,8 @@ class cgcnn(nn.Module):
                 self._regularized.append(self.conv_weights[-1])
             Fin = self.F[i]
         # fully connected head: input width is the number of vertices left (mean over F, :671-673)
-        M_last = self.L[-1].shape[0] // self.p[-1] if len(self.p) else M_0
+        # mpool1 is tf.nn.max_pool SAME: ceil(M / p) vertices survive (models_gcn.py:634-637)
+        M_last = -(-self.L[-1].shape[0] // self.p[-1]) if len(self.p) else M_0
         self.fc_weights, self.fc_bias = nn.ParameterList(), nn.ParameterList()
         width = M_last
         for Mi in self.M:

@@ -177,7 +177,7 @@ class FusedTrainer:
     """
 
     def __init__(self, model, lr=1e-3, distributed=None, use_cuda_graph=True, dropout=None, beta1=0.9, beta2=0.999,
-                 eps=1e-8, own_gemm=True, save_basis=True, fused_head=True, peer_allreduce=True):
+                 eps=1e-8, own_gemm=True, save_basis=True, fused_head=True, peer_allreduce=True, dropout_seed=None):
         import ctypes as C
 
         from . import _lib, ops
@@ -190,6 +190,11 @@ class FusedTrainer:
             dropout = getattr(model, "dropout", 1.0)
         self.keep = float(dropout) if dropout else 1.0
         self.own_gemm = own_gemm
+        # dropout stream: layer i draws with seed (dropout_seed + i); data-parallel ranks and differently seeded models
+        # draw different masks (the reference seeds tf.nn.dropout from the graph seed)
+        rank = dist.get_rank() if (dist.is_available() and dist.is_initialized() and distributed is not False) else 0
+        base = dropout_seed if dropout_seed is not None else 0x5eed + 0x9e3779b1 * rank + 7919 * int(getattr(model, "seed", 0) or 0)
+        self.dropout_seed = int(base) & 0x7FFFFFFF
         self.fused_head = fused_head
         self.save_basis = save_basis
         self.distributed = dist.is_available() and dist.is_initialized() if distributed is None else distributed
@@ -324,14 +329,14 @@ class FusedTrainer:
             if not use_own_gemm:
                 a = torch.addmm(m.fc_bias[i], a_in, W)
                 if hidden:
-                    rc = lib.gcnb_relu_dropout_fwd_f32(vp(a), a.shape[0], a.shape[1], a.shape[1], self.keep, 0x5eed + i,
+                    rc = lib.gcnb_relu_dropout_fwd_f32(vp(a), a.shape[0], a.shape[1], a.shape[1], self.keep, self.dropout_seed + i,
                                                        vp(self.state), stream)
                     self._lib.check(rc, "gcnb_relu_dropout_fwd_f32")
                 return a
             out = torch.empty((a_in.shape[0], W.shape[1]), dtype=torch.float32, device=x.device)
             if hidden:
                 return gemm_epi(a_in, W, out, m.fc_bias[i], a_in.shape[0], W.shape[1], W.shape[0], 0, 0,
-                                self._lib.EPI_RELU_DROPOUT, None, 0x5eed + i)
+                                self._lib.EPI_RELU_DROPOUT, None, self.dropout_seed + i)
             return gemm(a_in, W, out, m.fc_bias[i], a_in.shape[0], W.shape[1], W.shape[0], 0, 0)
 
         B = h0.shape[0]
@@ -347,7 +352,7 @@ class FusedTrainer:
             b1, b2, b3 = m.fc_bias
             rc = lib.gcnb_head_step_f32(vp(h0), vp(labels), vp(W1), vp(b1), vp(W2), vp(b2), vp(W3), vp(b3), vp(logits),
                                         vp(self._loss), g(W1), g(b1), g(W2), g(b2), g(W3), g(b3), vp(d), B, *widths,
-                                        self.keep, 0x5eed, 0x5eed + 1, vp(self.state), self.lr, self.b1, self.b2, 1,
+                                        self.keep, self.dropout_seed, self.dropout_seed + 1, vp(self.state), self.lr, self.b1, self.b2, 1,
                                         vp(ws), ws.numel(), stream)
             self._lib.check(rc, "gcnb_head_step_f32")
         else:

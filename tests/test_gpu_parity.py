@@ -756,7 +756,7 @@ def test_fused_trainer_with_dropout_matches_oracle(dev, graph_l4, graph):
     loss, logits = tr.step(T(xraw, dev), T(labels, dev, torch.long))
     torch.cuda.synchronize()
     # the first step draws its masks with the optimiser step count 0
-    masks = [O.counter_dropout_mask(B, 512, 0.5, 0x5eed, 0), O.counter_dropout_mask(B, 256, 0.5, 0x5eed + 1, 0)]
+    masks = [O.counter_dropout_mask(B, 512, 0.5, tr.dropout_seed, 0), O.counter_dropout_mask(B, 256, 0.5, tr.dropout_seed + 1, 0)]
     xperm = graclus.perm_data_3d(xraw, g["perm"])
     params = [dict(W=sd["conv%d/weights" % i], b=sd["conv%d/bias" % i].reshape(32), K=5, p=4) for i in (1, 2)]
     fcs = [(sd[s + "/weights"], sd[s + "/bias"]) for s in ("fc1", "fc2", "logits")]
