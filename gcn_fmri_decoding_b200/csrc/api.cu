@@ -1,6 +1,7 @@
 // extern "C" entry points of libgcnb200.so: argument validation, kernel-family dispatch, and the
 // small stand-alone kernels (b1relu/b2relu, mpool1, perm gather, mean over filters).
 #include <algorithm>
+#include <cstdlib>
 #include <atomic>
 #include <mutex>
 
@@ -19,6 +20,16 @@ void set_error(const char* fmt, ...) {
 
 static std::atomic<unsigned long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    // Off by default: measured on the config-2 step (B200, CUDA graph) 0.343 ms with the attribute vs 0.338 ms
+    // without -- back-to-back launches of ONE kernel gain 3-5 %, the mixed chain of the step loses it again.
+    const char* v = getenv("GCNB_PDL");
+    return v && v[0] == '1';
+  }();
+  return on;
+}
 
 int device_info(DeviceInfo* out) {
   static std::mutex mu;

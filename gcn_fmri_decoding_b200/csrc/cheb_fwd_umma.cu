@@ -116,6 +116,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
 #define TRACEP() do { } while (0)
 #endif
   TRACEP();
+  pdl_trigger();  // the next kernel of the stream may start its own prologue as soon as SMs free up
   if ((sb & 1023u) != 0) __trap();  // the swizzled operand layouts need a 1 KB aligned base
   if (tid == 0) {
     mbar_init(bar_mma(0), 1); mbar_init(bar_mma(1), 1);
@@ -252,12 +253,119 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   TRACEP();
+  // Everything above read static data only (operator, taps, bias, permutation).  From here on the kernel reads the
+  // previous layer's output and writes its own: wait for the predecessor in the stream (programmatic dependent launch).
+  pdl_wait();
 
 #ifdef GCNB_TRACE
   int tr_n = 0;
 #endif
   const int NI = P.NG * NS;  // work items (row group, window-slab) of one order
   const int nsync = (kSparseWarps + 1) * 32;
+
+  // ---- one epilogue task: halves [h0, h1) of the 32 filters of accumulator block (g, t) for TMEM lane quarter e -------
+  // thread = (window-slab, pooled vertex); the p sibling vertices of its pooling window sit in the same TMEM lane of p
+  // accumulator blocks: running maximum with the first-maximum rule, bias, ReLU, y / arg-max / mean stores
+  const int Mo = M >> log2p;
+  auto epi_task = [&](int tile, int buf, int e, int g, int t, int h0, int h1) {
+    const int p = P.p;
+    const bool pool_relu_fix = P.relu && p > 1;
+          const int rb0 = t * 128 + e * 32;
+          if (rb0 >= BQ) return;
+          const int rb = rb0 + lane;             // row inside a sibling block = (window-slab, pooled vertex)
+          const int s = rb / Q, j = rb - s * Q;
+          const int b = tile * P.S + s * G + g;
+          const bool valid = rb < BQ && j < Mo && b < P.B;
+          const long long orow = (long long)b * Mo + j;
+          const uint32_t tbase = tmem + ((uint32_t)(e * 32) << 16) + (uint32_t)(buf * P.acc_cols + (g * p * P.T + t) * 32);
+          float msum = 0.f;
+          for (int h = h0; h < h1; ++h) {
+            float m[16];
+            int idx[16];
+            tmem_ld16(tbase + h * 16, m);
+            if (P.bias_mode == GCNB_BIAS_PER_VERTEX && valid) {
+              const float* bp = P.bias + (long long)(j << log2p) * P.Fout + h * 16;
+#pragma unroll
+              for (int c4 = 0; c4 < 4; ++c4) {
+                if (h * 16 + c4 * 4 < P.Fout) {
+                  const float4 bv = __ldg(reinterpret_cast<const float4*>(bp + c4 * 4));
+                  m[c4 * 4] += bv.x; m[c4 * 4 + 1] += bv.y; m[c4 * 4 + 2] += bv.z; m[c4 * 4 + 3] += bv.w;
+                }
+              }
+            }
+#pragma unroll
+            for (int o = 0; o < 16; ++o) idx[o] = 0;
+            for (int i = 1; i < p; ++i) {
+              float a[16];
+              tmem_ld16(tbase + (uint32_t)(i * P.T * 32) + h * 16, a);
+              if (P.bias_mode == GCNB_BIAS_PER_VERTEX && valid) {
+                const float* bp = P.bias + (long long)((j << log2p) + i) * P.Fout + h * 16;
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4) {
+                  if (h * 16 + c4 * 4 < P.Fout) {
+                    const float4 bv = __ldg(reinterpret_cast<const float4*>(bp + c4 * 4));
+                    a[c4 * 4] += bv.x; a[c4 * 4 + 1] += bv.y; a[c4 * 4 + 2] += bv.z; a[c4 * 4 + 3] += bv.w;
+                  }
+                }
+              }
+#pragma unroll
+              for (int o = 0; o < 16; ++o) {
+                const bool gt = a[o] > m[o];  // strict: the first maximum wins (MaxPoolGrad)
+                m[o] = gt ? a[o] : m[o];
+                idx[o] = gt ? i : idx[o];
+              }
+            }
+            if (P.bias_mode == GCNB_BIAS_PER_FILTER) {
+#pragma unroll
+              for (int c4 = 0; c4 < 4; ++c4) {
+                const float4 bv = *reinterpret_cast<const float4*>(bias_s + h * 16 + c4 * 4);
+                m[c4 * 4] += bv.x; m[c4 * 4 + 1] += bv.y; m[c4 * 4 + 2] += bv.z; m[c4 * 4 + 3] += bv.w;
+              }
+            }
+            if (P.relu) {
+#pragma unroll
+              for (int o = 0; o < 16; ++o) {
+                // a window whose maximum is clipped is a tie of zeros after the ReLU: the first vertex is the arg-max
+                if (pool_relu_fix && !(m[o] > 0.f)) idx[o] = 0;
+                m[o] = fmaxf(m[o], 0.f);
+              }
+            }
+            if (valid) {
+              float* yp = P.y + orow * P.Fout + h * 16;
+#pragma unroll
+              for (int c4 = 0; c4 < 4; ++c4)
+                if (h * 16 + c4 * 4 < P.Fout)
+                  *reinterpret_cast<float4*>(yp + c4 * 4) = make_float4(m[c4 * 4], m[c4 * 4 + 1], m[c4 * 4 + 2], m[c4 * 4 + 3]);
+              if (P.argmax && p > 1) {
+                uint8_t* ap = P.argmax + orow * P.Fout + h * 16;
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4)
+                  if (h * 16 + c4 * 4 < P.Fout)
+                    *reinterpret_cast<uint32_t*>(ap + c4 * 4) = (uint32_t)idx[c4 * 4] | ((uint32_t)idx[c4 * 4 + 1] << 8) |
+                                                                ((uint32_t)idx[c4 * 4 + 2] << 16) |
+                                                                ((uint32_t)idx[c4 * 4 + 3] << 24);
+              }
+            }
+#pragma unroll
+            for (int o = 0; o < 16; ++o)
+              if (h * 16 + o < P.Fout) msum += m[o];
+          }
+          if (P.y_mean && valid && h0 == 0 && h1 == 2) P.y_mean[orow] = msum / (float)P.Fout;
+  };
+  // tasks of one tile per lane quarter; the LAST tile of a CTA is shared between the epilogue warp of the quarter and
+  // the five sparse warps that can reach the same TMEM lanes (they have nothing left to do)
+  const bool split_halves = P.y_mean == nullptr;  // the mean over filters needs both halves in one thread
+  const int ntask = G * P.T * (split_halves ? 2 : 1);
+  auto tail_tasks = [&](int tile, int buf, int e, int j) {  // participant j of 6 in quarter e
+    for (int k = j; k < ntask; k += 6) {
+      const int gt = split_halves ? (k >> 1) : k;
+      const int g = gt / P.T, t = gt - g * P.T;
+      if (split_halves) epi_task(tile, buf, e, g, t, k & 1, (k & 1) + 1);
+      else epi_task(tile, buf, e, g, t, 0, 2);
+    }
+  };
+  int my_tiles = 0;
+  for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) ++my_tiles;
 
   if (warp > kMmaWarp) {
     // =========================================== sparse warps ==================================================
@@ -408,6 +516,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
       }
       base = (base + K) & 1;
     }
+    // the CTA's last tile: help the epilogue warp of this warp's TMEM lane quarter
+    if (my_tiles > 0) {
+      const int it = my_tiles - 1;
+      const int buf = P.nacc == 2 ? (it & 1) : 0;
+      const int use = P.nacc == 2 ? (it >> 1) : it;
+      const int e = warp & 3;
+      const int j = 1 + (warp - (5 + ((e + 3) & 3))) / 4;  // sparse warps of quarter e, in warp order
+      mbar_wait(bar_full(buf), (uint32_t)use & 1u);
+      tc_fence_after();
+      tail_tasks(blockIdx.x + it * (int)gridDim.x, buf, e, j);
+      tc_fence_before();
+    }
   } else if (warp == kMmaWarp) {
     // =========================================== MMA warp ======================================================
     uint32_t n = 0;
@@ -467,9 +587,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
   } else {
     // =========================================== epilogue warps =================================================
     const int e = warp;  // TMEM lane quarter
-    const int p = P.p;
-    const int Mo = M >> log2p;
-    const bool pool_relu_fix = P.relu && p > 1;
     int it = 0;
     for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x, ++it) {
       const int buf = P.nacc == 2 ? (it & 1) : 0;
@@ -477,92 +594,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
       mbar_wait(bar_full(buf), (uint32_t)use & 1u);
       TRACE(3, e == 0);
       tc_fence_after();
+      if (it + 1 == my_tiles) {
+        tail_tasks(tile, buf, e, 0);
+      } else {
 #pragma unroll
-      for (int g = 0; g < G; ++g) {
-        for (int t = 0; t < P.T; ++t) {
-          const int rb0 = t * 128 + e * 32;
-          if (rb0 >= BQ) continue;
-          const int rb = rb0 + lane;             // row inside a sibling block = (window-slab, pooled vertex)
-          const int s = rb / Q, j = rb - s * Q;
-          const int b = tile * P.S + s * G + g;
-          const bool valid = rb < BQ && j < Mo && b < P.B;
-          const long long orow = (long long)b * Mo + j;
-          const uint32_t tbase = tmem + ((uint32_t)(e * 32) << 16) + (uint32_t)(buf * P.acc_cols + (g * p * P.T + t) * 32);
-          float msum = 0.f;
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            float m[16];
-            int idx[16];
-            tmem_ld16(tbase + h * 16, m);
-            if (P.bias_mode == GCNB_BIAS_PER_VERTEX && valid) {
-              const float* bp = P.bias + (long long)(j << log2p) * P.Fout + h * 16;
-#pragma unroll
-              for (int c4 = 0; c4 < 4; ++c4) {
-                if (h * 16 + c4 * 4 < P.Fout) {
-                  const float4 bv = __ldg(reinterpret_cast<const float4*>(bp + c4 * 4));
-                  m[c4 * 4] += bv.x; m[c4 * 4 + 1] += bv.y; m[c4 * 4 + 2] += bv.z; m[c4 * 4 + 3] += bv.w;
-                }
-              }
-            }
-#pragma unroll
-            for (int o = 0; o < 16; ++o) idx[o] = 0;
-            for (int i = 1; i < p; ++i) {
-              float a[16];
-              tmem_ld16(tbase + (uint32_t)(i * P.T * 32) + h * 16, a);
-              if (P.bias_mode == GCNB_BIAS_PER_VERTEX && valid) {
-                const float* bp = P.bias + (long long)((j << log2p) + i) * P.Fout + h * 16;
-#pragma unroll
-                for (int c4 = 0; c4 < 4; ++c4) {
-                  if (h * 16 + c4 * 4 < P.Fout) {
-                    const float4 bv = __ldg(reinterpret_cast<const float4*>(bp + c4 * 4));
-                    a[c4 * 4] += bv.x; a[c4 * 4 + 1] += bv.y; a[c4 * 4 + 2] += bv.z; a[c4 * 4 + 3] += bv.w;
-                  }
-                }
-              }
-#pragma unroll
-              for (int o = 0; o < 16; ++o) {
-                const bool gt = a[o] > m[o];  // strict: the first maximum wins (MaxPoolGrad)
-                m[o] = gt ? a[o] : m[o];
-                idx[o] = gt ? i : idx[o];
-              }
-            }
-            if (P.bias_mode == GCNB_BIAS_PER_FILTER) {
-#pragma unroll
-              for (int c4 = 0; c4 < 4; ++c4) {
-                const float4 bv = *reinterpret_cast<const float4*>(bias_s + h * 16 + c4 * 4);
-                m[c4 * 4] += bv.x; m[c4 * 4 + 1] += bv.y; m[c4 * 4 + 2] += bv.z; m[c4 * 4 + 3] += bv.w;
-              }
-            }
-            if (P.relu) {
-#pragma unroll
-              for (int o = 0; o < 16; ++o) {
-                // a window whose maximum is clipped is a tie of zeros after the ReLU: the first vertex is the arg-max
-                if (pool_relu_fix && !(m[o] > 0.f)) idx[o] = 0;
-                m[o] = fmaxf(m[o], 0.f);
-              }
-            }
-            if (valid) {
-              float* yp = P.y + orow * P.Fout + h * 16;
-#pragma unroll
-              for (int c4 = 0; c4 < 4; ++c4)
-                if (h * 16 + c4 * 4 < P.Fout)
-                  *reinterpret_cast<float4*>(yp + c4 * 4) = make_float4(m[c4 * 4], m[c4 * 4 + 1], m[c4 * 4 + 2], m[c4 * 4 + 3]);
-              if (P.argmax && p > 1) {
-                uint8_t* ap = P.argmax + orow * P.Fout + h * 16;
-#pragma unroll
-                for (int c4 = 0; c4 < 4; ++c4)
-                  if (h * 16 + c4 * 4 < P.Fout)
-                    *reinterpret_cast<uint32_t*>(ap + c4 * 4) = (uint32_t)idx[c4 * 4] | ((uint32_t)idx[c4 * 4 + 1] << 8) |
-                                                                ((uint32_t)idx[c4 * 4 + 2] << 16) |
-                                                                ((uint32_t)idx[c4 * 4 + 3] << 24);
-              }
-            }
-#pragma unroll
-            for (int o = 0; o < 16; ++o)
-              if (h * 16 + o < P.Fout) msum += m[o];
-          }
-          if (P.y_mean && valid) P.y_mean[orow] = msum / (float)P.Fout;
-        }
+        for (int g = 0; g < G; ++g)
+          for (int t = 0; t < P.T; ++t) epi_task(tile, buf, e, g, t, 0, 2);
       }
       TRACE(3, e == 0);
       tc_fence_before();
@@ -723,7 +760,7 @@ int umma_cheb_fwd(const float* x, const int32_t* perm, int M_in, const gcnb_csr&
 #define GCNB_UMMA_CASE(fp, mi)                                                                                      \
   if (pl.FP == fp && pl.MAXI == mi) {                                                                               \
     GCNB_CUDA(cudaFuncSetAttribute(k_cheb_fwd_umma<fp, mi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem)); \
-    k_cheb_fwd_umma<fp, mi><<<grid, kThreads, pl.smem, st>>>(P);                                                    \
+    GCNB_CUDA(launch_pdl(k_cheb_fwd_umma<fp, mi>, dim3(grid), dim3(kThreads), pl.smem, st, P));                      \
   }
   GCNB_UMMA_CASE(16, 3) GCNB_UMMA_CASE(16, 5) GCNB_UMMA_CASE(32, 3) GCNB_UMMA_CASE(32, 5)
 #undef GCNB_UMMA_CASE

@@ -72,7 +72,8 @@ __global__ void __launch_bounds__(896, 1) k_cheb_bwd_fused(const BwdParams P) {
   constexpr int NTF = MT * 2;  // n-tiles over the input features in the G contraction
   constexpr int NCH = MT * NT / 2;
 
-  // ---- once per CTA ---------------------------------------------------------------------------------------
+  // ---- once per CTA (static data only: runs ahead of the predecessor's completion under PDL) ------------------
+  pdl_trigger();
   if (!P.skip_dw) build_operator(P.rowptr, P.col, P.val, G.M, G.Mpad, P.nnz, RS, opL);
   if (need_dx && P.K > 1) build_operator(P.rowptr_t, P.col_t, P.val_t, G.M, G.Mpad, P.nnz, RS, opT);
   if (need_dx) {
@@ -103,6 +104,7 @@ __global__ void __launch_bounds__(896, 1) k_cheb_bwd_fused(const BwdParams P) {
 
   float dbacc = 0.f;  // this thread's filter (o = tid % FoP is the same in every iteration: FoP | blockDim)
 
+  pdl_wait();  // dy / y / arg-max (and everything this kernel writes) belong to the dependent part of the stream
   for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
     const int b0 = tile * G.S;
     __syncthreads();
@@ -321,6 +323,8 @@ __global__ void __launch_bounds__(896, 1) k_cheb_bwd_fused(const BwdParams P) {
 __global__ void k_dw_from_partials(const float* __restrict__ part, float* __restrict__ dW, int nblocks, int K, int MT,
                                    int NT, int Fin, int Fout, const float* __restrict__ db_part, float* __restrict__ db,
                                    int FoP) {
+  pdl_trigger();
+  pdl_wait();
   const int NCH = MT * NT / 2;
   const int total = K * NCH * 256;
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -505,7 +509,8 @@ int launch_dw_from_partials(const float* part, float* dW, int nblocks, int K, in
                             const float* db_part, float* db, int FoP, cudaStream_t st) {
   const int total = K * (MT * NT / 2) * 256;
   const int warps = total + (db_part != nullptr ? Fout : 0);
-  k_dw_from_partials<<<ceil_div(warps * 32, 256), 256, 0, st>>>(part, dW, nblocks, K, MT, NT, Fin, Fout, db_part, db, FoP);
+  GCNB_CUDA(launch_pdl(k_dw_from_partials, dim3(ceil_div(warps * 32, 256)), dim3(256), 0, st, part, dW, nblocks, K, MT, NT,
+                       Fin, Fout, db_part, db, FoP));
   GCNB_LAUNCH_CHECK("k_dw_from_partials");
   return GCNB_OK;
 }
@@ -545,7 +550,7 @@ template <int MT, int NT, int SLOTS>
 static int launch_bwd(const BwdParams& P, const BwdPlan& pl, int grid, cudaStream_t st) {
   auto kern = k_cheb_bwd_fused<MT, NT, SLOTS>;
   GCNB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-  kern<<<grid, pl.g.nwarps * 32, pl.smem, st>>>(P);
+  GCNB_CUDA(launch_pdl(kern, dim3(grid), dim3(pl.g.nwarps * 32), pl.smem, st, P));
   GCNB_LAUNCH_CHECK("k_cheb_bwd_fused");
   return GCNB_OK;
 }

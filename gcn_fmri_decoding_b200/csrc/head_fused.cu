@@ -80,7 +80,7 @@ __device__ __forceinline__ void tile_gemm(TileSmem& sm, int M, int N, int m0, in
     }
     __syncthreads();
     if (kc + TK < k1) fetch(kc + TK);  // in flight while this chunk is multiplied
-#pragma unroll
+#pragma unroll 8
     for (int k = 0; k < TK; ++k) {
       const float4 av = *reinterpret_cast<const float4*>(&sm.a[k][ty * 4]);
       const float4 bv = *reinterpret_cast<const float4*>(&sm.b[k][tx * 4]);
@@ -187,6 +187,7 @@ __device__ long long g_head_trace[32];
 
 __global__ void __launch_bounds__(HT, 1) k_head_step(const HeadParams P) {
   cg::grid_group grid = cg::this_grid();
+  pdl_trigger();  // the first backward kernel may be scheduled as soon as SMs free up; it waits for this grid
   HTRACE(0);
   // one shared buffer, three views: the GEMM tiles, the staging of the narrow products, rows of h2 (+ W3)
   __shared__ __align__(16) float smem_f[16 * 16 * 33];
