@@ -200,7 +200,7 @@ struct HeadParams {
   float *logits, *loss;
   float *gW1, *gb1, *gW2, *gb2, *gW3, *gb3, *d0;
   // scratch
-  float *h1, *h2, *d1, *d2, *d3, *part2, *partW2, *loss_rows;
+  float *h1, *h2, *d1, *d2, *d3, *part2, *partW2, *loss_rows, *part3, *part1, *part0;
   int B, n0, n1, n2, C;  // widths: a0 [B x n0], h1 [B x n1], h2 [B x n2], logits [B x C]
   float keep, inv_keep;
   unsigned seed1, seed2;

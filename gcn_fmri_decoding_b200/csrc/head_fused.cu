@@ -23,12 +23,21 @@ namespace cg = cooperative_groups;
 
 namespace gcnb {
 
+#ifdef GCNB_TRACE
+__device__ long long g_head_trace[32];
+#define HTRACE(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_head_trace[i] = clock64(); } while (0)
+#else
+#define HTRACE(i) do { } while (0)
+#endif
+
 constexpr int HT = 256;         // threads per CTA
 constexpr int TM = 64, TN = 64, TK = 32;
 constexpr int TS = TM + 4;      // shared tile row stride (floats): keeps 16-byte alignment of the float4 reads
 constexpr int SK2 = 4;          // K split of h1 W2 (too few output tiles otherwise)
 constexpr int SKW = 2;          // K (= batch) split of h1^T d2
 constexpr int SKC = 128;        // k chunk of the narrow products
+constexpr int SK3 = 8;          // batch split of h2^T d3 (16 column blocks alone would leave 130 CTAs waiting)
+constexpr int SK1 = 4;          // batch split of a0^T d1 and K split of d1 W1^T
 
 __host__ __device__ static inline int ceil_div_d(int a, int b) { return (a + b - 1) / b; }
 
@@ -96,14 +105,17 @@ __device__ __forceinline__ void tile_gemm(TileSmem& sm, int M, int N, int m0, in
 
 // Narrow products: out[j * soj + c * soc] = sum_k X(k, j) * Y(k, c) for j < Jv <= 16 and c < CY <= 32, k < Kd.
 // Both operands are staged through shared memory in chunks of SKC k (cooperative loads, next chunk in flight while
-// the current one is multiplied); thread (jl, cg) owns out(jl, cg) and out(jl, cg + 16) and walks k in order, so
-// there is no cross-thread reduction and the result is bit-reproducible.  kfast: k is the contiguous index of both
-// operands in memory (loads then run along k), else j / c are.  One copy of the code for its three users.
-__device__ __noinline__ void skinny16(float* sm /* >= SKC*17 + SKC*33 floats */, View X, int Jv, View Y, int CY, int Kd,
+// the current one is multiplied).  Thread (kq, jq, cg) owns a 4 x 2 block of outputs (j = 4 jq .., c = cg, cg + 16)
+// for the k of its quarter (k = kq mod 4): one LDS.128 + two LDS per eight FMAs -- the first version, one output pair
+// per thread, was bound by shared-memory wavefronts.  The four k-quarters are combined in a fixed order through
+// shared memory at the end: bit-reproducible.  kfast: k is the contiguous index of both operands in memory (loads
+// then run along k), else j / c are.  One copy of the code for its three users.
+constexpr int SXS = 20;  // row stride of the staged X chunk (floats): 16-byte aligned rows
+__device__ __noinline__ void skinny16(float* sm /* >= SKC*SXS + SKC*33 floats */, View X, int Jv, View Y, int CY, int Kd,
                                       bool kfast, float* out, long long soj, long long soc) {
-  float(*xs)[17] = reinterpret_cast<float(*)[17]>(sm);
-  float(*ys)[33] = reinterpret_cast<float(*)[33]>(sm + SKC * 17);
-  const int tid = threadIdx.x, jl = tid & 15, cg = tid >> 4;
+  float(*xs)[SXS] = reinterpret_cast<float(*)[SXS]>(sm);
+  float(*ys)[33] = reinterpret_cast<float(*)[33]>(sm + SKC * SXS);
+  const int tid = threadIdx.x, kq = tid >> 6, jq = tid & 3, cg = (tid >> 2) & 15;
   constexpr int NX = SKC * 16 / HT, NY = SKC * 32 / HT;
   float rx[NX], ry[NY];
   auto fetch = [&](int k0) {
@@ -120,7 +132,9 @@ __device__ __noinline__ void skinny16(float* sm /* >= SKC*17 + SKC*33 floats */,
       ry[i] = (k0 + kk < Kd && c < CY) ? Y.at(k0 + kk, c) : 0.f;
     }
   };
-  float acc0 = 0.f, acc1 = 0.f;
+  float acc[4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = 0.f;
   fetch(0);
   for (int k0 = 0; k0 < Kd; k0 += SKC) {
     __syncthreads();
@@ -139,15 +153,29 @@ __device__ __noinline__ void skinny16(float* sm /* >= SKC*17 + SKC*33 floats */,
     __syncthreads();
     if (k0 + SKC < Kd) fetch(k0 + SKC);
 #pragma unroll 8
-    for (int k = 0; k < SKC; ++k) {
-      const float x = xs[k][jl];
-      acc0 = fmaf(x, ys[k][cg], acc0);
-      acc1 = fmaf(x, ys[k][cg + 16], acc1);
+    for (int k = kq; k < SKC; k += 4) {
+      const float4 x = *reinterpret_cast<const float4*>(&xs[k][jq * 4]);
+      const float y0 = ys[k][cg], y1 = ys[k][cg + 16];
+      acc[0][0] = fmaf(x.x, y0, acc[0][0]); acc[0][1] = fmaf(x.x, y1, acc[0][1]);
+      acc[1][0] = fmaf(x.y, y0, acc[1][0]); acc[1][1] = fmaf(x.y, y1, acc[1][1]);
+      acc[2][0] = fmaf(x.z, y0, acc[2][0]); acc[2][1] = fmaf(x.z, y1, acc[2][1]);
+      acc[3][0] = fmaf(x.w, y0, acc[3][0]); acc[3][1] = fmaf(x.w, y1, acc[3][1]);
     }
   }
   __syncthreads();
-  if (jl < Jv && cg < CY) out[jl * soj + cg * soc] = acc0;
-  if (jl < Jv && cg + 16 < CY) out[jl * soj + (cg + 16) * soc] = acc1;
+  float* red = sm;  // [4 k-quarters][16 j][32 c]
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    red[(kq * 16 + jq * 4 + i) * 32 + cg] = acc[i][0];
+    red[(kq * 16 + jq * 4 + i) * 32 + cg + 16] = acc[i][1];
+  }
+  __syncthreads();
+  for (int o = tid; o < 16 * 32; o += HT) {
+    const int j = o >> 5, c = o & 31;
+    const float v = ((red[o] + red[512 + o]) + red[1024 + o]) + red[1536 + o];
+    if (j < Jv && c < CY) out[j * soj + c * soc] = v;
+  }
+  __syncthreads();
 }
 
 // out[c] = sum_r X[r][c] for 32 columns c0..c0+31: 8 row slices x 32 columns, fixed-order combine.
@@ -178,12 +206,6 @@ __device__ __noinline__ void colsum32(float* red /* [8][32] */, const float* X, 
   __syncthreads();
 }
 
-#ifdef GCNB_TRACE
-__device__ long long g_head_trace[32];
-#define HTRACE(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_head_trace[i] = clock64(); } while (0)
-#else
-#define HTRACE(i) do { } while (0)
-#endif
 
 __global__ void __launch_bounds__(HT, 1) k_head_step(const HeadParams P) {
   cg::grid_group grid = cg::this_grid();
@@ -192,7 +214,7 @@ __global__ void __launch_bounds__(HT, 1) k_head_step(const HeadParams P) {
   // one shared buffer, three views: the GEMM tiles, the staging of the narrow products, rows of h2 (+ W3)
   __shared__ __align__(16) float smem_f[16 * 16 * 33];
   static_assert(sizeof(TileSmem) <= sizeof(float) * 16 * 16 * 33, "tile view must fit");
-  static_assert(SKC * 17 + SKC * 33 <= 16 * 16 * 33, "narrow-product staging must fit");
+  static_assert(SKC * SXS + SKC * 33 <= 16 * 16 * 33, "narrow-product staging must fit");
   TileSmem& sm = *reinterpret_cast<TileSmem*>(smem_f);
   float* red = smem_f;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -338,11 +360,14 @@ __global__ void __launch_bounds__(HT, 1) k_head_step(const HeadParams P) {
 
   // ---- B1: gW3, gb3, d2 = (d3 W3^T) . mask2 ; mean loss ----------------------------------------------------------
   {
-    const int uW3 = ceil_div_d(n2, 16), uD2 = ceil_div_d(B * n2, HT * 4);
+    const int uW3 = ceil_div_d(n2, 16) * SK3, uD2 = ceil_div_d(B * n2, HT * 4);
     for (int u = bid; u < uW3 + 1 + uD2; u += nb) {
       if (u < uW3) {
-        const int j0 = u * 16;  // gW3[j][c] = sum_r h2[r][j] d3[r][c]
-        skinny16(red, View{P.h2 + j0, n2, 1}, min(16, n2 - j0), View{P.d3, C, 1}, C, B, false, P.gW3 + (long long)j0 * C, C, 1);
+        // partial of gW3[j][c] = sum_r h2[r][j] d3[r][c] over one slice of the batch, 16 columns j
+        const int j0 = (u / SK3) * 16, sp = u % SK3;
+        const int rper = ceil_div_d(B, SK3), r0 = sp * rper, r1 = min(B, r0 + rper);
+        skinny16(red, View{P.h2 + (long long)r0 * n2 + j0, n2, 1}, min(16, n2 - j0), View{P.d3 + (long long)r0 * C, C, 1}, C,
+                 max(r1 - r0, 0), false, P.part3 + (long long)sp * n2 * C + (long long)j0 * C, C, 1);
       } else if (u == uW3) {
         colsum32(red, P.d3, C, C, 0, B, P.gb3);
         float s = 0.f;  // mean loss, fixed order
@@ -357,19 +382,27 @@ __global__ void __launch_bounds__(HT, 1) k_head_step(const HeadParams P) {
         if (tid == 0) P.loss[0] = red[0] / (float)B;
         __syncthreads();
       } else {
+        // d2[r][n] = mask2 * sum_c d3[r][c] W3[n][c]: both C-long rows in registers before the first FMA
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int o = ((u - uW3 - 1) * 4 + i) * HT + tid;
           if (o < B * n2) {
             const int r = o / n2, n = o - r * n2;
-            float s = 0.f;
+            float sacc = 0.f;
             if (P.h2[o] > 0.f) {
               const float* dr = P.d3 + (long long)r * C;
               const float* wr = P.W3 + (long long)n * C;
-              for (int c = 0; c < C; ++c) s = fmaf(dr[c], __ldg(wr + c), s);
-              s *= P.inv_keep;
+              float dv[32], wv[32];
+#pragma unroll
+              for (int c = 0; c < 32; ++c) {
+                dv[c] = c < C ? dr[c] : 0.f;
+                wv[c] = c < C ? __ldg(wr + c) : 0.f;
+              }
+#pragma unroll
+              for (int c = 0; c < 32; ++c) sacc = fmaf(dv[c], wv[c], sacc);
+              sacc *= P.inv_keep;
             }
-            P.d2[o] = s;
+            P.d2[o] = sacc;
           }
         }
       }
@@ -388,9 +421,27 @@ __global__ void __launch_bounds__(HT, 1) k_head_step(const HeadParams P) {
 
   // ---- B2: partial gW2 = h1^T d2 (batch split SKW ways), d1 = (d2 W2^T) . mask1, gb2 -----------------------------
   {
-    const int uW = tm1 * tn2 * SKW, uD = tmB * tn1, uB = ceil_div_d(n2, 32);
+    const int uW = tm1 * tn2 * SKW, uD = tmB * tn1, uB = ceil_div_d(n2, 32), uR3 = ceil_div_d(n2 * C, HT * 4);
     const int bper = ceil_div_d(ceil_div_d(B, SKW), TK) * TK;
-    for (int u = bid; u < uW + uD + uB; u += nb) {
+    for (int u = bid; u < uW + uD + uB + uR3; u += nb) {
+      if (u >= uW + uD + uB) {  // gW3 = sum of the batch-slice partials of B1 (fixed order)
+        float v[4][SK3];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int o = ((u - uW - uD - uB) * 4 + i) * HT + tid;
+#pragma unroll
+          for (int q = 0; q < SK3; ++q) v[i][q] = o < n2 * C ? P.part3[(long long)q * n2 * C + o] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int o = ((u - uW - uD - uB) * 4 + i) * HT + tid;
+          float sacc = v[i][0];
+#pragma unroll
+          for (int q = 1; q < SK3; ++q) sacc += v[i][q];
+          if (o < n2 * C) P.gW3[o] = sacc;
+        }
+        continue;
+      }
       if (u < uW) {
         const int sp = u % SKW, t = u / SKW;
         const int m0 = (t / tn2) * TM, c0 = (t % tn2) * TN;
@@ -429,9 +480,10 @@ __global__ void __launch_bounds__(HT, 1) k_head_step(const HeadParams P) {
   grid.sync();
   HTRACE(10);
 
-  // ---- B3: gW2 = sum of partials, gW1 = a0^T d1, gb1, d0 = d1 W1^T ------------------------------------------------
+  // ---- B3: gW2 = sum of partials, gb1, slice partials of gW1 = a0^T d1 and of d0 = d1 W1^T ---------------------------
   {
-    const int uS = ceil_div_d(n1 * n2, HT * 8), uW1 = ceil_div_d(n1, 16), uB1 = ceil_div_d(n1, 32), uD0 = ceil_div_d(B, 16);
+    const int uS = ceil_div_d(n1 * n2, HT * 8), uW1 = ceil_div_d(n1, 16) * SK1, uB1 = ceil_div_d(n1, 32),
+              uD0 = ceil_div_d(B, 16) * SK1;
     for (int u = bid; u < uS + uW1 + uB1 + uD0; u += nb) {
       if (u < uS) {
         float v[8][SKW];
@@ -450,26 +502,50 @@ __global__ void __launch_bounds__(HT, 1) k_head_step(const HeadParams P) {
           if (o < (long long)n1 * n2) P.gW2[o] = sacc;
         }
       } else if (u < uS + uW1) {
-        const int j0 = (u - uS) * 16;  // gW1[m][n] = sum_r a0[r][m] d1[r][n] for 16 columns n
-        skinny16(red, View{P.d1 + j0, n1, 1}, min(16, n1 - j0), View{P.a0, n0, 1}, n0, B, false, P.gW1 + j0, 1, n1);
+        // partial of gW1[m][n] = sum_r a0[r][m] d1[r][n] over one slice of the batch, 16 columns n
+        const int t = u - uS, j0 = (t / SK1) * 16, sp = t % SK1;
+        const int rper = ceil_div_d(B, SK1), r0 = sp * rper, r1 = min(B, r0 + rper);
+        skinny16(red, View{P.d1 + (long long)r0 * n1 + j0, n1, 1}, min(16, n1 - j0), View{P.a0 + (long long)r0 * n0, n0, 1}, n0,
+                 max(r1 - r0, 0), false, P.part1 + (long long)sp * n0 * n1 + j0, 1, n1);
       } else if (u < uS + uW1 + uB1) {
         colsum32(red, P.d1, n1, n1, (u - uS - uW1) * 32, B, P.gb1);
       } else {
-        const int r0 = (u - uS - uW1 - uB1) * 16;  // d0[r][m] = sum_k d1[r][k] W1[m][k] for 16 rows r
-        skinny16(red, View{P.d1 + (long long)r0 * n1, 1, n1}, min(16, B - r0), View{P.W1, 1, n1}, n0, n1, true,
-                 P.d0 + (long long)r0 * n0, n0, 1);
+        // partial of d0[r][m] = sum_k d1[r][k] W1[m][k] over one slice of k, 16 rows r
+        const int t = u - uS - uW1 - uB1, r0 = (t / SK1) * 16, sp = t % SK1;
+        const int kper = ceil_div_d(n1, SK1), k0 = sp * kper, k1 = min(n1, k0 + kper);
+        skinny16(red, View{P.d1 + (long long)r0 * n1 + k0, 1, n1}, min(16, B - r0), View{P.W1 + k0, 1, n1}, n0, max(k1 - k0, 0),
+                 true, P.part0 + (long long)sp * B * n0 + (long long)r0 * n0, n0, 1);
       }
     }
   }
   HTRACE(11);
+  grid.sync();
+  HTRACE(12);
+
+  // ---- B4: gW1 and d0 = sums of their slice partials (fixed order) ---------------------------------------------------
+  {
+    const int nW = n0 * n1, nD = B * n0;
+    for (int o = bid * HT + tid; o < nW + nD; o += nb * HT) {
+      const float* src = o < nW ? P.part1 + o : P.part0 + (o - nW);
+      const long long stride = o < nW ? nW : nD;
+      float v[SK1];
+#pragma unroll
+      for (int q = 0; q < SK1; ++q) v[q] = src[q * stride];
+      float sacc = v[0];
+#pragma unroll
+      for (int q = 1; q < SK1; ++q) sacc += v[q];
+      if (o < nW) P.gW1[o] = sacc; else P.d0[o - nW] = sacc;
+    }
+  }
+  HTRACE(13);
 }
 
 
 // ---------------------------------------------------------------------------------------------------------------
 size_t head_step_workspace(int B, int n0, int n1, int n2, int C) {
-  (void)n0;
   size_t f = (size_t)B * n1 * 2 /*h1, d1*/ + (size_t)B * n2 * 2 /*h2, d2*/ + (size_t)B * C /*d3*/ +
-             (size_t)SK2 * B * n2 /*part2*/ + (size_t)SKW * n1 * n2 /*partW2*/ + (size_t)B /*loss rows*/;
+             (size_t)SK2 * B * n2 /*part2*/ + (size_t)SKW * n1 * n2 /*partW2*/ + (size_t)B /*loss rows*/ +
+             (size_t)SK3 * n2 * C /*part3*/ + (size_t)SK1 * n0 * n1 /*part1*/ + (size_t)SK1 * B * n0 /*part0*/;
   return f * sizeof(float) + 16 * 256;
 }
 
@@ -488,7 +564,10 @@ int head_step(const HeadParams& P0, Workspace& ws, cudaStream_t st) {
   P.part2 = ws.take<float>((size_t)SK2 * B * n2);
   P.partW2 = ws.take<float>((size_t)SKW * n1 * n2);
   P.loss_rows = ws.take<float>((size_t)B);
-  if (!P.loss_rows) {
+  P.part3 = ws.take<float>((size_t)SK3 * n2 * C);
+  P.part1 = ws.take<float>((size_t)SK1 * P.n0 * n1);
+  P.part0 = ws.take<float>((size_t)SK1 * B * P.n0);
+  if (!P.loss_rows || !P.part3 || !P.part1 || !P.part0) {
     set_error("gcnb_head_step_f32: workspace too small");
     return GCNB_ERR_WORKSPACE;
   }

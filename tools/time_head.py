@@ -63,6 +63,6 @@ if os.environ.get("GCNB_HEAD_TRACE"):
     h = C.CDLL(_lib.LIB_PATH)
     buf = (C.c_longlong * 32)()
     h.gcnb_debug_read_head_trace(buf)
-    v = [int(x) for x in buf[:12]]
-    names = ["F1", "sync", "F2", "sync", "F3", "sync", "B1", "sync", "B2", "sync", "B3"]
+    v = [int(x) for x in buf[:14]]
+    names = ["F1", "sync", "F2", "sync", "F3", "sync", "B1", "sync", "B2", "sync", "B3", "sync", "B4"]
     print("head phases (cycles):", " ".join("%s=%d" % (n, v[i + 1] - v[i]) for i, n in enumerate(names)))
