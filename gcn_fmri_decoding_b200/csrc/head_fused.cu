@@ -54,26 +54,39 @@ struct View {
 };
 
 // One 64x64 output tile of op(A) op(B) over k in [k0, k1): acc[i][j] of thread (ty, tx) = C[m0 + 4 ty + i][n0 + 4 tx + j].
-// A(m, k) / B(k, n) are element functors over global memory; a_kfast / b_kfast say which index is contiguous in
-// memory so that the cooperative tile loads coalesce.  (A shared, non-inlined body with run-time operand descriptors
-// was measured 20 % slower than these four specialised instances.)
-template <class FA, class FB>
-__device__ __forceinline__ void tile_gemm(TileSmem& sm, int M, int N, int m0, int n0, int k0, int k1, bool a_kfast,
-                                          bool b_kfast, FA A, FB Bf, float (&acc)[4][4]) {
+// Operands are strided views of global memory; AK / BK say which index is contiguous (so that the cooperative tile
+// loads coalesce): AK: A(m, k) = A[m * lda + k], else A[k * lda + m];  BK: B(k, n) = B[n * ldb + k], else B[k * ldb + n].
+// All per-element address arithmetic is hoisted out of the chunk loop (one pointer, one validity bit per element);
+// the next chunk's 16 loads are in flight while the current one is multiplied.  Plain (coherent) loads: some operands
+// were written earlier in this kernel.  The chunk loop is FFMA-issue bound (512 FFMA per thread and chunk).
+template <bool AK, bool BK>
+__device__ __forceinline__ void tile_gemm(TileSmem& sm, const float* A, int lda, const float* Bp,
+                                          int ldb, int M, int N, int m0, int n0, int k0, int k1, float (&acc)[4][4]) {
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  // element i of this thread: A: (k = ak0 + i*AKS, m = am0 + i*AMS), B likewise
+  const int ak0 = AK ? (tid & 31) : (tid >> 6), am0 = AK ? (tid >> 5) : (tid & 63);
+  const int bk0 = BK ? (tid & 31) : (tid >> 6), bn0 = BK ? (tid >> 5) : (tid & 63);
+  constexpr int AKS = AK ? 0 : 4, AMS = AK ? 8 : 0, BKS = BK ? 0 : 4, BNS = BK ? 8 : 0;
+  const float* pa = AK ? A + (long long)(m0 + am0) * lda + ak0 : A + (long long)ak0 * lda + (m0 + am0);
+  const float* pb = BK ? Bp + (long long)(n0 + bn0) * ldb + bk0 : Bp + (long long)bk0 * ldb + (n0 + bn0);
+  const long long sa = AK ? (long long)AMS * lda : (long long)AKS * lda, sb = BK ? (long long)BNS * ldb : (long long)BKS * ldb;
+  const long long ka = AK ? 1 : lda, kb = BK ? 1 : ldb;  // address step per unit of k
+  uint32_t va = 0, vb = 0;                               // row / column validity of the 8 elements
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    va |= (m0 + am0 + i * AMS < M ? 1u : 0u) << i;
+    vb |= (n0 + bn0 + i * BNS < N ? 1u : 0u) << i;
+  }
   float ra[8], rb[8];
   auto fetch = [&](int kc) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int e = i * HT + tid;
-      const int ak = a_kfast ? (e & 31) : (e >> 6), am = a_kfast ? (e >> 5) : (e & 63);
-      ra[i] = (m0 + am < M && kc + ak < k1) ? A(m0 + am, kc + ak) : 0.f;
-      const int bk = b_kfast ? (e & 31) : (e >> 6), bn = b_kfast ? (e >> 5) : (e & 63);
-      rb[i] = (n0 + bn < N && kc + bk < k1) ? Bf(kc + bk, n0 + bn) : 0.f;
+      ra[i] = ((va >> i) & 1u) && kc + ak0 + i * AKS < k1 ? pa[kc * ka + i * sa] : 0.f;
+      rb[i] = ((vb >> i) & 1u) && kc + bk0 + i * BKS < k1 ? pb[kc * kb + i * sb] : 0.f;
     }
   };
   fetch(k0);
@@ -81,14 +94,11 @@ __device__ __forceinline__ void tile_gemm(TileSmem& sm, int M, int N, int m0, in
     __syncthreads();  // the previous chunk has been consumed
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int e = i * HT + tid;
-      const int ak = a_kfast ? (e & 31) : (e >> 6), am = a_kfast ? (e >> 5) : (e & 63);
-      sm.a[ak][am] = ra[i];
-      const int bk = b_kfast ? (e & 31) : (e >> 6), bn = b_kfast ? (e >> 5) : (e & 63);
-      sm.b[bk][bn] = rb[i];
+      sm.a[ak0 + i * AKS][am0 + i * AMS] = ra[i];
+      sm.b[bk0 + i * BKS][bn0 + i * BNS] = rb[i];
     }
     __syncthreads();
-    if (kc + TK < k1) fetch(kc + TK);  // in flight while this chunk is multiplied
+    if (kc + TK < k1) fetch(kc + TK);
 #pragma unroll 8
     for (int k = 0; k < TK; ++k) {
       const float4 av = *reinterpret_cast<const float4*>(&sm.a[k][ty * 4]);
@@ -228,9 +238,7 @@ __global__ void __launch_bounds__(HT, 1) k_head_step(const HeadParams P) {
   // ---- F1: h1 = dropout(relu(a0 W1 + b1)) ---------------------------------------------------------------------
   for (int u = bid; u < tmB * tn1; u += nb) {
     const int m0 = (u / tn1) * TM, c0 = (u % tn1) * TN;
-    tile_gemm(sm, B, n1, m0, c0, 0, n0, true, false,
-              [&](int m, int k) { return __ldg(P.a0 + (long long)m * n0 + k); },
-              [&](int k, int n) { return __ldg(P.W1 + (long long)k * n1 + n); }, acc);
+    tile_gemm<true, false>(sm, P.a0, n0, P.W1, n1, B, n1, m0, c0, 0, n0, acc);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int m = m0 + ty * 4 + i;
@@ -256,9 +264,7 @@ __global__ void __launch_bounds__(HT, 1) k_head_step(const HeadParams P) {
       const int sp = u % SK2, t = u / SK2;
       const int m0 = (t / tn2) * TM, c0 = (t % tn2) * TN;
       const int k0 = sp * kper, k1 = min(n1, k0 + kper);
-      tile_gemm(sm, B, n2, m0, c0, k0, k1, true, false,
-                [&](int m, int k) { return P.h1[(long long)m * n1 + k]; },
-                [&](int k, int n) { return __ldg(P.W2 + (long long)k * n2 + n); }, acc);
+      tile_gemm<true, false>(sm, P.h1, n1, P.W2, n2, B, n2, m0, c0, k0, k1, acc);
       float* dst = P.part2 + (long long)sp * B * n2;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -446,9 +452,7 @@ __global__ void __launch_bounds__(HT, 1) k_head_step(const HeadParams P) {
         const int sp = u % SKW, t = u / SKW;
         const int m0 = (t / tn2) * TM, c0 = (t % tn2) * TN;
         const int k0 = sp * bper, k1 = min(B, k0 + bper);
-        tile_gemm(sm, n1, n2, m0, c0, k0, k1, false, false,
-                  [&](int m, int k) { return P.h1[(long long)k * n1 + m]; },
-                  [&](int k, int n) { return P.d2[(long long)k * n2 + n]; }, acc);
+        tile_gemm<false, false>(sm, P.h1, n1, P.d2, n2, n1, n2, m0, c0, k0, k1, acc);
         float* dst = P.partW2 + (long long)sp * n1 * n2;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -460,9 +464,7 @@ __global__ void __launch_bounds__(HT, 1) k_head_step(const HeadParams P) {
       } else if (u < uW + uD) {
         const int t = u - uW;
         const int m0 = (t / tn1) * TM, c0 = (t % tn1) * TN;
-        tile_gemm(sm, B, n1, m0, c0, 0, n2, true, true,
-                  [&](int m, int k) { return P.d2[(long long)m * n2 + k]; },
-                  [&](int k, int n) { return __ldg(P.W2 + (long long)n * n2 + k); }, acc);
+        tile_gemm<true, true>(sm, P.d2, n2, P.W2, n2, B, n1, m0, c0, 0, n2, acc);
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
