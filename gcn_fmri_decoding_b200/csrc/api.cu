@@ -31,6 +31,15 @@ bool pdl_enabled() {
   return on;
 }
 
+// GCNB_UMMA_ADJ=0 sends the input gradient back to k_cheb_bwd_fused (A/B runs); read once.
+static bool adjoint_umma_enabled() {
+  static const bool on = [] {
+    const char* v = getenv("GCNB_UMMA_ADJ");
+    return !(v && v[0] == '0');
+  }();
+  return on;
+}
+
 int device_info(DeviceInfo* out) {
   static std::mutex mu;
   static DeviceInfo cache[64];
@@ -303,6 +312,9 @@ int gcnb_cheb_bwd_f32(const float* x, const int32_t* perm, int M_in, const float
     // saved basis: the weight gradient is one streamed GEMM; the fused kernel only runs the adjoint recursion for dx
     rc = stack_dw(xstack, y, argmax, dy, dy_is_mean, dW, db, s, bias_mode, relu, ws, st);
     if (rc) return rc;
+    // dx = sum_k T_k(L~^T) dZ W_k^T: the tcgen05 forward kernel run on the transposed operator (cheb_fwd_umma.cu)
+    if (K > 1 && algo == GCNB_ALGO_AUTO && umma_adj_supported(s) && adjoint_umma_enabled())
+      return umma_cheb_adj(dy, dy_is_mean, y, argmax, *Lt, W, dx, s, relu, st);
     Workspace ws2(static_cast<char*>(workspace) + align_up(ws.used, 256), workspace_bytes - align_up(ws.used, 256));
     return fused_cheb_bwd(x, perm, M_in, y, argmax, dy, *L, Lt, W, dx, dW, db, s, bias_mode, relu, dy_is_mean, true, ws2, st);
   }

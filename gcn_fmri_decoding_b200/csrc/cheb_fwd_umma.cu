@@ -74,6 +74,14 @@ struct UmmaFwdParams {
   int tmem_cols; // allocated columns (power of two)
   int slab_rows; // rows of one state buffer incl. the zero row (multiple of 8)
   int debug;     // GCNB_TRACE builds only: bit0 skip the gathers, bit1 skip the tcgen05.mma issue
+  // Adjoint mode (the layer's input gradient): dx = sum_k T_k(L~^T) dZ W_k^T is the SAME computation as the forward
+  // with the transposed operator, the transposed taps and dZ as the input.  dZ (MaxPoolGrad o ReluGrad of the layer's
+  // output gradient) is rebuilt on the fly from the pooled tensors while order 0 is loaded; x / perm are unused.
+  int adj;              // 1: adjoint mode; Fin = the layer's Fout (contraction width), Fout = the layer's Fin
+  const float* adj_dy;  // [B][Mo][Fin], or [B][Mo] when adj_mean (gradient of the mean over filters)
+  const float* adj_y;   // [B][Mo][Fin] pooled layer output (ReLU mask), used when adj_relu
+  const uint8_t* adj_arg;  // [B][Mo][Fin] arg-max offsets, used when the layer pools (adj_log2p > 0)
+  int adj_log2p, adj_relu, adj_mean, adj_Mo;
   // byte offsets into dynamic shared memory
   int off_lo, off_wh, off_wl, off_wb, off_ent, off_grow, off_grho, off_gslot, off_glen, off_src, off_rlen, off_sorted, off_bias,
       off_bar, off_rp;
@@ -136,7 +144,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
     for (int u = 0; u < 4; ++u) {  // all four loads in flight before the first conversion
       const int idx = i0 + u * kThreads + tid;
       const int o = idx & 31, kk = idx >> 5, k = kk / FP, f = kk - k * FP;
-      wv[u] = (idx < K * FP * 32 && f < P.Fin && o < P.Fout) ? __ldg(P.W + ((long long)f * K + k) * P.Fout + o) : 0.f;
+      wv[u] = (idx < K * FP * 32 && f < P.Fin && o < P.Fout)
+                  ? __ldg(P.W + (P.adj ? ((long long)o * K + k) * P.Fin + f : ((long long)f * K + k) * P.Fout + o))
+                  : 0.f;
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -412,7 +422,34 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
         for (int u = 0; u < MAXI; ++u) {
           v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
           const int b = tile * P.S + (int)((it_pk[u] >> 16) & 0xff);
-          if (it_row[u] >= 0 && b < P.B) {
+          if (P.adj) {
+            if (it_row[u] >= 0 && b < P.B && fc * 4 < P.Fin) {
+              const int vtx = it_row[u], jj = vtx >> P.adj_log2p, ii = vtx & ((1 << P.adj_log2p) - 1);
+              const long long prow = (long long)b * P.adj_Mo + jj, gi = prow * P.Fin + fc * 4;
+              float4 d;
+              if (P.adj_mean) {
+                const float m = __ldg(P.adj_dy + prow) / (float)P.Fin;
+                d = make_float4(m, m, m, m);
+              } else {
+                d = __ldg(reinterpret_cast<const float4*>(P.adj_dy + gi));
+              }
+              if (P.adj_relu) {
+                const float4 yv = __ldg(reinterpret_cast<const float4*>(P.adj_y + gi));
+                if (!(yv.x > 0.f)) d.x = 0.f;
+                if (!(yv.y > 0.f)) d.y = 0.f;
+                if (!(yv.z > 0.f)) d.z = 0.f;
+                if (!(yv.w > 0.f)) d.w = 0.f;
+              }
+              if (P.adj_log2p > 0) {
+                const uint32_t am = __ldg(reinterpret_cast<const uint32_t*>(P.adj_arg + gi));
+                if ((int)(am & 0xff) != ii) d.x = 0.f;
+                if ((int)((am >> 8) & 0xff) != ii) d.y = 0.f;
+                if ((int)((am >> 16) & 0xff) != ii) d.z = 0.f;
+                if ((int)(am >> 24) != ii) d.w = 0.f;
+              }
+              v[u] = d;
+            }
+          } else if (it_row[u] >= 0 && b < P.B) {
             const int src = src_row[it_row[u]];
             if (src >= 0) {
               const float* xp = P.x + ((long long)b * P.M_in + src) * P.Fin + fc * 4;
@@ -446,7 +483,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
         float* spill = P.xstack ? P.xstack + (long long)k * P.B * M * FP : nullptr;
         const uint32_t dlo = sb + P.off_lo + lo_u * lo_bytes;
         const uint32_t srcb = sb + (uint32_t)(cur ^ 1) * buf_bytes, dst = sb + (uint32_t)cur * buf_bytes;
-        if (k == K - 1 && tile + (int)gridDim.x < P.ntiles) {
+        if (k == K - 1 && !P.adj && tile + (int)gridDim.x < P.ntiles) {
           // pull the next tile's raw windows into L2 while this order computes
 #pragma unroll
           for (int u = 0; u < MAXI; ++u) {
@@ -728,9 +765,16 @@ int umma_fwd_describe(const LayerShape& s, char* out, size_t n) {
                   ceil_div(s.B, pl.NS * pl.G));
 }
 
-int umma_cheb_fwd(const float* x, const int32_t* perm, int M_in, const gcnb_csr& L, const float* W, const float* bias,
-                  float* y, uint8_t* argmax, float* y_mean, float* xstack, const LayerShape& s, int bias_mode, int relu,
-                  cudaStream_t st) {
+struct UmmaAdjoint {
+  const float* dy;
+  const float* y;
+  const uint8_t* argmax;
+  int p, relu, dy_is_mean;
+};
+
+static int umma_launch(const float* x, const int32_t* perm, int M_in, const gcnb_csr& L, const float* W, const float* bias,
+                       float* y, uint8_t* argmax, float* y_mean, float* xstack, const LayerShape& s, int bias_mode, int relu,
+                       const UmmaAdjoint* adj, cudaStream_t st) {
   DeviceInfo di;
   int rc = device_info(&di);
   if (rc) return rc;
@@ -746,6 +790,14 @@ int umma_cheb_fwd(const float* x, const int32_t* perm, int M_in, const gcnb_csr&
   P.B = s.B; P.M = s.M; P.Fin = s.Fin; P.Fout = s.Fout; P.K = s.K; P.p = s.p; P.bias_mode = bias_mode; P.relu = relu;
   P.log2p = 0;
   while ((1 << P.log2p) < s.p) ++P.log2p;
+  if (adj) {
+    P.adj = 1;
+    P.adj_dy = adj->dy; P.adj_y = adj->y; P.adj_arg = adj->argmax;
+    P.adj_relu = adj->relu; P.adj_mean = adj->dy_is_mean;
+    P.adj_log2p = 0;
+    while ((1 << P.adj_log2p) < adj->p) ++P.adj_log2p;
+    P.adj_Mo = s.M >> P.adj_log2p;
+  }
   P.NS = pl.NS; P.S = pl.NS * pl.G; P.Q = pl.Q; P.BQ = pl.BQ; P.T = pl.T; P.NG = pl.NG; P.nlo = pl.nlo; P.nacc = pl.nacc;
   P.acc_cols = pl.acc_cols; P.tmem_cols = pl.tmem_cols; P.slab_rows = pl.slab_rows;
   P.ntiles = ceil_div(s.B, P.S);
@@ -766,6 +818,27 @@ int umma_cheb_fwd(const float* x, const int32_t* perm, int M_in, const gcnb_csr&
 #undef GCNB_UMMA_CASE
   GCNB_LAUNCH_CHECK("k_cheb_fwd_umma");
   return GCNB_OK;
+}
+
+int umma_cheb_fwd(const float* x, const int32_t* perm, int M_in, const gcnb_csr& L, const float* W, const float* bias,
+                  float* y, uint8_t* argmax, float* y_mean, float* xstack, const LayerShape& s, int bias_mode, int relu,
+                  cudaStream_t st) {
+  return umma_launch(x, perm, M_in, L, W, bias, y, argmax, y_mean, xstack, s, bias_mode, relu, nullptr, st);
+}
+
+// The layer's input gradient through the forward kernel: operator L~^T, taps W_k^T, input dZ (see UmmaFwdParams::adj).
+static LayerShape adjoint_shape(const LayerShape& s) { return LayerShape{s.B, s.M, s.nnz, s.Fout, s.Fin, s.K, 1}; }
+
+bool umma_adj_supported(const LayerShape& s) {
+  if ((s.Fout & 3) || (s.Fin & 3) || s.M % s.p != 0 || s.p > 255) return false;
+  return umma_fwd_supported(adjoint_shape(s));
+}
+
+int umma_cheb_adj(const float* dy, int dy_is_mean, const float* y, const uint8_t* argmax, const gcnb_csr& Lt, const float* W,
+                  float* dx, const LayerShape& s, int relu, cudaStream_t st) {
+  UmmaAdjoint a{dy, y, argmax, s.p, relu, dy_is_mean};
+  return umma_launch(nullptr, nullptr, s.M, Lt, W, nullptr, dx, nullptr, nullptr, nullptr, adjoint_shape(s), GCNB_BIAS_NONE, 0,
+                     &a, st);
 }
 
 }  // namespace gcnb

@@ -144,6 +144,11 @@ int umma_cheb_fwd(const float* x, const int32_t* perm, int M_in, const gcnb_csr&
                   float* y, uint8_t* argmax, float* y_mean, float* xstack, const LayerShape& s, int bias_mode, int relu,
                   cudaStream_t st);
 
+// input gradient dx of a layer through the same kernel (operator L~^T, taps W_k^T, dZ rebuilt from dy / y / argmax)
+bool umma_adj_supported(const LayerShape& s);
+int umma_cheb_adj(const float* dy, int dy_is_mean, const float* y, const uint8_t* argmax, const gcnb_csr& Lt, const float* W,
+                  float* dx, const LayerShape& s, int relu, cudaStream_t st);
+
 // ---- fused (shared-memory resident) path, fused_fwd.cu / fused_bwd.cu ------------------------
 bool fused_fwd_supported(const LayerShape& s);
 bool fused_bwd_supported(const LayerShape& s, bool need_dx);
