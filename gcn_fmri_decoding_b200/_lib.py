@@ -21,7 +21,8 @@ EPI_NONE, EPI_RELU_DROPOUT, EPI_MASK = 0, 1, 2
 class GcnbCsr(C.Structure):
     """``struct gcnb_csr`` -- device pointers of a rescaled Laplacian in CSR."""
 
-    _fields_ = [("rowptr", C.c_void_p), ("col", C.c_void_p), ("val", C.c_void_p), ("M", C.c_int32), ("nnz", C.c_int32)]
+    _fields_ = [("rowptr", C.c_void_p), ("col", C.c_void_p), ("val", C.c_void_p), ("M", C.c_int32), ("nnz", C.c_int32),
+                ("image", C.c_void_p), ("image_bytes", C.c_size_t)]
 
 
 _i, _p, _z = C.c_int, C.c_void_p, C.c_size_t
@@ -36,6 +37,8 @@ SIGNATURES = {
     "gcnb_cheb_workspace_bytes": (_z, [_i] * 10),
     "gcnb_cheb_fwd_describe": (_i, [_i] * 7 + [C.c_char_p, _z]),
     "gcnb_cheb_stack_width": (_i, [_i] * 7),
+    "gcnb_cheb_image_bytes": (_z, [_p, _p] + [_i] * 8),
+    "gcnb_cheb_image_build": (_i, [_p, _p, _p] + [_i] * 8 + [_p, _z]),
     "gcnb_cheb_fwd_f32": (_i, [_p, _p, _i, _CSRP, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _z, _p]),
     "gcnb_cheb_bwd_f32": (_i, [_p, _p, _i, _p, _p, _p, _i, _p, _CSRP, _CSRP, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _z, _p]),
     "gcnb_spectral_workspace_bytes": (_z, [_i] * 6),

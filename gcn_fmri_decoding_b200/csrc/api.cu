@@ -286,6 +286,19 @@ int gcnb_cheb_fwd_f32(const float* x, const int32_t* perm, int M_in, const gcnb_
   return rc;
 }
 
+size_t gcnb_cheb_image_bytes(const int32_t* rowptr, const int32_t* col, int B, int M, int nnz, int Fin, int Fout, int K,
+                             int p, int adjoint) {
+  if (!rowptr || !col || B < 1 || M < 1 || nnz < 0 || Fin < 1 || Fout < 1 || K < 1 || p < 1) return 0;
+  return cheb_image_bytes(rowptr, col, LayerShape{B, M, nnz, Fin, Fout, K, p}, adjoint);
+}
+
+int gcnb_cheb_image_build(const int32_t* rowptr, const int32_t* col, const float* val, int B, int M, int nnz, int Fin,
+                          int Fout, int K, int p, int adjoint, void* image_host, size_t image_bytes) {
+  GCNB_REQUIRE(rowptr && col && val && image_host && B >= 1 && M >= 1 && nnz >= 0 && Fin >= 1 && Fout >= 1 && K >= 1 && p >= 1,
+               "gcnb_cheb_image_build: bad arguments");
+  return cheb_image_build(rowptr, col, val, LayerShape{B, M, nnz, Fin, Fout, K, p}, adjoint, image_host, image_bytes);
+}
+
 int gcnb_cheb_bwd_f32(const float* x, const int32_t* perm, int M_in, const float* y, const uint8_t* argmax,
                       const float* dy, int dy_is_mean, const float* xstack, const gcnb_csr* L,
                       const gcnb_csr* Lt, const float* W, float* dx, float* dW, float* db, int B, int Fin,

@@ -22,6 +22,9 @@
 // x is read from HBM once, y written once; the K-stack only goes to HBM when the caller asks for it (training).
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
+#include <type_traits>
+#include <vector>
 
 #include "umma.cuh"
 
@@ -33,6 +36,7 @@ static constexpr int kSparseWarps = 20;
 static constexpr int kEpiWarps = 4;   // warps 0..3: warp w may only touch TMEM lanes 32w..32w+31
 static constexpr int kMmaWarp = 4;    // warp 4
 static constexpr int kThreads = (kSparseWarps + kEpiWarps + 1) * 32;
+static constexpr uint32_t kImgMagic = 0x494e4347u;  // "GCNI"
 static constexpr int kBarOrder = 1;   // named barrier: sparse warps + MMA warp, once per Chebyshev order
 
 #ifdef GCNB_TRACE
@@ -42,8 +46,14 @@ __device__ long long g_trace[4][512];
   do {                                                                             \
     if (blockIdx.x == 0 && lane == 0 && (cond) && tr_n < 512) g_trace[region][tr_n++] = clock64(); \
   } while (0)
+// per sparse warp, one chosen order (n == 2) of CTA 0: g_trace[1][64 + sw * 16 + slot]
+#define TRACEW(slot)                                                                              \
+  do {                                                                                            \
+    if (blockIdx.x == 0 && lane == 0 && n == 2) g_trace[1][64 + sw * 16 + (slot)] = clock64();     \
+  } while (0)
 #else
 #define TRACE(region, cond) do { } while (0)
+#define TRACEW(slot) do { } while (0)
 #endif
 
 struct UmmaFwdParams {
@@ -82,13 +92,19 @@ struct UmmaFwdParams {
   const float* adj_y;   // [B][Mo][Fin] pooled layer output (ReLU mask), used when adj_relu
   const uint8_t* adj_arg;  // [B][Mo][Fin] arg-max offsets, used when the layer pools (adj_log2p > 0)
   int adj_log2p, adj_relu, adj_mean, adj_Mo;
+  // Pre-built operator image (IMG kernels, see "operator image" below): copied to shared memory as is.
+  const unsigned char* image;
+  int img_bytes;     // multiple of 16
+  unsigned img_sig;  // geometry signature the image must carry
+  int n_groups;      // groups of 4 row blocks
+  int off_img, off_grp, off_blk;  // shared-memory offsets of the image copy, its group table and its block table
   // byte offsets into dynamic shared memory
   int off_lo, off_wh, off_wl, off_wb, off_ent, off_grow, off_grho, off_gslot, off_glen, off_src, off_rlen, off_sorted, off_bias,
       off_bar, off_rp;
 };
 
 // ---------------------------------------------------------------------------------------------------------------
-template <int FP, int MAXI>
+template <int FP, int MAXI, bool IMG>
 __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdParams P) {
   extern __shared__ __align__(1024) unsigned char smem[];
   constexpr int G = 32 / FP;    // windows per 128-byte row
@@ -160,103 +176,113 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
       }
     }
   }
-  // operator image: rows sorted by decreasing length; entries re-encoded as (gather code, value) in CSR order,
-  // every row starting on an even entry so that one LDS.128 fetches two entries
-  const int M4 = P.NG * 4;
-  int* bins = sorted;  // [M + 3]: bin b counts rows of length (M - b); the padding rows (length -1) come last;
-                       // bins[M + 2] = longest row.  (`sorted` itself is no longer materialised.)
-  for (int r = tid; r <= M; r += kThreads) rp[r] = __ldg(P.rowptr + r);
   for (int r = tid; r < M; r += kThreads) {
     int s = r;
     if (P.perm) { s = __ldg(P.perm + r); if (s < 0 || s >= P.M_in) s = -1; }
     src_row[r] = s;
   }
   if (tid < 32) bias_s[tid] = (P.bias_mode == GCNB_BIAS_PER_FILTER && tid < P.Fout) ? __ldg(P.bias + tid) : 0.f;
-  for (int i = tid; i < M + 3; i += kThreads) bins[i] = 0;
-  {
-    const int npairs = (P.nnz + M + 2) >> 1;  // zero entries everywhere (padding entry of odd rows: zero row, 0.0)
-    const uint32_t zc = gather_code(P.p * BQ);
-    int4* e4 = reinterpret_cast<int4*>(smem + P.off_ent);
-    for (int i = tid; i < npairs; i += kThreads) e4[i] = make_int4((int)zc, 0, (int)zc, 0);
-  }
-  TRACEP();
-  __syncthreads();
-  TRACEP();
-  for (int r = tid; r < M4; r += kThreads) {
-    const int l = r < M ? rp[r + 1] - rp[r] : -1;
-    rlen[r] = l;
-    atomicAdd(&bins[M - l], 1);
-    if (l > 0) atomicMax(&bins[M + 2], l);
-  }
-  {
-    // one thread per entry, eight at a time: all loads issued first, then eight independent bisections of rp
-    int2* ent = reinterpret_cast<int2*>(smem + P.off_ent);
-    for (int e0 = 0; e0 < P.nnz; e0 += kThreads * 8) {
-      int cc[8], lo[8];
-      float vv[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int e = e0 + u * kThreads + tid;
-        cc[u] = e < P.nnz ? __ldg(P.col + e) : 0;
-        vv[u] = e < P.nnz ? __ldg(P.val + e) : 0.f;
-        lo[u] = 0;
-      }
-      // largest r with rp[r] <= e: fixed-trip bisection over [0, 2^s) so that the eight chains interleave
-      for (int step = 1 << (31 - __clz(max(M, 1))); step > 0; step >>= 1) {
-#pragma unroll
+  if constexpr (IMG) {
+    // the operator image was built once on the host (gcnb_cheb_image_build): copy it as it is
+    const uint4* gi = reinterpret_cast<const uint4*>(P.image);
+    for (int i = tid; i < (P.img_bytes >> 4); i += kThreads)
+      *reinterpret_cast<uint4*>(smem + P.off_img + (size_t)i * 16) = __ldg(gi + i);
+    __syncthreads();
+    const uint32_t* hdr = reinterpret_cast<const uint32_t*>(smem + P.off_img);
+    if (hdr[0] != kImgMagic || hdr[1] != P.img_sig || hdr[2] != (uint32_t)P.img_bytes) __trap();  // image of another geometry
+  } else {
+    // operator image: rows sorted by decreasing length; entries re-encoded as (gather code, value) in CSR order,
+    // every row starting on an even entry so that one LDS.128 fetches two entries
+    const int M4 = P.NG * 4;
+    int* bins = sorted;  // [M + 3]: bin b counts rows of length (M - b); the padding rows (length -1) come last;
+                         // bins[M + 2] = longest row.  (`sorted` itself is no longer materialised.)
+    for (int r = tid; r <= M; r += kThreads) rp[r] = __ldg(P.rowptr + r);
+    for (int i = tid; i < M + 3; i += kThreads) bins[i] = 0;
+    {
+      const int npairs = (P.nnz + M + 2) >> 1;  // zero entries everywhere (padding entry of odd rows: zero row, 0.0)
+      const uint32_t zc = gather_code(P.p * BQ);
+      int4* e4 = reinterpret_cast<int4*>(smem + P.off_ent);
+      for (int i = tid; i < npairs; i += kThreads) e4[i] = make_int4((int)zc, 0, (int)zc, 0);
+    }
+    TRACEP();
+    __syncthreads();
+    TRACEP();
+    for (int r = tid; r < M4; r += kThreads) {
+      const int l = r < M ? rp[r + 1] - rp[r] : -1;
+      rlen[r] = l;
+      atomicAdd(&bins[M - l], 1);
+      if (l > 0) atomicMax(&bins[M + 2], l);
+    }
+    {
+      // one thread per entry, eight at a time: all loads issued first, then eight independent bisections of rp
+      int2* ent = reinterpret_cast<int2*>(smem + P.off_ent);
+      for (int e0 = 0; e0 < P.nnz; e0 += kThreads * 8) {
+        int cc[8], lo[8];
+        float vv[8];
+  #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          const int cand = lo[u] + step;
-          if (cand <= M && rp[min(cand, M)] <= e0 + u * kThreads + tid) lo[u] = cand;
+          const int e = e0 + u * kThreads + tid;
+          cc[u] = e < P.nnz ? __ldg(P.col + e) : 0;
+          vv[u] = e < P.nnz ? __ldg(P.val + e) : 0.f;
+          lo[u] = 0;
+        }
+        // largest r with rp[r] <= e: fixed-trip bisection over [0, 2^s) so that the eight chains interleave
+        for (int step = 1 << (31 - __clz(max(M, 1))); step > 0; step >>= 1) {
+  #pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int cand = lo[u] + step;
+            if (cand <= M && rp[min(cand, M)] <= e0 + u * kThreads + tid) lo[u] = cand;
+          }
+        }
+  #pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int e = e0 + u * kThreads + tid;
+          if (e < P.nnz) {
+            const int r = min(lo[u], M - 1);
+            ent[((rp[r] + r + 1) & ~1) + (e - rp[r])] = make_int2((int)gather_code(rho(cc[u])), __float_as_int(vv[u]));
+          }
         }
       }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int e = e0 + u * kThreads + tid;
-        if (e < P.nnz) {
-          const int r = min(lo[u], M - 1);
-          ent[((rp[r] + r + 1) & ~1) + (e - rp[r])] = make_int2((int)gather_code(rho(cc[u])), __float_as_int(vv[u]));
+    }
+    TRACEP();
+    __syncthreads();
+    TRACEP();
+    if (warp == 0) {
+      // exclusive prefix over the occupied bins [M - longest, M + 1] (rows sorted by decreasing length), one warp
+      const int first = M - bins[M + 2];
+      int carry = 0;
+      for (int b0 = first; b0 < M + 2; b0 += 32) {
+        const int i = b0 + lane;
+        const int v = i < M + 2 ? bins[i] : 0;
+        int x = v;
+  #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int y = __shfl_up_sync(0xffffffffu, x, d);
+          if (lane >= d) x += y;
         }
+        if (i < M + 2) bins[i] = carry + x - v;
+        carry += __shfl_sync(0xffffffffu, x, 31);
       }
     }
-  }
-  TRACEP();
-  __syncthreads();
-  TRACEP();
-  if (warp == 0) {
-    // exclusive prefix over the occupied bins [M - longest, M + 1] (rows sorted by decreasing length), one warp
-    const int first = M - bins[M + 2];
-    int carry = 0;
-    for (int b0 = first; b0 < M + 2; b0 += 32) {
-      const int i = b0 + lane;
-      const int v = i < M + 2 ? bins[i] : 0;
-      int x = v;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const int y = __shfl_up_sync(0xffffffffu, x, d);
-        if (lane >= d) x += y;
+    __syncthreads();
+    // every row takes its place in the sorted order (the order inside a bin is whatever the atomics give: it only
+    // decides which rows share a warp step, never a sum) and fills the group tables there
+    for (int r = tid; r < M4; r += kThreads) {
+      const int l = rlen[r];
+      const int i = atomicAdd(&bins[M - l], 1);
+      if (r < M) {
+        grow[i] = r;
+        grho[i] = rho(r);
+        gslot[i] = make_int2(((rp[r] + r + 1) & ~1) >> 1, l);
+      } else {
+        grow[i] = -1;
+        grho[i] = 0;
+        gslot[i] = make_int2(0, 0);
       }
-      if (i < M + 2) bins[i] = carry + x - v;
-      carry += __shfl_sync(0xffffffffu, x, 31);
     }
+    __syncthreads();
+    for (int g = tid; g < P.NG; g += kThreads) glen[g] = (gslot[g * 4].y + 1) >> 1;  // slot 0 holds the group's longest row
   }
-  __syncthreads();
-  // every row takes its place in the sorted order (the order inside a bin is whatever the atomics give: it only
-  // decides which rows share a warp step, never a sum) and fills the group tables there
-  for (int r = tid; r < M4; r += kThreads) {
-    const int l = rlen[r];
-    const int i = atomicAdd(&bins[M - l], 1);
-    if (r < M) {
-      grow[i] = r;
-      grho[i] = rho(r);
-      gslot[i] = make_int2(((rp[r] + r + 1) & ~1) >> 1, l);
-    } else {
-      grow[i] = -1;
-      grho[i] = 0;
-      gslot[i] = make_int2(0, 0);
-    }
-  }
-  __syncthreads();
-  for (int g = tid; g < P.NG; g += kThreads) glen[g] = (gslot[g * 4].y + 1) >> 1;  // slot 0 holds the group's longest row
   TRACEP();
   tc_fence_before();
   __syncthreads();
@@ -383,175 +409,347 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
     const int q = lane >> 3, c = lane & 7;
     const uint32_t c16 = (uint32_t)c << 4;
     const int gw = c / CPW, fc = c - gw * CPW;  // window inside the row, feature chunk inside the window
-    // The rows a lane works on never change: keep what the order loop needs of each of its (up to MAXI) items in
-    // registers -- state offset of its 16-byte chunk, address of its entry list, lengths, vertex id.
-    uint32_t it_off[MAXI], it_ent[MAXI], it_pk[MAXI];  // pk: own pairs | group pairs << 8 | window-in-tile << 16
-    int it_row[MAXI];                                   // vertex (-1: no work), for the global addresses
-#pragma unroll
-    for (int u = 0; u < MAXI; ++u) {
-      const int ii = u * kSparseWarps + ((u & 1) ? kSparseWarps - 1 - sw : sw);  // snake deal of the sorted groups
-      it_row[u] = -1;
-      it_off[u] = 0; it_ent[u] = sb + P.off_ent; it_pk[u] = 0;
-      if (ii < NI) {
-        const int g = ii / NS, s = ii - g * NS;
-        const int2 meta = gslot[g * 4 + q];
-        const int rr = grho[g * 4 + q] + s * Q;
-        it_row[u] = grow[g * 4 + q];
-        it_off[u] = slab_off(rr, c);
-        it_ent[u] = sb + P.off_ent + (uint32_t)meta.x * 16u;
-        it_pk[u] = (uint32_t)((meta.y + 1) >> 1) | ((uint32_t)glen[g] << 8) | ((uint32_t)(s * G + gw) << 16) |
-                   ((uint32_t)s << 24);
-      }
-    }
     // lo offset of the same chunk (64-byte rows, SWIZZLE_64B), from the state offset
     auto lo_of = [c](uint32_t off) {
       const uint32_t rr = off >> 7;
       return rr * 64u + ((((uint32_t)(c >> 1) ^ ((rr >> 1) & 3u)) << 4) | ((uint32_t)(c & 1) << 3));
     };
-    uint32_t n = 0;  // orders issued so far (all tiles)
-    int base = 0;
-    TRACE(0, sw == 0);
-    for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
-      // ---- order 0: the (gathered, zero padded) raw windows -----------------------------------------------
-      {
-        const uint32_t lo_u = P.nlo == 2 ? (n & 1u) : 0u;
-        if (P.nlo == 1 && n > 0) mbar_wait(bar_mma((n - 1) & 1), ((n - 1) >> 1) & 1);
-        const uint32_t dst = sb + (uint32_t)base * buf_bytes, dlo = sb + P.off_lo + lo_u * lo_bytes;
-        float4 v[MAXI];
-#pragma unroll
-        for (int u = 0; u < MAXI; ++u) {
-          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          const int b = tile * P.S + (int)((it_pk[u] >> 16) & 0xff);
-          if (P.adj) {
-            if (it_row[u] >= 0 && b < P.B && fc * 4 < P.Fin) {
-              const int vtx = it_row[u], jj = vtx >> P.adj_log2p, ii = vtx & ((1 << P.adj_log2p) - 1);
-              const long long prow = (long long)b * P.adj_Mo + jj, gi = prow * P.Fin + fc * 4;
-              float4 d;
-              if (P.adj_mean) {
-                const float m = __ldg(P.adj_dy + prow) / (float)P.Fin;
-                d = make_float4(m, m, m, m);
-              } else {
-                d = __ldg(reinterpret_cast<const float4*>(P.adj_dy + gi));
-              }
-              if (P.adj_relu) {
-                const float4 yv = __ldg(reinterpret_cast<const float4*>(P.adj_y + gi));
-                if (!(yv.x > 0.f)) d.x = 0.f;
-                if (!(yv.y > 0.f)) d.y = 0.f;
-                if (!(yv.z > 0.f)) d.z = 0.f;
-                if (!(yv.w > 0.f)) d.w = 0.f;
-              }
-              if (P.adj_log2p > 0) {
-                const uint32_t am = __ldg(reinterpret_cast<const uint32_t*>(P.adj_arg + gi));
-                if ((int)(am & 0xff) != ii) d.x = 0.f;
-                if ((int)((am >> 8) & 0xff) != ii) d.y = 0.f;
-                if ((int)((am >> 16) & 0xff) != ii) d.z = 0.f;
-                if ((int)(am >> 24) != ii) d.w = 0.f;
-              }
-              v[u] = d;
-            }
-          } else if (it_row[u] >= 0 && b < P.B) {
-            const int src = src_row[it_row[u]];
-            if (src >= 0) {
-              const float* xp = P.x + ((long long)b * P.M_in + src) * P.Fin + fc * 4;
-              const int nf = P.Fin - fc * 4;
-              if (nf > 0) v[u].x = __ldg(xp);
-              if (nf > 1) v[u].y = __ldg(xp + 1);
-              if (nf > 2) v[u].z = __ldg(xp + 2);
-              if (nf > 3) v[u].w = __ldg(xp + 3);
-            }
+    // value of element (vertex vtx, window b, features 4 fc .. 4 fc + 3) of order 0: the gathered, zero padded raw
+    // window, or (adjoint mode) dZ rebuilt from the pooled gradient, the ReLU mask and the arg-max
+    auto load_x0 = [&](int vtx, int b) -> float4 {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (vtx < 0 || b >= P.B) return v;
+      if (P.adj) {
+        if (fc * 4 < P.Fin) {
+          const int jj = vtx >> P.adj_log2p, ii = vtx & ((1 << P.adj_log2p) - 1);
+          const long long prow = (long long)b * P.adj_Mo + jj, gi = prow * P.Fin + fc * 4;
+          if (P.adj_mean) {
+            const float m = __ldg(P.adj_dy + prow) / (float)P.Fin;
+            v = make_float4(m, m, m, m);
+          } else {
+            v = __ldg(reinterpret_cast<const float4*>(P.adj_dy + gi));
+          }
+          if (P.adj_relu) {
+            const float4 yv = __ldg(reinterpret_cast<const float4*>(P.adj_y + gi));
+            if (!(yv.x > 0.f)) v.x = 0.f;
+            if (!(yv.y > 0.f)) v.y = 0.f;
+            if (!(yv.z > 0.f)) v.z = 0.f;
+            if (!(yv.w > 0.f)) v.w = 0.f;
+          }
+          if (P.adj_log2p > 0) {
+            const uint32_t am = __ldg(reinterpret_cast<const uint32_t*>(P.adj_arg + gi));
+            if ((int)(am & 0xff) != ii) v.x = 0.f;
+            if ((int)((am >> 8) & 0xff) != ii) v.y = 0.f;
+            if ((int)((am >> 16) & 0xff) != ii) v.z = 0.f;
+            if ((int)(am >> 24) != ii) v.w = 0.f;
           }
         }
-#pragma unroll
-        for (int u = 0; u < MAXI; ++u) {
-          if (it_row[u] >= 0) {
-            store_state_at(dst + it_off[u], dlo + lo_of(it_off[u]), v[u]);
-            const int b = tile * P.S + (int)((it_pk[u] >> 16) & 0xff);
-            if (P.xstack && b < P.B)
-              *reinterpret_cast<float4*>(P.xstack + ((long long)b * M + it_row[u]) * FP + fc * 4) = v[u];
-          }
+      } else {
+        const int src = src_row[vtx];
+        if (src >= 0) {
+          const float* xp = P.x + ((long long)b * P.M_in + src) * P.Fin + fc * 4;
+          const int nf = P.Fin - fc * 4;
+          if (nf > 0) v.x = __ldg(xp);
+          if (nf > 1) v.y = __ldg(xp + 1);
+          if (nf > 2) v.z = __ldg(xp + 2);
+          if (nf > 3) v.w = __ldg(xp + 3);
         }
-        TRACE(0, sw == 0);
-        fence_async_smem();
-        named_bar_sync(kBarOrder, nsync);
-        ++n;
       }
-      // ---- orders 1 .. K-1 --------------------------------------------------------------------------------
-      for (int k = 1; k < K; ++k) {
-        const int cur = (base + k) & 1;
-        const uint32_t lo_u = P.nlo == 2 ? (n & 1u) : 0u;
-        if (P.nlo == 1) mbar_wait(bar_mma((n - 1) & 1), ((n - 1) >> 1) & 1);
-        float* spill = P.xstack ? P.xstack + (long long)k * P.B * M * FP : nullptr;
-        const uint32_t dlo = sb + P.off_lo + lo_u * lo_bytes;
-        const uint32_t srcb = sb + (uint32_t)(cur ^ 1) * buf_bytes, dst = sb + (uint32_t)cur * buf_bytes;
-        if (k == K - 1 && !P.adj && tile + (int)gridDim.x < P.ntiles) {
-          // pull the next tile's raw windows into L2 while this order computes
+      return v;
+    };
+    if constexpr (IMG) {
+      // ---- row-blocked recursion over a host-built operator image -------------------------------------------
+      // Work item = (group of four row blocks, window-slab): quarter-warp q owns block q of the group = four
+      // consecutive vertices (the siblings of the Graclus ordering share most of their neighbours), lane c of the
+      // quarter owns the 16-byte chunk c of their rows.  The entry stream of a group lists, per step, one
+      // neighbour of each block (the union of its rows' neighbour sets, ascending) with the four weights of that
+      // neighbour (zero where a row does not have it): one gathered row feeds four rows.  Items are dealt to the
+      // warps in snake order of the length-sorted groups.
+      const uint32_t grp_tab = sb + P.off_grp, img0 = sb + P.off_img;
+      const uint16_t* blk = reinterpret_cast<const uint16_t*>(smem + P.off_blk);
+      auto item_of = [sw](int u) { return u * kSparseWarps + ((u & 1) ? kSparseWarps - 1 - sw : sw); };
+      auto row_of = [=](int vtx, int s) { return (vtx & pm1) * BQ + s * Q + (vtx >> log2p); };
+      uint32_t n = 0;  // orders issued so far (all tiles)
+      int base = 0;
+      TRACE(0, sw == 0);
+      for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+        // ---- order 0 ------------------------------------------------------------------------------------------
+        {
+          const uint32_t lo_u = P.nlo == 2 ? (n & 1u) : 0u;
+          if (P.nlo == 1 && n > 0) mbar_wait(bar_mma((n - 1) & 1), ((n - 1) >> 1) & 1);
+          const uint32_t dst = sb + (uint32_t)base * buf_bytes, dlo = sb + P.off_lo + lo_u * lo_bytes;
+          for (int u = 0, ii; (ii = item_of(u)) < NI; ++u) {
+            const int g = ii / NS, s = ii - g * NS;
+            const int beta = blk[g * 4 + q];
+            if (beta == 0xffff) continue;
+            const int b = tile * P.S + s * G + gw;
+            float4 v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = load_x0(beta * 4 + i, b);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int vtx = beta * 4 + i;
+              const uint32_t off = slab_off(row_of(vtx, s), c);
+              store_state_at(dst + off, dlo + lo_of(off), v[i]);
+              if (P.xstack && b < P.B)
+                *reinterpret_cast<float4*>(P.xstack + ((long long)b * M + vtx) * FP + fc * 4) = v[i];
+            }
+          }
+          TRACE(0, sw == 0);
+          fence_async_smem();
+          named_bar_sync(kBarOrder, nsync);
+          ++n;
+        }
+        // ---- orders 1 .. K-1 ----------------------------------------------------------------------------------
+        for (int k = 1; k < K; ++k) {
+          const int cur = (base + k) & 1;
+          const uint32_t lo_u = P.nlo == 2 ? (n & 1u) : 0u;
+          bool lo_free = P.nlo == 2;  // single remainder buffer: the tensor cores must be done with order n-1 first
+          float* spill = P.xstack ? P.xstack + (long long)k * P.B * M * FP : nullptr;
+          const uint32_t dlo = sb + P.off_lo + lo_u * lo_bytes;
+          const uint32_t srcb = sb + (uint32_t)(cur ^ 1) * buf_bytes, dst = sb + (uint32_t)cur * buf_bytes;
+          if (k == K - 1 && !P.adj && tile + (int)gridDim.x < P.ntiles) {
+            // pull the next tile's raw windows into L2 while this order computes
+            for (int u = 0, ii; (ii = item_of(u)) < NI; ++u) {
+              const int g = ii / NS, s = ii - g * NS;
+              const int beta = blk[g * 4 + q];
+              const int b = (tile + (int)gridDim.x) * P.S + s * G + gw;
+              if (beta != 0xffff && b < P.B && fc * 4 < P.Fin) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const int src = src_row[beta * 4 + i];
+                  if (src >= 0)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(P.x + ((long long)b * P.M_in + src) * P.Fin + fc * 4));
+                }
+              }
+            }
+          }
+          TRACEW(0);
+          // Remainder (lo) stores of the first two items wait in registers until the end of the order: with a single
+          // remainder buffer they may only land once the tensor cores are done with order n-1, and that wait is
+          // invisible behind the whole sparse phase instead of sitting in front of the first item's stores.
+          uint2 pend[2][4];
+          uint32_t pend_lo[2] = {0u, 0u};  // lo address of row 0 of the pending item (0: nothing pending)
+          auto do_item = [&](int u, int ii, auto slot_tag) {
+            constexpr int SLOT = decltype(slot_tag)::value;  // 0, 1: may keep its lo stores pending; -1: never
+            const int g = ii / NS, s = ii - g * NS;
+            const uint2 gr = lds64u(grp_tab + (uint32_t)g * 8u);  // (offset of the entry stream in the image, steps)
+            const int beta = blk[g * 4 + q];
+            const uint32_t srcs = srcb + ((uint32_t)(s * Q) << 7);  // window-slab offset keeps the swizzle phase
+            uint32_t wa = img0 + gr.x + (uint32_t)q * 16u, ca = img0 + gr.x + 128u + (uint32_t)q * 8u;
+            float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+            int steps = (int)gr.y;
+#ifdef GCNB_TRACE
+            if (P.debug & 1) steps = 0;
+#endif
+#pragma unroll 2
+            for (int j = 0; j < steps; j += 2) {
+              const uint2 cc = lds64u(ca);
+              const float4 w0 = lds128(wa), w1 = lds128(wa + 64u);
+              const float4 v0 = lds128(srcs + (cc.x ^ c16));
+              const float4 v1 = lds128(srcs + (cc.y ^ c16));
+              a0.x = fmaf(w0.x, v0.x, a0.x); a0.y = fmaf(w0.x, v0.y, a0.y); a0.z = fmaf(w0.x, v0.z, a0.z); a0.w = fmaf(w0.x, v0.w, a0.w);
+              a1.x = fmaf(w0.y, v0.x, a1.x); a1.y = fmaf(w0.y, v0.y, a1.y); a1.z = fmaf(w0.y, v0.z, a1.z); a1.w = fmaf(w0.y, v0.w, a1.w);
+              a2.x = fmaf(w0.z, v0.x, a2.x); a2.y = fmaf(w0.z, v0.y, a2.y); a2.z = fmaf(w0.z, v0.z, a2.z); a2.w = fmaf(w0.z, v0.w, a2.w);
+              a3.x = fmaf(w0.w, v0.x, a3.x); a3.y = fmaf(w0.w, v0.y, a3.y); a3.z = fmaf(w0.w, v0.z, a3.z); a3.w = fmaf(w0.w, v0.w, a3.w);
+              a0.x = fmaf(w1.x, v1.x, a0.x); a0.y = fmaf(w1.x, v1.y, a0.y); a0.z = fmaf(w1.x, v1.z, a0.z); a0.w = fmaf(w1.x, v1.w, a0.w);
+              a1.x = fmaf(w1.y, v1.x, a1.x); a1.y = fmaf(w1.y, v1.y, a1.y); a1.z = fmaf(w1.y, v1.z, a1.z); a1.w = fmaf(w1.y, v1.w, a1.w);
+              a2.x = fmaf(w1.z, v1.x, a2.x); a2.y = fmaf(w1.z, v1.y, a2.y); a2.z = fmaf(w1.z, v1.z, a2.z); a2.w = fmaf(w1.z, v1.w, a2.w);
+              a3.x = fmaf(w1.w, v1.x, a3.x); a3.y = fmaf(w1.w, v1.y, a3.y); a3.z = fmaf(w1.w, v1.z, a3.z); a3.w = fmaf(w1.w, v1.w, a3.w);
+              wa += 160u;
+              ca += 160u;
+            }
+            TRACEW(1 + u * 3);
+            if (SLOT < 0 && !lo_free) {
+              mbar_wait(bar_mma((n - 1) & 1), ((n - 1) >> 1) & 1);
+              lo_free = true;
+            }
+            TRACEW(2 + u * 3);
+            if (beta != 0xffff) {
+              const int b = tile * P.S + s * G + gw;
+              const float4 acc[4] = {a0, a1, a2, a3};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int vtx = beta * 4 + i;
+                const uint32_t off = slab_off(row_of(vtx, s), c);
+                float4 o = acc[i];
+                if (k > 1) {
+                  const float4 own = lds128(dst + off);
+                  o = make_float4(fmaf(2.f, o.x, -own.x), fmaf(2.f, o.y, -own.y), fmaf(2.f, o.z, -own.z), fmaf(2.f, o.w, -own.w));
+                }
+                sts128(dst + off, o);
+                const float rx = o.x - tf32_trunc(o.x), ry = o.y - tf32_trunc(o.y);
+                const float rz = o.z - tf32_trunc(o.z), rw = o.w - tf32_trunc(o.w);
+                const uint2 rem = make_uint2(pack_bf16(rx, ry), pack_bf16(rz, rw));
+                if (SLOT >= 0 && !lo_free) {
+                  pend[SLOT < 0 ? 0 : SLOT][i] = rem;
+                } else {
+                  sts64(dlo + lo_of(off), rem.x, rem.y);
+                }
+                if (spill && b < P.B) *reinterpret_cast<float4*>(spill + ((long long)b * M + vtx) * FP + fc * 4) = o;
+              }
+              if (SLOT >= 0 && !lo_free) pend_lo[SLOT < 0 ? 0 : SLOT] = 1u + (uint32_t)beta + ((uint32_t)s << 16);
+            }
+            TRACEW(3 + u * 3);
+          };
+          {
+            int u = 0, ii;
+            if ((ii = item_of(u)) < NI) { do_item(u, ii, std::integral_constant<int, 0>()); ++u; }
+            if (u == 1 && (ii = item_of(u)) < NI) { do_item(u, ii, std::integral_constant<int, 1>()); ++u; }
+            if (u == 2)
+              for (; (ii = item_of(u)) < NI; ++u) do_item(u, ii, std::integral_constant<int, -1>());
+          }
+          if (pend_lo[0] | pend_lo[1]) {  // (only set while the remainder buffer was still busy)
+            mbar_wait(bar_mma((n - 1) & 1), ((n - 1) >> 1) & 1);
+#pragma unroll
+            for (int sl = 0; sl < 2; ++sl) {
+              if (pend_lo[sl]) {
+                const int beta = (int)((pend_lo[sl] - 1u) & 0xffffu), s = (int)(pend_lo[sl] >> 16);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const uint32_t off = slab_off(row_of(beta * 4 + i, s), c);
+                  sts64(dlo + lo_of(off), pend[sl][i].x, pend[sl][i].y);
+                }
+              }
+            }
+          }
+          TRACE(0, sw == 0);
+          TRACEW(13);
+          fence_async_smem();
+          TRACEW(14);
+          named_bar_sync(kBarOrder, nsync);
+          TRACEW(15);
+          ++n;
+        }
+        base = (base + K) & 1;
+      }
+    } else {
+      // The rows a lane works on never change: keep what the order loop needs of each of its (up to MAXI) items in
+      // registers -- state offset of its 16-byte chunk, address of its entry list, lengths, vertex id.
+      uint32_t it_off[MAXI], it_ent[MAXI], it_pk[MAXI];  // pk: own pairs | group pairs << 8 | window-in-tile << 16
+      int it_row[MAXI];                                   // vertex (-1: no work), for the global addresses
+  #pragma unroll
+      for (int u = 0; u < MAXI; ++u) {
+        const int ii = u * kSparseWarps + ((u & 1) ? kSparseWarps - 1 - sw : sw);  // snake deal of the sorted groups
+        it_row[u] = -1;
+        it_off[u] = 0; it_ent[u] = sb + P.off_ent; it_pk[u] = 0;
+        if (ii < NI) {
+          const int g = ii / NS, s = ii - g * NS;
+          const int2 meta = gslot[g * 4 + q];
+          const int rr = grho[g * 4 + q] + s * Q;
+          it_row[u] = grow[g * 4 + q];
+          it_off[u] = slab_off(rr, c);
+          it_ent[u] = sb + P.off_ent + (uint32_t)meta.x * 16u;
+          it_pk[u] = (uint32_t)((meta.y + 1) >> 1) | ((uint32_t)glen[g] << 8) | ((uint32_t)(s * G + gw) << 16) |
+                     ((uint32_t)s << 24);
+        }
+      }
+      uint32_t n = 0;  // orders issued so far (all tiles)
+      int base = 0;
+      TRACE(0, sw == 0);
+      for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+        // ---- order 0: the (gathered, zero padded) raw windows -----------------------------------------------
+        {
+          const uint32_t lo_u = P.nlo == 2 ? (n & 1u) : 0u;
+          if (P.nlo == 1 && n > 0) mbar_wait(bar_mma((n - 1) & 1), ((n - 1) >> 1) & 1);
+          const uint32_t dst = sb + (uint32_t)base * buf_bytes, dlo = sb + P.off_lo + lo_u * lo_bytes;
+          float4 v[MAXI];
+  #pragma unroll
+          for (int u = 0; u < MAXI; ++u) {
+            v[u] = load_x0(it_row[u], tile * P.S + (int)((it_pk[u] >> 16) & 0xff));
+          }
 #pragma unroll
           for (int u = 0; u < MAXI; ++u) {
-            const int b = (tile + (int)gridDim.x) * P.S + (int)((it_pk[u] >> 16) & 0xff);
-            if (it_row[u] >= 0 && b < P.B && fc * 4 < P.Fin) {
-              const int src = src_row[it_row[u]];
-              if (src >= 0)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(P.x + ((long long)b * P.M_in + src) * P.Fin + fc * 4));
+            if (it_row[u] >= 0) {
+              store_state_at(dst + it_off[u], dlo + lo_of(it_off[u]), v[u]);
+              const int b = tile * P.S + (int)((it_pk[u] >> 16) & 0xff);
+              if (P.xstack && b < P.B)
+                *reinterpret_cast<float4*>(P.xstack + ((long long)b * M + it_row[u]) * FP + fc * 4) = v[u];
             }
           }
+          TRACE(0, sw == 0);
+          fence_async_smem();
+          named_bar_sync(kBarOrder, nsync);
+          ++n;
         }
-        // Two work items at a time (the snake deal makes neighbours in the list near-equal in length): twice the
-        // independent shared-memory loads in flight per warp.
-        auto finish = [&](int row, uint32_t off, uint32_t pk, float a0, float a1, float a2, float a3) {
-          if (row >= 0) {
-            float4 o;
-            if (k == 1) {
-              o = make_float4(a0, a1, a2, a3);
-            } else {
-              const float4 own = lds128(dst + off);
-              o = make_float4(fmaf(2.f, a0, -own.x), fmaf(2.f, a1, -own.y), fmaf(2.f, a2, -own.z), fmaf(2.f, a3, -own.w));
+        // ---- orders 1 .. K-1 --------------------------------------------------------------------------------
+        for (int k = 1; k < K; ++k) {
+          const int cur = (base + k) & 1;
+          const uint32_t lo_u = P.nlo == 2 ? (n & 1u) : 0u;
+          if (P.nlo == 1) mbar_wait(bar_mma((n - 1) & 1), ((n - 1) >> 1) & 1);
+          float* spill = P.xstack ? P.xstack + (long long)k * P.B * M * FP : nullptr;
+          const uint32_t dlo = sb + P.off_lo + lo_u * lo_bytes;
+          const uint32_t srcb = sb + (uint32_t)(cur ^ 1) * buf_bytes, dst = sb + (uint32_t)cur * buf_bytes;
+          if (k == K - 1 && !P.adj && tile + (int)gridDim.x < P.ntiles) {
+            // pull the next tile's raw windows into L2 while this order computes
+  #pragma unroll
+            for (int u = 0; u < MAXI; ++u) {
+              const int b = (tile + (int)gridDim.x) * P.S + (int)((it_pk[u] >> 16) & 0xff);
+              if (it_row[u] >= 0 && b < P.B && fc * 4 < P.Fin) {
+                const int src = src_row[it_row[u]];
+                if (src >= 0)
+                  asm volatile("prefetch.global.L2 [%0];" ::"l"(P.x + ((long long)b * P.M_in + src) * P.Fin + fc * 4));
+              }
             }
-            store_state_at(dst + off, dlo + lo_of(off), o);
-            const int b = tile * P.S + (int)((pk >> 16) & 0xff);
-            if (spill && b < P.B) *reinterpret_cast<float4*>(spill + ((long long)b * M + row) * FP + fc * 4) = o;
           }
-        };
-#pragma unroll
-        for (int u = 0; u < MAXI; u += 2) {
-          const bool two = u + 1 < MAXI;
-          const int u1 = two ? u + 1 : u;
-          const uint32_t pka = it_pk[u], pkb = two ? it_pk[u1] : 0u;
-          const int owna = (int)(pka & 0xff), ownb = (int)(pkb & 0xff);
-          int lim = max((int)((pka >> 8) & 0xff), (int)((pkb >> 8) & 0xff));
-#ifdef GCNB_TRACE
-          if (P.debug & 1) lim = 0;
-#endif
-          const uint32_t srca = srcb + ((pka >> 24) * (uint32_t)Q << 7);  // window-slab offset keeps the swizzle phase
-          const uint32_t srcq = srcb + ((pkb >> 24) * (uint32_t)Q << 7);
-          const uint32_t ea = it_ent[u], eb = it_ent[u1];
-          const int lasta = max(owna - 1, 0), lastb = max(ownb - 1, 0);
-          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
-          // Branch-free over the longest row of the two groups: a lane whose own row is shorter re-reads its last
-          // entry pair with zero weights.
-          for (int j = 0; j < lim; ++j) {
-            const int4 e = lds128i(ea + (uint32_t)min(j, lasta) * 16u);
-            const int4 f = lds128i(eb + (uint32_t)min(j, lastb) * 16u);
-            const float4 v0 = lds128(srca + ((uint32_t)e.x ^ c16));
-            const float4 v1 = lds128(srca + ((uint32_t)e.z ^ c16));
-            const float4 x0 = lds128(srcq + ((uint32_t)f.x ^ c16));
-            const float4 x1 = lds128(srcq + ((uint32_t)f.z ^ c16));
-            const bool la = j < owna, lb = two && j < ownb;
-            const float w0 = la ? __int_as_float(e.y) : 0.f, w1 = la ? __int_as_float(e.w) : 0.f;
-            const float z0 = lb ? __int_as_float(f.y) : 0.f, z1 = lb ? __int_as_float(f.w) : 0.f;
-            a0 = fmaf(w0, v0.x, a0); a1 = fmaf(w0, v0.y, a1); a2 = fmaf(w0, v0.z, a2); a3 = fmaf(w0, v0.w, a3);
-            b0 = fmaf(z0, x0.x, b0); b1 = fmaf(z0, x0.y, b1); b2 = fmaf(z0, x0.z, b2); b3 = fmaf(z0, x0.w, b3);
-            a0 = fmaf(w1, v1.x, a0); a1 = fmaf(w1, v1.y, a1); a2 = fmaf(w1, v1.z, a2); a3 = fmaf(w1, v1.w, a3);
-            b0 = fmaf(z1, x1.x, b0); b1 = fmaf(z1, x1.y, b1); b2 = fmaf(z1, x1.z, b2); b3 = fmaf(z1, x1.w, b3);
+          // Two work items at a time (the snake deal makes neighbours in the list near-equal in length): twice the
+          // independent shared-memory loads in flight per warp.
+          auto finish = [&](int row, uint32_t off, uint32_t pk, float a0, float a1, float a2, float a3) {
+            if (row >= 0) {
+              float4 o;
+              if (k == 1) {
+                o = make_float4(a0, a1, a2, a3);
+              } else {
+                const float4 own = lds128(dst + off);
+                o = make_float4(fmaf(2.f, a0, -own.x), fmaf(2.f, a1, -own.y), fmaf(2.f, a2, -own.z), fmaf(2.f, a3, -own.w));
+              }
+              store_state_at(dst + off, dlo + lo_of(off), o);
+              const int b = tile * P.S + (int)((pk >> 16) & 0xff);
+              if (spill && b < P.B) *reinterpret_cast<float4*>(spill + ((long long)b * M + row) * FP + fc * 4) = o;
+            }
+          };
+  #pragma unroll
+          for (int u = 0; u < MAXI; u += 2) {
+            const bool two = u + 1 < MAXI;
+            const int u1 = two ? u + 1 : u;
+            const uint32_t pka = it_pk[u], pkb = two ? it_pk[u1] : 0u;
+            const int owna = (int)(pka & 0xff), ownb = (int)(pkb & 0xff);
+            int lim = max((int)((pka >> 8) & 0xff), (int)((pkb >> 8) & 0xff));
+  #ifdef GCNB_TRACE
+            if (P.debug & 1) lim = 0;
+  #endif
+            const uint32_t srca = srcb + ((pka >> 24) * (uint32_t)Q << 7);  // window-slab offset keeps the swizzle phase
+            const uint32_t srcq = srcb + ((pkb >> 24) * (uint32_t)Q << 7);
+            const uint32_t ea = it_ent[u], eb = it_ent[u1];
+            const int lasta = max(owna - 1, 0), lastb = max(ownb - 1, 0);
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+            // Branch-free over the longest row of the two groups: a lane whose own row is shorter re-reads its last
+            // entry pair with zero weights.
+            for (int j = 0; j < lim; ++j) {
+              const int4 e = lds128i(ea + (uint32_t)min(j, lasta) * 16u);
+              const int4 f = lds128i(eb + (uint32_t)min(j, lastb) * 16u);
+              const float4 v0 = lds128(srca + ((uint32_t)e.x ^ c16));
+              const float4 v1 = lds128(srca + ((uint32_t)e.z ^ c16));
+              const float4 x0 = lds128(srcq + ((uint32_t)f.x ^ c16));
+              const float4 x1 = lds128(srcq + ((uint32_t)f.z ^ c16));
+              const bool la = j < owna, lb = two && j < ownb;
+              const float w0 = la ? __int_as_float(e.y) : 0.f, w1 = la ? __int_as_float(e.w) : 0.f;
+              const float z0 = lb ? __int_as_float(f.y) : 0.f, z1 = lb ? __int_as_float(f.w) : 0.f;
+              a0 = fmaf(w0, v0.x, a0); a1 = fmaf(w0, v0.y, a1); a2 = fmaf(w0, v0.z, a2); a3 = fmaf(w0, v0.w, a3);
+              b0 = fmaf(z0, x0.x, b0); b1 = fmaf(z0, x0.y, b1); b2 = fmaf(z0, x0.z, b2); b3 = fmaf(z0, x0.w, b3);
+              a0 = fmaf(w1, v1.x, a0); a1 = fmaf(w1, v1.y, a1); a2 = fmaf(w1, v1.z, a2); a3 = fmaf(w1, v1.w, a3);
+              b0 = fmaf(z1, x1.x, b0); b1 = fmaf(z1, x1.y, b1); b2 = fmaf(z1, x1.z, b2); b3 = fmaf(z1, x1.w, b3);
+            }
+            finish(it_row[u], it_off[u], pka, a0, a1, a2, a3);
+            if (two) finish(it_row[u1], it_off[u1], pkb, b0, b1, b2, b3);
           }
-          finish(it_row[u], it_off[u], pka, a0, a1, a2, a3);
-          if (two) finish(it_row[u1], it_off[u1], pkb, b0, b1, b2, b3);
+          TRACE(0, sw == 0);
+          fence_async_smem();
+          named_bar_sync(kBarOrder, nsync);
+          ++n;
         }
-        TRACE(0, sw == 0);
-        fence_async_smem();
-        named_bar_sync(kBarOrder, nsync);
-        ++n;
+        base = (base + K) & 1;
       }
-      base = (base + K) & 1;
     }
     // the CTA's last tile: help the epilogue warp of this warp's TMEM lane quarter
     if (my_tiles > 0) {
@@ -587,6 +785,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
 #ifdef GCNB_TRACE
           if (!(P.debug & 2))
 #endif
+          // Block-major issue order on purpose: the (up to ten) instructions of one accumulator block re-read the same
+          // rows of A back to back.  Measured (B200, conv1 shape, 40 MMAs of 128x32x8 per order): ~100 cycles per
+          // instruction this way -- the shared-memory read of A's 128 rows paces them, not the 16-cycle tensor floor --
+          // and ~300 cycles per instruction when consecutive instructions alternate between blocks (pass-major).
 #pragma unroll
           for (int g = 0; g < G; ++g) {
             for (int i = 0; i < P.p; ++i) {
@@ -657,12 +859,35 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
+// Operator image (gcnb_cheb_image_build, consumed by the IMG kernels).  Vertices are taken in blocks of four
+// consecutive rows (in the Graclus ordering: siblings, which share most of their neighbours); a block's entry list is
+// the ascending union of its rows' neighbour sets with the four weights per neighbour.  Blocks are sorted by list
+// length and grouped by four (one block per quarter-warp).  Layout, all offsets from the start of the image:
+//   [0, 64)    header: magic, signature, bytes, groups
+//   grp_off    groups x {u32 offset of the entry stream, u32 steps (even)}
+//   blk_off    groups x 4 x u16 block index (0xffff: no block in this quarter)
+//   ent_off    per group, per pair of steps (160 B): weights of step j for the 4 quarters (4 x 16 B), of step j+1
+//              (4 x 16 B), gather codes of (j, j+1) for the 4 quarters (4 x 8 B).  Padding steps gather the zero row.
+struct ImgGeom {
+  int nb, ng;
+  size_t grp_off, blk_off, ent_off;
+};
+static ImgGeom img_geom(int M) {
+  ImgGeom g;
+  g.nb = M / 4;
+  g.ng = ceil_div(g.nb, 4);
+  g.grp_off = 64;
+  g.blk_off = g.grp_off + align_up((size_t)g.ng * 8, 16);
+  g.ent_off = g.blk_off + align_up((size_t)g.ng * 8, 16);
+  return g;
+}
+
 struct UmmaFwdPlan {
-  bool ok;
+  bool ok, img;
   int FP, G, NS, Q, BQ, T, NG, nlo, nacc, acc_cols, tmem_cols, slab_rows, MAXI;
-  size_t smem;
+  size_t smem, img_bytes;
   int off_lo, off_wh, off_wl, off_wb, off_ent, off_grow, off_grho, off_gslot, off_glen, off_src, off_rlen, off_sorted,
-      off_bias, off_bar, off_rp;
+      off_bias, off_bar, off_rp, off_img;
 };
 
 static bool umma_enabled() {
@@ -673,23 +898,30 @@ static bool umma_enabled() {
   return on;
 }
 
-static UmmaFwdPlan plan_umma_fwd(const LayerShape& s, int sm_count, int smem_optin) {
+// ent_bytes < 0: the kernel builds its own (CSR-ordered) operator image in the prologue; otherwise the entry streams of
+// a host-built image take ent_bytes.
+static UmmaFwdPlan plan_umma_fwd(const LayerShape& s, int sm_count, int smem_optin, long long ent_bytes = -1) {
   UmmaFwdPlan pl{};
   pl.ok = false;
+  pl.img = ent_bytes >= 0;
   if (!umma_enabled()) return pl;
   if (s.Fin <= 8 || s.Fin > 32 || s.Fout < 4 || s.Fout > 32 || (s.Fout & 3)) return pl;
   if (s.p != 1 && s.p != 2 && s.p != 4 && s.p != 8) return pl;
   if (s.M % s.p != 0 || s.M < 1 || s.M > 2048 || s.K < 1 || s.B < 1) return pl;
+  if (pl.img && (s.M & 3)) return pl;
   pl.FP = s.Fin <= 16 ? 16 : 32;
   pl.G = 32 / pl.FP;
-  pl.NG = ceil_div(s.M, 4);
+  pl.NG = pl.img ? img_geom(s.M).ng : ceil_div(s.M, 4);
   pl.Q = (int)align_up((size_t)(s.M / s.p), 8);
+  pl.img_bytes = pl.img ? img_geom(s.M).ent_off + (size_t)ent_bytes : 0;
   const size_t taps = (size_t)s.K * pl.FP * 32 * 4;  // one tf32 image
-  const size_t ent = align_up(((size_t)s.nnz + s.M + 2) * 8, 16);
-  const size_t tables = 2 * (size_t)pl.NG * 16 /*grow, grho*/ + (size_t)pl.NG * 32 /*gslot*/ + align_up((size_t)pl.NG * 4, 16) +
-                        align_up((size_t)s.M * 4, 16) /*src*/ + 128 /*bias*/ + 64 /*barriers*/;
+  const size_t ent = pl.img ? pl.img_bytes : align_up(((size_t)s.nnz + s.M + 2) * 8, 16);
+  const size_t small = align_up((size_t)s.M * 4, 16) /*src*/ + 128 /*bias*/ + 64 /*barriers*/;
+  const size_t tables = pl.img ? small : 2 * (size_t)pl.NG * 16 /*grow, grho*/ + (size_t)pl.NG * 32 /*gslot*/ +
+                                             align_up((size_t)pl.NG * 4, 16) + small;
   // prologue-only scratch (rlen, sorted, rp) lives in the first remainder buffer
-  const size_t scratch = 2 * (size_t)pl.NG * 16 + align_up((size_t)(s.M + 3) * 4, 16) + align_up((size_t)(s.M + 1) * 4, 16);
+  const size_t scratch =
+      pl.img ? 0 : 2 * (size_t)pl.NG * 16 + align_up((size_t)(s.M + 3) * 4, 16) + align_up((size_t)(s.M + 1) * 4, 16);
   const size_t budget = std::min<size_t>((size_t)smem_optin, 227 * 1024);
   double best = 1e30;
   for (int ns = 1; ns <= 8; ++ns) {
@@ -697,8 +929,8 @@ static UmmaFwdPlan plan_umma_fwd(const LayerShape& s, int sm_count, int smem_opt
     const int acc_cols = pl.G * s.p * T * 32;
     if (acc_cols > 512) continue;
     const int rows = (int)align_up((size_t)s.p * BQ + 1, 8);
-    if ((size_t)rows * 128 >= (1u << 18)) continue;  // descriptors address 256 KB
-    if (pl.NG * ns > 5 * kSparseWarps) continue;      // a lane keeps at most 5 work items in registers
+    if ((size_t)rows * 128 >= (1u << 18)) continue;          // descriptors address 256 KB
+    if (!pl.img && pl.NG * ns > 5 * kSparseWarps) continue;  // a lane keeps at most 5 work items in registers
     for (int nlo = 2; nlo >= 1; --nlo) {
       const size_t need = 2 * (size_t)rows * 128 + (size_t)nlo * rows * 64 + 2 * taps + taps / 2 + ent + tables;
       // the last MMA tile of the last block reads up to row (p-1)*BQ + T*128: those bytes must exist in the allocation
@@ -706,7 +938,7 @@ static UmmaFwdPlan plan_umma_fwd(const LayerShape& s, int sm_count, int smem_opt
       if (need > budget || 2 * (size_t)rows * 128 + (over > 0 ? (size_t)over : 0) > need || scratch > (size_t)rows * 64) continue;
       const int tiles = ceil_div(s.B, ns * pl.G);
       // rounds of tiles over the SMs x work per tile; MMA rows wasted by a nearly empty last tile of a block count a little
-      const double cost = std::ceil((double)tiles / sm_count) * ns * (nlo == 2 ? 1.0 : 1.08) + 0.02 * T * 128.0 / BQ - 0.001 * ns;
+      const double cost = std::ceil((double)tiles / sm_count) * ns * (nlo == 2 || pl.img ? 1.0 : 1.08) + 0.02 * T * 128.0 / BQ - 0.001 * ns;
       if (cost < best) {
         best = cost;
         pl.NS = ns; pl.BQ = BQ; pl.T = T; pl.nlo = nlo; pl.acc_cols = acc_cols; pl.slab_rows = rows; pl.smem = need;
@@ -716,7 +948,7 @@ static UmmaFwdPlan plan_umma_fwd(const LayerShape& s, int sm_count, int smem_opt
   }
   if (best > 1e29) return pl;
   pl.nacc = 2 * pl.acc_cols <= 512 ? 2 : 1;
-  pl.MAXI = ceil_div(pl.NG * pl.NS, kSparseWarps) <= 3 ? 3 : 5;
+  pl.MAXI = pl.img ? 1 : (ceil_div(pl.NG * pl.NS, kSparseWarps) <= 3 ? 3 : 5);
   int cols = 32;
   while (cols < pl.nacc * pl.acc_cols) cols *= 2;
   pl.tmem_cols = cols;
@@ -725,11 +957,15 @@ static UmmaFwdPlan plan_umma_fwd(const LayerShape& s, int sm_count, int smem_opt
   pl.off_wh = (int)off; off += taps;
   pl.off_wl = (int)off; off += taps;
   pl.off_wb = (int)off; off += taps / 2;
-  pl.off_ent = (int)off; off += ent;
-  pl.off_grow = (int)off; off += (size_t)pl.NG * 16;
-  pl.off_grho = (int)off; off += (size_t)pl.NG * 16;
-  pl.off_gslot = (int)off; off += (size_t)pl.NG * 32;
-  pl.off_glen = (int)off; off += align_up((size_t)pl.NG * 4, 16);
+  if (pl.img) {
+    pl.off_img = (int)off; off += pl.img_bytes;
+  } else {
+    pl.off_ent = (int)off; off += ent;
+    pl.off_grow = (int)off; off += (size_t)pl.NG * 16;
+    pl.off_grho = (int)off; off += (size_t)pl.NG * 16;
+    pl.off_gslot = (int)off; off += (size_t)pl.NG * 32;
+    pl.off_glen = (int)off; off += align_up((size_t)pl.NG * 4, 16);
+  }
   pl.off_src = (int)off; off += align_up((size_t)s.M * 4, 16);
   pl.off_bias = (int)off; off += 128;
   pl.off_bar = (int)off; off += 64;
@@ -741,21 +977,33 @@ static UmmaFwdPlan plan_umma_fwd(const LayerShape& s, int sm_count, int smem_opt
   return pl;
 }
 
+static void plan_device(DeviceInfo* di) {
+  if (device_info(di) != GCNB_OK) {  // no device visible (shape queries on a CPU box): assume a B200
+    di->sm_count = 148;
+    di->smem_optin = 227 * 1024;
+  }
+}
+
+// what an image must agree on with the kernel that reads it
+static unsigned img_signature(const LayerShape& s, const UmmaFwdPlan& pl) {
+  unsigned h = 2166136261u;
+  const int v[] = {2 /*layout version*/, s.M, s.nnz, s.p, pl.FP, pl.NS, pl.Q, pl.BQ, pl.NG, (int)pl.img_bytes, kSparseWarps};
+  for (int x : v) {
+    h ^= (unsigned)x;
+    h *= 16777619u;
+  }
+  return h;
+}
+
 bool umma_fwd_supported(const LayerShape& s) {
   DeviceInfo di;
-  if (device_info(&di) != GCNB_OK) {  // no device visible (shape queries on a CPU box): assume a B200
-    di.sm_count = 148;
-    di.smem_optin = 227 * 1024;
-  }
+  plan_device(&di);
   return plan_umma_fwd(s, di.sm_count, di.smem_optin).ok;
 }
 
 int umma_fwd_describe(const LayerShape& s, char* out, size_t n) {
   DeviceInfo di;
-  if (device_info(&di) != GCNB_OK) {
-    di.sm_count = 148;
-    di.smem_optin = 227 * 1024;
-  }
+  plan_device(&di);
   const UmmaFwdPlan pl = plan_umma_fwd(s, di.sm_count, di.smem_optin);
   if (!pl.ok) return 0;
   return snprintf(out, n,
@@ -763,6 +1011,126 @@ int umma_fwd_describe(const LayerShape& s, char* out, size_t n) {
                   "%d MMA tiles/block, %d remainder buffers, %d accumulator buffers x %d TMEM columns, %zu B smem, %d tiles",
                   pl.FP, pl.NS * pl.G, pl.NS, pl.G, pl.BQ, pl.Q, pl.T, pl.nlo, pl.nacc, pl.acc_cols, pl.smem,
                   ceil_div(s.B, pl.NS * pl.G));
+}
+
+// ---- host-side image builder ----------------------------------------------------------------------------------
+struct BlockList {
+  std::vector<int> cols;
+  std::vector<float> w;  // 4 per column
+};
+
+static void block_lists(const int32_t* rowptr, const int32_t* col, const float* val, int M, std::vector<BlockList>* out) {
+  const int nb = M / 4;
+  out->assign(nb, BlockList());
+  for (int b = 0; b < nb; ++b) {
+    std::vector<int>& c = (*out)[b].cols;
+    for (int r = 4 * b; r < 4 * b + 4; ++r) c.insert(c.end(), col + rowptr[r], col + rowptr[r + 1]);
+    std::sort(c.begin(), c.end());
+    c.erase(std::unique(c.begin(), c.end()), c.end());
+    if (val) {
+      std::vector<float>& w = (*out)[b].w;
+      w.assign(c.size() * 4, 0.f);
+      for (int i = 0; i < 4; ++i) {
+        const int r = 4 * b + i;
+        for (int e = rowptr[r]; e < rowptr[r + 1]; ++e) {
+          const size_t at = std::lower_bound(c.begin(), c.end(), col[e]) - c.begin();
+          w[at * 4 + i] += val[e];  // duplicate entries of a row (never produced by scipy) add up
+        }
+      }
+    }
+  }
+}
+
+// blocks by decreasing list length (ties: by index), grouped by four; steps of a group = its longest list, made even
+static void group_blocks(const std::vector<BlockList>& bl, std::vector<int>* order, std::vector<int>* steps) {
+  const int nb = (int)bl.size();
+  order->resize(nb);
+  for (int i = 0; i < nb; ++i) (*order)[i] = i;
+  std::stable_sort(order->begin(), order->end(), [&](int a, int b) { return bl[a].cols.size() > bl[b].cols.size(); });
+  steps->clear();
+  for (int g = 0; g * 4 < nb; ++g) steps->push_back((int)((bl[(*order)[g * 4]].cols.size() + 1) & ~(size_t)1));
+}
+
+static bool csr_rows_valid(const int32_t* rowptr, const int32_t* col, int M, int nnz) {
+  if (!rowptr || !col || rowptr[0] != 0 || rowptr[M] != nnz) return false;
+  for (int r = 0; r < M; ++r)
+    if (rowptr[r + 1] < rowptr[r]) return false;
+  for (int e = 0; e < nnz; ++e)
+    if (col[e] < 0 || col[e] >= M) return false;
+  return true;
+}
+
+static LayerShape adjoint_shape(const LayerShape& s) { return LayerShape{s.B, s.M, s.nnz, s.Fout, s.Fin, s.K, 1}; }
+
+size_t cheb_image_bytes(const int32_t* rowptr, const int32_t* col, const LayerShape& layer, int adjoint) {
+  const LayerShape s = adjoint ? adjoint_shape(layer) : layer;
+  if (s.M < 4 || (s.M & 3) || !csr_rows_valid(rowptr, col, s.M, s.nnz)) return 0;
+  std::vector<BlockList> bl;
+  block_lists(rowptr, col, nullptr, s.M, &bl);
+  std::vector<int> order, steps;
+  group_blocks(bl, &order, &steps);
+  long long ent = 0;
+  for (int st : steps) ent += (long long)(st / 2) * 160;
+  DeviceInfo di;
+  plan_device(&di);
+  const UmmaFwdPlan pl = plan_umma_fwd(s, di.sm_count, di.smem_optin, ent);
+  return pl.ok ? pl.img_bytes : 0;
+}
+
+int cheb_image_build(const int32_t* rowptr, const int32_t* col, const float* val, const LayerShape& layer, int adjoint,
+                     void* out, size_t bytes) {
+  const LayerShape s = adjoint ? adjoint_shape(layer) : layer;
+  GCNB_REQUIRE(out && val && s.M >= 4 && (s.M & 3) == 0 && csr_rows_valid(rowptr, col, s.M, s.nnz),
+               "gcnb_cheb_image_build: needs host CSR arrays of a graph with M %% 4 == 0");
+  std::vector<BlockList> bl;
+  block_lists(rowptr, col, val, s.M, &bl);
+  std::vector<int> order, steps;
+  group_blocks(bl, &order, &steps);
+  long long ent = 0;
+  for (int st : steps) ent += (long long)(st / 2) * 160;
+  DeviceInfo di;
+  plan_device(&di);
+  const UmmaFwdPlan pl = plan_umma_fwd(s, di.sm_count, di.smem_optin, ent);
+  GCNB_REQUIRE(pl.ok, "gcnb_cheb_image_build: no image-based kernel for this shape");
+  GCNB_REQUIRE(bytes == pl.img_bytes, "gcnb_cheb_image_build: buffer has %zu bytes, the image needs %zu", bytes, pl.img_bytes);
+  const ImgGeom ge = img_geom(s.M);
+  unsigned char* img = static_cast<unsigned char*>(out);
+  memset(img, 0, bytes);
+  uint32_t* hdr = reinterpret_cast<uint32_t*>(img);
+  hdr[0] = kImgMagic;
+  hdr[1] = img_signature(s, pl);
+  hdr[2] = (uint32_t)bytes;
+  hdr[3] = (uint32_t)ge.ng;
+  uint32_t* grp = reinterpret_cast<uint32_t*>(img + ge.grp_off);
+  uint16_t* blk = reinterpret_cast<uint16_t*>(img + ge.blk_off);
+  int log2p = 0;
+  while ((1 << log2p) < s.p) ++log2p;
+  auto code_of = [&](int v) { return gather_code((v & (s.p - 1)) * pl.BQ + (v >> log2p)); };
+  const uint32_t zero_code = gather_code(s.p * pl.BQ);
+  size_t at = ge.ent_off;
+  for (int g = 0; g < ge.ng; ++g) {
+    grp[g * 2] = (uint32_t)at;
+    grp[g * 2 + 1] = (uint32_t)steps[g];
+    for (int q = 0; q < 4; ++q) blk[g * 4 + q] = g * 4 + q < ge.nb ? (uint16_t)order[g * 4 + q] : (uint16_t)0xffff;
+    for (int j = 0; j < steps[g]; ++j) {
+      unsigned char* pair = img + at + (size_t)(j / 2) * 160;
+      float* w = reinterpret_cast<float*>(pair + (j & 1) * 64);
+      uint32_t* codes = reinterpret_cast<uint32_t*>(pair + 128);
+      for (int q = 0; q < 4; ++q) {
+        uint32_t code = zero_code;
+        if (g * 4 + q < ge.nb) {
+          const BlockList& b = bl[order[g * 4 + q]];
+          if (j < (int)b.cols.size()) {
+            code = code_of(b.cols[j]);
+            for (int i = 0; i < 4; ++i) w[q * 4 + i] = b.w[(size_t)j * 4 + i];
+          }
+        }
+        codes[q * 2 + (j & 1)] = code;
+      }
+    }
+    at += (size_t)(steps[g] / 2) * 160;
+  }
+  return GCNB_OK;
 }
 
 struct UmmaAdjoint {
@@ -778,9 +1146,17 @@ static int umma_launch(const float* x, const int32_t* perm, int M_in, const gcnb
   DeviceInfo di;
   int rc = device_info(&di);
   if (rc) return rc;
-  const UmmaFwdPlan pl = plan_umma_fwd(s, di.sm_count, di.smem_optin);
+  const bool img = L.image != nullptr;
+  if (img) {
+    const size_t fixed = img_geom(s.M).ent_off;
+    GCNB_REQUIRE((s.M & 3) == 0 && L.image_bytes >= fixed && (L.image_bytes & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(L.image) & 15) == 0,
+                 "operator image: bad size or alignment");
+  }
+  const UmmaFwdPlan pl = img ? plan_umma_fwd(s, di.sm_count, di.smem_optin, (long long)(L.image_bytes - img_geom(s.M).ent_off))
+                             : plan_umma_fwd(s, di.sm_count, di.smem_optin);
   if (!pl.ok) {
-    set_error("tcgen05 forward does not support this shape");
+    set_error(img ? "the operator image does not belong to this layer shape" : "tcgen05 forward does not support this shape");
     return GCNB_ERR_INVALID;
   }
   UmmaFwdParams P{};
@@ -805,16 +1181,25 @@ static int umma_launch(const float* x, const int32_t* perm, int M_in, const gcnb
   P.off_grow = pl.off_grow; P.off_grho = pl.off_grho; P.off_gslot = pl.off_gslot; P.off_glen = pl.off_glen;
   P.off_src = pl.off_src; P.off_rlen = pl.off_rlen; P.off_sorted = pl.off_sorted; P.off_bias = pl.off_bias;
   P.off_bar = pl.off_bar; P.off_rp = pl.off_rp;
+  if (img) {
+    const ImgGeom ge = img_geom(s.M);
+    P.image = static_cast<const unsigned char*>(L.image);
+    P.img_bytes = (int)pl.img_bytes;
+    P.img_sig = img_signature(s, pl);
+    P.n_groups = ge.ng;
+    P.off_img = pl.off_img; P.off_grp = pl.off_img + (int)ge.grp_off; P.off_blk = pl.off_img + (int)ge.blk_off;
+  }
 #ifdef GCNB_TRACE
   P.debug = std::getenv("GCNB_UMMA_DEBUG") ? std::atoi(std::getenv("GCNB_UMMA_DEBUG")) : 0;
 #endif
   const int grid = std::min(P.ntiles, di.sm_count);
-#define GCNB_UMMA_CASE(fp, mi)                                                                                      \
-  if (pl.FP == fp && pl.MAXI == mi) {                                                                               \
-    GCNB_CUDA(cudaFuncSetAttribute(k_cheb_fwd_umma<fp, mi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem)); \
-    GCNB_CUDA(launch_pdl(k_cheb_fwd_umma<fp, mi>, dim3(grid), dim3(kThreads), pl.smem, st, P));                      \
+#define GCNB_UMMA_CASE(fp, mi, im)                                                                                      \
+  if (pl.FP == fp && pl.MAXI == mi && img == im) {                                                                      \
+    GCNB_CUDA(cudaFuncSetAttribute(k_cheb_fwd_umma<fp, mi, im>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem)); \
+    GCNB_CUDA(launch_pdl(k_cheb_fwd_umma<fp, mi, im>, dim3(grid), dim3(kThreads), pl.smem, st, P));                      \
   }
-  GCNB_UMMA_CASE(16, 3) GCNB_UMMA_CASE(16, 5) GCNB_UMMA_CASE(32, 3) GCNB_UMMA_CASE(32, 5)
+  GCNB_UMMA_CASE(16, 3, false) GCNB_UMMA_CASE(16, 5, false) GCNB_UMMA_CASE(32, 3, false) GCNB_UMMA_CASE(32, 5, false)
+  GCNB_UMMA_CASE(16, 1, true) GCNB_UMMA_CASE(32, 1, true)
 #undef GCNB_UMMA_CASE
   GCNB_LAUNCH_CHECK("k_cheb_fwd_umma");
   return GCNB_OK;
@@ -827,8 +1212,6 @@ int umma_cheb_fwd(const float* x, const int32_t* perm, int M_in, const gcnb_csr&
 }
 
 // The layer's input gradient through the forward kernel: operator L~^T, taps W_k^T, input dZ (see UmmaFwdParams::adj).
-static LayerShape adjoint_shape(const LayerShape& s) { return LayerShape{s.B, s.M, s.nnz, s.Fout, s.Fin, s.K, 1}; }
-
 bool umma_adj_supported(const LayerShape& s) {
   if ((s.Fout & 3) || (s.Fin & 3) || s.M % s.p != 0 || s.p > 255) return false;
   return umma_fwd_supported(adjoint_shape(s));

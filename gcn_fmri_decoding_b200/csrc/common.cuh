@@ -144,6 +144,10 @@ int umma_cheb_fwd(const float* x, const int32_t* perm, int M_in, const gcnb_csr&
                   float* y, uint8_t* argmax, float* y_mean, float* xstack, const LayerShape& s, int bias_mode, int relu,
                   cudaStream_t st);
 
+// host-built operator image of the row-blocked kernels (layer = the layer's shape; adjoint: image of the transpose)
+size_t cheb_image_bytes(const int32_t* rowptr, const int32_t* col, const LayerShape& layer, int adjoint);
+int cheb_image_build(const int32_t* rowptr, const int32_t* col, const float* val, const LayerShape& layer, int adjoint,
+                     void* out, size_t bytes);
 // input gradient dx of a layer through the same kernel (operator L~^T, taps W_k^T, dZ rebuilt from dy / y / argmax)
 bool umma_adj_supported(const LayerShape& s);
 int umma_cheb_adj(const float* dy, int dy_is_mean, const float* y, const uint8_t* argmax, const gcnb_csr& Lt, const float* W,

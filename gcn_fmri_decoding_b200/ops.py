@@ -82,7 +82,7 @@ def cheb_fwd(x: Tensor, perm: Optional[Tensor], rowptr: Tensor, col: Tensor, val
     L = _lib.lib()
     nbytes = L.gcnb_cheb_workspace_bytes(B, M, val.numel(), Fin, Fout, K, p, 0, 0, algo)
     ws = _workspace(nbytes, x.device)
-    csr = csr_struct(rowptr, col, val)
+    csr = csr_struct(rowptr, col, val, (B, Fin, Fout, K, p))
     rc = L.gcnb_cheb_fwd_f32(_ptr(x), _ptr(perm), M_in, C.byref(csr), _ptr(W), _ptr(bias), _ptr(y), _ptr(argmax), None,
                              None, B, Fin, Fout, K, p, bias_mode, int(relu), algo, _ptr(ws), ws.numel(), _stream(x))
     _lib.check(rc, "gcnb_cheb_fwd_f32")
@@ -115,7 +115,7 @@ def cheb_bwd(x: Tensor, perm: Optional[Tensor], y: Tensor, argmax: Tensor, dy: T
     nbytes = L.gcnb_cheb_workspace_bytes(B, M, val.numel(), Fin, Fout, K, p, 1, int(need_dx), algo)
     ws = _workspace(nbytes, x.device)
     csr = csr_struct(rowptr, col, val)
-    csr_t = csr_struct(rowptr_t, col_t, val_t)
+    csr_t = csr_struct(rowptr_t, col_t, val_t, (B, Fin, Fout, K, p))
     rc = L.gcnb_cheb_bwd_f32(_ptr(x), _ptr(perm), M_in, _ptr(y), _ptr(argmax), _ptr(dy), 0, None, C.byref(csr),
                              C.byref(csr_t), _ptr(W), _ptr(dx), _ptr(dW), _ptr(db), B, Fin, Fout, K, p, bias_mode,
                              int(relu), algo, _ptr(ws), ws.numel(), _stream(x))
@@ -151,7 +151,7 @@ def cheb_fwd_mean(x: Tensor, perm: Optional[Tensor], rowptr: Tensor, col: Tensor
     FP = L.gcnb_cheb_stack_width(B, M, val.numel(), Fin, Fout, K, p) if (want_stack and algo != ALGO_GENERAL) else 0
     stack = torch.empty((K, B, M, FP) if FP else (0,), dtype=torch.float32, device=x.device)
     ws = _workspace(L.gcnb_cheb_workspace_bytes(B, M, val.numel(), Fin, Fout, K, p, 0, 0, algo), x.device)
-    csr = csr_struct(rowptr, col, val)
+    csr = csr_struct(rowptr, col, val, (B, Fin, Fout, K, p))
     rc = L.gcnb_cheb_fwd_f32(_ptr(x), _ptr(perm), M_in, C.byref(csr), _ptr(W), _ptr(bias), _ptr(y), _ptr(argmax),
                              _ptr(ymean), _ptr(stack), B, Fin, Fout, K, p, bias_mode, int(relu), algo, _ptr(ws), ws.numel(),
                              _stream(x))
@@ -183,7 +183,7 @@ def cheb_bwd_into(x: Tensor, perm: Optional[Tensor], y: Tensor, argmax: Tensor, 
     L = _lib.lib()
     ws = _workspace(L.gcnb_cheb_workspace_bytes(B, M, val.numel(), Fin, Fout, K, p, 1, int(need_dx), algo), x.device)
     csr = csr_struct(rowptr, col, val)
-    csr_t = csr_struct(rowptr_t, col_t, val_t)
+    csr_t = csr_struct(rowptr_t, col_t, val_t, (B, Fin, Fout, K, p))
     rc = L.gcnb_cheb_bwd_f32(_ptr(x), _ptr(perm), M_in, _ptr(y), _ptr(argmax), _ptr(dy), int(dy_is_mean), _ptr(stack),
                              C.byref(csr),
                              C.byref(csr_t), _ptr(W), _ptr(dx), _ptr(dW_out), _ptr(db_out), B, Fin, Fout, K, p, bias_mode,

@@ -63,6 +63,12 @@ typedef struct gcnb_csr {
   const float* val;      /* [nnz] */
   int32_t M;
   int32_t nnz;
+  /* Optional (NULL / 0 = none): operator image pre-built on the host by gcnb_cheb_image_build for ONE layer shape
+   * and uploaded by the caller (16-byte aligned device memory).  The tcgen05 kernels then copy it instead of
+   * re-deriving their row-blocked work lists from the CSR arrays in every launch.  The CSR arrays stay mandatory
+   * (other kernels read them) and must describe the same matrix. */
+  const void* image;
+  size_t image_bytes;
 } gcnb_csr;
 
 GCNB_API int gcnb_version(void);
@@ -75,6 +81,18 @@ GCNB_API int gcnb_cheb_fused_supported(int B, int M, int nnz, int Fin, int Fout,
 
 /* Human-readable description of the forward kernel AUTO dispatch picks for this shape (diagnostics, bench records). */
 GCNB_API int gcnb_cheb_fwd_describe(int B, int M, int nnz, int Fin, int Fout, int K, int p, char* out, size_t n);
+
+/*
+ * Operator image of a layer (see gcnb_csr.image).  rowptr / col / val are HOST arrays of the rescaled Laplacian the
+ * layer is called with -- for adjoint != 0 of its TRANSPOSE, and the image then serves the input gradient of
+ * gcnb_cheb_bwd_f32 (pass it in Lt->image).  The shape arguments are the layer's (the same as in the fwd / bwd call);
+ * an image is only valid for that shape on that device model.  gcnb_cheb_image_bytes returns 0 when no image-based
+ * kernel exists for the shape (the calls then work without an image).  No CUDA calls besides a device-property query.
+ */
+GCNB_API size_t gcnb_cheb_image_bytes(const int32_t* rowptr, const int32_t* col, int B, int M, int nnz, int Fin, int Fout,
+                                      int K, int p, int adjoint);
+GCNB_API int gcnb_cheb_image_build(const int32_t* rowptr, const int32_t* col, const float* val, int B, int M, int nnz,
+                                   int Fin, int Fout, int K, int p, int adjoint, void* image_host, size_t image_bytes);
 
 /* Feature width FP of the saved-basis buffer `xstack` (K*B*M*FP floats, layout private to the library: [K][B][M][FP]
  * with padded FP for graphs the fused kernels hold in shared memory, vertex-major [K][M][B][Fin] for vertex-level

@@ -815,3 +815,35 @@ def test_fused_argmax_bit_exact_against_own_activations(dev, graph_l4, lvl, Fin,
     first = torch.where(win == mx, torch.arange(p, device=dev).view(1, 1, p, 1), torch.full((), p, device=dev)).min(2).values
     assert torch.equal(mx.squeeze(2), y)
     assert torch.equal(first.to(torch.uint8), am)
+
+
+@pytest.mark.parametrize("lvl,B,Fin,Fout,K,p,brelu", [(0, 9, 15, 32, 5, 4, "b1relu"), (2, 11, 32, 32, 5, 4, "b1relu"),
+                                                      (1, 5, 16, 32, 3, 2, "b2relu"), (2, 6, 12, 8, 2, 1, "b1relu"),
+                                                      (0, 300, 15, 32, 5, 4, "b1relu")])
+def test_operator_image_kernels_match_the_self_built_ones(dev, graph_l4, lvl, B, Fin, Fout, K, p, brelu):
+    """The row-blocked kernels fed by a host-built operator image (gcnb_cheb_image_build) add every row's terms in the
+    same (ascending column) order as the kernels that derive their work lists from the CSR arrays -- zero-weight terms
+    of sibling rows in between are exact no-ops -- so outputs and gradients must be IDENTICAL, not just close."""
+    from gcn_fmri_decoding_b200 import _lib, plan
+
+    L = graph_l4["L"][lvl]
+    M = L.shape[0]
+    rng = np.random.RandomState(lvl * 10 + B)
+    x = rng.randn(B, M, Fin).astype(np.float32)
+    W = (rng.randn(Fin * K, Fout) * 0.2).astype(np.float32)
+    b = (rng.randn(Fout) * 0.1).astype(np.float32) if brelu == "b1relu" else (rng.randn(M, Fout) * 0.1).astype(np.float32)
+    dy = rng.randn(B, M // p, Fout).astype(np.float32)
+    gp = plan.GraphPlan(L, dev)
+    assert gp.image((B, Fin, Fout, K, p)) is not None, "no image-based kernel for a benched shape family"
+    outs = []
+    for use in (True, False):
+        old = plan.USE_IMAGES
+        plan.USE_IMAGES = use
+        try:
+            outs.append(run_layer(dev, L, x, W, b, K, p, brelu, _lib.ALGO_AUTO, dy=dy))
+        finally:
+            plan.USE_IMAGES = old
+    for key in ("y", "argmax", "dx", "dW", "db"):
+        assert np.array_equal(outs[0][key], outs[1][key]), key
+    y64, tr = O.conv_stack(x, [L], [dict(W=W, b=b, K=K, p=p)], brelu=brelu, dtype=np.float64, keep=True)
+    assert rel_inf(outs[0]["y"], y64) <= TOL

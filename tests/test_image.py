@@ -1,0 +1,79 @@
+"""Host-side operator image (gcnb_cheb_image_build, include/gcnb200.h): decoding it must give back the rescaled
+Laplacian bit for bit -- every block's entry list is the union of its four rows' neighbour sets with the exact weights,
+padding steps gather the zero row with zero weights.  No GPU: the builder is host code."""
+import numpy as np
+import pytest
+
+
+def _decode(img, M, p_eff):
+    hdr = img[:64].view(np.uint32)
+    assert hdr[0] == 0x494E4347 and hdr[2] == img.size
+    ng = int(hdr[3])
+    grp = img[64:64 + ng * 8].view(np.uint32).reshape(ng, 2)
+    blk_off = 64 + ((ng * 8 + 15) // 16) * 16
+    blk = img[blk_off:blk_off + ng * 8].view(np.uint16).reshape(ng, 4)
+    assert sorted(int(b) for b in blk.ravel() if b != 0xFFFF) == list(range(M // 4))
+    assert (np.diff(grp[:, 1].astype(np.int64)) <= 0).all() and (grp[:, 1] % 2 == 0).all()  # sorted, even step counts
+    pairs = []
+    for g in range(ng):
+        off, steps = int(grp[g, 0]), int(grp[g, 1])
+        for t in range(steps // 2):
+            pair = img[off + t * 160:off + (t + 1) * 160]
+            pairs.append((g, pair[:128].view(np.float32).reshape(2, 4, 4), pair[128:160].view(np.uint32).reshape(4, 2)))
+    zero_row = max(int(c.max()) for _, _, c in pairs) >> 7  # the zero row is the last row of a state buffer
+    BQ, log2p = zero_row // p_eff, int(np.log2(p_eff))
+    row2v = {(v & (p_eff - 1)) * BQ + (v >> log2p): v for v in range(M)}
+    dense = np.zeros((M, M), np.float32)
+    for g, w, codes in pairs:
+        for q in range(4):
+            beta = int(blk[g, q])
+            for jj in range(2):
+                code = int(codes[q, jj])
+                row = code >> 7
+                assert (code >> 4) & 7 == row & 7 and code & 15 == 0  # SWIZZLE_128B phase of the gathered row
+                if row == zero_row:
+                    assert not w[jj, q].any()
+                    continue
+                assert beta != 0xFFFF
+                col = row2v[row]
+                for i in range(4):
+                    assert dense[beta * 4 + i, col] == 0
+                    dense[beta * 4 + i, col] = w[jj, q, i]
+    return dense
+
+
+@pytest.mark.parametrize("level,B,Fin,Fout,K,p,adjoint", [(0, 512, 15, 32, 5, 4, 0), (2, 512, 32, 32, 5, 4, 0),
+                                                          (2, 512, 32, 32, 5, 4, 1), (1, 64, 16, 32, 3, 2, 0),
+                                                          (2, 7, 12, 8, 2, 1, 0)])
+def test_image_decodes_to_the_operator(graph_l4, level, B, Fin, Fout, K, p, adjoint):
+    from gcn_fmri_decoding_b200 import _lib, graphs
+
+    Lr = graphs.rescale_L(graph_l4["L"][level], lmax=2)
+    rp, ci, v = graphs.csr_arrays(Lr, transpose=bool(adjoint))
+    M, nnz = Lr.shape[0], len(v)
+    lib = _lib.lib()
+    args = (B, M, nnz, Fin, Fout, K, p, adjoint)
+    n = lib.gcnb_cheb_image_bytes(rp.ctypes.data, ci.ctypes.data, *args)
+    assert n > 0 and n % 16 == 0
+    img = np.zeros(n, np.uint8)
+    _lib.check(lib.gcnb_cheb_image_build(rp.ctypes.data, ci.ctypes.data, v.ctypes.data, *args, img.ctypes.data, n), "build")
+    ref = np.asarray((Lr.T if adjoint else Lr).todense(), np.float32)
+    assert np.array_equal(_decode(img, M, 1 if adjoint else p), ref)
+    # wrong buffer size -> error code, message set
+    assert lib.gcnb_cheb_image_build(rp.ctypes.data, ci.ctypes.data, v.ctypes.data, *args, img.ctypes.data, n - 16) != 0
+    assert "image" in _lib.last_error()
+
+
+def test_image_unsupported_shapes_return_zero(graph_l4):
+    from gcn_fmri_decoding_b200 import _lib, graphs
+
+    lib = _lib.lib()
+    Lr = graphs.rescale_L(graph_l4["L"][3], lmax=2)  # M = 50: not a multiple of four
+    rp, ci, v = graphs.csr_arrays(Lr)
+    assert lib.gcnb_cheb_image_bytes(rp.ctypes.data, ci.ctypes.data, 8, 50, len(v), 32, 32, 5, 2, 0) == 0
+    Lr = graphs.rescale_L(graph_l4["L"][0], lmax=2)
+    rp, ci, v = graphs.csr_arrays(Lr)
+    assert lib.gcnb_cheb_image_bytes(rp.ctypes.data, ci.ctypes.data, 8, 400, len(v), 64, 32, 5, 4, 0) == 0  # Fin > 32
+    bad = rp.copy()
+    bad[5] = bad[6] + 1  # row pointers must not decrease
+    assert lib.gcnb_cheb_image_bytes(bad.ctypes.data, ci.ctypes.data, 8, 400, len(v), 15, 32, 5, 4, 0) == 0

@@ -36,7 +36,13 @@ names = ["sparse0", "items", "mma", "epi0"]
 for r in range(4):
     if r == 1:
         v = t[1][t[1] > 0] - t0
-        print("prologue", " ".join(str(int(a)) for a in v[:16]))
+        print("prologue", " ".join(str(int(a)) for a in t[1][:16][t[1][:16] > 0] - t0))
+        w = t[1][64:64 + 20 * 16].reshape(20, 16)
+        if (w > 0).any():
+            base = w[w > 0].min()
+            print("order n=2, per sparse warp: start | item0: loop, wait, finish | item1 ... | end, fenced, released (cycles from", int(base - t0), ")")
+            for sw in range(20):
+                print("  sw%2d" % sw, " ".join("%6d" % (int(a - base) if a > 0 else -1) for a in w[sw]))
         continue
     v = t[r][t[r] > 0] - t0
     print(names[r], len(v), " ".join(str(int(a)) for a in v[:64]))
