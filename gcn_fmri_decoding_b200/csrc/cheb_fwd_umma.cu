@@ -542,12 +542,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
 #ifdef GCNB_TRACE
             if (P.debug & 1) steps = 0;
 #endif
-#pragma unroll 2
+            // software pipeline: the codes and weights of the next pair of steps are in flight while this pair's two
+            // gathers return (the read past the last pair of a group stays inside the image / the tables behind it)
+            uint2 cc = lds64u(ca);
+            float4 w0 = lds128(wa), w1 = lds128(wa + 64u);
+#pragma unroll 1
             for (int j = 0; j < steps; j += 2) {
-              const uint2 cc = lds64u(ca);
-              const float4 w0 = lds128(wa), w1 = lds128(wa + 64u);
               const float4 v0 = lds128(srcs + (cc.x ^ c16));
               const float4 v1 = lds128(srcs + (cc.y ^ c16));
+              wa += 160u;
+              ca += 160u;
+              const uint2 ccn = lds64u(ca);
+              const float4 w0n = lds128(wa), w1n = lds128(wa + 64u);
               a0.x = fmaf(w0.x, v0.x, a0.x); a0.y = fmaf(w0.x, v0.y, a0.y); a0.z = fmaf(w0.x, v0.z, a0.z); a0.w = fmaf(w0.x, v0.w, a0.w);
               a1.x = fmaf(w0.y, v0.x, a1.x); a1.y = fmaf(w0.y, v0.y, a1.y); a1.z = fmaf(w0.y, v0.z, a1.z); a1.w = fmaf(w0.y, v0.w, a1.w);
               a2.x = fmaf(w0.z, v0.x, a2.x); a2.y = fmaf(w0.z, v0.y, a2.y); a2.z = fmaf(w0.z, v0.z, a2.z); a2.w = fmaf(w0.z, v0.w, a2.w);
@@ -556,8 +562,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
               a1.x = fmaf(w1.y, v1.x, a1.x); a1.y = fmaf(w1.y, v1.y, a1.y); a1.z = fmaf(w1.y, v1.z, a1.z); a1.w = fmaf(w1.y, v1.w, a1.w);
               a2.x = fmaf(w1.z, v1.x, a2.x); a2.y = fmaf(w1.z, v1.y, a2.y); a2.z = fmaf(w1.z, v1.z, a2.z); a2.w = fmaf(w1.z, v1.w, a2.w);
               a3.x = fmaf(w1.w, v1.x, a3.x); a3.y = fmaf(w1.w, v1.y, a3.y); a3.z = fmaf(w1.w, v1.z, a3.z); a3.w = fmaf(w1.w, v1.w, a3.w);
-              wa += 160u;
-              ca += 160u;
+              cc = ccn; w0 = w0n; w1 = w1n;
             }
             TRACEW(1 + u * 3);
             if (SLOT < 0 && !lo_free) {
@@ -776,38 +781,46 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
         TRACE(2, true);
         tc_fence_after();
         if (lane == 0) {
+          // ONE thread issues every MMA of the order, so the issue sequence itself is on the critical path (measured:
+          // ~4.5 K cycles per order when every instruction recomputed its descriptors from the block indices).  All
+          // descriptor halves that do not change are hoisted; per instruction only the 32-bit start-address fields move.
           const int cur = (base + k) & 1;
           const uint32_t lo_u = P.nlo == 2 ? (n & 1u) : 0u;
-          const uint32_t wh = sb + P.off_wh + (uint32_t)(k * (FP / 4) * 4) * 128u;
-          const uint32_t wl = sb + P.off_wl + (uint32_t)(k * (FP / 4) * 4) * 128u;
-          const uint32_t wb = sb + P.off_wb + (uint32_t)(k * (FP / 8) * 4) * 128u;
           const uint32_t sbuf = sb + (uint32_t)cur * buf_bytes, lbuf = sb + P.off_lo + lo_u * lo_bytes;
+          uint64_t bh[FP / 8], bl[FP / 8], bb[FP / 16];
+#pragma unroll
+          for (int j = 0; j < FP / 8; ++j) {
+            bh[j] = smem_desc(kDescTaps, sb + P.off_wh + (uint32_t)(k * (FP / 4) * 4) * 128u + j * 1024);
+            bl[j] = smem_desc(kDescTaps, sb + P.off_wl + (uint32_t)(k * (FP / 4) * 4) * 128u + j * 1024);
+          }
+#pragma unroll
+          for (int j = 0; j < FP / 16; ++j)
+            bb[j] = smem_desc(kDescTaps, sb + P.off_wb + (uint32_t)(k * (FP / 8) * 4) * 128u + j * 1024);
+          const uint32_t first_acc = k != 0;
+          uint32_t d = tmem + (uint32_t)(buf * P.acc_cols);
 #ifdef GCNB_TRACE
           if (!(P.debug & 2))
 #endif
-          // Block-major issue order on purpose: the (up to ten) instructions of one accumulator block re-read the same
-          // rows of A back to back.  Measured (B200, conv1 shape, 40 MMAs of 128x32x8 per order): ~100 cycles per
-          // instruction this way -- the shared-memory read of A's 128 rows paces them, not the 16-cycle tensor floor --
-          // and ~300 cycles per instruction when consecutive instructions alternate between blocks (pass-major).
 #pragma unroll
           for (int g = 0; g < G; ++g) {
+            // descriptor start-address fields (16-byte units) of block (g, i = 0, t = 0)
+            uint32_t ai = ((sbuf + (uint32_t)(g * FP * 4)) >> 4) & 0x3fffu, li = ((lbuf + (uint32_t)(g * FP * 2)) >> 4) & 0x3fffu;
             for (int i = 0; i < P.p; ++i) {
+              uint32_t at = ai, lt = li;
               for (int t = 0; t < P.T; ++t) {
-                const uint32_t d = tmem + (uint32_t)(buf * P.acc_cols + ((g * P.p + i) * P.T + t) * 32);
-                const uint32_t row0 = (uint32_t)(i * BQ + t * 128);
-                const uint32_t a = sbuf + row0 * 128u + (uint32_t)(g * FP * 4);
-                const uint32_t l = lbuf + row0 * 64u + (uint32_t)(g * FP * 2);
+                const uint64_t da = kDescSlab | at, dl = kDescLo | lt;
 #pragma unroll
-                for (int j = 0; j < FP / 8; ++j)
-                  mma_tf32(d, smem_desc(kDescSlab, a + j * 32), smem_desc(kDescTaps, wh + j * 1024), kIdescTf32,
-                           (k | j) != 0);
+                for (int j = 0; j < FP / 8; ++j) mma_tf32(d, da + 2 * j, bh[j], kIdescTf32, j ? 1u : first_acc);
 #pragma unroll
-                for (int j = 0; j < FP / 8; ++j)
-                  mma_tf32(d, smem_desc(kDescSlab, a + j * 32), smem_desc(kDescTaps, wl + j * 1024), kIdescTf32, 1);
+                for (int j = 0; j < FP / 8; ++j) mma_tf32(d, da + 2 * j, bl[j], kIdescTf32, 1);
 #pragma unroll
-                for (int j = 0; j < FP / 16; ++j)
-                  mma_bf16(d, smem_desc(kDescLo, l + j * 32), smem_desc(kDescTaps, wb + j * 1024), kIdescBf16, 1);
+                for (int j = 0; j < FP / 16; ++j) mma_bf16(d, dl + 2 * j, bb[j], kIdescBf16, 1);
+                d += 32;
+                at += 128 * 128 / 16;  // the next 128 rows of the block
+                lt += 128 * 64 / 16;
               }
+              ai += (uint32_t)BQ * 128 / 16;  // the next sibling block
+              li += (uint32_t)BQ * 64 / 16;
             }
           }
           mma_commit(bar_mma(n & 1));
@@ -830,7 +843,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
     for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x, ++it) {
       const int buf = P.nacc == 2 ? (it & 1) : 0;
       const int use = P.nacc == 2 ? (it >> 1) : it;
-      mbar_wait(bar_full(buf), (uint32_t)use & 1u);
+      mbar_wait_relaxed(bar_full(buf), (uint32_t)use & 1u);
       TRACE(3, e == 0);
       tc_fence_after();
       if (it + 1 == my_tiles) {
