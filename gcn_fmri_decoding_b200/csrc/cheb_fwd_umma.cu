@@ -537,7 +537,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
             const int beta = blk[g * 4 + q];
             const uint32_t srcs = srcb + ((uint32_t)(s * Q) << 7);  // window-slab offset keeps the swizzle phase
             uint32_t wa = img0 + gr.x + (uint32_t)q * 16u, ca = img0 + gr.x + 128u + (uint32_t)q * 8u;
-            float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+            // accumulators packed by PAIRS OF ROWS: c01[f] = (row 0, row 1) of feature f, c23[f] = (row 2, row 3).  One
+            // fma.rn.f32x2 (two IEEE fp32 FMAs, bit-identical to fmaf) multiplies the weight pair of two rows -- adjacent
+            // words of the entry stream -- by a duplicated gathered value: 12 issue slots per gathered row instead of 16
+            // (the loop is issue-bound).
+            uint64_t c01[4] = {0ull, 0ull, 0ull, 0ull}, c23[4] = {0ull, 0ull, 0ull, 0ull};
             int steps = (int)gr.y;
 #ifdef GCNB_TRACE
             if (P.debug & 1) steps = 0;
@@ -554,16 +558,27 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
               ca += 160u;
               const uint2 ccn = lds64u(ca);
               const float4 w0n = lds128(wa), w1n = lds128(wa + 64u);
-              a0.x = fmaf(w0.x, v0.x, a0.x); a0.y = fmaf(w0.x, v0.y, a0.y); a0.z = fmaf(w0.x, v0.z, a0.z); a0.w = fmaf(w0.x, v0.w, a0.w);
-              a1.x = fmaf(w0.y, v0.x, a1.x); a1.y = fmaf(w0.y, v0.y, a1.y); a1.z = fmaf(w0.y, v0.z, a1.z); a1.w = fmaf(w0.y, v0.w, a1.w);
-              a2.x = fmaf(w0.z, v0.x, a2.x); a2.y = fmaf(w0.z, v0.y, a2.y); a2.z = fmaf(w0.z, v0.z, a2.z); a2.w = fmaf(w0.z, v0.w, a2.w);
-              a3.x = fmaf(w0.w, v0.x, a3.x); a3.y = fmaf(w0.w, v0.y, a3.y); a3.z = fmaf(w0.w, v0.z, a3.z); a3.w = fmaf(w0.w, v0.w, a3.w);
-              a0.x = fmaf(w1.x, v1.x, a0.x); a0.y = fmaf(w1.x, v1.y, a0.y); a0.z = fmaf(w1.x, v1.z, a0.z); a0.w = fmaf(w1.x, v1.w, a0.w);
-              a1.x = fmaf(w1.y, v1.x, a1.x); a1.y = fmaf(w1.y, v1.y, a1.y); a1.z = fmaf(w1.y, v1.z, a1.z); a1.w = fmaf(w1.y, v1.w, a1.w);
-              a2.x = fmaf(w1.z, v1.x, a2.x); a2.y = fmaf(w1.z, v1.y, a2.y); a2.z = fmaf(w1.z, v1.z, a2.z); a2.w = fmaf(w1.z, v1.w, a2.w);
-              a3.x = fmaf(w1.w, v1.x, a3.x); a3.y = fmaf(w1.w, v1.y, a3.y); a3.z = fmaf(w1.w, v1.z, a3.z); a3.w = fmaf(w1.w, v1.w, a3.w);
+              {
+                const uint64_t wl = pack2(w0.x, w0.y), wh = pack2(w0.z, w0.w);
+                const uint64_t x = pack2(v0.x, v0.x), y = pack2(v0.y, v0.y), z = pack2(v0.z, v0.z), w = pack2(v0.w, v0.w);
+                c01[0] = fma2(wl, x, c01[0]); c23[0] = fma2(wh, x, c23[0]);
+                c01[1] = fma2(wl, y, c01[1]); c23[1] = fma2(wh, y, c23[1]);
+                c01[2] = fma2(wl, z, c01[2]); c23[2] = fma2(wh, z, c23[2]);
+                c01[3] = fma2(wl, w, c01[3]); c23[3] = fma2(wh, w, c23[3]);
+              }
+              {
+                const uint64_t wl = pack2(w1.x, w1.y), wh = pack2(w1.z, w1.w);
+                const uint64_t x = pack2(v1.x, v1.x), y = pack2(v1.y, v1.y), z = pack2(v1.z, v1.z), w = pack2(v1.w, v1.w);
+                c01[0] = fma2(wl, x, c01[0]); c23[0] = fma2(wh, x, c23[0]);
+                c01[1] = fma2(wl, y, c01[1]); c23[1] = fma2(wh, y, c23[1]);
+                c01[2] = fma2(wl, z, c01[2]); c23[2] = fma2(wh, z, c23[2]);
+                c01[3] = fma2(wl, w, c01[3]); c23[3] = fma2(wh, w, c23[3]);
+              }
               cc = ccn; w0 = w0n; w1 = w1n;
             }
+            float4 a0, a1, a2, a3;
+            unpack2(c01[0], a0.x, a1.x); unpack2(c01[1], a0.y, a1.y); unpack2(c01[2], a0.z, a1.z); unpack2(c01[3], a0.w, a1.w);
+            unpack2(c23[0], a2.x, a3.x); unpack2(c23[1], a2.y, a3.y); unpack2(c23[2], a2.z, a3.z); unpack2(c23[3], a2.w, a3.w);
             TRACEW(1 + u * 3);
             if (SLOT < 0 && !lo_free) {
               mbar_wait(bar_mma((n - 1) & 1), ((n - 1) >> 1) & 1);

@@ -318,34 +318,54 @@ __global__ void __launch_bounds__(896, 1) k_cheb_bwd_fused(const BwdParams P) {
   }
 }
 
-// dW[(f*K + k)*Fout + o] = sum over CTAs of the chunked partials; one warp per output element, lanes stride over
-// the CTAs, fixed-order shuffle tree.  The trailing warps reduce the per-filter bias-gradient partials.
-__global__ void k_dw_from_partials(const float* __restrict__ part, float* __restrict__ dW, int nblocks, int K, int MT,
-                                   int NT, int Fin, int Fout, const float* __restrict__ db_part, float* __restrict__ db,
-                                   int FoP) {
+// dW[(f*K + k)*Fout + o] = sum over CTAs of the chunked partials (and, in the trailing columns, the per-filter
+// bias-gradient partials).  A CTA owns 32 consecutive elements: lane = element, so every load of a warp is one
+// coalesced 128-byte line; its 8 warps split the CTAs' partials (many independent loads in flight per thread) and
+// are combined through shared memory in warp order -- a fixed summation order, bit-reproducible.
+__global__ void __launch_bounds__(256) k_dw_from_partials(const float* __restrict__ part, float* __restrict__ dW,
+                                                           int nblocks, int K, int MT, int NT, int Fin, int Fout,
+                                                           const float* __restrict__ db_part, float* __restrict__ db,
+                                                           int FoP) {
+  __shared__ float red[8][32];
   pdl_trigger();
   pdl_wait();
   const int NCH = MT * NT / 2;
   const int total = K * NCH * 256;
-  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (w < total) {
-    float s = 0.f;
-    for (int b = lane; b < nblocks; b += 32) s += part[(size_t)b * total + w];
+  const int ntot = total + (db_part != nullptr ? Fout : 0);
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const int w = blockIdx.x * 32 + lane;
+  float s = 0.f;
+  if (w < ntot) {
+    const float* src = w < total ? part + w : db_part + (w - total);
+    const size_t stride = w < total ? (size_t)total : (size_t)FoP;
+    const int per = (nblocks + 7) >> 3, b0 = wp * per, b1 = min(nblocks, b0 + per);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int b = b0;
+#pragma unroll 4
+    for (; b + 3 < b1; b += 4) {
+      a0 += src[(size_t)b * stride];
+      a1 += src[(size_t)(b + 1) * stride];
+      a2 += src[(size_t)(b + 2) * stride];
+      a3 += src[(size_t)(b + 3) * stride];
+    }
+    for (; b < b1; ++b) a0 += src[(size_t)b * stride];
+    s = (a0 + a1) + (a2 + a3);
+  }
+  red[wp][lane] = s;
+  __syncthreads();
+  if (wp != 0 || w >= ntot) return;
+  s = red[0][lane];
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+  for (int i = 1; i < 8; ++i) s += red[i][lane];
+  if (w < total) {
     const int e = w & 255, chunk = (w >> 8) % NCH, k = w / (256 * NCH);
     const int m = chunk / (NT / 2), np = chunk % (NT / 2);
     const int reg = e >> 5, ln = e & 31, gg = ln >> 2, tt = ln & 3;
     const int n = 2 * np + (reg >> 2), c = reg & 3;
     const int f = m * 16 + gg + ((c & 2) ? 8 : 0), o = n * 8 + 2 * tt + (c & 1);
-    if (lane == 0 && f < Fin && o < Fout) dW[((size_t)f * K + k) * Fout + o] = s;
-  } else if (db_part != nullptr && w < total + Fout) {
-    const int o = w - total;
-    float s = 0.f;
-    for (int b = lane; b < nblocks; b += 32) s += db_part[(size_t)b * FoP + o];
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-    if (lane == 0) db[o] = s;
+    if (f < Fin && o < Fout) dW[((size_t)f * K + k) * Fout + o] = s;
+  } else {
+    db[w - total] = s;
   }
 }
 
@@ -508,8 +528,8 @@ bool fused_bwd_supported(const LayerShape& s, bool need_dx) { return plan_bwd(s,
 int launch_dw_from_partials(const float* part, float* dW, int nblocks, int K, int MT, int NT, int Fin, int Fout,
                             const float* db_part, float* db, int FoP, cudaStream_t st) {
   const int total = K * (MT * NT / 2) * 256;
-  const int warps = total + (db_part != nullptr ? Fout : 0);
-  GCNB_CUDA(launch_pdl(k_dw_from_partials, dim3(ceil_div(warps * 32, 256)), dim3(256), 0, st, part, dW, nblocks, K, MT, NT,
+  const int elems = total + (db_part != nullptr ? Fout : 0);
+  GCNB_CUDA(launch_pdl(k_dw_from_partials, dim3(ceil_div(elems, 32)), dim3(256), 0, st, part, dW, nblocks, K, MT, NT,
                        Fin, Fout, db_part, db, FoP));
   GCNB_LAUNCH_CHECK("k_dw_from_partials");
   return GCNB_OK;

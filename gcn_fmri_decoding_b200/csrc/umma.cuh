@@ -175,6 +175,21 @@ __device__ __forceinline__ void sts64(uint32_t a, uint32_t x, uint32_t y) {
   asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
 }
 
+// ---- packed fp32 pairs (fma.rn.f32x2: two independent IEEE fp32 FMAs in one issue slot) ------------------------------
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
 // ---- operand layouts ----------------------------------------------------------------------------------------
 // byte offset of 16-byte chunk c (0..7) of state row r inside a slab
 __device__ __forceinline__ uint32_t slab_off(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
