@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgcnb200.so")
+# GCNB_LIB_PATH: load another build of the same library (e.g. the -DGCNB_TRACE debug build of tools/build_trace.sh)
+LIB_PATH = os.environ.get("GCNB_LIB_PATH") or os.path.join(_HERE, "libgcnb200.so")
 
 GCNB_OK = 0
 BIAS_NONE, BIAS_PER_FILTER, BIAS_PER_VERTEX = 0, 1, 2

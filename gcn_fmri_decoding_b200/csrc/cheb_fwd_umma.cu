@@ -3,7 +3,7 @@
 // Replaces cgcnn.chebyshev5 / chebyshev2 + b1relu / b2relu + mpool1 (models_gcn.py:587-617, 558-585, 619-639).
 //
 // One persistent CTA per SM, 25 warps with three roles:
-//   * 20 "sparse" warps run the recursion X_k = 2 L~ X_{k-1} - X_{k-2} out of shared memory.  The state of a tile
+//   * 20 "sparse" warps (24 measured slower: the recursion is bound by shared-memory wavefronts, not by warps) run the recursion X_k = 2 L~ X_{k-1} - X_{k-2} out of shared memory.  The state of a tile
 //     of windows lives in two ping-pong slabs of 128-byte rows (row = vertex, 32 floats = G windows x FP features,
 //     SWIZZLE_128B): a neighbour row is one conflict-free LDS.128 per lane, 8 lanes per row, 4 rows per warp step.
 //     Rows are sorted by length once per CTA and dealt to the warps in groups of four (snake order) so that the
@@ -36,6 +36,7 @@ static constexpr int kSparseWarps = 20;
 static constexpr int kEpiWarps = 4;   // warps 0..3: warp w may only touch TMEM lanes 32w..32w+31
 static constexpr int kMmaWarp = 4;    // warp 4
 static constexpr int kThreads = (kSparseWarps + kEpiWarps + 1) * 32;
+static_assert(kSparseWarps % 4 == 0, "the tail epilogue deals the sparse warps to the four TMEM lane quarters");
 static constexpr uint32_t kImgMagic = 0x494e4347u;  // "GCNI"
 static constexpr int kBarOrder = 1;   // named barrier: sparse warps + MMA warp, once per Chebyshev order
 
@@ -54,6 +55,22 @@ __device__ long long g_trace[4][512];
 #else
 #define TRACE(region, cond) do { } while (0)
 #define TRACEW(slot) do { } while (0)
+#endif
+#ifdef GCNB_TRACE
+// order 0 of CTA 0's first two tiles, per sparse warp: g_trace[3][64 + (tile index) * 160 + sw * 8 + slot]
+#define TRACE0(slot)                                                                                     \
+  do {                                                                                                   \
+    if (blockIdx.x == 0 && lane == 0 && n <= (uint32_t)K) g_trace[3][64 + (n ? 160 : 0) + sw * 8 + (slot)] = clock64(); \
+  } while (0)
+#else
+#define TRACE0(slot) do { } while (0)
+#endif
+#ifdef GCNB_TRACE
+#define TRACE_NOSPILL ((P.debug & 4) != 0)  // image kernels: skip the basis stores
+#define TRACE_NOLOAD ((P.debug & 8) != 0)   // image kernels: order 0 is all zeros (no global loads)
+#else
+#define TRACE_NOSPILL false
+#define TRACE_NOLOAD false
 #endif
 
 struct UmmaFwdParams {
@@ -95,6 +112,7 @@ struct UmmaFwdParams {
   // Pre-built operator image (IMG kernels, see "operator image" below): copied to shared memory as is.
   const unsigned char* image;
   int img_bytes;     // multiple of 16
+  int stage;         // image kernels, forward: the raw windows of a tile are staged with one TMA bulk copy
   unsigned img_sig;  // geometry signature the image must carry
   int n_groups;      // groups of 4 row blocks
   int off_img, off_grp, off_blk;  // shared-memory offsets of the image copy, its group table and its block table
@@ -128,6 +146,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
   auto bar_mma = [bar0](uint32_t i) { return bar0 + i * 8u; };          // tcgen05.mma of order n done (n & 1)
   auto bar_full = [bar0](uint32_t i) { return bar0 + 16u + i * 8u; };   // accumulator buffer i complete
   auto bar_empty = [bar0](uint32_t i) { return bar0 + 32u + i * 8u; };  // accumulator buffer i drained
+  const uint32_t bar_stage = bar0 + 56u;                                 // raw windows of a tile staged (TMA)
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + P.off_bar + 48);
   // state row of vertex v inside window-slab 0 (sibling-major)
   auto rho = [=](int v) { return (v & pm1) * BQ + (v >> log2p); };
@@ -146,6 +165,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
     mbar_init(bar_mma(0), 1); mbar_init(bar_mma(1), 1);
     mbar_init(bar_full(0), 1); mbar_init(bar_full(1), 1);
     mbar_init(bar_empty(0), kEpiWarps); mbar_init(bar_empty(1), kEpiWarps);
+    mbar_init(bar_stage, 1);
     mbar_init_fence();
   }
   if (warp == kMmaWarp) tmem_alloc(sb + P.off_bar + 48, (uint32_t)P.tmem_cols);
@@ -284,6 +304,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
     for (int g = tid; g < P.NG; g += kThreads) glen[g] = (gslot[g * 4].y + 1) >> 1;  // slot 0 holds the group's longest row
   }
   TRACEP();
+  fence_async_smem();  // the zeroed state buffers are about to be written through the async proxy (staging copy)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -389,11 +410,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
           if (P.y_mean && valid && h0 == 0 && h1 == 2) P.y_mean[orow] = msum / (float)P.Fout;
   };
   // tasks of one tile per lane quarter; the LAST tile of a CTA is shared between the epilogue warp of the quarter and
-  // the five sparse warps that can reach the same TMEM lanes (they have nothing left to do)
+  // the kSparseWarps / 4 sparse warps that can reach the same TMEM lanes (they have nothing left to do)
   const bool split_halves = P.y_mean == nullptr;  // the mean over filters needs both halves in one thread
   const int ntask = G * P.T * (split_halves ? 2 : 1);
-  auto tail_tasks = [&](int tile, int buf, int e, int j) {  // participant j of 6 in quarter e
-    for (int k = j; k < ntask; k += 6) {
+  constexpr int kTailShare = 1 + kSparseWarps / 4;
+  auto tail_tasks = [&](int tile, int buf, int e, int j) {  // participant j of kTailShare in quarter e
+    for (int k = j; k < ntask; k += kTailShare) {
       const int gt = split_halves ? (k >> 1) : k;
       const int g = gt / P.T, t = gt - g * P.T;
       if (split_halves) epi_task(tile, buf, e, g, t, k & 1, (k & 1) + 1);
@@ -470,6 +492,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
       auto item_of = [sw](int u) { return u * kSparseWarps + ((u & 1) ? kSparseWarps - 1 - sw : sw); };
       auto row_of = [=](int vtx, int s) { return (vtx & pm1) * BQ + s * Q + (vtx >> log2p); };
       uint32_t n = 0;  // orders issued so far (all tiles)
+      uint32_t stage_phase = 0;
       int base = 0;
       TRACE(0, sw == 0);
       for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
@@ -478,6 +501,54 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
           const uint32_t lo_u = P.nlo == 2 ? (n & 1u) : 0u;
           if (P.nlo == 1 && n > 0) mbar_wait(bar_mma((n - 1) & 1), ((n - 1) >> 1) & 1);
           const uint32_t dst = sb + (uint32_t)base * buf_bytes, dlo = sb + P.off_lo + lo_u * lo_bytes;
+          if (P.stage) {
+            // Forward, staged: ONE TMA bulk copy brings the tile's raw windows (contiguous in HBM) into the state buffer
+            // this order does not write -- it held X_{K-1} of the previous tile and is dead once that tile's last MMA has
+            // read it -- and the Graclus gather + zero padding happens shared -> shared.  (Block-wise global loads of
+            // 60-byte rows cost four scalar loads per lane, eight cache lines per instruction: measured 10-15 K cycles
+            // per tile against ~4 K for the copy.)
+            TRACE0(0);
+            const int b0 = tile * P.S, nw = min(P.S, P.B - b0);
+            const uint32_t stage = sb + (uint32_t)(base ^ 1) * buf_bytes;
+            const uint32_t wbytes = (uint32_t)(P.M_in * P.Fin) * 4u;
+            if (sw == 0 && lane == 0) {
+              if (n > 0) mbar_wait(bar_mma((n - 1) & 1), ((n - 1) >> 1) & 1);  // the tensor cores are done with that buffer
+              mbar_expect_tx(bar_stage, (uint32_t)nw * wbytes);
+              bulk_g2s(stage, P.x + (long long)b0 * P.M_in * P.Fin, (uint32_t)nw * wbytes, bar_stage);
+            }
+            mbar_wait(bar_stage, stage_phase);
+            stage_phase ^= 1u;
+            TRACE0(1);
+            for (int u = 0, ii; (ii = item_of(u)) < NI; ++u) {
+              const int g = ii / NS, s = ii - g * NS;
+              const int beta = blk[g * 4 + q];
+              if (beta == 0xffff) continue;
+              const int w = s * G + gw, b = b0 + w;
+              const int nf = P.Fin - fc * 4;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int vtx = beta * 4 + i;
+                const int src = src_row[vtx];
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (src >= 0 && w < nw && nf > 0 && !TRACE_NOLOAD) {
+                  const uint32_t a = stage + (uint32_t)w * wbytes + (uint32_t)(src * P.Fin + fc * 4) * 4u;
+                  if (nf > 3 && (a & 15u) == 0) {
+                    v = lds128(a);
+                  } else {
+                    v.x = lds32(a);
+                    if (nf > 1) v.y = lds32(a + 4);
+                    if (nf > 2) v.z = lds32(a + 8);
+                    if (nf > 3) v.w = lds32(a + 12);
+                  }
+                }
+                const uint32_t off = slab_off(row_of(vtx, s), c);
+                store_state_at(dst + off, dlo + lo_of(off), v);
+                if (P.xstack && b < P.B && !TRACE_NOSPILL)
+                  *reinterpret_cast<float4*>(P.xstack + ((long long)b * M + vtx) * FP + fc * 4) = v;
+              }
+              TRACE0(2 + u);
+            }
+          } else
           for (int u = 0, ii; (ii = item_of(u)) < NI; ++u) {
             const int g = ii / NS, s = ii - g * NS;
             const int beta = blk[g * 4 + q];
@@ -485,19 +556,22 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
             const int b = tile * P.S + s * G + gw;
             float4 v[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) v[i] = load_x0(beta * 4 + i, b);
+            for (int i = 0; i < 4; ++i) v[i] = load_x0(beta * 4 + i, TRACE_NOLOAD ? P.B : b);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int vtx = beta * 4 + i;
               const uint32_t off = slab_off(row_of(vtx, s), c);
               store_state_at(dst + off, dlo + lo_of(off), v[i]);
-              if (P.xstack && b < P.B)
+              if (P.xstack && b < P.B && !TRACE_NOSPILL)
                 *reinterpret_cast<float4*>(P.xstack + ((long long)b * M + vtx) * FP + fc * 4) = v[i];
             }
           }
           TRACE(0, sw == 0);
+          TRACE0(5);
           fence_async_smem();
+          TRACE0(6);
           named_bar_sync(kBarOrder, nsync);
+          TRACE0(7);
           ++n;
         }
         // ---- orders 1 .. K-1 ----------------------------------------------------------------------------------
@@ -505,7 +579,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
           const int cur = (base + k) & 1;
           const uint32_t lo_u = P.nlo == 2 ? (n & 1u) : 0u;
           bool lo_free = P.nlo == 2;  // single remainder buffer: the tensor cores must be done with order n-1 first
-          float* spill = P.xstack ? P.xstack + (long long)k * P.B * M * FP : nullptr;
+          float* spill = (P.xstack && !TRACE_NOSPILL) ? P.xstack + (long long)k * P.B * M * FP : nullptr;
           const uint32_t dlo = sb + P.off_lo + lo_u * lo_bytes;
           const uint32_t srcb = sb + (uint32_t)(cur ^ 1) * buf_bytes, dst = sb + (uint32_t)cur * buf_bytes;
           if (k == K - 1 && !P.adj && tile + (int)gridDim.x < P.ntiles) {
@@ -795,10 +869,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
         named_bar_sync(kBarOrder, nsync);  // X_k (and its remainder) is complete in shared memory
         TRACE(2, true);
         tc_fence_after();
-        if (lane == 0) {
-          // ONE thread issues every MMA of the order, so the issue sequence itself is on the critical path (measured:
-          // ~4.5 K cycles per order when every instruction recomputed its descriptors from the block indices).  All
-          // descriptor halves that do not change are hoisted; per instruction only the 32-bit start-address fields move.
+        {
+          // The whole warp walks the (warp-uniform) issue loop and only the tcgen05 instructions themselves are
+          // predicated on the elected lane: descriptor arithmetic then stays in the uniform datapath instead of a
+          // per-instruction register -> uniform-register waterfall inside a divergent branch.
+          const bool leader = elect_one();
+          // ONE thread issues every MMA of the order.  Inside an `if (lane == 0)` branch ptxas wraps every tcgen05.mma in
+          // a register -> uniform-register waterfall loop (~18 instructions each); under the load of the sparse warps that
+          // made the issue of the 40 MMAs of an order take 5-8 K cycles, i.e. as long as the sparse phase itself (clock64
+          // trace of CTA 0).  With the elect.sync predicate the sequence is a handful of uniform adds per instruction and
+          // the tensor-core work of an order (issue + execution) is ~400 cycles, off the critical path.
           const int cur = (base + k) & 1;
           const uint32_t lo_u = P.nlo == 2 ? (n & 1u) : 0u;
           const uint32_t sbuf = sb + (uint32_t)cur * buf_bytes, lbuf = sb + P.off_lo + lo_u * lo_bytes;
@@ -812,24 +892,33 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
           for (int j = 0; j < FP / 16; ++j)
             bb[j] = smem_desc(kDescTaps, sb + P.off_wb + (uint32_t)(k * (FP / 8) * 4) * 128u + j * 1024);
           const uint32_t first_acc = k != 0;
-          uint32_t d = tmem + (uint32_t)(buf * P.acc_cols);
+          const uint32_t d0 = tmem + (uint32_t)(buf * P.acc_cols);
 #ifdef GCNB_TRACE
+          const bool t_tf32 = !(P.debug & 16), t_lo = !(P.debug & 64), t_bf16 = !(P.debug & 32);
           if (!(P.debug & 2))
+#else
+          constexpr bool t_tf32 = true, t_lo = true, t_bf16 = true;
 #endif
 #pragma unroll
           for (int g = 0; g < G; ++g) {
             // descriptor start-address fields (16-byte units) of block (g, i = 0, t = 0)
             uint32_t ai = ((sbuf + (uint32_t)(g * FP * 4)) >> 4) & 0x3fffu, li = ((lbuf + (uint32_t)(g * FP * 2)) >> 4) & 0x3fffu;
+            uint32_t d = d0 + (uint32_t)(g * P.p * P.T * 32);
             for (int i = 0; i < P.p; ++i) {
               uint32_t at = ai, lt = li;
               for (int t = 0; t < P.T; ++t) {
                 const uint64_t da = kDescSlab | at, dl = kDescLo | lt;
+                if (leader) {
 #pragma unroll
-                for (int j = 0; j < FP / 8; ++j) mma_tf32(d, da + 2 * j, bh[j], kIdescTf32, j ? 1u : first_acc);
+                  for (int j = 0; j < FP / 8; ++j)
+                    if (t_tf32) mma_tf32(d, da + 2 * j, bh[j], kIdescTf32, j ? 1u : first_acc);
 #pragma unroll
-                for (int j = 0; j < FP / 8; ++j) mma_tf32(d, da + 2 * j, bl[j], kIdescTf32, 1);
+                  for (int j = 0; j < FP / 8; ++j)
+                    if (t_tf32 && t_lo) mma_tf32(d, da + 2 * j, bl[j], kIdescTf32, 1);
 #pragma unroll
-                for (int j = 0; j < FP / 16; ++j) mma_bf16(d, dl + 2 * j, bb[j], kIdescBf16, 1);
+                  for (int j = 0; j < FP / 16; ++j)
+                    if (t_bf16) mma_bf16(d, dl + 2 * j, bb[j], kIdescBf16, 1);
+                }
                 d += 32;
                 at += 128 * 128 / 16;  // the next 128 rows of the block
                 lt += 128 * 64 / 16;
@@ -838,8 +927,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
               li += (uint32_t)BQ * 64 / 16;
             }
           }
-          mma_commit(bar_mma(n & 1));
-          if (k == K - 1) mma_commit(bar_full(buf));
+          if (leader) {
+            mma_commit(bar_mma(n & 1));
+            if (k == K - 1) mma_commit(bar_full(buf));
+          }
         }
         __syncwarp();
         TRACE(2, true);
@@ -921,6 +1012,14 @@ struct UmmaFwdPlan {
 static bool umma_enabled() {
   static const bool on = [] {
     const char* v = std::getenv("GCNB_UMMA");
+    return !(v && v[0] == '0');
+  }();
+  return on;
+}
+
+static bool stage_enabled() {
+  static const bool on = [] {
+    const char* v = std::getenv("GCNB_STAGE");
     return !(v && v[0] == '0');
   }();
   return on;
@@ -1216,6 +1315,10 @@ static int umma_launch(const float* x, const int32_t* perm, int M_in, const gcnb
     P.img_sig = img_signature(s, pl);
     P.n_groups = ge.ng;
     P.off_img = pl.off_img; P.off_grp = pl.off_img + (int)ge.grp_off; P.off_blk = pl.off_img + (int)ge.blk_off;
+    // bulk copies need 16-byte aligned windows; the staged tile lies inside one state buffer, clear of its zero row
+    const size_t wbytes = (size_t)M_in * s.Fin * 4;
+    P.stage = !adj && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (wbytes & 15) == 0 &&
+              (size_t)P.S * wbytes <= (size_t)s.p * pl.BQ * 128 && stage_enabled();
   }
 #ifdef GCNB_TRACE
   P.debug = std::getenv("GCNB_UMMA_DEBUG") ? std::atoi(std::getenv("GCNB_UMMA_DEBUG")) : 0;

@@ -46,3 +46,11 @@ for r in range(4):
         continue
     v = t[r][t[r] > 0] - t0
     print(names[r], len(v), " ".join(str(int(a)) for a in v[:64]))
+
+for ti in range(2):
+    w = t[3][64 + ti * 160:64 + ti * 160 + 160].reshape(20, 8)
+    if (w > 0).any():
+        base = w[w > 0].min()
+        print("order 0 of tile %d, per sparse warp: start, staged | item0 item1 done | (5) end, fenced, released (cycles from %d)" % (ti, int(base - t0)))
+        for sw in range(20):
+            print("  o0 sw%2d" % sw, " ".join("%6d" % (int(a - base) if a > 0 else -1) for a in w[sw]))
