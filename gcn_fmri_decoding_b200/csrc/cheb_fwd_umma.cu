@@ -599,13 +599,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
             }
           }
           TRACEW(0);
-          // Remainder (lo) stores of the first two items wait in registers until the end of the order: with a single
-          // remainder buffer they may only land once the tensor cores are done with order n-1, and that wait is
-          // invisible behind the whole sparse phase instead of sitting in front of the first item's stores.
-          uint2 pend[2][4];
-          uint32_t pend_lo[2] = {0u, 0u};  // lo address of row 0 of the pending item (0: nothing pending)
-          auto do_item = [&](int u, int ii, auto slot_tag) {
-            constexpr int SLOT = decltype(slot_tag)::value;  // 0, 1: may keep its lo stores pending; -1: never
+          // With a single remainder buffer the lo stores of this order must not land before the tensor cores are done
+          // with order n-1: since the MMAs of an order take ~400 cycles (issued right after the barrier) that wait is over
+          // long before the first item reaches its stores.
+          auto do_item = [&](int u, int ii) {
             const int g = ii / NS, s = ii - g * NS;
             const uint2 gr = lds64u(grp_tab + (uint32_t)g * 8u);  // (offset of the entry stream in the image, steps)
             const int beta = blk[g * 4 + q];
@@ -654,7 +651,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
             unpack2(c01[0], a0.x, a1.x); unpack2(c01[1], a0.y, a1.y); unpack2(c01[2], a0.z, a1.z); unpack2(c01[3], a0.w, a1.w);
             unpack2(c23[0], a2.x, a3.x); unpack2(c23[1], a2.y, a3.y); unpack2(c23[2], a2.z, a3.z); unpack2(c23[3], a2.w, a3.w);
             TRACEW(1 + u * 3);
-            if (SLOT < 0 && !lo_free) {
+            if (!lo_free) {
               mbar_wait(bar_mma((n - 1) & 1), ((n - 1) >> 1) & 1);
               lo_free = true;
             }
@@ -675,38 +672,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
                 const float rx = o.x - tf32_trunc(o.x), ry = o.y - tf32_trunc(o.y);
                 const float rz = o.z - tf32_trunc(o.z), rw = o.w - tf32_trunc(o.w);
                 const uint2 rem = make_uint2(pack_bf16(rx, ry), pack_bf16(rz, rw));
-                if (SLOT >= 0 && !lo_free) {
-                  pend[SLOT < 0 ? 0 : SLOT][i] = rem;
-                } else {
-                  sts64(dlo + lo_of(off), rem.x, rem.y);
-                }
+                sts64(dlo + lo_of(off), rem.x, rem.y);
                 if (spill && b < P.B) *reinterpret_cast<float4*>(spill + ((long long)b * M + vtx) * FP + fc * 4) = o;
               }
-              if (SLOT >= 0 && !lo_free) pend_lo[SLOT < 0 ? 0 : SLOT] = 1u + (uint32_t)beta + ((uint32_t)s << 16);
             }
             TRACEW(3 + u * 3);
           };
-          {
-            int u = 0, ii;
-            if ((ii = item_of(u)) < NI) { do_item(u, ii, std::integral_constant<int, 0>()); ++u; }
-            if (u == 1 && (ii = item_of(u)) < NI) { do_item(u, ii, std::integral_constant<int, 1>()); ++u; }
-            if (u == 2)
-              for (; (ii = item_of(u)) < NI; ++u) do_item(u, ii, std::integral_constant<int, -1>());
-          }
-          if (pend_lo[0] | pend_lo[1]) {  // (only set while the remainder buffer was still busy)
-            mbar_wait(bar_mma((n - 1) & 1), ((n - 1) >> 1) & 1);
-#pragma unroll
-            for (int sl = 0; sl < 2; ++sl) {
-              if (pend_lo[sl]) {
-                const int beta = (int)((pend_lo[sl] - 1u) & 0xffffu), s = (int)(pend_lo[sl] >> 16);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const uint32_t off = slab_off(row_of(beta * 4 + i, s), c);
-                  sts64(dlo + lo_of(off), pend[sl][i].x, pend[sl][i].y);
-                }
-              }
-            }
-          }
+          for (int u = 0, ii; (ii = item_of(u)) < NI; ++u) do_item(u, ii);
           TRACE(0, sw == 0);
           TRACEW(13);
           fence_async_smem();
