@@ -329,6 +329,9 @@ class TrainWorkload:
         self.h2d = per + B * 8
         self.d2h = 4
         self.nh = nh
+        # the ring slots are bound inputs: a step reads its batch in place (no copy into a static graph buffer)
+        for xb, yb in zip(self.ring_x, self.ring_y):
+            self.trainer.bind_inputs(xb, yb)
 
     def count_launches(self):
         tr = self.trainer
@@ -358,6 +361,8 @@ class TrainWorkload:
         self.pin_y = [torch.as_tensor(synth.labels(B, seed=i)).pin_memory() for i in range(4)]
         self.dbuf_x = [torch.empty(B, 360, 15, device=dev) for _ in range(2)]
         self.dbuf_y = [torch.empty(B, dtype=torch.long, device=dev) for _ in range(2)]
+        for s in range(2):  # what train.InputPipeline does with its slots
+            self.trainer.bind_inputs(self.dbuf_x[s], self.dbuf_y[s])
 
     def e2e_copy(self, i, s):
         self.dbuf_x[s].copy_(self.pin_x[i % 4], non_blocking=True)

@@ -147,13 +147,28 @@ def fit(model, train_data, train_labels, val_data=None, val_labels=None, trainer
     indices = collections.deque()
     losses, t0 = [], time.time()
     dev = model.dev
-    for step in range(1, num_steps + 1):
+    def draw():
         if len(indices) < model.batch_size:
             indices.extend(rng.permutation(n))
         idx = [indices.popleft() for _ in range(model.batch_size)]
-        x = torch.as_tensor(np.asarray(train_data[idx]), dtype=torch.float32, device=dev)
-        y = torch.as_tensor(np.asarray(train_labels[idx]), dtype=torch.long, device=dev)
-        loss, _ = trainer.step(x, y, dropout=model.dropout if model.dropout else 1.0)
+        return (np.ascontiguousarray(train_data[idx], dtype=np.float32), np.ascontiguousarray(train_labels[idx]).astype(np.int64))
+
+    # a FusedTrainer is fed through the asynchronous input pipeline: the copy of batch i+1 overlaps step i
+    pipe = None
+    if isinstance(trainer, FusedTrainer) and trainer.use_cuda_graph and torch.device(dev).type == "cuda":
+        pipe = InputPipeline(trainer, (model.batch_size,) + tuple(train_data.shape[1:]))
+        if num_steps > 0:
+            pipe.feed(*draw())
+    for step in range(1, num_steps + 1):
+        if pipe is not None:
+            if step < num_steps:
+                pipe.feed(*draw())
+            loss, _ = pipe.step()
+        else:
+            xb, yb = draw()
+            x = torch.as_tensor(xb, dtype=torch.float32, device=dev)
+            y = torch.as_tensor(yb, dtype=torch.long, device=dev)
+            loss, _ = trainer.step(x, y, dropout=model.dropout if model.dropout else 1.0)
         losses.append(float(loss))
         if verbose and (step % model.eval_frequency == 0 or step == num_steps):
             msg = "step %d / %d (epoch %.2f): loss %.4f" % (step, num_steps, step * model.batch_size / n, losses[-1])
@@ -245,7 +260,9 @@ class FusedTrainer:
         if self.distributed:
             dist.broadcast(self.flat_p, src=0)
         self.use_cuda_graph = use_cuda_graph
-        self._graphs = {}
+        self._graphs = {}   # (gradient-buffer parity, bound-input key or None) -> (graph, outputs)
+        self._bound = {}    # (x.data_ptr(), labels.data_ptr()) -> tensors registered by bind_inputs
+        self._sx = self._sl = None
         self._loss = torch.zeros((), dtype=torch.float32, device=dev)
 
     def _setup_peer_buffers(self, dev):
@@ -459,34 +476,123 @@ class FusedTrainer:
             self._par ^= 1                      # the next step writes the other gradient buffer
         if not self.use_cuda_graph:
             return self._step_impl(x, labels)
-        if par not in self._graphs:
-            if not self._graphs:
+        key = (x.data_ptr(), labels.data_ptr())
+        if key in self._bound and self._bound[key][0].shape == x.shape:
+            graph, out = self._graph_for(par, key, *self._bound[key])   # reads x / labels where they are: no copy
+        else:
+            if self._sx is None or self._sx.shape != x.shape:
                 self._sx, self._sl = torch.empty_like(x), torch.empty_like(labels)
-            self._sx.copy_(x)
-            self._sl.copy_(labels)
-            snap = [t.clone() for t in (self.flat_p, self.flat_m, self.flat_v, self.state)]
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                for _ in range(3):
-                    self._step_impl(self._sx, self._sl)
-                    if self._peer is not None:
-                        # warm-up steps reuse ONE gradient buffer back to back: let every peer finish reading it
-                        torch.cuda.synchronize()
-                        dist.barrier()
-            torch.cuda.current_stream().wait_stream(side)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                out = self._step_impl(self._sx, self._sl)
-            self._graphs[par] = (graph, out)
-            with torch.no_grad():
-                for t, s in zip((self.flat_p, self.flat_m, self.flat_v, self.state), snap):
-                    t.copy_(s)
-            if self._peer is not None:
-                torch.cuda.synchronize()
-                dist.barrier()
-        self._sx.copy_(x, non_blocking=True)
-        self._sl.copy_(labels, non_blocking=True)
-        graph, out = self._graphs[par]
+                self._graphs = {k: v for k, v in self._graphs.items() if k[1] is not None}
+            self._sx.copy_(x, non_blocking=True)
+            self._sl.copy_(labels, non_blocking=True)
+            graph, out = self._graph_for(par, None, self._sx, self._sl)
         graph.replay()
+        return out
+
+    def bind_inputs(self, x, labels):
+        """Register device tensors the caller refills IN PLACE (slots of an input ring): ``step(x, labels)`` on them
+        replays a graph that reads them where they are, without the copy into the trainer's own static buffer
+        (11 MB device-to-device per step at B = 512).  The tensors are kept alive by the trainer.  With data
+        parallelism every rank must bind the same number of inputs in the same order (capturing runs collectives)."""
+        if not self.use_cuda_graph:
+            return
+        key = (x.data_ptr(), labels.data_ptr())
+        self._bound[key] = (x, labels)
+        for par in range(len(self._gbufs)):
+            self._graph_for(par, key, x, labels)
+
+    def _graph_for(self, par, key, x, labels):
+        """The captured step of gradient-buffer parity ``par`` reading ``x`` / ``labels`` (captured on first use:
+        three eager warm-up steps on a side stream, then the capture; optimiser state restored afterwards)."""
+        if (par, key) in self._graphs:
+            return self._graphs[(par, key)]
+        keep = (self.flat_g, self.gview)
+        self.flat_g, self.gview = self._gbufs[par], self._gviews[par]
+        snap = [t.clone() for t in (self.flat_p, self.flat_m, self.flat_v, self.state)]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                self._step_impl(x, labels)
+                if self._peer is not None:
+                    # warm-up steps reuse ONE gradient buffer back to back: let every peer finish reading it
+                    torch.cuda.synchronize()
+                    dist.barrier()
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = self._step_impl(x, labels)
+        self._graphs[(par, key)] = (graph, out)
+        with torch.no_grad():
+            for t, q in zip((self.flat_p, self.flat_m, self.flat_v, self.state), snap):
+                t.copy_(q)
+        if self._peer is not None:
+            torch.cuda.synchronize()
+            dist.barrier()
+        self.flat_g, self.gview = keep
+        return self._graphs[(par, key)]
+
+
+class InputPipeline:
+    """Asynchronous input feed of a ``FusedTrainer`` (the reference feeds ``feed_dict`` copies,
+    models_gcn.py:142-146): batches go from (pinned) host memory to ``depth`` device slots on a copy stream while the
+    previous step runs; the slots are bound to the trainer, so a step reads its batch in place.
+
+        pipe = InputPipeline(trainer, (B, n_vertices, channel))
+        pipe.feed(x0, y0)
+        for x, y in batches:          # host arrays / tensors
+            pipe.feed(x, y)           # H2D of the NEXT batch overlaps ...
+            loss, logits = pipe.step()  # ... the step on the previous one
+    """
+
+    def __init__(self, trainer, x_shape, depth=2, label_dtype=torch.long):
+        dev = trainer.flat_p.device
+        self.trainer, self.depth = trainer, depth
+        self.dx = [torch.empty(*x_shape, dtype=torch.float32, device=dev) for _ in range(depth)]
+        self.dy = [torch.empty(x_shape[0], dtype=label_dtype, device=dev) for _ in range(depth)]
+        self.hx = [torch.empty(*x_shape, dtype=torch.float32).pin_memory() for _ in range(depth)]
+        self.hy = [torch.empty(x_shape[0], dtype=label_dtype).pin_memory() for _ in range(depth)]
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.ready = [torch.cuda.Event() for _ in range(depth)]    # slot filled
+        self.freed = [torch.cuda.Event() for _ in range(depth)]    # slot consumed by its step
+        self.staged = [torch.cuda.Event() for _ in range(depth)]   # pinned staging buffer of the slot copied out
+        for s in range(depth):
+            trainer.bind_inputs(self.dx[s], self.dy[s])
+            self.freed[s].record(torch.cuda.current_stream())
+            self.staged[s].record(self.copy_stream)
+        self._head = self._tail = 0   # slots fed / stepped so far
+
+    def feed(self, x, labels):
+        """Queue one batch: asynchronous copy into the next free slot (pageable inputs are staged through a pinned
+        buffer of the slot first)."""
+        if self._head - self._tail >= self.depth:
+            raise RuntimeError("InputPipeline: all %d slots are full -- call step() first" % self.depth)
+        s = self._head % self.depth
+        x, labels = torch.as_tensor(x), torch.as_tensor(labels)
+        if not (x.is_cuda or x.is_pinned()):
+            self.staged[s].synchronize()
+            self.hx[s].copy_(x)
+            x = self.hx[s]
+        if not (labels.is_cuda or labels.is_pinned()):
+            self.staged[s].synchronize()
+            self.hy[s].copy_(labels)
+            labels = self.hy[s]
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.freed[s])
+            self.dx[s].copy_(x, non_blocking=True)
+            self.dy[s].copy_(labels, non_blocking=True)
+            self.staged[s].record(self.copy_stream)
+            self.ready[s].record(self.copy_stream)
+        self._head += 1
+
+    def step(self):
+        """Run the training step on the oldest queued batch; returns what ``FusedTrainer.step`` returns."""
+        if self._tail >= self._head:
+            raise RuntimeError("InputPipeline: nothing queued -- call feed() first")
+        s = self._tail % self.depth
+        main = torch.cuda.current_stream()
+        main.wait_event(self.ready[s])
+        out = self.trainer.step(self.dx[s], self.dy[s])
+        self.freed[s].record(main)
+        self._tail += 1
         return out

@@ -634,18 +634,20 @@ def test_full_size_properties(dev, graph_l4):
             assert float((other - ys[0]).abs().max()) <= 1e-4 * float(ys[0].abs().max())
 
 
-@pytest.mark.parametrize("B", [3, 4])
-def test_large_graph_general_path(dev, B):
-    """Vertex-level graph (config 5 family, scaled down): HBM-resident operator, K=25.  B=4 makes the vertex-major
-    rows 16-byte multiples (TMA-staged SpMM) and leaves ragged last tiles in the tensor-core contractions."""
+@pytest.mark.parametrize("n,B", [(3000, 3), (3000, 4), (32492, 8)])
+def test_large_graph_general_path(dev, n, B):
+    """Vertex-level graph (config 5 family): HBM-resident operator, K=25.  B=4 makes the vertex-major rows 16-byte
+    multiples (TMA-staged SpMM) and leaves ragged last tiles in the tensor-core contractions; (32492, 8) is BASELINE
+    config 5's own graph size (the sphere kNN graph bench.py --config 5 runs on) at a batch the fp64 oracle finishes
+    in seconds -- forward and backward (dx, dW, db)."""
     from gcn_fmri_decoding_b200 import synth
 
-    L = synth.fibonacci_sphere_graph(3000, 6)
+    L = synth.fibonacci_sphere_graph(n, 6)
     rng = np.random.RandomState(9)
-    x = rng.randn(B, 3000, 15).astype(np.float32)
+    x = rng.randn(B, n, 15).astype(np.float32)
     W = (rng.randn(15 * 25, 32) * 0.05).astype(np.float32)
     b = np.full(32, 0.2, np.float32)
-    dy = rng.randn(B, 3000, 32).astype(np.float32)
+    dy = rng.randn(B, n, 32).astype(np.float32)
     pr = [dict(W=W, b=b, K=25, p=1)]
     y64, tr = O.conv_stack(x, [L], pr, dtype=np.float64, keep=True)
     # A pre-activation within fp32 rounding of zero makes the ReLU mask (hence the gradient routed through that one
@@ -847,3 +849,34 @@ def test_operator_image_kernels_match_the_self_built_ones(dev, graph_l4, lvl, B,
         assert np.array_equal(outs[0][key], outs[1][key]), key
     y64, tr = O.conv_stack(x, [L], [dict(W=W, b=b, K=K, p=p)], brelu=brelu, dtype=np.float64, keep=True)
     assert rel_inf(outs[0]["y"], y64) <= TOL
+
+
+def test_input_pipeline_and_bound_inputs_equal_plain_steps(dev, graph_l4):
+    """train.InputPipeline (pinned host -> device slots on a copy stream, slots bound with FusedTrainer.bind_inputs so the
+    captured step reads them in place) must train exactly like plain step() calls on device tensors: same kernels, same
+    dropout stream, deterministic reductions -> bit-identical losses and parameters."""
+    from gcn_fmri_decoding_b200 import synth
+    from gcn_fmri_decoding_b200.train import FusedTrainer, InputPipeline
+
+    g = graph_l4
+    B, steps = 16, 5
+    xs = [synth.bold_windows(B, seed=40 + i) for i in range(steps)]
+    ys = [synth.labels(B, seed=40 + i) for i in range(steps)]
+
+    def make():
+        model = build_model(g, [32, 32], [5, 5], [4, 4], [512, 256, 22], "chebyshev5", "b1relu", dev, perm=g["perm"])
+        return FusedTrainer(model, distributed=False, use_cuda_graph=True, dropout=0.5, dropout_seed=77)
+
+    plain, piped = make(), make()
+    ref = [float(plain.step(T(x, dev), T(y, dev, torch.long))[0]) for x, y in zip(xs, ys)]
+    pipe = InputPipeline(piped, (B, 360, 15))
+    got = []
+    pipe.feed(xs[0], ys[0])
+    for i in range(steps):
+        if i + 1 < steps:
+            pipe.feed(xs[i + 1], ys[i + 1])      # the copy of the next batch overlaps this step
+        got.append(float(pipe.step()[0]))         # (the returned tensors are the graph's static outputs: read them now)
+    assert got == ref
+    assert torch.equal(plain.flat_p, piped.flat_p)
+    with pytest.raises(RuntimeError):
+        pipe.step()                               # nothing queued
