@@ -33,7 +33,10 @@ for r in rows:
         cur["rows"].append(r)
 stalls = ["stall_barrier", "stall_long_sb", "stall_short_sb", "stall_mio", "stall_wait", "stall_math", "stall_lg",
           "stall_not_selected", "stall_selected", "stall_dispatch", "stall_branch_resolving", "stall_no_inst", "stall_membar"]
+seen = set()
 for kq in kern:
+    if not kq["rows"] or "Address" not in kq["rows"][0]:
+        continue  # the source page repeats each kernel's marker row: keep the block that carries the table
     h = kq["rows"][0]
     ia, isrc, iex, ismp = h.index("Address"), h.index("Source"), h.index("Instructions Executed"), h.index("# Samples")
     data = []
