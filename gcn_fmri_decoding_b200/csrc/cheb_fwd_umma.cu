@@ -168,46 +168,67 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
     mbar_init(bar_stage, 1);
     mbar_init_fence();
   }
+  if constexpr (IMG) {
+    // the operator image was built once on the host (gcnb_cheb_image_build): ONE TMA bulk copy brings it in as it is
+    // while the rest of the prologue runs (first phase of the staging barrier)
+    if (tid == 0) {
+      mbar_expect_tx(bar_stage, (uint32_t)P.img_bytes);
+      bulk_g2s(sb + P.off_img, P.image, (uint32_t)P.img_bytes, bar_stage);
+    }
+  }
   if (warp == kMmaWarp) tmem_alloc(sb + P.off_bar + 48, (uint32_t)P.tmem_cols);
-  // zero the state buffers: the zero row behind every buffer and the padding rows of the blocks stay zero (the
-  // remainder buffers need no initialisation -- garbage there only reaches accumulator rows nobody reads -- and
-  // host the prologue's scratch tables rlen / sorted / rp until the first order overwrites them)
-  for (uint32_t a = tid * 16u; a < (uint32_t)P.off_lo; a += kThreads * 16u) sts128(sb + a, make_float4(0.f, 0.f, 0.f, 0.f));
-  // taps: tf32 hi / lo and bf16 images, contraction index kk = k*FP + f  (W row = f*K + k, models_gcn.py:611-615)
-  for (int i0 = 0; i0 < K * FP * 32; i0 += kThreads * 4) {
-    float wv[4];
+  // taps: tf32 hi / lo and bf16 images, contraction index kk = k*FP + f  (W row = f*K + k, models_gcn.py:611-615).
+  // The global loads of the first batch (and of the permutation / bias) are in flight while the state buffers are zeroed.
+  // element idx -> (filter o, contraction index kk): the 32 lanes of a warp cover (o & 7) x (kk & 3), i.e. all 32 banks of
+  // the tap images (the natural order, lane = filter, stores with 4-way bank conflicts)
+  auto tap_o = [](int idx) { return (idx & 7) | (((idx >> 5) & 3) << 3); };
+  auto tap_kk = [](int idx) { return ((idx >> 3) & 3) | ((idx >> 7) << 2); };
+  auto tap_load = [&](int i0, float (&wv)[4]) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {  // all four loads in flight before the first conversion
+    for (int u = 0; u < 4; ++u) {
       const int idx = i0 + u * kThreads + tid;
-      const int o = idx & 31, kk = idx >> 5, k = kk / FP, f = kk - k * FP;
+      const int o = tap_o(idx), kk = tap_kk(idx), k = kk / FP, f = kk - k * FP;
       wv[u] = (idx < K * FP * 32 && f < P.Fin && o < P.Fout)
                   ? __ldg(P.W + (P.adj ? ((long long)o * K + k) * P.Fin + f : ((long long)f * K + k) * P.Fout + o))
                   : 0.f;
     }
+  };
+  auto tap_store = [&](int i0, const float (&wv)[4]) {
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int idx = i0 + u * kThreads + tid;
       if (idx < K * FP * 32) {
-        const int o = idx & 31, kk = idx >> 5;
+        const int o = tap_o(idx), kk = tap_kk(idx);
         const float w = wv[u], hi = tf32_rna(w), lo = tf32_rna(w - hi);
         *reinterpret_cast<float*>(smem + P.off_wh + tap_off_tf32(kk, o)) = hi;
         *reinterpret_cast<float*>(smem + P.off_wl + tap_off_tf32(kk, o)) = lo;
         *reinterpret_cast<__nv_bfloat16*>(smem + P.off_wb + tap_off_bf16(kk, o)) = __float2bfloat16_rn(w);
       }
     }
+  };
+  float wv0[4];
+  tap_load(0, wv0);
+  int perm0 = tid;
+  if (P.perm && tid < M) perm0 = __ldg(P.perm + tid);
+  const float bias0 = (tid < 32 && P.bias_mode == GCNB_BIAS_PER_FILTER && tid < P.Fout) ? __ldg(P.bias + tid) : 0.f;
+  // zero the state buffers: the zero row behind every buffer and the padding rows of the blocks stay zero (the
+  // remainder buffers need no initialisation -- garbage there only reaches accumulator rows nobody reads -- and
+  // host the prologue's scratch tables rlen / sorted / rp until the first order overwrites them)
+  for (uint32_t a = tid * 16u; a < (uint32_t)P.off_lo; a += kThreads * 16u) sts128(sb + a, make_float4(0.f, 0.f, 0.f, 0.f));
+  tap_store(0, wv0);
+  for (int i0 = kThreads * 4; i0 < K * FP * 32; i0 += kThreads * 4) {
+    float wv[4];
+    tap_load(i0, wv);
+    tap_store(i0, wv);
   }
   for (int r = tid; r < M; r += kThreads) {
-    int s = r;
-    if (P.perm) { s = __ldg(P.perm + r); if (s < 0 || s >= P.M_in) s = -1; }
+    int s = r == tid ? perm0 : r;
+    if (P.perm) { if (r != tid) s = __ldg(P.perm + r); if (s < 0 || s >= P.M_in) s = -1; }
     src_row[r] = s;
   }
-  if (tid < 32) bias_s[tid] = (P.bias_mode == GCNB_BIAS_PER_FILTER && tid < P.Fout) ? __ldg(P.bias + tid) : 0.f;
+  if (tid < 32) bias_s[tid] = bias0;
   if constexpr (IMG) {
-    // the operator image was built once on the host (gcnb_cheb_image_build): copy it as it is
-    const uint4* gi = reinterpret_cast<const uint4*>(P.image);
-    for (int i = tid; i < (P.img_bytes >> 4); i += kThreads)
-      *reinterpret_cast<uint4*>(smem + P.off_img + (size_t)i * 16) = __ldg(gi + i);
-    __syncthreads();
+    mbar_wait(bar_stage, 0);  // the image has landed
     const uint32_t* hdr = reinterpret_cast<const uint32_t*>(smem + P.off_img);
     if (hdr[0] != kImgMagic || hdr[1] != P.img_sig || hdr[2] != (uint32_t)P.img_bytes) __trap();  // image of another geometry
   } else {
@@ -492,7 +513,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
       auto item_of = [sw](int u) { return u * kSparseWarps + ((u & 1) ? kSparseWarps - 1 - sw : sw); };
       auto row_of = [=](int vtx, int s) { return (vtx & pm1) * BQ + s * Q + (vtx >> log2p); };
       uint32_t n = 0;  // orders issued so far (all tiles)
-      uint32_t stage_phase = 0;
+      uint32_t stage_phase = 1;  // phase 0 of the staging barrier brought the operator image in
       int base = 0;
       TRACE(0, sw == 0);
       for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {

@@ -255,6 +255,11 @@ class cgcnn(nn.Module):
 
     def forward(self, x, dropout=1.0, gather=None):
         if gather is None:
+            # raw [B, n_input_vertices, C] windows are permuted in the first layer's load; already permuted / padded
+            # [B, M_0, C] input is not.  The two cannot be told apart by shape when coarsening added no fake vertices.
+            if self.perm is not None and self.n_input_vertices == self.L[0].shape[0]:
+                raise ValueError("cgcnn.forward: with perm set and n_input_vertices == M_0 say gather=True (raw windows) "
+                                 "or gather=False (already permuted) -- the shapes are identical")
             gather = self.perm is not None and x.shape[1] == self.n_input_vertices != self.L[0].shape[0]
         return self._inference(x, dropout, gather)
 
