@@ -880,3 +880,62 @@ def test_input_pipeline_and_bound_inputs_equal_plain_steps(dev, graph_l4):
     assert torch.equal(plain.flat_p, piped.flat_p)
     with pytest.raises(RuntimeError):
         pipe.step()                               # nothing queued
+
+
+def _random_tcgen05_cases(n=14, seed=2026):
+    rng = np.random.RandomState(seed)
+    cases = []
+    while len(cases) < n:
+        lvl = int(rng.randint(0, 4))                    # M = 400, 200, 100, 50
+        p = int(rng.choice([1, 2, 4, 8]))
+        Fin, Fout = int(rng.randint(9, 33)), int(4 * rng.randint(1, 9))
+        K, B = int(rng.randint(1, 8)), int(rng.choice([1, 2, 5, 37, 130]))
+        brelu = str(rng.choice(["b1relu", "b2relu"]))
+        M = 400 >> lvl
+        if M % p:
+            continue
+        cases.append((lvl, B, Fin, Fout, K, p, brelu))
+    return cases
+
+
+@pytest.mark.parametrize("lvl,B,Fin,Fout,K,p,brelu", _random_tcgen05_cases())
+def test_layer_random_shapes(dev, graph_l4, lvl, B, Fin, Fout, K, p, brelu):
+    """Seeded random layer shapes around the tcgen05 kernel's domain (9 <= Fin <= 32, Fout a multiple of 4, any K, p in
+    {1,2,4,8}, ragged batches): forward (y, arg-max) and backward (dx through the adjoint mode, dW/db from the saved
+    basis) against the fp64 oracle, with and without the host-built operator image where the shape has one."""
+    from gcn_fmri_decoding_b200 import _lib, plan
+
+    L = graph_l4["L"][lvl]
+    M = L.shape[0]
+    rng = np.random.RandomState(1000 * lvl + 10 * B + K)
+    x = rng.randn(B, M, Fin).astype(np.float32)
+    W = (rng.randn(Fin * K, Fout) * (0.4 / np.sqrt(Fin * K))).astype(np.float32)
+    b = (rng.randn(Fout) * 0.1).astype(np.float32) if brelu == "b1relu" else (rng.randn(M, Fout) * 0.1).astype(np.float32)
+    dy = rng.randn(B, M // p, Fout).astype(np.float32)
+    pr = [dict(W=W, b=b, K=K, p=p)]
+    y64, tr = O.conv_stack(x, [L], pr, brelu=brelu, dtype=np.float64, keep=True)
+    # elements whose ReLU / pooling decision sits within fp32 rounding of a tie are coin tosses (see
+    # test_large_graph_general_path): take them out of dy
+    a64 = tr[0]["a"]
+    pre = tr[0]["z"] + b                                     # pre-activation; max-pool(relu(.)) = relu(max(.))
+    win = np.sort(pre.reshape(B, M // p, p, Fout), axis=2)
+    eps = 1e-5 * np.abs(pre).max()
+    tie = np.abs(win[:, :, -1]) < eps                        # the ReLU of the window maximum
+    if p > 1:
+        tie |= ((win[:, :, -1] - win[:, :, -2]) < eps) & (win[:, :, -1] > -eps)   # which vertex is the maximum
+    dy[tie] = 0.0
+    dx64, g64 = O.conv_stack_bwd(tr, [L], pr, dy, brelu=brelu, dtype=np.float64, first_needs_dx=True)
+    # (AUTO dispatch: all but the shapes whose tables do not fit beside two state buffers run k_cheb_fwd_umma)
+    for use_images in (True, False):
+        old = plan.USE_IMAGES
+        plan.USE_IMAGES = use_images
+        try:
+            r = run_layer(dev, L, x, W, b, K, p, brelu, _lib.ALGO_AUTO, dy=dy)
+        finally:
+            plan.USE_IMAGES = old
+        tag = "images=%s" % use_images
+        assert rel_inf(r["y"], y64) <= TOL, tag
+        check_argmax(r["argmax"], a64, p, tag) if p > 1 else None
+        assert rel_inf(r["dW"], g64[0]["dW"]) <= TOL, tag
+        assert rel_inf(r["db"], g64[0]["db"]) <= TOL, tag
+        assert rel_inf(r["dx"], dx64) <= TOL, tag
