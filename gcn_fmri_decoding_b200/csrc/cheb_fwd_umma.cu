@@ -38,6 +38,7 @@ static constexpr int kMmaWarp = 4;    // warp 4
 static constexpr int kThreads = (kSparseWarps + kEpiWarps + 1) * 32;
 static_assert(kSparseWarps % 4 == 0, "the tail epilogue deals the sparse warps to the four TMEM lane quarters");
 static constexpr uint32_t kImgMagic = 0x494e4347u;  // "GCNI"
+static constexpr uint32_t kImgPair = 144;            // bytes of one pair of steps in the entry stream of an operator image
 static constexpr int kBarOrder = 1;   // named barrier: sparse warps + MMA warp, once per Chebyshev order
 
 #ifdef GCNB_TRACE
@@ -628,7 +629,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
             const uint2 gr = lds64u(grp_tab + (uint32_t)g * 8u);  // (offset of the entry stream in the image, steps)
             const int beta = blk[g * 4 + q];
             const uint32_t srcs = srcb + ((uint32_t)(s * Q) << 7);  // window-slab offset keeps the swizzle phase
-            uint32_t wa = img0 + gr.x + (uint32_t)q * 16u, ca = img0 + gr.x + 128u + (uint32_t)q * 8u;
+            uint32_t wa = img0 + gr.x + (uint32_t)q * 16u, ca = img0 + gr.x + 128u + (uint32_t)q * 4u;
             // accumulators packed by PAIRS OF ROWS: c01[f] = (row 0, row 1) of feature f, c23[f] = (row 2, row 3).  One
             // fma.rn.f32x2 (two IEEE fp32 FMAs, bit-identical to fmaf) multiplies the weight pair of two rows -- adjacent
             // words of the entry stream -- by a duplicated gathered value: 12 issue slots per gathered row instead of 16
@@ -640,15 +641,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
 #endif
             // software pipeline: the codes and weights of the next pair of steps are in flight while this pair's two
             // gathers return (the read past the last pair of a group stays inside the image / the tables behind it)
-            uint2 cc = lds64u(ca);
+            uint32_t cc = lds32u(ca);  // two 16-bit row codes: (row * 8 + (row & 7)) << 4 is the gather code
             float4 w0 = lds128(wa), w1 = lds128(wa + 64u);
 #pragma unroll 1
             for (int j = 0; j < steps; j += 2) {
-              const float4 v0 = lds128(srcs + (cc.x ^ c16));
-              const float4 v1 = lds128(srcs + (cc.y ^ c16));
-              wa += 160u;
-              ca += 160u;
-              const uint2 ccn = lds64u(ca);
+              const float4 v0 = lds128(srcs + (((cc & 0xffffu) << 4) ^ c16));
+              const float4 v1 = lds128(srcs + (((cc >> 12) & 0xffff0u) ^ c16));
+              wa += kImgPair;
+              ca += kImgPair;
+              const uint32_t ccn = lds32u(ca);
               const float4 w0n = lds128(wa), w1n = lds128(wa + 64u);
               {
                 const uint64_t wl = pack2(w0.x, w0.y), wh = pack2(w0.z, w0.w);
@@ -978,8 +979,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
 //   [0, 64)    header: magic, signature, bytes, groups
 //   grp_off    groups x {u32 offset of the entry stream, u32 steps (even)}
 //   blk_off    groups x 4 x u16 block index (0xffff: no block in this quarter)
-//   ent_off    per group, per pair of steps (160 B): weights of step j for the 4 quarters (4 x 16 B), of step j+1
-//              (4 x 16 B), gather codes of (j, j+1) for the 4 quarters (4 x 8 B).  Padding steps gather the zero row.
+//   ent_off    per group, per pair of steps (144 B): weights of step j for the 4 quarters (4 x 16 B), of step j+1
+//              (4 x 16 B), 16-bit row codes of (j, j+1) for the 4 quarters (4 x 4 B); code = row * 8 + (row & 7), i.e. the
+//              gather code (row * 128 + swizzle phase) >> 4.  Padding steps gather the zero row.
 struct ImgGeom {
   int nb, ng;
   size_t grp_off, blk_off, ent_off;
@@ -1107,7 +1109,7 @@ static void plan_device(DeviceInfo* di) {
 // what an image must agree on with the kernel that reads it
 static unsigned img_signature(const LayerShape& s, const UmmaFwdPlan& pl) {
   unsigned h = 2166136261u;
-  const int v[] = {2 /*layout version*/, s.M, s.nnz, s.p, pl.FP, pl.NS, pl.Q, pl.BQ, pl.NG, (int)pl.img_bytes, kSparseWarps};
+  const int v[] = {3 /*layout version*/, s.M, s.nnz, s.p, pl.FP, pl.NS, pl.Q, pl.BQ, pl.NG, (int)pl.img_bytes, kSparseWarps};
   for (int x : v) {
     h ^= (unsigned)x;
     h *= 16777619u;
@@ -1190,7 +1192,7 @@ size_t cheb_image_bytes(const int32_t* rowptr, const int32_t* col, const LayerSh
   std::vector<int> order, steps;
   group_blocks(bl, &order, &steps);
   long long ent = 0;
-  for (int st : steps) ent += (long long)(st / 2) * 160;
+  for (int st : steps) ent += (long long)(st / 2) * kImgPair;
   DeviceInfo di;
   plan_device(&di);
   const UmmaFwdPlan pl = plan_umma_fwd(s, di.sm_count, di.smem_optin, ent);
@@ -1207,7 +1209,7 @@ int cheb_image_build(const int32_t* rowptr, const int32_t* col, const float* val
   std::vector<int> order, steps;
   group_blocks(bl, &order, &steps);
   long long ent = 0;
-  for (int st : steps) ent += (long long)(st / 2) * 160;
+  for (int st : steps) ent += (long long)(st / 2) * kImgPair;
   DeviceInfo di;
   plan_device(&di);
   const UmmaFwdPlan pl = plan_umma_fwd(s, di.sm_count, di.smem_optin, ent);
@@ -1225,19 +1227,20 @@ int cheb_image_build(const int32_t* rowptr, const int32_t* col, const float* val
   uint16_t* blk = reinterpret_cast<uint16_t*>(img + ge.blk_off);
   int log2p = 0;
   while ((1 << log2p) < s.p) ++log2p;
-  auto code_of = [&](int v) { return gather_code((v & (s.p - 1)) * pl.BQ + (v >> log2p)); };
-  const uint32_t zero_code = gather_code(s.p * pl.BQ);
+  auto code16 = [](int row) { return (uint16_t)(gather_code(row) >> 4); };  // rows < 2048 (256 KB of descriptors)
+  auto code_of = [&](int v) { return code16((v & (s.p - 1)) * pl.BQ + (v >> log2p)); };
+  const uint16_t zero_code = code16(s.p * pl.BQ);
   size_t at = ge.ent_off;
   for (int g = 0; g < ge.ng; ++g) {
     grp[g * 2] = (uint32_t)at;
     grp[g * 2 + 1] = (uint32_t)steps[g];
     for (int q = 0; q < 4; ++q) blk[g * 4 + q] = g * 4 + q < ge.nb ? (uint16_t)order[g * 4 + q] : (uint16_t)0xffff;
     for (int j = 0; j < steps[g]; ++j) {
-      unsigned char* pair = img + at + (size_t)(j / 2) * 160;
+      unsigned char* pair = img + at + (size_t)(j / 2) * kImgPair;
       float* w = reinterpret_cast<float*>(pair + (j & 1) * 64);
-      uint32_t* codes = reinterpret_cast<uint32_t*>(pair + 128);
+      uint16_t* codes = reinterpret_cast<uint16_t*>(pair + 128);
       for (int q = 0; q < 4; ++q) {
-        uint32_t code = zero_code;
+        uint16_t code = zero_code;
         if (g * 4 + q < ge.nb) {
           const BlockList& b = bl[order[g * 4 + q]];
           if (j < (int)b.cols.size()) {
@@ -1248,7 +1251,7 @@ int cheb_image_build(const int32_t* rowptr, const int32_t* col, const float* val
         codes[q * 2 + (j & 1)] = code;
       }
     }
-    at += (size_t)(steps[g] / 2) * 160;
+    at += (size_t)(steps[g] / 2) * kImgPair;
   }
   return GCNB_OK;
 }

@@ -190,6 +190,11 @@ __device__ __forceinline__ uint2 lds64u(uint32_t a) {
   asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
   return v;
 }
+__device__ __forceinline__ uint32_t lds32u(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
 __device__ __forceinline__ void sts128(uint32_t a, float4 v) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }

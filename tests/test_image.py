@@ -18,9 +18,9 @@ def _decode(img, M, p_eff):
     for g in range(ng):
         off, steps = int(grp[g, 0]), int(grp[g, 1])
         for t in range(steps // 2):
-            pair = img[off + t * 160:off + (t + 1) * 160]
-            pairs.append((g, pair[:128].view(np.float32).reshape(2, 4, 4), pair[128:160].view(np.uint32).reshape(4, 2)))
-    zero_row = max(int(c.max()) for _, _, c in pairs) >> 7  # the zero row is the last row of a state buffer
+            pair = img[off + t * 144:off + (t + 1) * 144]
+            pairs.append((g, pair[:128].view(np.float32).reshape(2, 4, 4), pair[128:144].view(np.uint16).reshape(4, 2)))
+    zero_row = max(int(c.max()) for _, _, c in pairs) >> 3  # the zero row is the last row of a state buffer
     BQ, log2p = zero_row // p_eff, int(np.log2(p_eff))
     row2v = {(v & (p_eff - 1)) * BQ + (v >> log2p): v for v in range(M)}
     dense = np.zeros((M, M), np.float32)
@@ -28,9 +28,9 @@ def _decode(img, M, p_eff):
         for q in range(4):
             beta = int(blk[g, q])
             for jj in range(2):
-                code = int(codes[q, jj])
-                row = code >> 7
-                assert (code >> 4) & 7 == row & 7 and code & 15 == 0  # SWIZZLE_128B phase of the gathered row
+                code = int(codes[q, jj])                             # 16-bit row code = gather code >> 4
+                row = code >> 3
+                assert code & 7 == row & 7                           # SWIZZLE_128B phase of the gathered row
                 if row == zero_row:
                     assert not w[jj, q].any()
                     continue

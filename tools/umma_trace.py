@@ -16,14 +16,26 @@ if which == "f1":
     x = torch.randn(512, 360, 15, device=dev)
     W = torch.randn(75, 32, device=dev) * .2
     pt = torch.as_tensor(perm, dtype=torch.int32, device=dev)
-else:
+elif which == "f2":
     pl = GraphPlan(L[2], dev)
     x = torch.randn(512, 100, 32, device=dev)
     W = torch.randn(160, 32, device=dev) * .2
     pt = None
-b = torch.full((32,), .2, device=dev)
-for _ in range(3):
-    ops.cheb_fwd(x, pt, *pl.tensors(), W, b, 5, 4, 1, True, True, 0)
+else:  # "c1": a middle layer of the config-1 network (M=372, 32->32, p=1, b2relu, B=128, inference: no basis kept)
+    A1, gs1, perm1, L1 = synth.brain_graph(1)
+    pl = GraphPlan(L1[0], dev)
+    x = torch.randn(128, 372, 32, device=dev)
+    W = torch.randn(160, 32, device=dev) * .2
+    pt = None
+if which == "c1":
+    b = torch.full((372, 32), .2, device=dev)
+    print(_lib.describe_fwd(128, 372, pl.nnz, 32, 32, 5, 1))
+    for _ in range(3):
+        ops.cheb_fwd(x, pt, *pl.tensors(), W, b, 5, 1, 2, True, False, 0)
+else:
+    b = torch.full((32,), .2, device=dev)
+    for _ in range(3):
+        ops.cheb_fwd(x, pt, *pl.tensors(), W, b, 5, 4, 1, True, True, 0)
 torch.cuda.synchronize()
 lib = _lib.lib()
 lib._handle if False else None
