@@ -286,6 +286,30 @@ int gcnb_cheb_fwd_f32(const float* x, const int32_t* perm, int M_in, const gcnb_
   return rc;
 }
 
+int gcnb_cheb_stack_supported(const gcnb_csr* L, int B, int F, int K, int nlayers) {
+  if (!L || B < 1 || K < 1 || nlayers < 1 || nlayers > 8 || L->M < 1) return 0;
+  return umma_stack_supported(LayerShape{B, L->M, L->nnz, F, F, K, 1}, *L) ? 1 : 0;
+}
+
+int gcnb_cheb_stack_fwd_f32(const float* x, const gcnb_csr* L, const float* const* W, const float* const* bias, float* y,
+                            int nlayers, int B, int F, int K, int bias_mode, int relu, gcnb_stream_t stream) {
+  GCNB_REQUIRE(nlayers >= 1 && nlayers <= 8 && W != nullptr, "gcnb_cheb_stack_fwd_f32: 1..8 layers, W must not be NULL");
+  int rc = check_layer("gcnb_cheb_stack_fwd_f32", L, B, F, F, K, 1, bias_mode,
+                       bias_mode == GCNB_BIAS_NONE ? reinterpret_cast<const float*>(1) : (bias ? bias[0] : nullptr));
+  if (rc) return rc;
+  GCNB_REQUIRE(x && y, "gcnb_cheb_stack_fwd_f32: x and y must not be NULL");
+  for (int l = 0; l < nlayers; ++l)
+    GCNB_REQUIRE(W[l] != nullptr && (bias_mode == GCNB_BIAS_NONE || (bias && bias[l] != nullptr)),
+                 "gcnb_cheb_stack_fwd_f32: W / bias of layer %d is NULL", l);
+  LayerShape s{B, L->M, L->nnz, F, F, K, 1};
+  if (!umma_stack_supported(s, *L)) {
+    set_error("gcnb_cheb_stack_fwd_f32: needs F = 32, M %% 4 = 0 and the operator image of this layer shape in L->image "
+              "(gcnb_cheb_image_build); got F=%d M=%d image=%s", F, L->M, L->image ? "yes" : "none");
+    return GCNB_ERR_INVALID;
+  }
+  return umma_cheb_stack_fwd(x, *L, W, bias, y, nlayers, s, bias_mode, relu, static_cast<cudaStream_t>(stream));
+}
+
 size_t gcnb_cheb_image_bytes(const int32_t* rowptr, const int32_t* col, int B, int M, int nnz, int Fin, int Fout, int K,
                              int p, int adjoint) {
   if (!rowptr || !col || B < 1 || M < 1 || nnz < 0 || Fin < 1 || Fout < 1 || K < 1 || p < 1) return 0;

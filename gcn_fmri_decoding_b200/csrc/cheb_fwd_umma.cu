@@ -40,6 +40,7 @@ static_assert(kSparseWarps % 4 == 0, "the tail epilogue deals the sparse warps t
 static constexpr uint32_t kImgMagic = 0x494e4347u;  // "GCNI"
 static constexpr uint32_t kImgPair = 144;            // bytes of one pair of steps in the entry stream of an operator image
 static constexpr int kBarOrder = 1;   // named barrier: sparse warps + MMA warp, once per Chebyshev order
+static constexpr int kBarLayer = 2;   // named barrier: all warps, between two layers of a stack (see UmmaFwdParams::nlayers)
 
 #ifdef GCNB_TRACE
 // debug builds only (-DGCNB_TRACE): clock64 stamps of CTA 0's roles, read back by gcnb_debug_read_trace
@@ -65,6 +66,12 @@ __device__ long long g_trace[4][512];
   } while (0)
 #else
 #define TRACE0(slot) do { } while (0)
+#endif
+#ifdef GCNB_TRACE
+// first layer boundary of a stack, per warp w (sparse warps 0..19, epilogue warps 20..23): g_trace[0][256 + w * 8 + slot]
+#define TRACEB(w, slot) do { if (blockIdx.x == 0 && lane == 0 && it == 0) g_trace[0][256 + (w) * 8 + (slot)] = clock64(); } while (0)
+#else
+#define TRACEB(w, slot) do { } while (0)
 #endif
 #ifdef GCNB_TRACE
 #define TRACE_NOSPILL ((P.debug & 4) != 0)  // image kernels: skip the basis stores
@@ -114,6 +121,13 @@ struct UmmaFwdParams {
   const unsigned char* image;
   int img_bytes;     // multiple of 16
   int stage;         // image kernels, forward: the raw windows of a tile are staged with one TMA bulk copy
+  // Layer stack (image kernels, inference): nlayers > 1 runs a stack of identical layers (same graph, p = 1,
+  // Fin = Fout = 32, same K / bias mode / ReLU) on a tile back to back -- the output of a layer is written from TMEM
+  // straight into the state buffer as order 0 of the next one and never leaves the SM.  Layer l reads Wl[l] / biasl[l];
+  // W / bias above are layer 0's / the last layer's.
+  int nlayers;
+  const float* Wl[8];
+  const float* biasl[8];
   unsigned img_sig;  // geometry signature the image must carry
   int n_groups;      // groups of 4 row blocks
   int off_img, off_grp, off_blk;  // shared-memory offsets of the image copy, its group table and its block table
@@ -123,7 +137,8 @@ struct UmmaFwdParams {
 };
 
 // ---------------------------------------------------------------------------------------------------------------
-template <int FP, int MAXI, bool IMG>
+// STACK: the layer-stack variant (UmmaFwdParams::nlayers > 1); the single-layer instances carry none of its code
+template <int FP, int MAXI, bool IMG, bool STACK>
 __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdParams P) {
   extern __shared__ __align__(1024) unsigned char smem[];
   constexpr int G = 32 / FP;    // windows per 128-byte row
@@ -142,7 +157,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
   int* rlen = reinterpret_cast<int*>(smem + P.off_rlen);       // [NG*4]
   int* sorted = reinterpret_cast<int*>(smem + P.off_sorted);   // [NG*4]
   int* rp = reinterpret_cast<int*>(smem + P.off_rp);           // [M+1] row pointers
-  float* bias_s = reinterpret_cast<float*>(smem + P.off_bias); // [32]
+  float* bias_s = reinterpret_cast<float*>(smem + P.off_bias); // [nlayers][32]; the epilogue of the last layer reads the last row
   const uint32_t bar0 = sb + P.off_bar;
   auto bar_mma = [bar0](uint32_t i) { return bar0 + i * 8u; };          // tcgen05.mma of order n done (n & 1)
   auto bar_full = [bar0](uint32_t i) { return bar0 + 16u + i * 8u; };   // accumulator buffer i complete
@@ -184,20 +199,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
   // the tap images (the natural order, lane = filter, stores with 4-way bank conflicts)
   auto tap_o = [](int idx) { return (idx & 7) | (((idx >> 5) & 3) << 3); };
   auto tap_kk = [](int idx) { return ((idx >> 3) & 3) | ((idx >> 7) << 2); };
-  auto tap_load = [&](int i0, float (&wv)[4]) {
+  // (nt threads with index t share the conversion: the whole CTA in the prologue, the sparse warps between layers)
+  auto tap_load = [&](const float* Wsrc, int i0, int t, int nt, float (&wv)[4]) {
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int idx = i0 + u * kThreads + tid;
+      const int idx = i0 + u * nt + t;
       const int o = tap_o(idx), kk = tap_kk(idx), k = kk / FP, f = kk - k * FP;
       wv[u] = (idx < K * FP * 32 && f < P.Fin && o < P.Fout)
-                  ? __ldg(P.W + (P.adj ? ((long long)o * K + k) * P.Fin + f : ((long long)f * K + k) * P.Fout + o))
+                  ? __ldg(Wsrc + (P.adj ? ((long long)o * K + k) * P.Fin + f : ((long long)f * K + k) * P.Fout + o))
                   : 0.f;
     }
   };
-  auto tap_store = [&](int i0, const float (&wv)[4]) {
+  auto tap_store = [&](int i0, int t, int nt, const float (&wv)[4]) {
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int idx = i0 + u * kThreads + tid;
+      const int idx = i0 + u * nt + t;
       if (idx < K * FP * 32) {
         const int o = tap_o(idx), kk = tap_kk(idx);
         const float w = wv[u], hi = tf32_rna(w), lo = tf32_rna(w - hi);
@@ -207,27 +223,37 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
       }
     }
   };
+  auto taps_of = [&](const float* Wsrc, int t, int nt) {  // all tap images of one layer
+    for (int i0 = 0; i0 < K * FP * 32; i0 += nt * 4) {
+      float wv[4];
+      tap_load(Wsrc, i0, t, nt, wv);
+      tap_store(i0, t, nt, wv);
+    }
+  };
   float wv0[4];
-  tap_load(0, wv0);
+  tap_load(P.W, 0, tid, kThreads, wv0);
   int perm0 = tid;
   if (P.perm && tid < M) perm0 = __ldg(P.perm + tid);
-  const float bias0 = (tid < 32 && P.bias_mode == GCNB_BIAS_PER_FILTER && tid < P.Fout) ? __ldg(P.bias + tid) : 0.f;
+  const int nlayers = STACK ? P.nlayers : 1;
+  float bias0 = 0.f;
+  if (tid < 32 * nlayers && P.bias_mode == GCNB_BIAS_PER_FILTER && (tid & 31) < P.Fout)
+    bias0 = __ldg((nlayers > 1 ? P.biasl[tid >> 5] : P.bias) + (tid & 31));
   // zero the state buffers: the zero row behind every buffer and the padding rows of the blocks stay zero (the
   // remainder buffers need no initialisation -- garbage there only reaches accumulator rows nobody reads -- and
   // host the prologue's scratch tables rlen / sorted / rp until the first order overwrites them)
   for (uint32_t a = tid * 16u; a < (uint32_t)P.off_lo; a += kThreads * 16u) sts128(sb + a, make_float4(0.f, 0.f, 0.f, 0.f));
-  tap_store(0, wv0);
+  tap_store(0, tid, kThreads, wv0);
   for (int i0 = kThreads * 4; i0 < K * FP * 32; i0 += kThreads * 4) {
     float wv[4];
-    tap_load(i0, wv);
-    tap_store(i0, wv);
+    tap_load(P.W, i0, tid, kThreads, wv);
+    tap_store(i0, tid, kThreads, wv);
   }
   for (int r = tid; r < M; r += kThreads) {
     int s = r == tid ? perm0 : r;
     if (P.perm) { if (r != tid) s = __ldg(P.perm + r); if (s < 0 || s >= P.M_in) s = -1; }
     src_row[r] = s;
   }
-  if (tid < 32) bias_s[tid] = bias0;
+  if (tid < 32 * nlayers) bias_s[tid] = bias0;
   if constexpr (IMG) {
     mbar_wait(bar_stage, 0);  // the image has landed
     const uint32_t* hdr = reinterpret_cast<const uint32_t*>(smem + P.off_img);
@@ -397,7 +423,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
             if (P.bias_mode == GCNB_BIAS_PER_FILTER) {
 #pragma unroll
               for (int c4 = 0; c4 < 4; ++c4) {
-                const float4 bv = *reinterpret_cast<const float4*>(bias_s + h * 16 + c4 * 4);
+                const float4 bv = *reinterpret_cast<const float4*>(bias_s + (nlayers - 1) * 32 + h * 16 + c4 * 4);
                 m[c4 * 4] += bv.x; m[c4 * 4 + 1] += bv.y; m[c4 * 4 + 2] += bv.z; m[c4 * 4 + 3] += bv.w;
               }
             }
@@ -444,8 +470,54 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
       else epi_task(tile, buf, e, g, t, 0, 2);
     }
   };
+  // Between two layers of a stack (p = 1, 32 -> 32): one half (16 filters) of accumulator tile t for TMEM lane quarter e.
+  // thread = vertex: bias of layer l, ReLU, and the row goes straight into the state buffer (+ its bf16 remainder) as
+  // order 0 of layer l + 1.
+  // (the bias of the task is loaded separately so that a caller can have it in flight before the accumulators are final)
+  auto inner_bias = [&](int e, int t, int h, int l, float (&bv)[16]) {
+    const int rb = t * 128 + e * 32 + lane;
+#pragma unroll
+    for (int o = 0; o < 16; ++o) bv[o] = 0.f;
+    if (rb >= M || t * 128 + e * 32 >= BQ) return;
+    if (P.bias_mode == GCNB_BIAS_PER_VERTEX) {
+      const float* bp = P.biasl[l] + (long long)rb * P.Fout + h * 16;
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        const float4 q4 = __ldg(reinterpret_cast<const float4*>(bp + c4 * 4));
+        bv[c4 * 4] = q4.x; bv[c4 * 4 + 1] = q4.y; bv[c4 * 4 + 2] = q4.z; bv[c4 * 4 + 3] = q4.w;
+      }
+    } else if (P.bias_mode == GCNB_BIAS_PER_FILTER) {
+#pragma unroll
+      for (int o = 0; o < 16; ++o) bv[o] = bias_s[l * 32 + h * 16 + o];
+    }
+  };
+  auto inner_task = [&](int buf, int e, int t, int h, const float (&bv)[16], uint32_t dst, uint32_t dlo) {
+    if (t * 128 + e * 32 >= BQ) return;
+    const int rb = t * 128 + e * 32 + lane;  // row = vertex
+    float m[16];
+    tmem_ld16(tmem + ((uint32_t)(e * 32) << 16) + (uint32_t)(buf * P.acc_cols + t * 32 + h * 16), m);
+    if (rb >= M) return;
+#pragma unroll
+    for (int c4 = 0; c4 < 4; ++c4) {
+      float4 v = make_float4(m[c4 * 4] + bv[c4 * 4], m[c4 * 4 + 1] + bv[c4 * 4 + 1], m[c4 * 4 + 2] + bv[c4 * 4 + 2],
+                             m[c4 * 4 + 3] + bv[c4 * 4 + 3]);
+      if (P.relu) v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+      const int c = h * 4 + c4;
+      store_state_at(dst + slab_off(rb, c), dlo + lo_off(rb, c), v);
+    }
+  };
+  // this participant's share of the drain between two layers; the bias of its first task is already in bv0
+  auto inner_share = [&](int buf, int e, int j, int l, const float (&bv0)[16], uint32_t dst, uint32_t dlo) {
+    if (j < P.T * 2) inner_task(buf, e, j >> 1, j & 1, bv0, dst, dlo);
+    for (int k2 = j + kTailShare; k2 < P.T * 2; k2 += kTailShare) {
+      float bv[16];
+      inner_bias(e, k2 >> 1, k2 & 1, l, bv);
+      inner_task(buf, e, k2 >> 1, k2 & 1, bv, dst, dlo);
+    }
+  };
   int my_tiles = 0;
   for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) ++my_tiles;
+  const int my_iters = my_tiles * nlayers;  // (tile, layer) passes of this CTA
 
   if (warp > kMmaWarp) {
     // =========================================== sparse warps ==================================================
@@ -515,11 +587,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
       auto row_of = [=](int vtx, int s) { return (vtx & pm1) * BQ + s * Q + (vtx >> log2p); };
       uint32_t n = 0;  // orders issued so far (all tiles)
       uint32_t stage_phase = 1;  // phase 0 of the staging barrier brought the operator image in
-      int base = 0;
+      int base = 0, it = 0;
       TRACE(0, sw == 0);
-      for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
-        // ---- order 0 ------------------------------------------------------------------------------------------
-        {
+      for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x)
+      for (int l = 0; l < nlayers; ++l, ++it) {
+        // ---- order 0 (first layer of a stack: from HBM; later layers: written by the drain of the layer before) ----
+        if (l == 0) {
+          if (STACK && nlayers > 1 && it > 0) {
+            // the tap images still hold the last layer's: rebuild layer 0's once the tensor cores are done with them
+            mbar_wait(bar_mma((n - 1) & 1), ((n - 1) >> 1) & 1);
+            taps_of(P.Wl[0], sw * 32 + lane, kSparseWarps * 32);
+          }
           const uint32_t lo_u = P.nlo == 2 ? (n & 1u) : 0u;
           if (P.nlo == 1 && n > 0) mbar_wait(bar_mma((n - 1) & 1), ((n - 1) >> 1) & 1);
           const uint32_t dst = sb + (uint32_t)base * buf_bytes, dlo = sb + P.off_lo + lo_u * lo_bytes;
@@ -604,7 +682,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
           float* spill = (P.xstack && !TRACE_NOSPILL) ? P.xstack + (long long)k * P.B * M * FP : nullptr;
           const uint32_t dlo = sb + P.off_lo + lo_u * lo_bytes;
           const uint32_t srcb = sb + (uint32_t)(cur ^ 1) * buf_bytes, dst = sb + (uint32_t)cur * buf_bytes;
-          if (k == K - 1 && !P.adj && tile + (int)gridDim.x < P.ntiles) {
+          if (k == K - 1 && !P.adj && l == nlayers - 1 && tile + (int)gridDim.x < P.ntiles) {
             // pull the next tile's raw windows into L2 while this order computes
             for (int u = 0, ii; (ii = item_of(u)) < NI; ++u) {
               const int g = ii / NS, s = ii - g * NS;
@@ -710,6 +788,42 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
           ++n;
         }
         base = (base + K) & 1;
+        if (STACK && l + 1 < nlayers) {
+          // ---- layer boundary: taps of the next layer, accumulators -> order 0 of the next layer ---------------------
+          const int buf = P.nacc == 2 ? (it & 1) : 0;
+          const int use = P.nacc == 2 ? (it >> 1) : it;
+          const int e = warp & 3;
+          const int j = 1 + (warp - (5 + ((e + 3) & 3))) / 4;  // sparse warps of TMEM lane quarter e, in warp order
+          // static data first: the next layer's taps and this warp's bias rows are in flight while the last MMA finishes
+          constexpr int nt = kSparseWarps * 32;
+          const int t_ = sw * 32 + lane;
+          float w0[4], w1[4], bv0[16];
+          TRACEB(sw, 0);
+          tap_load(P.Wl[l + 1], 0, t_, nt, w0);
+          tap_load(P.Wl[l + 1], nt * 4, t_, nt, w1);
+          inner_bias(e, j >> 1, j & 1, l, bv0);
+          TRACEB(sw, 1);
+          mbar_wait(bar_full(buf), (uint32_t)use & 1u);  // the layer's last MMA is complete: taps and remainder free
+          tc_fence_after();
+          TRACEB(sw, 2);
+          tap_store(0, t_, nt, w0);
+          tap_store(nt * 4, t_, nt, w1);
+          for (int i0 = 2 * nt * 4; i0 < K * FP * 32; i0 += nt * 4) {
+            float wv[4];
+            tap_load(P.Wl[l + 1], i0, t_, nt, wv);
+            tap_store(i0, t_, nt, wv);
+          }
+          const uint32_t dst = sb + (uint32_t)base * buf_bytes, dlo = sb + P.off_lo + (P.nlo == 2 ? (n & 1u) : 0u) * lo_bytes;
+          TRACEB(sw, 3);
+          inner_share(buf, e, j, l, bv0, dst, dlo);
+          TRACEB(sw, 4);
+          tc_fence_before();
+          fence_async_smem();
+          TRACEB(sw, 5);
+          named_bar_sync(kBarLayer, kThreads);
+          TRACEB(sw, 6);
+          ++n;
+        }
       }
     } else {
       // The rows a lane works on never change: keep what the order loop needs of each of its (up to MAXI) items in
@@ -841,26 +955,29 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
     }
     // the CTA's last tile: help the epilogue warp of this warp's TMEM lane quarter
     if (my_tiles > 0) {
-      const int it = my_tiles - 1;
+      const int it = my_iters - 1;
       const int buf = P.nacc == 2 ? (it & 1) : 0;
       const int use = P.nacc == 2 ? (it >> 1) : it;
       const int e = warp & 3;
       const int j = 1 + (warp - (5 + ((e + 3) & 3))) / 4;  // sparse warps of quarter e, in warp order
       mbar_wait(bar_full(buf), (uint32_t)use & 1u);
       tc_fence_after();
-      tail_tasks(blockIdx.x + it * (int)gridDim.x, buf, e, j);
+      tail_tasks(blockIdx.x + (my_tiles - 1) * (int)gridDim.x, buf, e, j);
       tc_fence_before();
     }
   } else if (warp == kMmaWarp) {
     // =========================================== MMA warp ======================================================
     uint32_t n = 0;
     int base = 0, it = 0;
-    for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x)
+    for (int l = 0; l < nlayers; ++l, ++it) {
       const int buf = P.nacc == 2 ? (it & 1) : 0;
       const int use = P.nacc == 2 ? (it >> 1) : it;  // earlier uses of this accumulator buffer
       if (use > 0) mbar_wait(bar_empty(buf), (uint32_t)(use - 1) & 1u);
       for (int k = 0; k < K; ++k) {
-        named_bar_sync(kBarOrder, nsync);  // X_k (and its remainder) is complete in shared memory
+        // X_k (and its remainder) is complete in shared memory; order 0 of a later layer comes from the drain
+        if (STACK && k == 0 && l > 0) named_bar_sync(kBarLayer, kThreads);
+        else named_bar_sync(kBarOrder, nsync);
         TRACE(2, true);
         tc_fence_after();
         {
@@ -940,13 +1057,32 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
     // =========================================== epilogue warps =================================================
     const int e = warp;  // TMEM lane quarter
     int it = 0;
-    for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x, ++it) {
+    for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x)
+    for (int l = 0; l < nlayers; ++l, ++it) {
       const int buf = P.nacc == 2 ? (it & 1) : 0;
       const int use = P.nacc == 2 ? (it >> 1) : it;
+      float bv0[16];
+      if (STACK && l + 1 < nlayers) inner_bias(e, 0, 0, l, bv0);  // static: loaded before the accumulators are final
       mbar_wait_relaxed(bar_full(buf), (uint32_t)use & 1u);
       TRACE(3, e == 0);
       tc_fence_after();
-      if (it + 1 == my_tiles) {
+      if (STACK && l + 1 < nlayers) {
+        // layer boundary: this warp's share of the drain into order 0 of the next layer (participant 0 of its quarter)
+        const uint32_t n_next = (uint32_t)(it + 1) * (uint32_t)K;
+        const uint32_t dst = sb + (n_next & 1u) * buf_bytes, dlo = sb + P.off_lo + (P.nlo == 2 ? (n_next & 1u) : 0u) * lo_bytes;
+        TRACEB(20 + e, 2);
+        inner_share(buf, e, 0, l, bv0, dst, dlo);
+        TRACEB(20 + e, 4);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty(buf));
+        fence_async_smem();
+        TRACEB(20 + e, 5);
+        named_bar_sync(kBarLayer, kThreads);
+        TRACEB(20 + e, 6);
+        continue;
+      }
+      if (it + 1 == my_iters) {
         tail_tasks(tile, buf, e, 0);
       } else {
 #pragma unroll
@@ -1038,7 +1174,7 @@ static UmmaFwdPlan plan_umma_fwd(const LayerShape& s, int sm_count, int smem_opt
   pl.img_bytes = pl.img ? img_geom(s.M).ent_off + (size_t)ent_bytes : 0;
   const size_t taps = (size_t)s.K * pl.FP * 32 * 4;  // one tf32 image
   const size_t ent = pl.img ? pl.img_bytes : align_up(((size_t)s.nnz + s.M + 2) * 8, 16);
-  const size_t small = align_up((size_t)s.M * 4, 16) /*src*/ + 128 /*bias*/ + 64 /*barriers*/;
+  const size_t small = align_up((size_t)s.M * 4, 16) /*src*/ + 8 * 128 /*bias rows of up to 8 stacked layers*/ + 64 /*barriers*/;
   const size_t tables = pl.img ? small : 2 * (size_t)pl.NG * 16 /*grow, grho*/ + (size_t)pl.NG * 32 /*gslot*/ +
                                              align_up((size_t)pl.NG * 4, 16) + small;
   // prologue-only scratch (rlen, sorted, rp) lives in the first remainder buffer
@@ -1089,7 +1225,7 @@ static UmmaFwdPlan plan_umma_fwd(const LayerShape& s, int sm_count, int smem_opt
     pl.off_glen = (int)off; off += align_up((size_t)pl.NG * 4, 16);
   }
   pl.off_src = (int)off; off += align_up((size_t)s.M * 4, 16);
-  pl.off_bias = (int)off; off += 128;
+  pl.off_bias = (int)off; off += 8 * 128;
   pl.off_bar = (int)off; off += 64;
   pl.off_rlen = pl.off_lo;
   pl.off_sorted = pl.off_rlen + pl.NG * 16;
@@ -1263,9 +1399,15 @@ struct UmmaAdjoint {
   int p, relu, dy_is_mean;
 };
 
+struct UmmaStack {  // a stack of identical layers run back to back on a tile (UmmaFwdParams::nlayers)
+  int nlayers;
+  const float* const* W;
+  const float* const* bias;
+};
+
 static int umma_launch(const float* x, const int32_t* perm, int M_in, const gcnb_csr& L, const float* W, const float* bias,
                        float* y, uint8_t* argmax, float* y_mean, float* xstack, const LayerShape& s, int bias_mode, int relu,
-                       const UmmaAdjoint* adj, cudaStream_t st) {
+                       const UmmaAdjoint* adj, cudaStream_t st, const UmmaStack* stack = nullptr) {
   DeviceInfo di;
   int rc = device_info(&di);
   if (rc) return rc;
@@ -1289,6 +1431,21 @@ static int umma_launch(const float* x, const int32_t* perm, int M_in, const gcnb
   P.B = s.B; P.M = s.M; P.Fin = s.Fin; P.Fout = s.Fout; P.K = s.K; P.p = s.p; P.bias_mode = bias_mode; P.relu = relu;
   P.log2p = 0;
   while ((1 << P.log2p) < s.p) ++P.log2p;
+  P.nlayers = 1;
+  P.Wl[0] = W;
+  P.biasl[0] = bias;
+  if (stack) {
+    GCNB_REQUIRE(img && !adj && stack->nlayers >= 1 && stack->nlayers <= 8 && s.p == 1 && s.Fin == 32 && s.Fout == 32 &&
+                     xstack == nullptr && y_mean == nullptr,
+                 "layer stack: needs an operator image, p = 1, Fin = Fout = 32, 1..8 layers, inference outputs only");
+    P.nlayers = stack->nlayers;
+    for (int l = 0; l < stack->nlayers; ++l) {
+      P.Wl[l] = stack->W[l];
+      P.biasl[l] = stack->bias ? stack->bias[l] : nullptr;
+    }
+    P.W = P.Wl[0];
+    P.bias = P.biasl[stack->nlayers - 1];
+  }
   if (adj) {
     P.adj = 1;
     P.adj_dy = adj->dy; P.adj_y = adj->y; P.adj_arg = adj->argmax;
@@ -1320,13 +1477,14 @@ static int umma_launch(const float* x, const int32_t* perm, int M_in, const gcnb
   P.debug = std::getenv("GCNB_UMMA_DEBUG") ? std::atoi(std::getenv("GCNB_UMMA_DEBUG")) : 0;
 #endif
   const int grid = std::min(P.ntiles, di.sm_count);
-#define GCNB_UMMA_CASE(fp, mi, im)                                                                                      \
-  if (pl.FP == fp && pl.MAXI == mi && img == im) {                                                                      \
-    GCNB_CUDA(cudaFuncSetAttribute(k_cheb_fwd_umma<fp, mi, im>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem)); \
-    GCNB_CUDA(launch_pdl(k_cheb_fwd_umma<fp, mi, im>, dim3(grid), dim3(kThreads), pl.smem, st, P));                      \
+#define GCNB_UMMA_CASE(fp, mi, im, stk)                                                                                 \
+  if (pl.FP == fp && pl.MAXI == mi && img == im && (P.nlayers > 1) == stk) {                                            \
+    GCNB_CUDA(cudaFuncSetAttribute(k_cheb_fwd_umma<fp, mi, im, stk>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem)); \
+    GCNB_CUDA(launch_pdl(k_cheb_fwd_umma<fp, mi, im, stk>, dim3(grid), dim3(kThreads), pl.smem, st, P));                 \
   }
-  GCNB_UMMA_CASE(16, 3, false) GCNB_UMMA_CASE(16, 5, false) GCNB_UMMA_CASE(32, 3, false) GCNB_UMMA_CASE(32, 5, false)
-  GCNB_UMMA_CASE(16, 1, true) GCNB_UMMA_CASE(32, 1, true)
+  GCNB_UMMA_CASE(16, 3, false, false) GCNB_UMMA_CASE(16, 5, false, false) GCNB_UMMA_CASE(32, 3, false, false)
+  GCNB_UMMA_CASE(32, 5, false, false) GCNB_UMMA_CASE(16, 1, true, false) GCNB_UMMA_CASE(32, 1, true, false)
+  GCNB_UMMA_CASE(32, 1, true, true)
 #undef GCNB_UMMA_CASE
   GCNB_LAUNCH_CHECK("k_cheb_fwd_umma");
   return GCNB_OK;
@@ -1336,6 +1494,24 @@ int umma_cheb_fwd(const float* x, const int32_t* perm, int M_in, const gcnb_csr&
                   float* y, uint8_t* argmax, float* y_mean, float* xstack, const LayerShape& s, int bias_mode, int relu,
                   cudaStream_t st) {
   return umma_launch(x, perm, M_in, L, W, bias, y, argmax, y_mean, xstack, s, bias_mode, relu, nullptr, st);
+}
+
+// A stack of `nlayers` identical layers (same operator, p = 1, 32 -> 32 filters, same K / bias mode / ReLU) in ONE launch:
+// activations stay in shared memory / TMEM between the layers (the production network of model.py:271-274 is six such
+// layers).  Needs the operator image of the layer shape.
+bool umma_stack_supported(const LayerShape& s, const gcnb_csr& L) {
+  if (L.image == nullptr || s.p != 1 || s.Fin != 32 || s.Fout != 32 || (s.M & 3)) return false;
+  if (L.image_bytes < img_geom(s.M).ent_off) return false;
+  DeviceInfo di;
+  plan_device(&di);
+  return plan_umma_fwd(s, di.sm_count, di.smem_optin, (long long)(L.image_bytes - img_geom(s.M).ent_off)).ok;
+}
+
+int umma_cheb_stack_fwd(const float* x, const gcnb_csr& L, const float* const* W, const float* const* bias, float* y,
+                        int nlayers, const LayerShape& s, int bias_mode, int relu, cudaStream_t st) {
+  UmmaStack stk{nlayers, W, bias};
+  return umma_launch(x, nullptr, s.M, L, W[0], bias ? bias[nlayers - 1] : nullptr, y, nullptr, nullptr, nullptr, s, bias_mode,
+                     relu, nullptr, st, &stk);
 }
 
 // The layer's input gradient through the forward kernel: operator L~^T, taps W_k^T, input dZ (see UmmaFwdParams::adj).

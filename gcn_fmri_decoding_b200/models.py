@@ -230,8 +230,18 @@ class cgcnn(nn.Module):
         if gather and not self.fused:
             x = ops.perm_gather(x, self.perm)
             gather = False
-        for i in range(len(self.p)):
+        i, n = 0, len(self.p)
+        while i < n:
             if self.fused:
+                j = self._stack_run(i, x) if not (gather and i == 0) else i + 1
+                if j - i >= 2:
+                    # a run of identical layers (the production network, model.py:271-274): ONE launch, the activations
+                    # never leave the SM between the layers
+                    pl = self._plan(self.L[i])
+                    x = ops.cheb_stack_fwd(x, pl.rowptr, pl.col, pl.val, self.conv_weights[i:j], self.conv_bias[i:j],
+                                           self.K[i], self._bias_mode(), True)
+                    i = j
+                    continue
                 x = self.conv(i, x, gather=gather and i == 0)
             else:
                 self._layer = i
@@ -241,7 +251,23 @@ class cgcnn(nn.Module):
                     x = self.pool(x, self.p[i])
                 finally:
                     self._layer = None
+            i += 1
         return x
+
+    def _stack_run(self, i, x):
+        """End (exclusive) of the run of layers starting at ``i`` that ``ops.cheb_stack_fwd`` can take in one launch:
+        inference, Chebyshev filter, no pooling, 32 -> 32 filters, same operator and K."""
+        if torch.is_grad_enabled() or self.filter_name == "fourier" or self.algo == ops.ALGO_GENERAL or x.shape[2] != 32:
+            return i + 1
+        j = i
+        while (j < len(self.p) and j - i < 8 and self.p[j] == 1 and self.F[j] == 32 and self.K[j] == self.K[i]
+               and self.L[j] is self.L[i]):
+            j += 1
+        if j - i >= 2:
+            pl = self._plan(self.L[i])
+            if not ops.cheb_stack_supported(pl.rowptr, pl.col, pl.val, x.shape[0], 32, self.K[i], j - i):
+                return i + 1
+        return max(j, i + 1)
 
     def _inference(self, x, dropout=1.0, gather=False):
         """logits = head(conv_stack(x)); ``dropout`` is the keep probability, as in the reference."""

@@ -89,6 +89,41 @@ def cheb_fwd(x: Tensor, perm: Optional[Tensor], rowptr: Tensor, col: Tensor, val
     return y, argmax
 
 
+def cheb_stack_supported(rowptr: Tensor, col: Tensor, val: Tensor, B: int, F: int, K: int, nlayers: int) -> bool:
+    """Whether ``cheb_stack_fwd`` can run ``nlayers`` identical F -> F layers (p = 1) on this operator in one launch."""
+    if nlayers < 1 or nlayers > 8 or F != 32 or not val.is_cuda:
+        return False
+    csr = csr_struct(rowptr, col, val, (B, F, F, K, 1))
+    return bool(_lib.lib().gcnb_cheb_stack_supported(C.byref(csr), B, F, K, nlayers))
+
+
+def cheb_stack_fwd(x: Tensor, rowptr: Tensor, col: Tensor, val: Tensor, Ws, biases, K: int, bias_mode: int,
+                   relu: bool) -> Tensor:
+    """A run of identical ChebyNet layers (same operator, p = 1, 32 -> 32, same K) as ONE launch of the tcgen05 kernel
+    (``gcnb_cheb_stack_fwd_f32``): activations stay on the SM between the layers.  Inference only (no autograd);
+    bit-identical to calling ``cheb_fwd`` layer by layer."""
+    _check_x(x)
+    x = x.contiguous()
+    B, M, F = x.shape
+    n = len(Ws)
+    Ws = [w.contiguous() for w in Ws]
+    for w in Ws:
+        if w.shape != (F * K, F):
+            raise ValueError("every W of the stack must be [F*K, F] = [%d, %d], got %s" % (F * K, F, tuple(w.shape)))
+    if bias_mode != BIAS_NONE:
+        want = F if bias_mode == BIAS_PER_FILTER else M * F
+        biases = [b.contiguous() for b in biases]
+        if len(biases) != n or any(b.numel() != want for b in biases):
+            raise ValueError("one bias per layer with %d elements is required for bias_mode=%d" % (want, bias_mode))
+    y = torch.empty_like(x)
+    wp = (C.c_void_p * n)(*[w.data_ptr() for w in Ws])
+    bp = (C.c_void_p * n)(*[b.data_ptr() for b in biases]) if bias_mode != BIAS_NONE else None
+    csr = csr_struct(rowptr, col, val, (B, F, F, K, 1))
+    rc = _lib.lib().gcnb_cheb_stack_fwd_f32(_ptr(x), C.byref(csr), wp, bp, _ptr(y), n, B, F, K, bias_mode, int(relu), _stream(x))
+    _lib.check(rc, "gcnb_cheb_stack_fwd_f32")
+    return y
+
+
 @cheb_fwd.register_fake
 def _(x, perm, rowptr, col, val, rowptr_t, col_t, val_t, W, bias, K, p, bias_mode, relu, want_argmax, algo):
     B = x.shape[0]

@@ -94,6 +94,19 @@ GCNB_API size_t gcnb_cheb_image_bytes(const int32_t* rowptr, const int32_t* col,
 GCNB_API int gcnb_cheb_image_build(const int32_t* rowptr, const int32_t* col, const float* val, int B, int M, int nnz,
                                    int Fin, int Fout, int K, int p, int adjoint, void* image_host, size_t image_bytes);
 
+/*
+ * A stack of `nlayers` (1..8) identical ChebyNet layers in ONE launch -- the reference's production network is six
+ * such layers (model.py:271-274; conv loop models_gcn.py:658-668): same operator, p = 1 (no pooling), F -> F filters
+ * with F = 32, the same K / bias mode / ReLU, weights W[l] [F*K, F] and biases bias[l] per layer (host arrays of
+ * device pointers).  x [B, M, F] -> y [B, M, F]; the activations between the layers stay on the SM.  Needs the
+ * operator image of the layer shape in L->image (gcnb_cheb_image_build(..., Fin = Fout = F, p = 1, adjoint = 0));
+ * results are bit-identical to nlayers calls of gcnb_cheb_fwd_f32.  Inference only (no arg-max, no saved basis).
+ */
+GCNB_API int gcnb_cheb_stack_supported(const gcnb_csr* L, int B, int F, int K, int nlayers);
+GCNB_API int gcnb_cheb_stack_fwd_f32(const float* x, const gcnb_csr* L, const float* const* W, const float* const* bias,
+                                     float* y, int nlayers, int B, int F, int K, int bias_mode, int relu,
+                                     gcnb_stream_t stream);
+
 /* Feature width FP of the saved-basis buffer `xstack` (K*B*M*FP floats, layout private to the library: [K][B][M][FP]
  * with padded FP for graphs the fused kernels hold in shared memory, vertex-major [K][M][B][Fin] for vertex-level
  * graphs on the general path), or 0 when this shape keeps no basis. */

@@ -939,3 +939,50 @@ def test_layer_random_shapes(dev, graph_l4, lvl, B, Fin, Fout, K, p, brelu):
         assert rel_inf(r["dW"], g64[0]["dW"]) <= TOL, tag
         assert rel_inf(r["db"], g64[0]["db"]) <= TOL, tag
         assert rel_inf(r["dx"], dx64) <= TOL, tag
+
+
+@pytest.mark.parametrize("brelu,nlayers,B", [("b2relu", 5, 19), ("b1relu", 3, 150), ("b2relu", 8, 2)])
+def test_layer_stack_is_bit_identical_to_layer_by_layer(dev, graph_l1, brelu, nlayers, B):
+    """gcnb_cheb_stack_fwd_f32: a run of identical p = 1, 32 -> 32 layers in one launch (the production network's
+    layers 2-6, model.py:271-274) gives bit for bit what the same layers give one launch at a time -- and hence the
+    oracle's result within the layer tolerance; cgcnn.conv_stack picks it by itself under no_grad."""
+    from gcn_fmri_decoding_b200 import ops
+    from gcn_fmri_decoding_b200.plan import GraphPlan
+
+    L = graph_l1["L"][0]
+    M = L.shape[0]
+    pl = GraphPlan(L, dev)
+    rng = np.random.RandomState(nlayers)
+    x = rng.randn(B, M, 32).astype(np.float32)
+    Ws = [(rng.randn(32 * 5, 32) * (0.5 / np.sqrt(160))).astype(np.float32) for _ in range(nlayers)]
+    bs = [(rng.randn(32) * 0.1).astype(np.float32) if brelu == "b1relu" else (rng.randn(M, 32) * 0.1).astype(np.float32)
+          for _ in range(nlayers)]
+    mode = ops.BIAS_PER_FILTER if brelu == "b1relu" else ops.BIAS_PER_VERTEX
+    xt, Wt, bt = T(x, dev), [T(w, dev) for w in Ws], [T(b, dev) for b in bs]
+    assert ops.cheb_stack_supported(pl.rowptr, pl.col, pl.val, B, 32, 5, nlayers)
+    y = ops.cheb_stack_fwd(xt, pl.rowptr, pl.col, pl.val, Wt, bt, 5, mode, True)
+    h = xt
+    for w, b in zip(Wt, bt):
+        h = ops.cheb_fwd(h, None, *pl.tensors(), w, b, 5, 1, mode, True, False, ops.ALGO_AUTO)[0]
+    assert torch.equal(y, h)
+    y64 = O.conv_stack(x, [L] * nlayers, [dict(W=w, b=b, K=5, p=1) for w, b in zip(Ws, bs)], brelu=brelu, dtype=np.float64)
+    assert rel_inf(y.cpu().numpy(), y64) <= TOL * nlayers
+
+
+def test_model_uses_the_layer_stack_under_no_grad(dev, graph_l1):
+    """config 1 (six p = 1 layers): the model's inference path takes layers 2-6 in one launch and returns the same
+    logits as the layer-by-layer path that autograd uses."""
+    from gcn_fmri_decoding_b200 import _lib
+
+    g = graph_l1
+    model = build_model(g, [32] * 6, [5] * 6, [1] * 6, [512, 256, 22], "chebyshev5", "b2relu", dev, perm=g["perm"])
+    x = T(np.random.RandomState(3).randn(9, 360, 15).astype(np.float32), dev)
+    lib = _lib.lib()
+    c0 = lib.gcnb_launch_count()
+    with torch.no_grad():
+        a = model(x)
+    torch.cuda.synchronize()
+    launches = lib.gcnb_launch_count() - c0
+    b = model(x)          # grad enabled: one launch per layer
+    assert torch.equal(a, b.detach())
+    assert launches <= 4, launches   # layer 1, the stack of layers 2-6, mean over filters (+ nothing else from this library)

@@ -27,11 +27,14 @@ else:  # "c1": a middle layer of the config-1 network (M=372, 32->32, p=1, b2rel
     x = torch.randn(128, 372, 32, device=dev)
     W = torch.randn(160, 32, device=dev) * .2
     pt = None
-if which == "c1":
+if which in ("c1", "c1s"):
     b = torch.full((372, 32), .2, device=dev)
     print(_lib.describe_fwd(128, 372, pl.nnz, 32, 32, 5, 1))
     for _ in range(3):
-        ops.cheb_fwd(x, pt, *pl.tensors(), W, b, 5, 1, 2, True, False, 0)
+        if which == "c1s":  # layers 2-6 of the config-1 network in one launch
+            ops.cheb_stack_fwd(x, pl.rowptr, pl.col, pl.val, [W] * 5, [b] * 5, 5, 2, True)
+        else:
+            ops.cheb_fwd(x, pt, *pl.tensors(), W, b, 5, 1, 2, True, False, 0)
 else:
     b = torch.full((32,), .2, device=dev)
     for _ in range(3):
@@ -66,3 +69,10 @@ for ti in range(2):
         print("order 0 of tile %d, per sparse warp: start, staged | item0 item1 done | (5) end, fenced, released (cycles from %d)" % (ti, int(base - t0)))
         for sw in range(20):
             print("  o0 sw%2d" % sw, " ".join("%6d" % (int(a - base) if a > 0 else -1) for a in w[sw]))
+
+w = t[0][256:256 + 24 * 8].reshape(24, 8)
+if (w > 0).any():
+    base = w[w > 0].min()
+    print("first layer boundary, per warp (sparse 0-19, epilogue 20-23): start, loads issued, accumulators final, taps stored, drained, fenced, released (cycles from %d)" % int(base - t0))
+    for i in range(24):
+        print("  lb w%2d" % i, " ".join("%6d" % (int(a - base) if a > 0 else -1) for a in w[i][:7]))
