@@ -32,7 +32,7 @@ __device__ long long g_head_trace[32];
 
 constexpr int HT = 256;         // threads per CTA
 constexpr int TM = 64, TN = 64, TK = 32;
-constexpr int TS = TM + 4;      // shared tile row stride (floats): keeps 16-byte alignment of the float4 reads
+constexpr int TS = TM + 8;      // shared tile row stride (floats): 16-byte aligned rows, conflict-free mma fragment loads (72 = 8 mod 32)
 constexpr int SK2 = 4;          // K split of h1 W2 (too few output tiles otherwise)
 constexpr int SKW = 2;          // K (= batch) split of h1^T d2
 constexpr int SKC = 128;        // k chunk of the narrow products
@@ -58,15 +58,30 @@ struct View {
 // loads coalesce): AK: A(m, k) = A[m * lda + k], else A[k * lda + m];  BK: B(k, n) = B[n * ldb + k], else B[k * ldb + n].
 // All per-element address arithmetic is hoisted out of the chunk loop (one pointer, one validity bit per element);
 // the next chunk's 16 loads are in flight while the current one is multiplied.  Plain (coherent) loads: some operands
-// were written earlier in this kernel.  The chunk loop is FFMA-issue bound (512 FFMA per thread and chunk).
+// were written earlier in this kernel.  The chunk loop runs on the tensor cores (3xTF32 mma.sync; the FFMA version it
+// replaces was issue bound at 512 FFMA per thread and chunk).
+__device__ __forceinline__ void split_hl(float v, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(v) & 0xffffe000u;            // what the tensor core keeps of an fp32 operand
+  lo = __float_as_uint(v - __uint_as_float(hi));    // exact remainder
+}
+__device__ __forceinline__ void mma8(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
 template <bool AK, bool BK>
 __device__ __forceinline__ void tile_gemm(TileSmem& sm, const float* A, int lda, const float* Bp,
                                           int ldb, int M, int N, int m0, int n0, int k0, int k1, float (&acc)[4][4]) {
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int lane = tid & 31, wid = tid >> 5, g8 = lane >> 2, t4 = lane & 3;
+  const int mw = (wid & 3) * 16, nw = (wid >> 2) * 32;
+  float c[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) c[i][j] = 0.f;
   // element i of this thread: A: (k = ak0 + i*AKS, m = am0 + i*AMS), B likewise
   const int ak0 = AK ? (tid & 31) : (tid >> 6), am0 = AK ? (tid >> 5) : (tid & 63);
   const int bk0 = BK ? (tid & 31) : (tid >> 6), bn0 = BK ? (tid >> 5) : (tid & 63);
@@ -81,15 +96,17 @@ __device__ __forceinline__ void tile_gemm(TileSmem& sm, const float* A, int lda,
     va |= (m0 + am0 + i * AMS < M ? 1u : 0u) << i;
     vb |= (n0 + bn0 + i * BNS < N ? 1u : 0u) << i;
   }
-  float ra[8], rb[8];
-  auto fetch = [&](int kc) {
+  // two chunks of loads in flight (a tile is one CTA's whole phase: the chain of chunk loads is its critical path)
+  float ra[8], rb[8], ra2[8], rb2[8];
+  auto fetch = [&](int kc, float (&qa)[8], float (&qb)[8]) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      ra[i] = ((va >> i) & 1u) && kc + ak0 + i * AKS < k1 ? pa[kc * ka + i * sa] : 0.f;
-      rb[i] = ((vb >> i) & 1u) && kc + bk0 + i * BKS < k1 ? pb[kc * kb + i * sb] : 0.f;
+      qa[i] = ((va >> i) & 1u) && kc + ak0 + i * AKS < k1 ? pa[kc * ka + i * sa] : 0.f;
+      qb[i] = ((vb >> i) & 1u) && kc + bk0 + i * BKS < k1 ? pb[kc * kb + i * sb] : 0.f;
     }
   };
-  fetch(k0);
+  fetch(k0, ra, rb);
+  fetch(k0 + TK, ra2, rb2);  // (all zeros past k1)
   for (int kc = k0; kc < k1; kc += TK) {
     __syncthreads();  // the previous chunk has been consumed
 #pragma unroll
@@ -98,17 +115,47 @@ __device__ __forceinline__ void tile_gemm(TileSmem& sm, const float* A, int lda,
       sm.b[bk0 + i * BKS][bn0 + i * BNS] = rb[i];
     }
     __syncthreads();
-    if (kc + TK < k1) fetch(kc + TK);
-#pragma unroll 8
-    for (int k = 0; k < TK; ++k) {
-      const float4 av = *reinterpret_cast<const float4*>(&sm.a[k][ty * 4]);
-      const float4 bv = *reinterpret_cast<const float4*>(&sm.b[k][tx * 4]);
-      const float a4[4] = {av.x, av.y, av.z, av.w}, b4[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a4[i], b4[j], acc[i][j]);
+    for (int i = 0; i < 8; ++i) {
+      ra[i] = ra2[i];
+      rb[i] = rb2[i];
     }
+    if (kc + 2 * TK < k1) fetch(kc + 2 * TK, ra2, rb2);
+    // 3xTF32 on the tensor cores (mma.sync m16n8k8): warp w owns rows 16 (w & 3) .., columns 32 (w >> 2) .. of the tile.
+    // Both operands are split by truncation (hi = top 19 bits, lo = exact remainder): the dropped lo*lo term and the
+    // truncation of lo are ~2^-20 relative -- fp32-level products at a sixth of the FFMA issue slots.
+#pragma unroll
+    for (int ks = 0; ks < TK / 8; ++ks) {
+      const int kb = ks * 8;
+      uint32_t ah[4], al[4];
+      split_hl(sm.a[kb + t4][mw + g8], ah[0], al[0]);
+      split_hl(sm.a[kb + t4][mw + g8 + 8], ah[1], al[1]);
+      split_hl(sm.a[kb + t4 + 4][mw + g8], ah[2], al[2]);
+      split_hl(sm.a[kb + t4 + 4][mw + g8 + 8], ah[3], al[3]);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        uint32_t bh0, bl0, bh1, bl1;
+        split_hl(sm.b[kb + t4][nw + nt * 8 + g8], bh0, bl0);
+        split_hl(sm.b[kb + t4 + 4][nw + nt * 8 + g8], bh1, bl1);
+        mma8(c[nt], al, bh0, bh1);
+        mma8(c[nt], ah, bl0, bl1);
+        mma8(c[nt], ah, bh0, bh1);
+      }
+    }
+  }
+  __syncthreads();
+  // accumulator fragments -> the 4 x 4 register tiles the phase epilogues are written for, through the tile buffer
+  float(*ct)[TS] = reinterpret_cast<float(*)[TS]>(&sm);  // [TM][TS]: a and b are contiguous
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    *reinterpret_cast<float2*>(&ct[mw + g8][nw + nt * 8 + 2 * t4]) = make_float2(c[nt][0], c[nt][1]);
+    *reinterpret_cast<float2*>(&ct[mw + g8 + 8][nw + nt * 8 + 2 * t4]) = make_float2(c[nt][2], c[nt][3]);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 v = *reinterpret_cast<const float4*>(&ct[ty * 4 + i][tx * 4]);
+    acc[i][0] = v.x; acc[i][1] = v.y; acc[i][2] = v.z; acc[i][3] = v.w;
   }
   __syncthreads();
 }
