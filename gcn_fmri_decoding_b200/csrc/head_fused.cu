@@ -25,14 +25,17 @@ namespace gcnb {
 
 #ifdef GCNB_TRACE
 __device__ long long g_head_trace[32];
-#define HTRACE(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_head_trace[i] = clock64(); } while (0)
+__device__ long long g_head_cta[160][16];  // every CTA's own clock at every trace point (per-SM clocks: use differences)
+#define HTRACE(i) do { if (threadIdx.x == 0) { const long long c_ = clock64(); if (blockIdx.x == 0) g_head_trace[i] = c_; if (blockIdx.x < 160) g_head_cta[blockIdx.x][i] = c_; } } while (0)
 #else
 #define HTRACE(i) do { } while (0)
 #endif
 
 constexpr int HT = 256;         // threads per CTA
 constexpr int TM = 64, TN = 64, TK = 32;
-constexpr int TS = TM + 8;      // shared tile row stride (floats): 16-byte aligned rows, conflict-free mma fragment loads (72 = 8 mod 32)
+constexpr int TS = TM + 9;      // shared tile row stride (floats), 9 mod 32: the transposing stores of k-contiguous operands
+                                // (32 lanes = 32 k, one column) hit 32 banks, the mma fragment loads (4 k x 8 columns) nearly so
+constexpr int CTS = TM + 4;     // row stride of the accumulator hand-over tile (16-byte aligned rows)
 constexpr int SK2 = 4;          // K split of h1 W2 (too few output tiles otherwise)
 constexpr int SKW = 2;          // K (= batch) split of h1^T d2
 constexpr int SKC = 128;        // k chunk of the narrow products
@@ -145,7 +148,8 @@ __device__ __forceinline__ void tile_gemm(TileSmem& sm, const float* A, int lda,
   }
   __syncthreads();
   // accumulator fragments -> the 4 x 4 register tiles the phase epilogues are written for, through the tile buffer
-  float(*ct)[TS] = reinterpret_cast<float(*)[TS]>(&sm);  // [TM][TS]: a and b are contiguous
+  float(*ct)[CTS] = reinterpret_cast<float(*)[CTS]>(&sm);  // [TM][CTS] over the (contiguous) a and b tiles
+  static_assert(sizeof(float) * TM * CTS <= sizeof(TileSmem), "hand-over tile must fit");
 #pragma unroll
   for (int nt = 0; nt < 4; ++nt) {
     *reinterpret_cast<float2*>(&ct[mw + g8][nw + nt * 8 + 2 * t4]) = make_float2(c[nt][0], c[nt][1]);
@@ -676,6 +680,9 @@ int gcnb_head_step_f32(const float* a0, const int64_t* labels, const float* W1, 
 }  // extern "C"
 
 #ifdef GCNB_TRACE
+extern "C" __attribute__((visibility("default"))) int gcnb_debug_read_head_cta(long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, gcnb::g_head_cta, sizeof(long long) * 160 * 16);
+}
 extern "C" __attribute__((visibility("default"))) int gcnb_debug_read_head_trace(long long* out) {
   return (int)cudaMemcpyFromSymbol(out, gcnb::g_head_trace, sizeof(long long) * 32);
 }

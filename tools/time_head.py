@@ -66,3 +66,14 @@ if os.environ.get("GCNB_HEAD_TRACE"):
     v = [int(x) for x in buf[:14]]
     names = ["F1", "sync", "F2", "sync", "F3", "sync", "B1", "sync", "B2", "sync", "B3", "sync", "B4"]
     print("head phases (cycles):", " ".join("%s=%d" % (n, v[i + 1] - v[i]) for i, n in enumerate(names)))
+    import numpy as np
+    big = (C.c_longlong * (160 * 16))()
+    h.gcnb_debug_read_head_cta(big)
+    a = np.array(big[:]).reshape(160, 16)[:148]
+    for i, n in enumerate(names):
+        if n == "sync":
+            continue
+        d = a[:, i + 1] - a[:, i]
+        order = np.argsort(-d)
+        print("%s per CTA: median %d max %d; slowest CTAs %s" % (n, int(np.median(d)), int(d.max()),
+              " ".join("%d:%d" % (int(b), int(d[b])) for b in order[:8])))
