@@ -255,6 +255,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
   }
   if (tid < 32 * nlayers) bias_s[tid] = bias0;
   if constexpr (IMG) {
+    __syncthreads();          // (thread 0 initialised the barrier: nobody may poll it before that is certain)
     mbar_wait(bar_stage, 0);  // the image has landed
     const uint32_t* hdr = reinterpret_cast<const uint32_t*>(smem + P.off_img);
     if (hdr[0] != kImgMagic || hdr[1] != P.img_sig || hdr[2] != (uint32_t)P.img_bytes) __trap();  // image of another geometry
@@ -1193,6 +1194,9 @@ static UmmaFwdPlan plan_umma_fwd(const LayerShape& s, int sm_count, int smem_opt
       const size_t need = 2 * (size_t)rows * 128 + (size_t)nlo * rows * 64 + 2 * taps + taps / 2 + ent + tables;
       // the last MMA tile of the last block reads up to row (p-1)*BQ + T*128: those bytes must exist in the allocation
       const long long over = ((long long)(s.p - 1) * BQ + T * 128 - rows) * 128;
+      // a second remainder buffer is a convenience (no waiting for the previous order's MMAs, which take ~400 cycles): only
+      // when it leaves 8 KB of the SM's shared memory free -- tools that instrument a launch (ncu --set full) need some
+      if (nlo == 2 && need + 8192 > budget) continue;
       if (need > budget || 2 * (size_t)rows * 128 + (over > 0 ? (size_t)over : 0) > need || scratch > (size_t)rows * 64) continue;
       const int tiles = ceil_div(s.B, ns * pl.G);
       // rounds of tiles over the SMs x work per tile; MMA rows wasted by a nearly empty last tile of a block count a little
