@@ -1183,7 +1183,11 @@ static UmmaFwdPlan plan_umma_fwd(const LayerShape& s, int sm_count, int smem_opt
       pl.img ? 0 : 2 * (size_t)pl.NG * 16 + align_up((size_t)(s.M + 3) * 4, 16) + align_up((size_t)(s.M + 1) * 4, 16);
   const size_t budget = std::min<size_t>((size_t)smem_optin, 227 * 1024);
   double best = 1e30;
-  for (int ns = 1; ns <= 8; ++ns) {
+  static const int ns_cap = [] {  // A/B knob: GCNB_UMMA_NS_MAX caps the window-slabs per tile
+    const char* v = std::getenv("GCNB_UMMA_NS_MAX");
+    return v ? std::max(1, std::atoi(v)) : 8;
+  }();
+  for (int ns = 1; ns <= std::min(8, ns_cap); ++ns) {
     const int BQ = ns * pl.Q, T = ceil_div(BQ, 128);
     const int acc_cols = pl.G * s.p * T * 32;
     if (acc_cols > 512) continue;

@@ -76,6 +76,7 @@ __device__ __forceinline__ float lds32(uint32_t a) {
 
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  __syncwarp();  // bar.sync is an aligned barrier: the warp must arrive converged (lanes may have left a loop separately)
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
