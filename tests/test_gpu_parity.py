@@ -986,3 +986,27 @@ def test_model_uses_the_layer_stack_under_no_grad(dev, graph_l1):
     b = model(x)          # grad enabled: one launch per layer
     assert torch.equal(a, b.detach())
     assert launches <= 4, launches   # layer 1, the stack of layers 2-6, mean over filters (+ nothing else from this library)
+
+
+def test_fit_runs_through_the_input_pipeline(dev, graph_l4):
+    """train.fit (the reference's training loop, models_gcn.py:112-184) with a FusedTrainer feeds the batches through
+    train.InputPipeline: the loss history is finite, reproducible, and the parameters move."""
+    from gcn_fmri_decoding_b200 import synth
+    from gcn_fmri_decoding_b200.train import FusedTrainer, fit
+
+    g = graph_l4
+    data = synth.bold_windows(64, seed=9)
+    labels = synth.labels(64, seed=9)
+
+    def run():
+        model = build_model(g, [32, 32], [5, 5], [4, 4], [512, 256, 22], "chebyshev5", "b1relu", dev, perm=g["perm"])
+        model.batch_size, model.num_epochs, model.eval_frequency, model.dropout = 16, 2, 10 ** 9, 0.5
+        tr = FusedTrainer(model, distributed=False, use_cuda_graph=True, dropout_seed=5)
+        p0 = tr.flat_p.clone()
+        losses = fit(model, data, labels, trainer=tr, seed=3, verbose=False)
+        return losses, float((tr.flat_p - p0).abs().max())
+
+    a, moved = run()
+    b, _ = run()
+    assert len(a) == 8 and np.all(np.isfinite(a)) and moved > 0
+    assert a == b
