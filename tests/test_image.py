@@ -77,3 +77,30 @@ def test_image_unsupported_shapes_return_zero(graph_l4):
     bad = rp.copy()
     bad[5] = bad[6] + 1  # row pointers must not decrease
     assert lib.gcnb_cheb_image_bytes(bad.ctypes.data, ci.ctypes.data, 8, 400, len(v), 15, 32, 5, 4, 0) == 0
+
+
+def test_production_layer_shape_has_an_image_and_a_stack_kernel(graph_l1):
+    """The 372-vertex, 32 -> 32, p = 1 layers of the production network (config 1) must fit an operator image beside their
+    state (16-bit row codes; the 32-bit format did not) -- the layer-stack kernel needs it.  Host-side queries only."""
+    import ctypes as C
+
+    from gcn_fmri_decoding_b200 import _lib, graphs
+
+    lib = _lib.lib()
+    Lr = graphs.rescale_L(graph_l1["L"][0], lmax=2)
+    rp, ci, v = graphs.csr_arrays(Lr)
+    M, nnz = Lr.shape[0], len(v)
+    assert M == 372
+    n = lib.gcnb_cheb_image_bytes(rp.ctypes.data, ci.ctypes.data, 128, M, nnz, 32, 32, 5, 1, 0)
+    assert 0 < n < 64 * 1024 and n % 16 == 0
+    img = np.zeros(n, np.uint8)
+    _lib.check(lib.gcnb_cheb_image_build(rp.ctypes.data, ci.ctypes.data, v.ctypes.data, 128, M, nnz, 32, 32, 5, 1, 0,
+                                         img.ctypes.data, n), "build")
+    assert np.array_equal(_decode(img, M, 1), np.asarray(Lr.todense(), np.float32))
+    # the support query looks at the shape and at the presence / size of the image only (no device access)
+    csr = _lib.GcnbCsr(rp.ctypes.data, ci.ctypes.data, v.ctypes.data, M, nnz, img.ctypes.data, n)
+    assert lib.gcnb_cheb_stack_supported(C.byref(csr), 128, 32, 5, 5) == 1
+    assert lib.gcnb_cheb_stack_supported(C.byref(csr), 128, 32, 5, 9) == 0      # at most eight layers
+    assert lib.gcnb_cheb_stack_supported(C.byref(csr), 128, 16, 5, 5) == 0      # 32 -> 32 filters only
+    bare = _lib.GcnbCsr(rp.ctypes.data, ci.ctypes.data, v.ctypes.data, M, nnz, None, 0)
+    assert lib.gcnb_cheb_stack_supported(C.byref(bare), 128, 32, 5, 5) == 0     # needs the image
