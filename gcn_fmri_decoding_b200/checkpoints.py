@@ -1,0 +1,122 @@
+"""Checkpoints under the reference's variable names, and the "best k" bookkeeping of its training loop.
+
+The reference saves TensorFlow-1.x checkpoints (``tf.train.Saver``, ``lib_new/models_gcn.py:220``) whose variables are
+named ``conv{i}/weights``, ``conv{i}/bias``, ``fc{i}/weights`` ... ``logits/bias`` (``:662``, ``:343``, ``:351``, ``:675``,
+``:680``); ``fit`` keeps the best three by validation accuracy (``lib_new/checkmat.py:8-84``, used at
+``models_gcn.py:127,175``) and ``evaluate`` restores the latest one (``:89-90``).  TensorFlow is not available here, so
+the container is a NumPy ``.npz`` with exactly those names (``W`` as ``[Fin*K, Fout]``, row ``f*K + k``): a
+reference-side ``{v.name[:-2]: sess.run(v) for v in tf.trainable_variables()}`` dump loads unchanged.
+"""
+from __future__ import annotations
+
+import glob
+import json
+import os
+
+import numpy as np
+
+INDEX_NAME = "best_checkpoints"  # the JSON index the reference keeps in the checkpoint directory
+
+
+def save_checkpoint(model, path, step=None):
+    """Write the model's parameters as ``<path>[-<step>].npz`` under the TF variable names; returns the file name."""
+    name = path if step is None else "%s-%d" % (path, int(step))
+    if not name.endswith(".npz"):
+        name += ".npz"
+    os.makedirs(os.path.dirname(os.path.abspath(name)), exist_ok=True)
+    np.savez(name, **{k.replace("/", "__"): v for k, v in model.state_dict_tf().items()})
+    return name
+
+
+def load_checkpoint(model, path):
+    """Load a file written by ``save_checkpoint`` (or any ``.npz`` keyed by the TF variable names, ``/`` or ``__``)."""
+    with np.load(path) as z:
+        d = {k.replace("__", "/"): z[k] for k in z.files}
+    model.load_state_dict_tf(d)
+    return model
+
+
+def latest_checkpoint(directory, prefix="model"):
+    """The checkpoint with the highest step in ``directory`` (``tf.train.latest_checkpoint``), or None."""
+    best, best_step = None, -1
+    for f in glob.glob(os.path.join(directory, prefix + "-*.npz")):
+        try:
+            step = int(os.path.basename(f)[len(prefix) + 1:-4])
+        except ValueError:
+            continue
+        if step > best_step:
+            best, best_step = f, step
+    return best
+
+
+class BestCheckpoints:
+    """Keep the ``num_to_keep`` best checkpoints of a run in ``save_dir``, ranked by a validation value.
+
+    ``handle(value, model, step)`` has the semantics of the reference's ``BestCheckpointSaver.handle``: below capacity
+    every checkpoint is kept; at capacity a new one replaces the worst unless every kept value is at least as good.
+    The JSON index ``best_checkpoints`` maps file names to values, as in the reference.
+    """
+
+    def __init__(self, save_dir, num_to_keep=3, maximize=True, prefix="best.ckpt"):
+        self.save_dir, self.num_to_keep, self.maximize, self.prefix = save_dir, int(num_to_keep), bool(maximize), prefix
+        os.makedirs(save_dir, exist_ok=True)
+        self.index_file = os.path.join(save_dir, INDEX_NAME)
+
+    def _load(self):
+        if not os.path.exists(self.index_file):
+            return {}
+        with open(self.index_file) as f:
+            return json.load(f)
+
+    def _store(self, index):
+        with open(self.index_file, "w") as f:
+            json.dump(index, f, indent=3)
+
+    def _ranked(self, index):
+        return sorted(index, key=index.get, reverse=self.maximize)  # best first
+
+    def handle(self, value, model, step):
+        """Returns the file written, or None when the checkpoint did not make it into the best ``num_to_keep``."""
+        value = float(value)
+        index = self._load()
+        name = "%s-%d.npz" % (self.prefix, int(step))
+        if len(index) >= self.num_to_keep:
+            better = (lambda kept: kept >= value) if self.maximize else (lambda kept: kept <= value)
+            if all(better(v) for v in index.values()):
+                return None
+            worst = self._ranked(index)[-1]
+            index.pop(worst)
+            try:
+                os.remove(os.path.join(self.save_dir, worst))
+            except FileNotFoundError:
+                pass
+        index[name] = value
+        self._store(index)
+        return save_checkpoint(model, os.path.join(self.save_dir, name))
+
+    def best(self):
+        """Path of the best checkpoint kept so far (``checkmat.get_best_checkpoint``), or None."""
+        index = self._load()
+        return os.path.join(self.save_dir, self._ranked(index)[0]) if index else None
+
+
+def classification_summary(labels, predictions, loss=None):
+    """The figures ``cgcnn.evaluate`` reports (``models_gcn.py:103-109``): accuracy and weighted F1 in percent, the
+    number of correct predictions and the reference's one-line summary string."""
+    labels, predictions = np.asarray(labels).astype(np.int64), np.asarray(predictions).astype(np.int64)
+    n = len(labels)
+    ncorrect = int((labels == predictions).sum())
+    accuracy = 100.0 * ncorrect / max(n, 1)
+    # weighted F1: per-class F1 averaged with the class supports (sklearn.metrics.f1_score(average='weighted'))
+    f1 = 0.0
+    for c in np.unique(labels):
+        tp = float(((predictions == c) & (labels == c)).sum())
+        fp = float(((predictions == c) & (labels != c)).sum())
+        fn = float(((predictions != c) & (labels == c)).sum())
+        denom = 2 * tp + fp + fn
+        f1 += (2 * tp / denom if denom > 0 else 0.0) * float((labels == c).sum())
+    f1 = 100.0 * f1 / max(n, 1)
+    string = "accuracy: {:.2f} ({:d} / {:d}), f1 (weighted): {:.2f}".format(accuracy, ncorrect, n, f1)
+    if loss is not None:
+        string += ", loss: {:.2e}".format(loss)
+    return string, accuracy, f1

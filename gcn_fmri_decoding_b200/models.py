@@ -321,6 +321,18 @@ class cgcnn(nn.Module):
             return preds, total * bs / size
         return preds
 
+    def evaluate(self, data, labels, checkpoint=None):
+        """``(summary string, accuracy %, weighted F1 %, loss)`` over a full data set, like the reference's ``evaluate``
+        (models_gcn.py:72-110); ``checkpoint`` (a file written by ``checkpoints.save_checkpoint``) is restored first,
+        as the reference restores the latest checkpoint."""
+        from . import checkpoints
+
+        if checkpoint is not None:
+            checkpoints.load_checkpoint(self, checkpoint)
+        predictions, loss = self.predict(data, labels)
+        string, accuracy, f1 = checkpoints.classification_summary(labels, predictions, loss)
+        return string, accuracy, f1, loss
+
     # ------------------------------------------------------------------ TF-style names for checkpoints
     def state_dict_tf(self):
         """Parameters under the reference's TF variable names (models_gcn.py:662,343,351,675,680)."""

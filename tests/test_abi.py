@@ -102,3 +102,40 @@ def test_layers_refuse_cpu_tensors(graph_l4):
     m = cgcnn(L=graph_l4["L"][4:], F=[4], K=[2], p=[1], M=[3], channel=2, device="cpu")
     with pytest.raises((ValueError, NotImplementedError, RuntimeError)):
         m(torch.zeros(2, 25, 2))
+
+
+def test_checkpoints_roundtrip_and_best_k(graph_l4, tmp_path):
+    """checkpoints.py: parameters survive a save / load under the reference's TF variable names, and BestCheckpoints
+    keeps the best k by value with the reference's replacement rule (checkmat.py:43-84)."""
+    import json
+    import os
+
+    from gcn_fmri_decoding_b200 import checkpoints
+    from gcn_fmri_decoding_b200.models import cgcnn
+
+    def make(seed):
+        return cgcnn(L=graph_l4["L"], F=[32, 32], K=[5, 5], p=[4, 4], M=[512, 256, 22], channel=15, device="cpu", seed=seed)
+
+    a, b = make(1), make(2)
+    f = checkpoints.save_checkpoint(a, str(tmp_path / "model"), step=7)
+    assert f.endswith("model-7.npz") and checkpoints.latest_checkpoint(str(tmp_path)) == f
+    with np.load(f) as z:
+        assert "conv1__weights" in z.files and z["conv1__weights"].shape == (75, 32) and "logits__bias" in z.files
+    checkpoints.load_checkpoint(b, f)
+    for k, v in a.state_dict_tf().items():
+        assert np.array_equal(v, b.state_dict_tf()[k]), k
+    keep = checkpoints.BestCheckpoints(str(tmp_path / "best"), num_to_keep=2, maximize=True)
+    assert keep.handle(0.50, a, 1) and keep.handle(0.70, a, 2)
+    assert keep.handle(0.40, a, 3) is None                    # worse than everything kept
+    assert keep.handle(0.60, a, 4)                            # replaces the 0.50 checkpoint
+    index = json.load(open(os.path.join(str(tmp_path / "best"), "best_checkpoints")))
+    assert sorted(index.values()) == [0.60, 0.70] and not os.path.exists(str(tmp_path / "best" / "best.ckpt-1.npz"))
+    assert keep.best().endswith("best.ckpt-2.npz")
+    s, acc, f1 = checkpoints.classification_summary([0, 1, 1, 2], [0, 1, 2, 2], loss=0.5)
+    assert abs(acc - 75.0) < 1e-9 and "3 / 4" in s
+    try:
+        import sklearn.metrics
+
+        assert abs(f1 - 100 * sklearn.metrics.f1_score([0, 1, 1, 2], [0, 1, 2, 2], average="weighted")) < 1e-9
+    except ImportError:
+        pass
