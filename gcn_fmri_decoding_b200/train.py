@@ -131,7 +131,11 @@ class Trainer:
 
 
 def shard(n, rank, world):
-    """Contiguous slice of ``range(n)`` rank ``rank`` of ``world`` owns (windows [r*n/G, (r+1)*n/G))."""
+    """Contiguous slice of ``range(n)`` rank ``rank`` of ``world`` owns (windows [r*n/G, (r+1)*n/G)).
+
+    The trainers average the ranks' gradients with equal weights (SUM / world), which is the gradient of the global-batch
+    mean only for EQUAL shards: feed them batches with ``n % world == 0`` (config 4: 4096 over 2/4/8 GPUs), or drop the
+    remainder -- uneven shards would weight the windows of the smaller ranks more."""
     base, rem = divmod(n, world)
     lo = rank * base + min(rank, rem)
     return lo, lo + base + (1 if rank < rem else 0)
