@@ -1,9 +1,14 @@
+# last check of the round: GPU tests, smoke(), evaluate() on the device, the default bench line
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -4 > gpurun_out/r2l_tests.log; tail -2 gpurun_out/r2l_tests.log
-python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -1
-timeout 300 python bench.py > gpurun_out/r2l_bench.json 2> gpurun_out/r2l_bench.err; echo rc=$?
-python - <<'P'
-import json
-d=json.loads(open("gpurun_out/r2l_bench.json").read().strip().splitlines()[-1])
-print(round(d["value"]), "ms", round(d["ms_per_step"],4), "e2e", round(d["e2e"]["value"]), "frac", round(d["roofline"]["frac"],4), "cpu", d["cpu_baseline"] and round(d["cpu_baseline"]["value"]), d["clocks"]["sm_mhz"], d["clocks"]["reasons"], d["gpu_launches_per_step"])
+timeout 600 python -m pytest tests -m gpu -q 2>&1 | tail -2
+python - <<'P' 2>&1 | tail -2
+import numpy as np, torch
+from gcn_fmri_decoding_b200 import synth, checkpoints
+from gcn_fmri_decoding_b200.models import cgcnn
+A, gs, perm, L = synth.brain_graph(4)
+m = cgcnn(L=L, F=[32, 32], K=[5, 5], p=[4, 4], M=[512, 256, 22], channel=15, device="cuda", seed=1, batch_size=32, perm=perm, n_input_vertices=360)
+x, y = synth.bold_windows(70, seed=2), synth.labels(70, seed=2)
+f = checkpoints.save_checkpoint(m, "/tmp/ck/model", step=3)
+print(m.evaluate(x, y, checkpoint=f)[0])
 P
+timeout 200 python bench.py --steps 100 --warmup 10 --no-cpu-baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['ms_per_step'], round(d['value']), round(d['e2e']['value']))"
