@@ -568,8 +568,9 @@ class PredictWorkload:
             top = kernels[1]
             if ops.cheb_stack_supported(pl.rowptr, pl.col, pl.val, B, 32, 5, 5):
                 # what the model's inference path launches for layers 2-6: ONE kernel, activations stay on the SM
+                taps = [model._tap_image(q) for q in range(1, 6)]   # pre-split tap images, as the model's own path uses
                 f3 = lambda i: ops.cheb_stack_fwd(hs[i], pl.rowptr, pl.col, pl.val, model.conv_weights[1:6], model.conv_bias[1:6],
-                                                  5, mode, True)
+                                                  5, mode, True, tap_images=taps)
                 one = layer_bytes(B, 372, 372, 32, 32, 5, 1, pl.nnz, 372 * 32, False, False)
                 nbytes = one + 4 * (4 * (32 * 5 * 32 + 372 * 32))   # + the weights and biases of four more layers
                 sec, per_call = graph_timed(torch, lib, f3, n)

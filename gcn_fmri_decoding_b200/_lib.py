@@ -41,7 +41,9 @@ SIGNATURES = {
     "gcnb_cheb_image_bytes": (_z, [_p, _p] + [_i] * 8),
     "gcnb_cheb_image_build": (_i, [_p, _p, _p] + [_i] * 8 + [_p, _z]),
     "gcnb_cheb_stack_supported": (_i, [_CSRP, _i, _i, _i, _i]),
-    "gcnb_cheb_stack_fwd_f32": (_i, [_p, _CSRP, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "gcnb_cheb_stack_fwd_f32": (_i, [_p, _CSRP, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "gcnb_cheb_tap_image_bytes": (_z, [_i, _i, _i]),
+    "gcnb_cheb_tap_image_build": (_i, [_p, _i, _i, _i, _p, _z]),
     "gcnb_cheb_fwd_f32": (_i, [_p, _p, _i, _CSRP, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _z, _p]),
     "gcnb_cheb_bwd_f32": (_i, [_p, _p, _i, _p, _p, _p, _i, _p, _CSRP, _CSRP, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _z, _p]),
     "gcnb_spectral_workspace_bytes": (_z, [_i] * 6),

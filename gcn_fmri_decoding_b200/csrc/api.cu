@@ -291,8 +291,15 @@ int gcnb_cheb_stack_supported(const gcnb_csr* L, int B, int F, int K, int nlayer
   return umma_stack_supported(LayerShape{B, L->M, L->nnz, F, F, K, 1}, *L) ? 1 : 0;
 }
 
-int gcnb_cheb_stack_fwd_f32(const float* x, const gcnb_csr* L, const float* const* W, const float* const* bias, float* y,
-                            int nlayers, int B, int F, int K, int bias_mode, int relu, gcnb_stream_t stream) {
+size_t gcnb_cheb_tap_image_bytes(int Fin, int Fout, int K) { return cheb_tap_image_bytes(Fin, Fout, K); }
+
+int gcnb_cheb_tap_image_build(const float* W_host, int Fin, int Fout, int K, void* image_host, size_t image_bytes) {
+  return cheb_tap_image_build(W_host, Fin, Fout, K, image_host, image_bytes);
+}
+
+int gcnb_cheb_stack_fwd_f32(const float* x, const gcnb_csr* L, const float* const* W, const float* const* bias,
+                            const void* const* tap_images, float* y, int nlayers, int B, int F, int K, int bias_mode,
+                            int relu, gcnb_stream_t stream) {
   GCNB_REQUIRE(nlayers >= 1 && nlayers <= 8 && W != nullptr, "gcnb_cheb_stack_fwd_f32: 1..8 layers, W must not be NULL");
   int rc = check_layer("gcnb_cheb_stack_fwd_f32", L, B, F, F, K, 1, bias_mode,
                        bias_mode == GCNB_BIAS_NONE ? reinterpret_cast<const float*>(1) : (bias ? bias[0] : nullptr));
@@ -307,7 +314,7 @@ int gcnb_cheb_stack_fwd_f32(const float* x, const gcnb_csr* L, const float* cons
               "(gcnb_cheb_image_build); got F=%d M=%d image=%s", F, L->M, L->image ? "yes" : "none");
     return GCNB_ERR_INVALID;
   }
-  return umma_cheb_stack_fwd(x, *L, W, bias, y, nlayers, s, bias_mode, relu, static_cast<cudaStream_t>(stream));
+  return umma_cheb_stack_fwd(x, *L, W, bias, tap_images, y, nlayers, s, bias_mode, relu, static_cast<cudaStream_t>(stream));
 }
 
 size_t gcnb_cheb_image_bytes(const int32_t* rowptr, const int32_t* col, int B, int M, int nnz, int Fin, int Fout, int K,

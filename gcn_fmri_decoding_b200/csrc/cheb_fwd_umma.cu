@@ -128,6 +128,10 @@ struct UmmaFwdParams {
   int nlayers;
   const float* Wl[8];
   const float* biasl[8];
+  // Pre-split tap images (gcnb_cheb_tap_image_build): the exact bytes of the three tap arrays of a layer (tf32 hi, tf32 lo,
+  // bf16) in their shared-memory layout.  tapimg[l] != NULL: copied by TMA instead of being split from W in the kernel.
+  const unsigned char* tapimg[8];
+  int tap_bytes;  // 2.5 x K * FP * 32 * 4
   unsigned img_sig;  // geometry signature the image must carry
   int n_groups;      // groups of 4 row blocks
   int off_img, off_grp, off_blk;  // shared-memory offsets of the image copy, its group table and its block table
@@ -188,8 +192,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
     // the operator image was built once on the host (gcnb_cheb_image_build): ONE TMA bulk copy brings it in as it is
     // while the rest of the prologue runs (first phase of the staging barrier)
     if (tid == 0) {
-      mbar_expect_tx(bar_stage, (uint32_t)P.img_bytes);
+      const bool tap0 = STACK && P.tapimg[0] != nullptr;
+      mbar_expect_tx(bar_stage, (uint32_t)P.img_bytes + (tap0 ? (uint32_t)P.tap_bytes : 0u));
       bulk_g2s(sb + P.off_img, P.image, (uint32_t)P.img_bytes, bar_stage);
+      if (tap0) bulk_g2s(sb + P.off_wh, P.tapimg[0], (uint32_t)P.tap_bytes, bar_stage);
     }
   }
   if (warp == kMmaWarp) tmem_alloc(sb + P.off_bar + 48, (uint32_t)P.tmem_cols);
@@ -230,8 +236,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
       tap_store(i0, t, nt, wv);
     }
   };
-  float wv0[4];
-  tap_load(P.W, 0, tid, kThreads, wv0);
+  const bool split_taps0 = !(STACK && IMG && P.tapimg[0] != nullptr);  // else: layer 0's taps arrive by TMA (above)
+  float wv0[4] = {0.f, 0.f, 0.f, 0.f};
+  if (split_taps0) tap_load(P.W, 0, tid, kThreads, wv0);
   int perm0 = tid;
   if (P.perm && tid < M) perm0 = __ldg(P.perm + tid);
   const int nlayers = STACK ? P.nlayers : 1;
@@ -242,11 +249,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
   // remainder buffers need no initialisation -- garbage there only reaches accumulator rows nobody reads -- and
   // host the prologue's scratch tables rlen / sorted / rp until the first order overwrites them)
   for (uint32_t a = tid * 16u; a < (uint32_t)P.off_lo; a += kThreads * 16u) sts128(sb + a, make_float4(0.f, 0.f, 0.f, 0.f));
-  tap_store(0, tid, kThreads, wv0);
-  for (int i0 = kThreads * 4; i0 < K * FP * 32; i0 += kThreads * 4) {
-    float wv[4];
-    tap_load(P.W, i0, tid, kThreads, wv);
-    tap_store(i0, tid, kThreads, wv);
+  if (split_taps0) {
+    tap_store(0, tid, kThreads, wv0);
+    for (int i0 = kThreads * 4; i0 < K * FP * 32; i0 += kThreads * 4) {
+      float wv[4];
+      tap_load(P.W, i0, tid, kThreads, wv);
+      tap_store(i0, tid, kThreads, wv);
+    }
   }
   for (int r = tid; r < M; r += kThreads) {
     int s = r == tid ? perm0 : r;
@@ -597,7 +606,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
           if (STACK && nlayers > 1 && it > 0) {
             // the tap images still hold the last layer's: rebuild layer 0's once the tensor cores are done with them
             mbar_wait(bar_mma((n - 1) & 1), ((n - 1) >> 1) & 1);
-            taps_of(P.Wl[0], sw * 32 + lane, kSparseWarps * 32);
+            if (P.tapimg[0] != nullptr) {
+              if (sw == 0 && lane == 0) {
+                mbar_expect_tx(bar_stage, (uint32_t)P.tap_bytes);
+                bulk_g2s(sb + P.off_wh, P.tapimg[0], (uint32_t)P.tap_bytes, bar_stage);
+              }
+              mbar_wait(bar_stage, stage_phase);
+              stage_phase ^= 1u;
+            } else {
+              taps_of(P.Wl[0], sw * 32 + lane, kSparseWarps * 32);
+            }
           }
           const uint32_t lo_u = P.nlo == 2 ? (n & 1u) : 0u;
           if (P.nlo == 1 && n > 0) mbar_wait(bar_mma((n - 1) & 1), ((n - 1) >> 1) & 1);
@@ -798,25 +816,39 @@ __global__ void __launch_bounds__(kThreads, 1) k_cheb_fwd_umma(const UmmaFwdPara
           // static data first: the next layer's taps and this warp's bias rows are in flight while the last MMA finishes
           constexpr int nt = kSparseWarps * 32;
           const int t_ = sw * 32 + lane;
-          float w0[4], w1[4], bv0[16];
+          float w0[4] = {0.f, 0.f, 0.f, 0.f}, w1[4] = {0.f, 0.f, 0.f, 0.f}, bv0[16];
+          const bool tap_tma = P.tapimg[l + 1] != nullptr;  // pre-split taps: one TMA bulk copy instead of the re-split
           TRACEB(sw, 0);
-          tap_load(P.Wl[l + 1], 0, t_, nt, w0);
-          tap_load(P.Wl[l + 1], nt * 4, t_, nt, w1);
+          if (!tap_tma) {
+            tap_load(P.Wl[l + 1], 0, t_, nt, w0);
+            tap_load(P.Wl[l + 1], nt * 4, t_, nt, w1);
+          }
           inner_bias(e, j >> 1, j & 1, l, bv0);
           TRACEB(sw, 1);
           mbar_wait(bar_full(buf), (uint32_t)use & 1u);  // the layer's last MMA is complete: taps and remainder free
           tc_fence_after();
           TRACEB(sw, 2);
-          tap_store(0, t_, nt, w0);
-          tap_store(nt * 4, t_, nt, w1);
-          for (int i0 = 2 * nt * 4; i0 < K * FP * 32; i0 += nt * 4) {
-            float wv[4];
-            tap_load(P.Wl[l + 1], i0, t_, nt, wv);
-            tap_store(i0, t_, nt, wv);
+          if (tap_tma) {
+            if (sw == 0 && lane == 0) {
+              mbar_expect_tx(bar_stage, (uint32_t)P.tap_bytes);
+              bulk_g2s(sb + P.off_wh, P.tapimg[l + 1], (uint32_t)P.tap_bytes, bar_stage);
+            }
+          } else {
+            tap_store(0, t_, nt, w0);
+            tap_store(nt * 4, t_, nt, w1);
+            for (int i0 = 2 * nt * 4; i0 < K * FP * 32; i0 += nt * 4) {
+              float wv[4];
+              tap_load(P.Wl[l + 1], i0, t_, nt, wv);
+              tap_store(i0, t_, nt, wv);
+            }
           }
           const uint32_t dst = sb + (uint32_t)base * buf_bytes, dlo = sb + P.off_lo + (P.nlo == 2 ? (n & 1u) : 0u) * lo_bytes;
           TRACEB(sw, 3);
           inner_share(buf, e, j, l, bv0, dst, dlo);
+          if (tap_tma) {  // the copy ran beside the drain
+            mbar_wait(bar_stage, stage_phase);
+            stage_phase ^= 1u;
+          }
           TRACEB(sw, 4);
           tc_fence_before();
           fence_async_smem();
@@ -1411,6 +1443,7 @@ struct UmmaStack {  // a stack of identical layers run back to back on a tile (U
   int nlayers;
   const float* const* W;
   const float* const* bias;
+  const void* const* tap_images;  // nullable; entries nullable (device pointers, 16-byte aligned)
 };
 
 static int umma_launch(const float* x, const int32_t* perm, int M_in, const gcnb_csr& L, const float* W, const float* bias,
@@ -1447,10 +1480,15 @@ static int umma_launch(const float* x, const int32_t* perm, int M_in, const gcnb
                      xstack == nullptr && y_mean == nullptr,
                  "layer stack: needs an operator image, p = 1, Fin = Fout = 32, 1..8 layers, inference outputs only");
     P.nlayers = stack->nlayers;
+    P.tap_bytes = (int)(2 * (size_t)s.K * pl.FP * 32 * 4 + (size_t)s.K * pl.FP * 32 * 2);
     for (int l = 0; l < stack->nlayers; ++l) {
       P.Wl[l] = stack->W[l];
       P.biasl[l] = stack->bias ? stack->bias[l] : nullptr;
+      P.tapimg[l] = stack->tap_images ? static_cast<const unsigned char*>(stack->tap_images[l]) : nullptr;
+      GCNB_REQUIRE((reinterpret_cast<uintptr_t>(P.tapimg[l]) & 15) == 0, "layer stack: tap image %d is not 16-byte aligned", l);
     }
+    GCNB_REQUIRE(pl.off_wl == pl.off_wh + (int)((size_t)s.K * pl.FP * 32 * 4) && pl.off_wb == pl.off_wl + (pl.off_wl - pl.off_wh) &&
+                     (pl.off_wh & 15) == 0, "layer stack: tap arrays are not contiguous");
     P.W = P.Wl[0];
     P.bias = P.biasl[stack->nlayers - 1];
   }
@@ -1515,9 +1553,48 @@ bool umma_stack_supported(const LayerShape& s, const gcnb_csr& L) {
   return plan_umma_fwd(s, di.sm_count, di.smem_optin, (long long)(L.image_bytes - img_geom(s.M).ent_off)).ok;
 }
 
-int umma_cheb_stack_fwd(const float* x, const gcnb_csr& L, const float* const* W, const float* const* bias, float* y,
-                        int nlayers, const LayerShape& s, int bias_mode, int relu, cudaStream_t st) {
-  UmmaStack stk{nlayers, W, bias};
+// ---- pre-split tap images (host side) ----------------------------------------------------------------------------
+// The kernel's tap split, bit for bit: cvt.rna.tf32.f32 = round to nearest, ties away from zero, to a 10-bit mantissa;
+// the bf16 image is round-to-nearest-even of the fp32 weight.
+static inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+static inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+static inline float host_tf32_rna(float x) { return u2f((f2u(x) + 0x1000u) & 0xffffe000u); }
+static inline uint16_t host_bf16_rn(float x) {
+  const uint32_t u = f2u(x);
+  return (uint16_t)((u + 0x7fffu + ((u >> 16) & 1u)) >> 16);
+}
+
+size_t cheb_tap_image_bytes(int Fin, int Fout, int K) {
+  if (Fin <= 8 || Fin > 32 || Fout < 4 || Fout > 32 || (Fout & 3) || K < 1) return 0;
+  const size_t FP = Fin <= 16 ? 16 : 32;
+  return 2 * (size_t)K * FP * 32 * 4 + (size_t)K * FP * 32 * 2;
+}
+
+int cheb_tap_image_build(const float* W, int Fin, int Fout, int K, void* out, size_t bytes) {
+  GCNB_REQUIRE(W && out && bytes != 0 && bytes == cheb_tap_image_bytes(Fin, Fout, K),
+               "gcnb_cheb_tap_image_build: bad arguments or buffer size");
+  const int FP = Fin <= 16 ? 16 : 32;
+  const size_t taps = (size_t)K * FP * 32 * 4;
+  unsigned char* img = static_cast<unsigned char*>(out);
+  memset(img, 0, bytes);
+  for (int kk = 0; kk < K * FP; ++kk) {
+    const int k = kk / FP, f = kk - k * FP;
+    for (int o = 0; o < 32; ++o) {
+      const float w = (f < Fin && o < Fout) ? W[((size_t)f * K + k) * Fout + o] : 0.f;
+      const float hi = host_tf32_rna(w), lo = host_tf32_rna(w - hi);
+      memcpy(img + tap_off_tf32(kk, o), &hi, 4);
+      memcpy(img + taps + tap_off_tf32(kk, o), &lo, 4);
+      const uint16_t b = host_bf16_rn(w);
+      memcpy(img + 2 * taps + tap_off_bf16(kk, o), &b, 2);
+    }
+  }
+  return GCNB_OK;
+}
+
+int umma_cheb_stack_fwd(const float* x, const gcnb_csr& L, const float* const* W, const float* const* bias,
+                        const void* const* tap_images, float* y, int nlayers, const LayerShape& s, int bias_mode, int relu,
+                        cudaStream_t st) {
+  UmmaStack stk{nlayers, W, bias, tap_images};
   return umma_launch(x, nullptr, s.M, L, W[0], bias ? bias[nlayers - 1] : nullptr, y, nullptr, nullptr, nullptr, s, bias_mode,
                      relu, nullptr, st, &stk);
 }

@@ -150,8 +150,11 @@ int cheb_image_build(const int32_t* rowptr, const int32_t* col, const float* val
                      void* out, size_t bytes);
 // a stack of identical layers (p = 1, 32 -> 32, same operator image) in one launch
 bool umma_stack_supported(const LayerShape& s, const gcnb_csr& L);
-int umma_cheb_stack_fwd(const float* x, const gcnb_csr& L, const float* const* W, const float* const* bias, float* y,
-                        int nlayers, const LayerShape& s, int bias_mode, int relu, cudaStream_t st);
+int umma_cheb_stack_fwd(const float* x, const gcnb_csr& L, const float* const* W, const float* const* bias,
+                        const void* const* tap_images, float* y, int nlayers, const LayerShape& s, int bias_mode, int relu,
+                        cudaStream_t st);
+size_t cheb_tap_image_bytes(int Fin, int Fout, int K);
+int cheb_tap_image_build(const float* W, int Fin, int Fout, int K, void* out, size_t bytes);
 // input gradient dx of a layer through the same kernel (operator L~^T, taps W_k^T, dZ rebuilt from dy / y / argmax)
 bool umma_adj_supported(const LayerShape& s);
 int umma_cheb_adj(const float* dy, int dy_is_mean, const float* y, const uint8_t* argmax, const gcnb_csr& Lt, const float* W,

@@ -239,7 +239,8 @@ class cgcnn(nn.Module):
                     # never leave the SM between the layers
                     pl = self._plan(self.L[i])
                     x = ops.cheb_stack_fwd(x, pl.rowptr, pl.col, pl.val, self.conv_weights[i:j], self.conv_bias[i:j],
-                                           self.K[i], self._bias_mode(), True)
+                                           self.K[i], self._bias_mode(), True,
+                                           tap_images=[self._tap_image(q) for q in range(i, j)])
                     i = j
                     continue
                 x = self.conv(i, x, gather=gather and i == 0)
@@ -253,6 +254,15 @@ class cgcnn(nn.Module):
                     self._layer = None
             i += 1
         return x
+
+    def _tap_image(self, i):
+        """Pre-split tap image of conv layer ``i`` (cached per weight version: rebuilt when the weights change)."""
+        W = self.conv_weights[i]
+        key = (W.data_ptr(), W._version)
+        cache = self.__dict__.setdefault("_tap_images", {})
+        if cache.get(i, (None, None))[0] != key:
+            cache[i] = (key, ops.cheb_tap_image(W, W.shape[0] // self.K[i], self.K[i]))
+        return cache[i][1]
 
     def _stack_run(self, i, x):
         """End (exclusive) of the run of layers starting at ``i`` that ``ops.cheb_stack_fwd`` can take in one launch:

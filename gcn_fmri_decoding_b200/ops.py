@@ -19,6 +19,7 @@ from __future__ import annotations
 import ctypes as C
 from typing import Optional, Tuple
 
+import numpy as np
 import torch
 from torch import Tensor
 
@@ -97,8 +98,22 @@ def cheb_stack_supported(rowptr: Tensor, col: Tensor, val: Tensor, B: int, F: in
     return bool(_lib.lib().gcnb_cheb_stack_supported(C.byref(csr), B, F, K, nlayers))
 
 
+def cheb_tap_image(W: Tensor, Fin: int, K: int) -> Optional[Tensor]:
+    """Pre-split tap image of a layer's weights ``W [Fin*K, Fout]`` as a device byte tensor (``gcnb_cheb_tap_image_build``
+    on the host, then uploaded), or None for widths the tcgen05 kernel does not take.  Valid for these weight VALUES."""
+    L = _lib.lib()
+    Fout = int(W.shape[1])
+    n = L.gcnb_cheb_tap_image_bytes(Fin, Fout, K)
+    if not n:
+        return None
+    host_w = np.ascontiguousarray(W.detach().to("cpu", torch.float32).numpy())
+    img = np.zeros(n, np.uint8)
+    _lib.check(L.gcnb_cheb_tap_image_build(host_w.ctypes.data, Fin, Fout, K, img.ctypes.data, n), "gcnb_cheb_tap_image_build")
+    return torch.from_numpy(img).to(W.device)
+
+
 def cheb_stack_fwd(x: Tensor, rowptr: Tensor, col: Tensor, val: Tensor, Ws, biases, K: int, bias_mode: int,
-                   relu: bool) -> Tensor:
+                   relu: bool, tap_images=None) -> Tensor:
     """A run of identical ChebyNet layers (same operator, p = 1, 32 -> 32, same K) as ONE launch of the tcgen05 kernel
     (``gcnb_cheb_stack_fwd_f32``): activations stay on the SM between the layers.  Inference only (no autograd);
     bit-identical to calling ``cheb_fwd`` layer by layer."""
@@ -118,8 +133,14 @@ def cheb_stack_fwd(x: Tensor, rowptr: Tensor, col: Tensor, val: Tensor, Ws, bias
     y = torch.empty_like(x)
     wp = (C.c_void_p * n)(*[w.data_ptr() for w in Ws])
     bp = (C.c_void_p * n)(*[b.data_ptr() for b in biases]) if bias_mode != BIAS_NONE else None
+    tp = None
+    if tap_images is not None:
+        if len(tap_images) != n:
+            raise ValueError("tap_images must have one entry (tensor or None) per layer")
+        tp = (C.c_void_p * n)(*[None if t is None else t.data_ptr() for t in tap_images])
     csr = csr_struct(rowptr, col, val, (B, F, F, K, 1))
-    rc = _lib.lib().gcnb_cheb_stack_fwd_f32(_ptr(x), C.byref(csr), wp, bp, _ptr(y), n, B, F, K, bias_mode, int(relu), _stream(x))
+    rc = _lib.lib().gcnb_cheb_stack_fwd_f32(_ptr(x), C.byref(csr), wp, bp, tp, _ptr(y), n, B, F, K, bias_mode, int(relu),
+                                            _stream(x))
     _lib.check(rc, "gcnb_cheb_stack_fwd_f32")
     return y
 

@@ -101,11 +101,20 @@ GCNB_API int gcnb_cheb_image_build(const int32_t* rowptr, const int32_t* col, co
  * device pointers).  x [B, M, F] -> y [B, M, F]; the activations between the layers stay on the SM.  Needs the
  * operator image of the layer shape in L->image (gcnb_cheb_image_build(..., Fin = Fout = F, p = 1, adjoint = 0));
  * results are bit-identical to nlayers calls of gcnb_cheb_fwd_f32.  Inference only (no arg-max, no saved basis).
+ * tap_images (NULL, or a host array of nlayers device pointers, entries may be NULL): pre-split tap images of the
+ * layers' weights (gcnb_cheb_tap_image_build, uploaded by the caller, 16-byte aligned) -- the kernel then copies a
+ * layer's taps with one bulk copy instead of splitting W at every layer boundary.  An image belongs to the weight
+ * values it was built from.
  */
 GCNB_API int gcnb_cheb_stack_supported(const gcnb_csr* L, int B, int F, int K, int nlayers);
 GCNB_API int gcnb_cheb_stack_fwd_f32(const float* x, const gcnb_csr* L, const float* const* W, const float* const* bias,
-                                     float* y, int nlayers, int B, int F, int K, int bias_mode, int relu,
-                                     gcnb_stream_t stream);
+                                     const void* const* tap_images, float* y, int nlayers, int B, int F, int K,
+                                     int bias_mode, int relu, gcnb_stream_t stream);
+/* Host side: the three tap arrays of a layer (tf32 hi / lo parts and the bf16 image of W [Fin*K, Fout]) in the
+ * kernel's shared-memory layout, bit for bit what the kernel derives from W itself.  _bytes returns 0 for widths the
+ * tcgen05 kernel does not take. */
+GCNB_API size_t gcnb_cheb_tap_image_bytes(int Fin, int Fout, int K);
+GCNB_API int gcnb_cheb_tap_image_build(const float* W_host, int Fin, int Fout, int K, void* image_host, size_t image_bytes);
 
 /* Feature width FP of the saved-basis buffer `xstack` (K*B*M*FP floats, layout private to the library: [K][B][M][FP]
  * with padded FP for graphs the fused kernels hold in shared memory, vertex-major [K][M][B][Fin] for vertex-level

@@ -965,6 +965,12 @@ def test_layer_stack_is_bit_identical_to_layer_by_layer(dev, graph_l1, brelu, nl
     for w, b in zip(Wt, bt):
         h = ops.cheb_fwd(h, None, *pl.tensors(), w, b, 5, 1, mode, True, False, ops.ALGO_AUTO)[0]
     assert torch.equal(y, h)
+    # pre-split tap images (one TMA bulk copy per layer instead of the in-kernel split): bit for bit the same taps
+    imgs = [ops.cheb_tap_image(w, 32, 5) for w in Wt]
+    assert all(i is not None and i.numel() == 51200 for i in imgs)
+    assert torch.equal(ops.cheb_stack_fwd(xt, pl.rowptr, pl.col, pl.val, Wt, bt, 5, mode, True, tap_images=imgs), y)
+    mixed = [img if q % 2 == 0 else None for q, img in enumerate(imgs)]
+    assert torch.equal(ops.cheb_stack_fwd(xt, pl.rowptr, pl.col, pl.val, Wt, bt, 5, mode, True, tap_images=mixed), y)
     y64 = O.conv_stack(x, [L] * nlayers, [dict(W=w, b=b, K=5, p=1) for w, b in zip(Ws, bs)], brelu=brelu, dtype=np.float64)
     assert rel_inf(y.cpu().numpy(), y64) <= TOL * nlayers
 
