@@ -104,3 +104,49 @@ def test_production_layer_shape_has_an_image_and_a_stack_kernel(graph_l1):
     assert lib.gcnb_cheb_stack_supported(C.byref(csr), 128, 16, 5, 5) == 0      # 32 -> 32 filters only
     bare = _lib.GcnbCsr(rp.ctypes.data, ci.ctypes.data, v.ctypes.data, M, nnz, None, 0)
     assert lib.gcnb_cheb_stack_supported(C.byref(bare), 128, 32, 5, 5) == 0     # needs the image
+
+
+def _tf32_rna(x):
+    """cvt.rna.tf32.f32 on the host: round to nearest, ties away from zero, 10 mantissa bits kept."""
+    u = np.ascontiguousarray(x, np.float32).view(np.uint32)
+    return ((u + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+def _bf16_rne(x):
+    u = np.ascontiguousarray(x, np.float32).view(np.uint32).astype(np.uint64)
+    return ((u + 0x7FFF + ((u >> 16) & 1)) >> 16).astype(np.uint16)
+
+
+@pytest.mark.parametrize("Fin,Fout,K", [(32, 32, 5), (15, 32, 5), (12, 8, 2), (32, 4, 1)])
+def test_tap_image_is_the_split_of_the_weights(Fin, Fout, K):
+    """gcnb_cheb_tap_image_build (host code, include/gcnb200.h): three planes in the kernel's shared-memory layout --
+    tf32 hi = rna(W), tf32 lo = rna(W - hi), bf16 = rne(W) -- of W[fin*K + k, fout] (models_gcn.py:613-616), zero in
+    the padding of the filter dimensions.  hi + lo carries W to 2^-21."""
+    from gcn_fmri_decoding_b200 import _lib
+
+    lib = _lib.lib()
+    n = lib.gcnb_cheb_tap_image_bytes(Fin, Fout, K)
+    FP = 16 if Fin <= 16 else 32
+    plane = K * FP * 32 * 4
+    assert n == 2 * plane + plane // 2
+    W = (np.random.RandomState(Fin * 100 + Fout + K).randn(Fin * K, Fout) * 0.3).astype(np.float32)
+    W[0, 0], W[-1, -1] = 0.0, np.float32(1 + 2.0 ** -11)  # an exact zero and a rounding tie of the tf32 split
+    img = np.full(n, 0xAB, np.uint8)
+    _lib.check(lib.gcnb_cheb_tap_image_build(W.ctypes.data, Fin, Fout, K, img.ctypes.data, n), "tap image")
+    kk, o = np.meshgrid(np.arange(K * FP), np.arange(32), indexing="ij")
+    off32 = ((kk >> 2) * 4 + (o >> 3)) * 128 + (o & 7) * 16 + (kk & 3) * 4
+    off16 = ((kk >> 3) * 4 + (o >> 3)) * 128 + (o & 7) * 16 + (kk & 7) * 2
+    assert len(np.unique(off32)) == off32.size and off32.max() == plane - 4       # the layout is a permutation
+    assert len(np.unique(off16)) == off16.size and off16.max() == plane // 2 - 2
+    hi = img[:plane].view(np.float32)[off32 // 4]
+    lo = img[plane:2 * plane].view(np.float32)[off32 // 4]
+    bf = img[2 * plane:].view(np.uint16)[off16 // 2]
+    k, f = kk // FP, kk % FP
+    want = np.where((f < Fin) & (o < Fout), W[np.minimum(f, Fin - 1) * K + k, np.minimum(o, Fout - 1)], np.float32(0))
+    want = want.astype(np.float32)
+    assert np.array_equal(hi.view(np.uint32), _tf32_rna(want).view(np.uint32))
+    assert np.array_equal(lo.view(np.uint32), _tf32_rna(want - _tf32_rna(want)).view(np.uint32))
+    assert np.array_equal(bf, _bf16_rne(want))
+    assert np.abs((hi.astype(np.float64) + lo) - want).max() <= 2.0 ** -21 * np.abs(want).max()
+    assert lib.gcnb_cheb_tap_image_bytes(8, 32, 5) == 0 and lib.gcnb_cheb_tap_image_bytes(32, 30, 5) == 0
+    assert lib.gcnb_cheb_tap_image_build(W.ctypes.data, Fin, Fout, K, img.ctypes.data, n - 16) != 0  # wrong size: refused

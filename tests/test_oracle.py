@@ -161,3 +161,124 @@ def test_oracle_against_live_reference(graph_l4):
         Lt_ref = graph.rescale_L(sp.csr_matrix(L, copy=True), lmax=2)
         X = rng.randn(L.shape[0], 9).astype(np.float32)
         assert np.array_equal(graph.chebyshev(Lt_ref, X, K), O.chebyshev_basis(O.rescale_L(L), X, K))
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# A second, independent transcription of the TF graph -- the reference's ops replaced one for one by their torch (CPU,
+# fp64) counterparts IN THE REFERENCE'S ORDER (transpose -> reshape -> sparse matmul -> concat -> transpose -> matmul),
+# differentiated by torch.autograd where the reference calls tf.gradients (models_gcn.py:298).  TF 1.x cannot run here,
+# so this is the closest stand-in for "the graph as executed": the NumPy oracle's hand-written forward AND backward must
+# agree with an autograd engine that never saw the oracle's formulas.
+def _torch_network(x, labels, Ls, params, fcs, regularization, filt, brelu, masks=None, keep=1.0):
+    import torch
+    import torch.nn.functional as TF
+
+    t = lambda a: torch.tensor(np.asarray(a, np.float64), requires_grad=True)  # noqa: E731
+    x = torch.tensor(np.asarray(x, np.float64))
+    leaves = dict(W=[t(p["W"]) for p in params], b=[t(p["b"]) for p in params], fcW=[t(W) for W, _ in fcs],
+                  fcb=[t(b) for _, b in fcs])
+    for i, (L, pr) in enumerate(zip(Ls, params)):
+        N, M, Fin = x.shape
+        K, p, W, b = pr["K"], pr["p"], leaves["W"][i], leaves["b"][i]
+        if filt == "fourier":  # models_gcn.py:512-539
+            _, U = np.linalg.eigh(L.toarray())  # graph.fourier (graph.py:110-128), algo 'eigh', in L's own dtype
+            U = torch.tensor(np.ascontiguousarray(U.T).astype(np.float64))
+            xf = torch.matmul(U, x.permute(1, 2, 0).reshape(M, Fin * N)).reshape(M, Fin, N)
+            xf = torch.matmul(W, xf)                                     # [M, Fout, Fin] x [M, Fin, N]
+            xf = xf.permute(2, 1, 0).reshape(N * W.shape[1], M)
+            z = torch.matmul(xf, U).reshape(N, W.shape[1], M).permute(0, 2, 1)
+        else:  # models_gcn.py:587-617 (chebyshev5); chebyshev2 (:558-585) is the same arithmetic
+            Lr = sp.csr_matrix(L, dtype=np.float64)
+            Lr = (Lr / (2 / 2) - sp.identity(M, format="csr", dtype=np.float64)).tocoo()  # graph.rescale_L, lmax = 2
+            Lt = torch.sparse_coo_tensor(np.vstack((Lr.row, Lr.col)), Lr.data, Lr.shape, check_invariants=True).coalesce()
+            x0 = x.permute(1, 2, 0).reshape(M, Fin * N)
+            xs = [x0]
+            if K > 1:
+                x1 = torch.sparse.mm(Lt, x0)
+                xs.append(x1)
+            for _ in range(2, K):
+                x2 = 2 * torch.sparse.mm(Lt, x1) - x0
+                xs.append(x2)
+                x0, x1 = x1, x2
+            xk = torch.stack(xs, 0).reshape(K, M, Fin, N).permute(3, 1, 2, 0).reshape(N * M, Fin * K)
+            z = torch.matmul(xk, W).reshape(N, M, W.shape[1])
+        a = torch.relu(z + (b.reshape(1, 1, -1) if brelu == "b1relu" else b.reshape(1, M, -1)))  # :619-629
+        if p > 1:  # :631-639, SAME: ceil(M/p) windows, padding split pad//2 in front, never the maximum
+            Mo = -(-M // p)
+            pad = Mo * p - M
+            a = TF.pad(a.permute(0, 2, 1), (pad // 2, pad - pad // 2), value=float("-inf"))
+            a = TF.max_pool1d(a, p, p).permute(0, 2, 1)
+        x = a
+    h = x.mean(-1)  # :673
+    for i in range(len(fcs)):
+        h = torch.matmul(h, leaves["fcW"][i]) + leaves["fcb"][i]
+        if i < len(fcs) - 1:
+            h = torch.relu(h)
+            if masks is not None:  # tf.nn.dropout(x, keep_prob): kept values scaled by 1/keep (:677)
+                h = h * torch.tensor(masks[i]) / keep
+    ce = TF.cross_entropy(h, torch.tensor(np.asarray(labels, np.int64)))  # :255-257
+    regs = ([] if filt == "chebyshev2" else leaves["W"]) + leaves["fcW"] + leaves["fcb"]  # :253-262, _weight/_bias_variable
+    loss = ce + regularization * sum((v ** 2).sum() / 2 for v in regs)
+    flat = leaves["W"] + leaves["b"] + leaves["fcW"] + leaves["fcb"]
+    grads = torch.autograd.grad(loss, flat)
+    n, m = len(params), len(fcs)
+    g = [v.numpy() for v in grads]
+    return float(loss.detach()), h.detach().numpy(), g[:n], g[n:2 * n], g[2 * n:2 * n + m], g[2 * n + m:]
+
+
+@pytest.mark.parametrize("filt,brelu,lvls,ps,K,keep", [("chebyshev5", "b1relu", (0, 2), (4, 4), 5, 0.5),   # config 2
+                                                        ("chebyshev5", "b2relu", (3, 3), (1, 1), 3, 1.0),   # config 1 style
+                                                        ("chebyshev2", "b1relu", (2, 3), (2, 4), 2, 1.0),   # config 3a
+                                                        ("fourier", "b1relu", (3, 4), (2, 1), 0, 0.5)])     # config 3b
+def test_network_step_against_torch_autograd_twin(graph_l4, filt, brelu, lvls, ps, K, keep):
+    rng = np.random.RandomState(11)
+    Ls = [graph_l4["L"][l] for l in lvls]
+    B, Fs, widths = 5, (3, 6, 4), (7, 5, 4)
+    params = []
+    for i, L in enumerate(Ls):
+        M, Fin, Fout = L.shape[0], Fs[i], Fs[i + 1]
+        W = rng.randn(M, Fout, Fin) * 0.3 if filt == "fourier" else rng.randn(Fin * K, Fout) * 0.3
+        b = rng.randn(M, Fout) * 0.1 if brelu == "b2relu" else rng.randn(Fout) * 0.1
+        params.append(dict(W=W, b=b, K=K, p=ps[i]))
+    x = rng.randn(B, Ls[0].shape[0], Fs[0])
+    labels = rng.randint(0, widths[-1], B)
+    M_last = -(-Ls[-1].shape[0] // ps[-1])  # SAME pooling: ceil (the chebyshev2 case pools 50 vertices by 4 -> 13)
+    dims = (M_last,) + widths
+    fcs = [(rng.randn(dims[i], dims[i + 1]) * 0.2, rng.randn(dims[i + 1]) * 0.1) for i in range(len(widths))]
+    masks = None if keep == 1.0 else [(rng.rand(B, w) < keep).astype(np.float64) for w in widths[:-1]]
+    val, cg, fg = O.network_step(x, labels, Ls, params, fcs, 5e-4, filter=filt, brelu=brelu, dtype=np.float64,
+                                 dropout_masks=masks, keep=keep)
+    tval, tlogits, tW, tb, tfW, tfb = _torch_network(x, labels, Ls, params, fcs, 5e-4, filt, brelu, masks, keep)
+    assert abs(val - tval) <= 1e-12 * abs(tval)
+    for i in range(len(Ls)):
+        assert rel_inf(cg[i]["dW"], tW[i]) <= 1e-11, (i, "dW")
+        assert rel_inf(np.asarray(cg[i]["db"]).reshape(tb[i].shape), tb[i]) <= 1e-11, (i, "db")
+    for i in range(len(fcs)):
+        assert rel_inf(fg[i][0], tfW[i]) <= 1e-11 and rel_inf(fg[i][1], tfb[i]) <= 1e-11, i
+    # inference path of the oracle (conv_stack + head, no dropout) against the twin's logits
+    if masks is None:
+        logits = O.head(O.conv_stack(x, Ls, params, filter=filt, brelu=brelu, dtype=np.float64), fcs, np.float64)
+        assert rel_inf(logits, tlogits) <= 1e-12
+
+
+@pytest.mark.parametrize("M,p", [(10, 4), (7, 2), (9, 8), (16, 4), (5, 1)])
+def test_mpool1_ragged_against_torch_same_padding(M, p):
+    """SAME max-pooling of a ragged vertex axis and the MaxPoolGrad routing (oracle mpool1 / mpool1_bwd, models_gcn.py:
+    631-639) against torch's max_pool1d + autograd over an explicit -inf padding; values are distinct, so no ties."""
+    import torch
+    import torch.nn.functional as TF
+
+    rng = np.random.RandomState(M * 10 + p)
+    x = rng.permutation(3 * M * 4).reshape(3, M, 4).astype(np.float64)
+    y, am = O.mpool1(x, p, with_argmax=True)
+    dy = rng.randn(*y.shape)
+    dx = O.mpool1_bwd(dy, am, p, M) if p > 1 else dy
+    xt = torch.tensor(x, requires_grad=True)
+    if p > 1:
+        Mo = -(-M // p)
+        pad = Mo * p - M
+        yt = TF.max_pool1d(TF.pad(xt.permute(0, 2, 1), (pad // 2, pad - pad // 2), value=float("-inf")), p, p).permute(0, 2, 1)
+    else:
+        yt = xt * 1
+    (gx,) = torch.autograd.grad((yt * torch.tensor(dy)).sum(), xt)
+    assert np.array_equal(y, yt.detach().numpy()) and np.array_equal(dx, gx.numpy())
