@@ -139,3 +139,47 @@ def test_checkpoints_roundtrip_and_best_k(graph_l4, tmp_path):
         assert abs(f1 - 100 * sklearn.metrics.f1_score([0, 1, 1, 2], [0, 1, 2, 2], average="weighted")) < 1e-9
     except ImportError:
         pass
+
+
+def test_legacy_pooled_six_layer_configuration():
+    """The reference's older six-layer network (HCP_task_fmri_gcn_test8.py:1633-1636): F=[32,32,64,64,128,128],
+    p=[1,4,1,4,1,4], K=[20,10,10,10,5,5] on a 6-level coarsening.  Host side only: Laplacian selection
+    (models_gcn.py:462-469: layers 1-2 use L[0], 3-4 L[2], 5-6 L[4]), parameter shapes under the TF names, and the oracle
+    running the same configuration (narrower filters) against the torch-autograd twin."""
+    from gcn_fmri_decoding_b200 import graclus, synth
+    from gcn_fmri_decoding_b200.models import cgcnn
+    from oracle import layers_np as O
+    from test_oracle import _torch_network
+
+    _, gs, perm, L = synth.brain_graph(6)
+    sizes = [l.shape[0] for l in L]
+    assert len(L) == 7 and all(a == 2 * b for a, b in zip(sizes, sizes[1:]))
+    F, p, K = [32, 32, 64, 64, 128, 128], [1, 4, 1, 4, 1, 4], [20, 10, 10, 10, 5, 5]
+    m = cgcnn(L=L, F=F, K=K, p=p, M=[512, 256, 22], channel=15, device="cpu", perm=perm, n_input_vertices=360)
+    assert [l.shape[0] for l in m.L] == [sizes[0], sizes[0], sizes[2], sizes[2], sizes[4], sizes[4]]
+    sd = m.state_dict_tf()
+    fin = [15] + F[:-1]
+    for i in range(6):
+        assert sd["conv%d/weights" % (i + 1)].shape == (fin[i] * K[i], F[i])
+        assert sd["conv%d/bias" % (i + 1)].shape == (1, 1, F[i])
+    assert sd["fc1/weights"].shape == (sizes[6], 512)  # mean over the 128 filters leaves one value per coarsest vertex
+    # the oracle on this layer pattern (filters scaled down 8x to keep the CPU test short) against the autograd twin
+    rng = np.random.RandomState(5)
+    Fs = [15] + [f // 8 for f in F]
+    params = [dict(W=rng.randn(Fs[i] * K[i], Fs[i + 1]) * (0.5 / np.sqrt(Fs[i] * K[i])), b=rng.randn(Fs[i + 1]) * 0.1,
+                   K=K[i], p=p[i]) for i in range(6)]
+    Ls = O.select_laplacians(L, p)
+    assert [l.shape[0] for l in Ls] == [l.shape[0] for l in m.L]
+    x = graclus.perm_data_3d(synth.bold_windows(3, seed=9), perm).astype(np.float64)
+    labels = synth.labels(3, seed=9)
+    dims = (sizes[6], 6, 5, 22)
+    fcs = [(rng.randn(dims[i], dims[i + 1]) * 0.3, rng.randn(dims[i + 1]) * 0.1) for i in range(3)]
+    val, cg, fg = O.network_step(x, labels, Ls, params, fcs, 5e-4, dtype=np.float64)
+    tval, _, tW, tb, tfW, tfb = _torch_network(x, labels, Ls, params, fcs, 5e-4, "chebyshev5", "b1relu")
+    assert np.isfinite(val) and abs(val - tval) <= 1e-11 * abs(tval)
+    for i in range(6):
+        # T_19 of the recursion amplifies rounding: gradients agree to 1e-9 of their largest entry
+        assert np.abs(cg[i]["dW"] - tW[i]).max() <= 1e-9 * np.abs(tW[i]).max(), i
+        assert np.abs(np.asarray(cg[i]["db"]).reshape(tb[i].shape) - tb[i]).max() <= 1e-9 * np.abs(tb[i]).max(), i
+    for i in range(3):
+        assert np.abs(fg[i][0] - tfW[i]).max() <= 1e-9 * np.abs(tfW[i]).max(), i
