@@ -166,6 +166,18 @@ def cpu_step_times(cfg, n_windows, reps, warm, cores, mode=None):
 CPU_PROBE = {"train": 128, "predict": 64, "vertex": 2}
 
 
+def cpu_model():
+    """Host CPU model string (printed with every CPU number)."""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.lower().startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def run_reference(args, cfg):
     """--impl reference: the CPU implementation of the path (oracle port), all host threads, bounded sample."""
     if int(os.environ.get("RANK", "0")) != 0:
@@ -187,7 +199,7 @@ def run_reference(args, cfg):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": {"workload": cfg["workload"], "sample": "%d windows per step" % n},
-        "cpu_baseline": {"value": value, "unit": "windows/s", "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": "windows/s", "cores": cores, "kind": "port", "cpu": cpu_model(),
                          "sample": "%d-window %s of the NumPy/SciPy oracle, %d steps, %s"
                                    % (n, what, args.steps, CPU_MODE_TEXT[mode])},
         "e2e": {"value": value, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -792,7 +804,7 @@ def main():
         gran = 32 if cfg["kind"] == "train" else (16 if cfg["kind"] == "predict" else 1)
         n = int(min(cfg["batch"], max(gran, (n0 / probe[0] * 4.0) // gran * gran)))   # ~4 s of CPU work per step
         times, mode = cpu_step_times(cfg, n, 5, 1, cores, mode)
-        cpu = {"value": n / float(np.median(times)), "unit": "windows/s", "cores": cores, "kind": "port",
+        cpu = {"value": n / float(np.median(times)), "unit": "windows/s", "cores": cores, "kind": "port", "cpu": cpu_model(),
                "sample": "%d-window %s of the NumPy/SciPy oracle, median of 5 after 1 warm-up, %s"
                          % (n, wl.cpu_what, CPU_MODE_TEXT[mode])}
 
