@@ -120,3 +120,49 @@ def classification_summary(labels, predictions, loss=None):
     if loss is not None:
         string += ", loss: {:.2e}".format(loss)
     return string, accuracy, f1
+
+
+def confusion_matrix(labels, predictions, n_classes):
+    """``C[i, j]`` = windows of class ``i`` predicted as ``j`` over ``range(n_classes)`` -- what the reference prints with
+    ``sklearn.metrics.confusion_matrix(labels, predictions, labels=range(len(target_name)))`` (models_gcn.py:98-99);
+    labels or predictions outside the range are left out, as sklearn does."""
+    labels, predictions = np.asarray(labels).astype(np.int64), np.asarray(predictions).astype(np.int64)
+    ok = (labels >= 0) & (labels < n_classes) & (predictions >= 0) & (predictions < n_classes)
+    C = np.zeros((n_classes, n_classes), np.int64)
+    np.add.at(C, (labels[ok], predictions[ok]), 1)
+    return C
+
+
+def classification_report(labels, predictions, target_names):
+    """Per-class precision / recall / F1 / support table over ``range(len(target_names))`` plus the accuracy, macro and
+    weighted averages -- the text the reference prints through ``sklearn.metrics.classification_report`` when
+    ``evaluate`` is given ``target_name`` (models_gcn.py:94-97).  Returns ``(text, rows)`` with ``rows[name] =
+    (precision, recall, f1, support)``; undefined ratios count as 0, like sklearn's ``zero_division`` default."""
+    labels, predictions = np.asarray(labels).astype(np.int64), np.asarray(predictions).astype(np.int64)
+    n_classes = len(target_names)
+    rows, width = {}, max([len(str(t)) for t in target_names] + [len("weighted avg")])
+    head = "{:>{w}s} {:>9s} {:>9s} {:>9s} {:>9s}".format("", "precision", "recall", "f1-score", "support", w=width)
+    lines = [head, ""]
+    P, R, F, S = [], [], [], []
+    for c, name in enumerate(target_names):
+        tp = float(((predictions == c) & (labels == c)).sum())
+        npred, support = float((predictions == c).sum()), int((labels == c).sum())
+        prec = tp / npred if npred > 0 else 0.0
+        rec = tp / support if support > 0 else 0.0
+        f1 = 2 * prec * rec / (prec + rec) if prec + rec > 0 else 0.0
+        rows[str(name)] = (prec, rec, f1, support)
+        P.append(prec), R.append(rec), F.append(f1), S.append(support)
+        lines.append("{:>{w}s} {:>9.2f} {:>9.2f} {:>9.2f} {:>9d}".format(str(name), prec, rec, f1, support, w=width))
+    total = int(np.sum(S))
+    Wt = np.asarray(S, np.float64) / max(total, 1)
+    # sklearn prints 'accuracy' when the label set covers every label seen, 'micro avg' otherwise; with all classes
+    # listed the two coincide
+    acc = float((labels == predictions).sum()) / max(len(labels), 1)
+    rows["accuracy"] = (acc, acc, acc, total)
+    rows["macro avg"] = (float(np.mean(P)), float(np.mean(R)), float(np.mean(F)), total)
+    rows["weighted avg"] = (float(np.dot(P, Wt)), float(np.dot(R, Wt)), float(np.dot(F, Wt)), total)
+    lines.append("")
+    lines.append("{:>{w}s} {:>9s} {:>9s} {:>9.2f} {:>9d}".format("accuracy", "", "", acc, total, w=width))
+    for key in ("macro avg", "weighted avg"):
+        lines.append("{:>{w}s} {:>9.2f} {:>9.2f} {:>9.2f} {:>9d}".format(key, *rows[key], w=width))
+    return "\n".join(lines) + "\n", rows

@@ -331,15 +331,20 @@ class cgcnn(nn.Module):
             return preds, total * bs / size
         return preds
 
-    def evaluate(self, data, labels, checkpoint=None):
+    def evaluate(self, data, labels, checkpoint=None, target_name=None):
         """``(summary string, accuracy %, weighted F1 %, loss)`` over a full data set, like the reference's ``evaluate``
         (models_gcn.py:72-110); ``checkpoint`` (a file written by ``checkpoints.save_checkpoint``) is restored first,
-        as the reference restores the latest checkpoint."""
+        as the reference restores the latest checkpoint.  With ``target_name`` (class names) the per-class report and
+        the confusion matrix are printed first, as the reference does (:94-101)."""
         from . import checkpoints
 
         if checkpoint is not None:
             checkpoints.load_checkpoint(self, checkpoint)
         predictions, loss = self.predict(data, labels)
+        if target_name is not None:
+            print(checkpoints.classification_report(labels, predictions, target_name)[0])
+            print("Confusion Matrix:")
+            print(checkpoints.confusion_matrix(labels, predictions, len(target_name)))
         string, accuracy, f1 = checkpoints.classification_summary(labels, predictions, loss)
         return string, accuracy, f1, loss
 

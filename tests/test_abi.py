@@ -183,3 +183,30 @@ def test_legacy_pooled_six_layer_configuration():
         assert np.abs(np.asarray(cg[i]["db"]).reshape(tb[i].shape) - tb[i]).max() <= 1e-9 * np.abs(tb[i]).max(), i
     for i in range(3):
         assert np.abs(fg[i][0] - tfW[i]).max() <= 1e-9 * np.abs(tfW[i]).max(), i
+
+
+def test_classification_report_and_confusion_matrix_match_sklearn():
+    """checkpoints.classification_report / confusion_matrix (what the reference's evaluate prints with target_name,
+    models_gcn.py:94-101) against scikit-learn, including a class that is never predicted and one without support."""
+    import sklearn.metrics
+
+    from gcn_fmri_decoding_b200 import checkpoints
+
+    rng = np.random.RandomState(4)
+    names = ["task%d" % i for i in range(6)]
+    y = rng.randint(0, 5, 300)                      # class 5 has no support
+    pred = np.where(rng.rand(300) < 0.7, y, rng.randint(0, 6, 300))
+    pred[pred == 3] = 2                             # class 3 is never predicted
+    text, rows = checkpoints.classification_report(y, pred, names)
+    ref = sklearn.metrics.classification_report(y, pred, labels=range(6), target_names=names, output_dict=True,
+                                                zero_division=0)
+    for name in names + ["macro avg", "weighted avg"]:
+        for got, key in zip(rows[name], ("precision", "recall", "f1-score", "support")):
+            assert abs(got - ref[name][key]) <= 1e-12, (name, key)
+    assert abs(rows["accuracy"][0] - sklearn.metrics.accuracy_score(y, pred)) <= 1e-12
+    assert all(n in text for n in names) and "weighted avg" in text
+    C = checkpoints.confusion_matrix(y, pred, 6)
+    assert np.array_equal(C, sklearn.metrics.confusion_matrix(y, pred, labels=range(6)))
+    s, acc, f1 = checkpoints.classification_summary(y, pred)
+    assert abs(f1 - 100 * sklearn.metrics.f1_score(y, pred, average="weighted")) <= 1e-9
+    assert abs(acc - 100 * sklearn.metrics.accuracy_score(y, pred)) <= 1e-9
