@@ -4,8 +4,10 @@ The reference saves TensorFlow-1.x checkpoints (``tf.train.Saver``, ``lib_new/mo
 named ``conv{i}/weights``, ``conv{i}/bias``, ``fc{i}/weights`` ... ``logits/bias`` (``:662``, ``:343``, ``:351``, ``:675``,
 ``:680``); ``fit`` keeps the best three by validation accuracy (``lib_new/checkmat.py:8-84``, used at
 ``models_gcn.py:127,175``) and ``evaluate`` restores the latest one (``:89-90``).  TensorFlow is not available here, so
-the container is a NumPy ``.npz`` with exactly those names (``W`` as ``[Fin*K, Fout]``, row ``f*K + k``): a
-reference-side ``{v.name[:-2]: sess.run(v) for v in tf.trainable_variables()}`` dump loads unchanged.
+the native container is a NumPy ``.npz`` with exactly those names (``W`` as ``[Fin*K, Fout]``, row ``f*K + k``): a
+reference-side ``{v.name[:-2]: sess.run(v) for v in tf.trainable_variables()}`` dump loads unchanged.  TensorFlow's own
+V2 checkpoint files (``<prefix>.index`` / ``.data-*``) are read and written by ``tf_bundle.py`` in plain Python;
+``load_checkpoint`` accepts such a prefix too.
 """
 from __future__ import annotations
 
@@ -29,7 +31,12 @@ def save_checkpoint(model, path, step=None):
 
 
 def load_checkpoint(model, path):
-    """Load a file written by ``save_checkpoint`` (or any ``.npz`` keyed by the TF variable names, ``/`` or ``__``)."""
+    """Load a file written by ``save_checkpoint`` (or any ``.npz`` keyed by the TF variable names, ``/`` or ``__``), or a
+    TensorFlow V2 checkpoint given by its prefix (``<path>.index`` exists: read by ``tf_bundle``, no TensorFlow needed)."""
+    if os.path.exists(path + ".index"):
+        from . import tf_bundle
+
+        return tf_bundle.load_tf_checkpoint(model, path)
     with np.load(path) as z:
         d = {k.replace("__", "/"): z[k] for k in z.files}
     model.load_state_dict_tf(d)
