@@ -44,15 +44,18 @@ def load_checkpoint(model, path):
 
 
 def latest_checkpoint(directory, prefix="model"):
-    """The checkpoint with the highest step in ``directory`` (``tf.train.latest_checkpoint``), or None."""
+    """The checkpoint with the highest step in ``directory`` (``tf.train.latest_checkpoint``), or None: a ``.npz`` file
+    of ``save_checkpoint``, or the prefix of a TensorFlow checkpoint (``<prefix>-<step>.index``) -- either loads with
+    ``load_checkpoint``."""
     best, best_step = None, -1
-    for f in glob.glob(os.path.join(directory, prefix + "-*.npz")):
-        try:
-            step = int(os.path.basename(f)[len(prefix) + 1:-4])
-        except ValueError:
-            continue
-        if step > best_step:
-            best, best_step = f, step
+    for ext in (".npz", ".index"):
+        for f in glob.glob(os.path.join(directory, prefix + "-*" + ext)):
+            try:
+                step = int(os.path.basename(f)[len(prefix) + 1:-len(ext)])
+            except ValueError:
+                continue
+            if step > best_step:
+                best, best_step = (f if ext == ".npz" else f[:-len(ext)]), step
     return best
 
 

@@ -154,5 +154,7 @@ def test_model_checkpoint_in_tf_format(graph_l4, tmp_path):
     from gcn_fmri_decoding_b200 import checkpoints
 
     c = checkpoints.load_checkpoint(make(3), prefix)   # the generic loader recognises a TF prefix
+    tb.save_tf_checkpoint(a, str(tmp_path / "best.ckpt"), step=300)
+    assert checkpoints.latest_checkpoint(str(tmp_path), prefix="best.ckpt") == prefix   # highest step, TF files included
     assert all(np.array_equal(v, c.state_dict_tf()[k]) for k, v in a.state_dict_tf().items())
     assert int(tb.read_tf_checkpoint(prefix, names=["global_step"])["global_step"]) == 1200
