@@ -103,10 +103,10 @@ class cgcnn(nn.Module):
         for i in range(len(self.p)):
             Mi = self.L[i].shape[0]
             if filter == "fourier":
-                W = self._init_weight(rng, (Mi, self.F[i], Fin), fan_in=self.F[i] * Fin)
+                W = self._init_weight(rng, (Mi, self.F[i], Fin))
                 regularize = True  # models_gcn.py:538
             else:
-                W = self._init_weight(rng, (Fin * self.K[i], self.F[i]), fan_in=Fin * self.K[i])
+                W = self._init_weight(rng, (Fin * self.K[i], self.F[i]))
                 regularize = filter == "chebyshev5"  # :615 regularised, chebyshev2 :583 not
             bshape = (1, 1, self.F[i]) if brelu == "b1relu" else (1, Mi, self.F[i])
             self.conv_weights.append(nn.Parameter(torch.from_numpy(W).to(self.dev)))
@@ -120,7 +120,7 @@ class cgcnn(nn.Module):
         self.fc_weights, self.fc_bias = nn.ParameterList(), nn.ParameterList()
         width = M_last
         for Mi in self.M:
-            W = self._init_weight(rng, (width, Mi), fan_in=width)
+            W = self._init_weight(rng, (width, Mi))
             self.fc_weights.append(nn.Parameter(torch.from_numpy(W).to(self.dev)))
             self.fc_bias.append(nn.Parameter(torch.full((Mi,), 0.2, dtype=torch.float32, device=self.dev)))
             self._regularized += [self.fc_weights[-1], self.fc_bias[-1]]  # fc: both regularised (:652-653)
@@ -129,11 +129,17 @@ class cgcnn(nn.Module):
             self.describe()
 
     # ------------------------------------------------------------------ helpers
-    def _init_weight(self, rng, shape, fan_in):
+    def _init_weight(self, rng, shape):
         if self.initial == "normal":  # tf.truncated_normal_initializer(0, 0.2), models_gcn.py:333
             return synth.truncated_normal(rng, shape, 0.2)
-        # variance_scaling(factor=2, FAN_IN, normal) = truncated normal with std sqrt(2/fan_in)/.8796
-        return synth.truncated_normal(rng, shape, math.sqrt(2.0 / fan_in) / 0.87962566103423978)
+        # 'he' (models_gcn.py:334-337): tf.contrib.layers.variance_scaling_initializer(factor=2.0, mode='FAN_IN',
+        # uniform=False) takes fan_in = shape[-2] * prod(shape[:-2]) -- Fin*K for a Chebyshev filter, M*Fout (sic) for
+        # the [M, Fout, Fin] spectral weight -- and draws a truncated normal of stddev sqrt(1.3 * factor / fan_in)
+        # (contrib's constant 1.3 ~ 1/0.8796^2 compensates the truncation at two standard deviations)
+        fan_in = float(shape[-2] if len(shape) > 1 else shape[-1])
+        for dim in shape[:-2]:
+            fan_in *= float(dim)
+        return synth.truncated_normal(rng, shape, math.sqrt(1.3 * 2.0 / fan_in))
 
     def _plan(self, L):
         key = id(L)

@@ -210,3 +210,22 @@ def test_classification_report_and_confusion_matrix_match_sklearn():
     s, acc, f1 = checkpoints.classification_summary(y, pred)
     assert abs(f1 - 100 * sklearn.metrics.f1_score(y, pred, average="weighted")) <= 1e-9
     assert abs(acc - 100 * sklearn.metrics.accuracy_score(y, pred)) <= 1e-9
+
+
+def test_he_initialiser_follows_tf_contrib_variance_scaling(graph_l4):
+    """initial='he' (models_gcn.py:334-337, the production setting of model.py): truncated normal of stddev
+    sqrt(1.3 * 2 / fan_in) with tf.contrib's fan_in = shape[-2] * prod(shape[:-2]); nothing beyond two stddev."""
+    from gcn_fmri_decoding_b200.models import cgcnn
+
+    m = cgcnn(L=graph_l4["L"], F=[32, 32], K=[5, 5], p=[4, 4], M=[512, 256, 22], channel=15, device="cpu", initial="he")
+    sd = m.state_dict_tf()
+    for name, fan_in in (("conv1/weights", 75), ("conv2/weights", 160), ("fc1/weights", 25), ("fc2/weights", 512)):
+        s = np.sqrt(1.3 * 2.0 / fan_in)
+        w = sd[name]
+        assert abs(w).max() <= 2 * s * (1 + 1e-6), name
+        assert abs(w.std() / (0.87962566 * s) - 1) < 0.05, (name, w.std(), s)   # std of a 2-sigma truncated normal
+    assert np.all(sd["conv1/bias"] == np.float32(0.2))
+    f = cgcnn(L=graph_l4["L"][2:], F=[8], K=[0], p=[2], M=[22], channel=4, filter="fourier", device="cpu", initial="he")
+    w = f.state_dict_tf()["conv1/weights"]          # [M=100, Fout=8, Fin=4]: fan_in = 8 * 100
+    s = np.sqrt(2.6 / 800)
+    assert w.shape == (100, 8, 4) and abs(w).max() <= 2 * s * (1 + 1e-6) and abs(w.std() / (0.87962566 * s) - 1) < 0.05
