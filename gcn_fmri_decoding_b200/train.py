@@ -53,14 +53,57 @@ class TFAdam:
         for p in self.params:
             p.grad = None
 
+    def state(self):
+        """Every tensor a warm-up before a graph capture must put back."""
+        return self.m + self.v + [self.b1_pow, self.b2_pow]
+
+
+class TFDecayedSGD:
+    """The reference's ``momentum == 0`` branch (models_gcn.py:283-292): ``tf.train.GradientDescentOptimizer`` on
+    ``tf.train.exponential_decay(learning_rate, global_step, decay_steps, decay_rate, staircase=True)`` --
+    ``p -= lr * decay_rate ** floor(global_step / decay_steps) * g`` with ``global_step`` the number of updates applied
+    so far (no decay when ``decay_rate == 1``, :284).  No script of the reference selects it (``momentum = 0.9``
+    everywhere: model.py:172); it exists so that a ``cgcnn(momentum=0)`` trains as the reference would.  The step counter
+    lives on the device (CUDA-graph replays advance it)."""
+
+    def __init__(self, params, lr, decay_steps=None, decay_rate=1.0):
+        self.params = [p for p in params]
+        self.lr, self.decay_rate = float(lr), float(decay_rate)
+        self.decay_steps = float(decay_steps) if decay_steps else None
+        if self.decay_rate != 1.0 and not self.decay_steps:
+            raise ValueError("decay_rate != 1 needs decay_steps (models_gcn.py:284-286)")
+        self.global_step = torch.zeros((), dtype=torch.float64, device=self.params[0].device)
+
+    @torch.no_grad()
+    def step(self, grads=None):
+        grads = [p.grad for p in self.params] if grads is None else grads
+        if self.decay_rate != 1.0:
+            lr = self.lr * torch.pow(torch.tensor(self.decay_rate, dtype=torch.float64, device=self.global_step.device),
+                                     torch.floor(self.global_step / self.decay_steps))
+            upd = torch._foreach_mul(grads, -lr.to(torch.float32))
+            torch._foreach_add_(self.params, upd)
+        else:
+            torch._foreach_add_(self.params, grads, alpha=-self.lr)
+        self.global_step.add_(1)
+
+    def state(self):
+        return [self.global_step]
+
 
 class Trainer:
-    """Forward + loss + backward + (all-reduce) + Adam for a ``cgcnn``; optionally CUDA-graph captured."""
+    """Forward + loss + backward + (all-reduce) + optimiser for a ``cgcnn``; optionally CUDA-graph captured.
+
+    Optimiser as the reference picks it (models_gcn.py:291-296): Adam(0.001) unless the model says ``momentum == 0``,
+    which selects plain SGD on the exponentially decayed ``learning_rate``."""
 
     def __init__(self, model, lr=1e-3, distributed=None, use_cuda_graph=False):
         self.model = model
         self.params = [p for p in model.parameters()]
-        self.opt = TFAdam(self.params, lr=lr)
+        if getattr(model, "momentum", 0.9) == 0:
+            self.opt = TFDecayedSGD(self.params, getattr(model, "learning_rate", lr), getattr(model, "decay_steps", None),
+                                    getattr(model, "decay_rate", 1.0))
+        else:
+            self.opt = TFAdam(self.params, lr=lr)
         self.distributed = dist.is_available() and dist.is_initialized() if distributed is None else distributed
         self.world = dist.get_world_size() if self.distributed else 1
         sizes = [p.numel() for p in self.params]
@@ -115,19 +158,14 @@ class Trainer:
         return self._out
 
     def _snapshot(self):
-        return ([p.detach().clone() for p in self.params], [m.clone() for m in self.opt.m],
-                [v.clone() for v in self.opt.v], self.opt.b1_pow.clone(), self.opt.b2_pow.clone())
+        return [p.detach().clone() for p in self.params], [t.clone() for t in self.opt.state()]
 
     def _restore(self, s):
         with torch.no_grad():
             for p, q in zip(self.params, s[0]):
                 p.copy_(q)
-            for a, b in zip(self.opt.m, s[1]):
+            for a, b in zip(self.opt.state(), s[1]):
                 a.copy_(b)
-            for a, b in zip(self.opt.v, s[2]):
-                a.copy_(b)
-            self.opt.b1_pow.copy_(s[3])
-            self.opt.b2_pow.copy_(s[4])
 
 
 def shard(n, rank, world):
@@ -201,6 +239,10 @@ class FusedTrainer:
 
         from . import _lib, ops
 
+        if getattr(model, "momentum", 0.9) == 0:
+            raise NotImplementedError("FusedTrainer implements the Adam branch of the reference's optimiser choice "
+                                      "(models_gcn.py:294, what every reference script selects); momentum == 0 (decayed "
+                                      "SGD, :291-292) trains through train.Trainer")
         self.model, self.lr, self.b1, self.b2, self.eps = model, lr, beta1, beta2, eps
         self.C, self._lib, self.ops = C, _lib, ops
         # keep-probability of the FC dropout: the model's own (what Trainer and the reference use, models_gcn.py:145,677)

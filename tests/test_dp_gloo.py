@@ -112,3 +112,56 @@ def test_two_ranks_equal_one_process_on_the_full_batch():
     for a, b, w in zip(got0, got1, want):
         assert torch.equal(a, b)  # replicas stay identical
         assert torch.allclose(a, w, rtol=1e-5, atol=1e-6)  # mean of shard-means == full-batch mean
+
+
+def test_momentum_zero_selects_decayed_sgd_like_the_reference():
+    """models_gcn.py:283-292: momentum == 0 -> GradientDescentOptimizer on the staircase-decayed learning rate;
+    anything else -> Adam(0.001).  Also: the state a CUDA-graph warm-up must restore is complete for both."""
+    from gcn_fmri_decoding_b200.train import FusedTrainer, TFDecayedSGD
+
+    x, y = _data()
+    net = TinyNet(seed=3)
+    net.momentum, net.learning_rate, net.decay_rate, net.decay_steps = 0, 0.1, 0.5, 2
+    tr = Trainer(net, distributed=False)
+    assert isinstance(tr.opt, TFDecayedSGD)
+    ref = [p.detach().clone().double() for p in net.parameters()]
+    twin = TinyNet(seed=3)
+    for step in range(5):
+        loss = twin.loss(twin(x), y)
+        grads = torch.autograd.grad(loss, list(twin.parameters()))
+        lr = 0.1 * 0.5 ** (step // 2)                         # staircase: global_step counts applied updates
+        with torch.no_grad():
+            for p, g in zip(twin.parameters(), grads):
+                p -= lr * g
+        tr.step(x, y)
+        for a, b in zip(net.parameters(), twin.parameters()):
+            assert torch.allclose(a, b, rtol=1e-6, atol=1e-7), step
+    assert float(tr.opt.global_step) == 5
+    snap = tr._snapshot()
+    tr.step(x, y)
+    tr._restore(snap)
+    assert float(tr.opt.global_step) == 5
+    for a, b in zip(net.parameters(), snap[0]):
+        assert torch.equal(a, b)
+    # Adam: snapshot / restore puts back parameters, both moments and both power accumulators
+    adam = Trainer(TinyNet(seed=4), distributed=False)
+    assert isinstance(adam.opt, TFAdam) and len(adam.opt.state()) == 2 * 3 + 2
+    adam.step(x, y)
+    snap = adam._snapshot()
+    before = [t.clone() for t in adam.opt.state()]
+    adam.step(x, y)
+    assert not torch.equal(adam.opt.b1_pow, before[-2])
+    adam._restore(snap)
+    assert all(torch.equal(a, b) for a, b in zip(adam.opt.state(), before))
+    # no decay: plain SGD; decay without decay_steps is refused; the fused trainer refuses momentum == 0 loudly
+    net2 = TinyNet(seed=5)
+    net2.momentum, net2.learning_rate, net2.decay_rate, net2.decay_steps = 0, 0.05, 1, None
+    p0 = [p.detach().clone() for p in net2.parameters()]
+    g = torch.autograd.grad(net2.loss(net2(x), y), list(net2.parameters()))
+    Trainer(net2, distributed=False).step(x, y)
+    for a, b, gg in zip(net2.parameters(), p0, g):
+        assert torch.allclose(a, b - 0.05 * gg, rtol=1e-6, atol=1e-8)
+    with pytest.raises(ValueError):
+        TFDecayedSGD(list(net2.parameters()), 0.1, None, 0.9)
+    with pytest.raises(NotImplementedError, match="momentum"):
+        FusedTrainer(net2)
