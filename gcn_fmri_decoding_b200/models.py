@@ -337,6 +337,65 @@ class cgcnn(nn.Module):
             return preds, total * bs / size
         return preds
 
+    # ------------------------------------------------------------------ base_model's small public methods
+    def inference(self, data, dropout=1.0):
+        """Logits of a batch (models_gcn.py:224-239)."""
+        return self._inference(data, dropout)
+
+    def probabilities(self, logits):
+        """Class probabilities (models_gcn.py:241-245: ``tf.nn.softmax``)."""
+        return torch.softmax(logits, dim=1)
+
+    def prediction(self, logits):
+        """Predicted classes (models_gcn.py:247-251: ``tf.argmax(logits, axis=1)``)."""
+        return torch.argmax(logits, dim=1)
+
+    def get_var(self, name):
+        """Value of a variable by its TF name, e.g. ``'conv1/weights'`` (models_gcn.py:186-191)."""
+        sd = self.state_dict_tf()
+        key = name[:-2] if name.endswith(":0") else name
+        if key not in sd:
+            raise KeyError("no variable %r (have: %s)" % (name, ", ".join(sd)))
+        return sd[key]
+
+    def fit(self, train_data, train_labels, val_data, val_labels, best_checkpoint_dir=None, trainer=None):
+        """The reference's ``fit`` (models_gcn.py:112-184): ``num_epochs * n / batch_size`` steps on random batches (NumPy's
+        global generator, as there), every ``eval_frequency`` steps the validation set is evaluated and the three best
+        checkpoints by validation accuracy are kept (checkmat.py, directory ``best_checkpoint_dir`` or
+        ``checkpoints/<dir_name>/model``).  Returns ``(accuracies, losses, t_step)`` like the reference.  On a CUDA
+        device the steps run through ``train.FusedTrainer`` fed by ``train.InputPipeline``."""
+        import os
+        import time
+
+        from . import checkpoints, train
+
+        if trainer is None:
+            fused = self.dev.type == "cuda" and self.momentum != 0
+            trainer = train.FusedTrainer(self) if fused else train.Trainer(self)
+        path = best_checkpoint_dir or os.path.join("checkpoints", self.dir_name, "model")
+        keeper = checkpoints.BestCheckpoints(path, num_to_keep=3, maximize=True)
+        n = train_data.shape[0]
+        print("training with {} steps in total with batch_size={} and epochs={} for training_set={}:".format(
+            int(self.num_epochs * n / self.batch_size), self.batch_size, self.num_epochs, n))
+        accuracies, losses = [], []
+        t_process, t_wall = time.process_time(), time.time()
+
+        def on_eval(step, num_steps, loss_average):
+            print("step {} / {} (epoch {:.2f} / {}):".format(step, num_steps, step * self.batch_size / n, self.num_epochs))
+            print("  loss_average = {:.2e}".format(loss_average))
+            string, accuracy, f1, loss = self.evaluate(val_data, val_labels)
+            accuracies.append(accuracy)
+            losses.append(loss)
+            print("  validation {}".format(string))
+            print("  time: {:.0f}s (wall {:.0f}s)".format(time.process_time() - t_process, time.time() - t_wall))
+            keeper.handle(accuracy, self, step)
+
+        history = train.fit(self, train_data, train_labels, trainer=trainer, seed=None, verbose=False, on_eval=on_eval)
+        if accuracies:
+            print("validation accuracy: peak = {:.2f}, mean = {:.2f}".format(max(accuracies), np.mean(accuracies[-10:])))
+        t_step = (time.time() - t_wall) / max(len(history), 1)
+        return accuracies, losses, t_step
+
     def evaluate(self, data, labels, checkpoint=None, target_name=None):
         """``(summary string, accuracy %, weighted F1 %, loss)`` over a full data set, like the reference's ``evaluate``
         (models_gcn.py:72-110); ``checkpoint`` (a file written by ``checkpoints.save_checkpoint``) is restored first,

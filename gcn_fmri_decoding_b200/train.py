@@ -179,11 +179,16 @@ def shard(n, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def fit(model, train_data, train_labels, val_data=None, val_labels=None, trainer=None, seed=0, verbose=True):
+def fit(model, train_data, train_labels, val_data=None, val_labels=None, trainer=None, seed=0, verbose=True,
+        on_eval=None):
     """The reference's training loop (models_gcn.py:112-184): epochs of random batches from a deque of
-    shuffled indices, dropout keep-prob ``model.dropout``, periodic validation.  Returns the loss history."""
+    shuffled indices, dropout keep-prob ``model.dropout``, periodic validation.  Returns the loss history.
+
+    ``seed=None`` draws the permutations from NumPy's global generator, as the reference does (:140);
+    ``on_eval(step, num_steps, loss)`` replaces the built-in report at every evaluation point (``cgcnn.fit`` uses it
+    for the reference's validation / best-checkpoint bookkeeping)."""
     trainer = trainer or Trainer(model)
-    rng = np.random.RandomState(seed)
+    rng = np.random if seed is None else np.random.RandomState(seed)
     n = train_data.shape[0]
     num_steps = int(model.num_epochs * n / model.batch_size)
     indices = collections.deque()
@@ -212,7 +217,10 @@ def fit(model, train_data, train_labels, val_data=None, val_labels=None, trainer
             y = torch.as_tensor(yb, dtype=torch.long, device=dev)
             loss, _ = trainer.step(x, y, dropout=model.dropout if model.dropout else 1.0)
         losses.append(float(loss))
-        if verbose and (step % model.eval_frequency == 0 or step == num_steps):
+        if on_eval is not None:
+            if step % model.eval_frequency == 0 or step == num_steps:
+                on_eval(step, num_steps, losses[-1])
+        elif verbose and (step % model.eval_frequency == 0 or step == num_steps):
             msg = "step %d / %d (epoch %.2f): loss %.4f" % (step, num_steps, step * model.batch_size / n, losses[-1])
             if val_data is not None:
                 pred, vloss = model.predict(val_data, val_labels)

@@ -229,3 +229,52 @@ def test_he_initialiser_follows_tf_contrib_variance_scaling(graph_l4):
     w = f.state_dict_tf()["conv1/weights"]          # [M=100, Fout=8, Fin=4]: fan_in = 8 * 100
     s = np.sqrt(2.6 / 800)
     assert w.shape == (100, 8, 4) and abs(w).max() <= 2 * s * (1 + 1e-6) and abs(w.std() / (0.87962566 * s) - 1) < 0.05
+
+
+def test_reference_style_fit_and_small_methods(graph_l4, tmp_path, monkeypatch, capsys):
+    """cgcnn.fit / get_var / probabilities / prediction with the reference's signatures and return values
+    (models_gcn.py:112-191, :241-251).  Host logic only: the step and the evaluation are stubbed (they need the GPU and
+    are covered by the GPU tests); checked here: step count, evaluation points, best-3 checkpoint bookkeeping, the
+    (accuracies, losses, t_step) tuple."""
+    import json
+    import os
+
+    import torch
+
+    from gcn_fmri_decoding_b200.models import cgcnn
+
+    m = cgcnn(L=graph_l4["L"], F=[32, 32], K=[5, 5], p=[4, 4], M=[512, 256, 22], channel=15, device="cpu",
+              batch_size=8, num_epochs=3, eval_frequency=4, dropout=0.5, dir_name="run1")
+    assert np.array_equal(m.get_var("conv1/weights:0"), m.state_dict_tf()["conv1/weights"])
+    assert m.get_var("logits/bias").shape == (22,)
+    with pytest.raises(KeyError):
+        m.get_var("conv7/weights")
+    lg = torch.tensor([[0.0, 2.0, 1.0], [3.0, 0.0, 0.0]])
+    assert m.prediction(lg).tolist() == [1, 0] and torch.allclose(m.probabilities(lg).sum(1), torch.ones(2))
+
+    seen = []
+
+    class StubTrainer:
+        def step(self, x, y, dropout=None):
+            assert tuple(x.shape) == (8, 360, 15) and x.dtype == torch.float32 and y.dtype == torch.long and dropout == 0.5
+            seen.append(y.clone())
+            return torch.tensor(1.0 / len(seen)), None
+
+    accs = iter([40.0, 55.0, 50.0, 60.0, 45.0, 58.0])
+    monkeypatch.setattr(m, "evaluate", lambda d, l, **kw: ("accuracy: stub", next(accs), 0.0, 0.25))
+    data = np.zeros((32, 360, 15), np.float32)
+    labels = np.arange(32) % 21
+    np.random.seed(0)
+    accuracies, losses, t_step = m.fit(data, labels, data[:8], labels[:8], best_checkpoint_dir=str(tmp_path / "best"),
+                                       trainer=StubTrainer())
+    assert len(seen) == 12                                   # int(3 epochs * 32 / 8)
+    assert accuracies == [40.0, 55.0, 50.0] and losses == [0.25] * 3 and t_step > 0      # evaluated at steps 4, 8, 12
+    # every window is used once per pass before any is used twice (the reference's deque of permutations)
+    first_pass = torch.cat(seen[:4]).numpy()
+    assert sorted(first_pass.tolist()) == sorted(labels.tolist())
+    index = json.load(open(tmp_path / "best" / "best_checkpoints"))
+    assert index == {"best.ckpt-4.npz": 40.0, "best.ckpt-8.npz": 55.0, "best.ckpt-12.npz": 50.0}
+    assert all(os.path.exists(tmp_path / "best" / k) for k in index)
+    out = capsys.readouterr().out
+    assert "training with 12 steps in total with batch_size=8 and epochs=3 for training_set=32:" in out
+    assert "validation accuracy: peak = 55.00, mean = 48.33" in out and "step 12 / 12 (epoch 3.00 / 3):" in out
