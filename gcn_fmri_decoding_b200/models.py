@@ -314,10 +314,13 @@ class cgcnn(nn.Module):
         return ce
 
     @torch.no_grad()
-    def predict(self, data, labels=None):
-        """Batched prediction with the reference's zero-padded last batch (models_gcn.py:31-71)."""
+    def predict(self, data, labels=None, return_logits=False):
+        """Batched prediction with the reference's zero-padded last batch (models_gcn.py:31-71); with ``return_logits``
+        the logits ``[size, n_classes]`` are returned as a third (second, without labels) value -- what
+        ``model_perf.predict`` collects (:1012-1016)."""
         size = data.shape[0]
         preds = np.empty(size)
+        all_logits = np.empty((size, self.M[-1]), np.float32) if return_logits else None
         total = 0.0
         bs = self.batch_size
         for begin in range(0, size, bs):
@@ -333,9 +336,12 @@ class cgcnn(nn.Module):
                     l = 0.0
                 total += l
             preds[begin:end] = logits.argmax(1)[: end - begin].cpu().numpy()
-        if labels is not None:
-            return preds, total * bs / size
-        return preds
+            if return_logits:
+                all_logits[begin:end] = logits[: end - begin].detach().cpu().numpy()
+        out = (preds, total * bs / size) if labels is not None else (preds,)
+        if return_logits:
+            out += (all_logits,)
+        return out if len(out) > 1 else out[0]
 
     # ------------------------------------------------------------------ base_model's small public methods
     def inference(self, data, dropout=1.0):

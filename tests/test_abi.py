@@ -278,3 +278,74 @@ def test_reference_style_fit_and_small_methods(graph_l4, tmp_path, monkeypatch, 
     out = capsys.readouterr().out
     assert "training with 12 steps in total with batch_size=8 and epochs=3 for training_set=32:" in out
     assert "validation accuracy: peak = 55.00, mean = 48.33" in out and "step 12 / 12 (epoch 3.00 / 3):" in out
+
+
+def test_model_perf_harness(graph_l4, tmp_path, monkeypatch, capsys):
+    """perf.model_perf (models_gcn.py:936-1075): test() book-keeping and predict()'s checkpoint choice, reports and
+    per-subject / per-time-point tables against scikit-learn.  The network itself is stubbed (GPU code)."""
+    import sklearn.metrics
+
+    from gcn_fmri_decoding_b200 import checkpoints, tf_bundle
+    from gcn_fmri_decoding_b200.models import cgcnn
+    from gcn_fmri_decoding_b200.perf import model_perf
+
+    def make(seed):
+        return cgcnn(L=graph_l4["L"], F=[32, 32], K=[5, 5], p=[4, 4], M=[512, 256, 6], channel=15, device="cpu", seed=seed)
+
+    trained, m = make(1), make(2)
+    run = tmp_path / "run"
+    # a run directory as the reference's BestCheckpointSaver leaves it: the state file lists the kept checkpoints best first
+    tf_bundle.save_tf_checkpoint(make(5), str(run / "model" / "best.ckpt"), step=100)
+    tf_bundle.save_tf_checkpoint(trained, str(run / "model" / "best.ckpt"), step=300)
+    (run / "model" / "checkpoint").write_text('model_checkpoint_path: "best.ckpt-300"\n'
+                                              'all_model_checkpoint_paths: "best.ckpt-300"\n'
+                                              'all_model_checkpoint_paths: "best.ckpt-100"\n')
+    rng = np.random.RandomState(2)
+    n_sub, per_sub, names = 4, 34, ["t%d" % i for i in range(6)]
+    y = rng.randint(0, 6, n_sub * per_sub)
+    pred = np.where(rng.rand(len(y)) < 0.6, y, rng.randint(0, 6, len(y))).astype(np.float64)
+    logits = rng.randn(len(y), 6).astype(np.float32)
+    calls = {}
+
+    def fake_predict(data, labels=None, return_logits=False):
+        calls["bs"] = m.batch_size
+        return pred, 0.125, logits
+
+    monkeypatch.setattr(m, "predict", fake_predict)
+    perf = model_perf()
+    lg, pl, loss, acc = perf.predict(run, np.zeros((len(y), 360, 15), np.float32), y, target_name=names, batch_size=64, model=m)
+    assert calls["bs"] == 64 and m.batch_size != 64                      # the harness' batch size, then restored
+    assert all(np.array_equal(v, m.state_dict_tf()[k]) for k, v in trained.state_dict_tf().items())   # best.ckpt-300
+    assert lg is logits and np.array_equal(pl, pred) and loss == 0.125
+    assert abs(acc[0] - 100 * sklearn.metrics.accuracy_score(y, pred)) < 1e-9
+    out = capsys.readouterr().out
+    assert "Confusion Matrix:" in out and "f1 (weighted):" in out and "best.ckpt-300" in out
+    _, _, _, table = perf.predict(run, None, y, target_name=names, model=m, sub_name=["s%d" % i for i in range(n_sub)])
+    assert table.shape == (n_sub, 7)
+    ys, ps = y.reshape(n_sub, -1), pred.reshape(n_sub, -1)
+    for si in range(n_sub):
+        assert abs(table[si, -1] - sklearn.metrics.f1_score(ys[si], ps[si], average="weighted")) < 1e-12
+        for li in range(6):
+            mask = ys[si] == li
+            assert abs(table[si, li] - sklearn.metrics.f1_score(ys[si, mask], ps[si, mask], average="weighted")) < 1e-12
+    _, _, _, per_t = perf.predict(run, None, y, target_name=names, model=m, trial_dura=17, flag_starttr=True)
+    yt, pt = y.reshape(-1, 17), pred.reshape(-1, 17)
+    assert per_t.shape == (6, 17)
+    mask = yt[:, 3] == 2
+    assert abs(per_t[2, 3] - 100 * sklearn.metrics.accuracy_score(yt[mask, 3], pt[mask, 3])) < 1e-9
+    with pytest.raises(ValueError, match="model="):
+        perf.predict(run, None, y, target_name=names)
+    # without TensorFlow's state file: the best of a BestCheckpoints index
+    run2 = tmp_path / "run2"
+    keep = checkpoints.BestCheckpoints(str(run2 / "model"), num_to_keep=3)
+    keep.handle(0.4, make(7), 10), keep.handle(0.9, trained, 20), keep.handle(0.5, make(8), 30)
+    m2 = make(9)
+    monkeypatch.setattr(m2, "predict", fake_predict)
+    perf.predict(run2, None, y, model=m2)
+    assert all(np.array_equal(v, m2.state_dict_tf()[k]) for k, v in trained.state_dict_tf().items())
+    # test(): fit + two evaluations, figures stored under the experiment's name
+    monkeypatch.setattr(m, "fit", lambda *a, **k: ([50.0, 60.0], [1.0, 0.8], 0.01))
+    monkeypatch.setattr(m, "evaluate", lambda d, l, target_name=None: ("accuracy: stub", float(len(l)), 1.0, 0.5))
+    perf.test(m, "cheby", dict(K=5), None, [0] * 7, None, None, None, [0] * 3)
+    assert perf.names == {"cheby"} and perf.fit_accuracies["cheby"] == [50.0, 60.0] and perf.fit_time["cheby"] == 0.01
+    assert perf.train_accuracy["cheby"] == 7.0 and perf.test_accuracy["cheby"] == 3.0 and perf.params["cheby"] == dict(K=5)
