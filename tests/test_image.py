@@ -150,3 +150,44 @@ def test_tap_image_is_the_split_of_the_weights(Fin, Fout, K):
     assert np.abs((hi.astype(np.float64) + lo) - want).max() <= 2.0 ** -21 * np.abs(want).max()
     assert lib.gcnb_cheb_tap_image_bytes(8, 32, 5) == 0 and lib.gcnb_cheb_tap_image_bytes(32, 30, 5) == 0
     assert lib.gcnb_cheb_tap_image_build(W.ctypes.data, Fin, Fout, K, img.ctypes.data, n - 16) != 0  # wrong size: refused
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_image_of_random_operators_decodes_exactly(seed):
+    """Seeded sweep of the host image builder over operators that are NOT Graclus Laplacians: random sparsity (empty
+    rows, rows up to 40 entries, entries on the diagonal), sizes up to what shared memory can take, every pooling size
+    and the adjoint flag.  Whenever the library offers an image it must decode to the operator exactly; when it
+    declines (returns 0 bytes) that is a size decision, never an error."""
+    import scipy.sparse as sp
+
+    from gcn_fmri_decoding_b200 import _lib
+
+    rng = np.random.RandomState(100 + seed)
+    M = int(rng.choice([8, 36, 100, 252, 372, 400, 512, 1000]))
+    p = int(rng.choice([q for q in (1, 2, 4, 8) if M % q == 0]))
+    Fin = int(rng.choice([9, 15, 16, 17, 32]))
+    Fout = int(rng.choice([4, 8, 32]))
+    K = int(rng.randint(1, 7))
+    adjoint = int(rng.randint(0, 2))
+    deg = rng.randint(0, int(rng.choice([3, 10, 25])) + 1, M)
+    deg[rng.rand(M) < 0.1] = 0                                         # empty rows (the reference's fake vertices)
+    rows = np.repeat(np.arange(M), deg)
+    cols = rng.randint(0, M, len(rows))
+    A = sp.csr_matrix((rng.randn(len(rows)).astype(np.float32), (rows, cols)), shape=(M, M))
+    A.sum_duplicates()
+    A.sort_indices()
+    A.data[A.data == 0] = 1.0
+    rp, ci, v = A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data.astype(np.float32)
+    lib = _lib.lib()
+    args = (8, M, len(v), Fin, Fout, K, p, adjoint)
+    n = lib.gcnb_cheb_image_bytes(rp.ctypes.data, ci.ctypes.data, *args)
+    if not adjoint and M <= 400 and len(v) <= 4000:
+        assert n > 0, "small forward operators must get an image"  # (adjoint mode swaps Fin / Fout: narrow Fout declines)
+    if n == 0:
+        return
+    assert n % 16 == 0
+    img = np.zeros(n, np.uint8)
+    _lib.check(lib.gcnb_cheb_image_build(rp.ctypes.data, ci.ctypes.data, v.ctypes.data, *args, img.ctypes.data, n), "build")
+    if len(v) == 0:
+        return
+    assert np.array_equal(_decode(img, M, 1 if adjoint else p), np.asarray(A.todense(), np.float32))
