@@ -191,3 +191,27 @@ def test_image_of_random_operators_decodes_exactly(seed):
     if len(v) == 0:
         return
     assert np.array_equal(_decode(img, M, 1 if adjoint else p), np.asarray(A.todense(), np.float32))
+
+
+def test_three_term_split_error_model():
+    """Numerics of the tcgen05 contraction, emulated on the CPU: z = trunc_tf32(X) tf32(W) +
+    trunc_tf32(X) tf32(W - tf32(W)) + bf16(X - trunc_tf32(X)) bf16(W) with exact products and wide accumulation.  The
+    terms left out are (X - X_hi)(W - bf16 W), the bf16 rounding of the remainder and W - W_hi - W_lo: at most
+    (2^-10 2^-9 + 2^-10 2^-9 + 2^-22) |x||w| < 4.1e-6 |x||w| per product -- two orders below the 1e-4 parity tolerance,
+    which is why one bf16 remainder term is enough.  Checked on operands shaped like conv 1 of config 2 (75 -> 32)."""
+    rng = np.random.RandomState(0)
+    X = (rng.randn(4096, 75) * np.exp(rng.randn(4096, 75))).astype(np.float32)      # wide dynamic range
+    W = (rng.randn(75, 32) * 0.2).astype(np.float32)
+    x_hi = (X.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)              # what kind::tf32 reads of X
+    x_lo = (_bf16_rne(X - x_hi).astype(np.uint32) << 16).view(np.float32)
+    w_hi = _tf32_rna(W)
+    w_lo = _tf32_rna(W - w_hi)
+    w_b = (_bf16_rne(W).astype(np.uint32) << 16).view(np.float32)
+    f8 = np.float64
+    z = x_hi.astype(f8) @ w_hi.astype(f8) + x_hi.astype(f8) @ w_lo.astype(f8) + x_lo.astype(f8) @ w_b.astype(f8)
+    exact = X.astype(f8) @ W.astype(f8)
+    bound = 4.1e-6 * (np.abs(X).astype(f8) @ np.abs(W).astype(f8))
+    assert np.all(np.abs(z - exact) <= bound)
+    assert np.abs(z - exact).max() / np.abs(exact).max() < 2e-6                        # the parity norm: far below 1e-4
+    one_pass = x_hi.astype(f8) @ w_hi.astype(f8)                                        # plain TF32 would NOT do:
+    assert np.abs(one_pass - exact).max() / np.abs(exact).max() > 1e-4
