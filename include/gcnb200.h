@@ -76,14 +76,15 @@ GCNB_API const char* gcnb_last_error_string(void);
 /* Number of kernels this library has enqueued in this process so far (diagnostic; monotonic). */
 GCNB_API unsigned long long gcnb_launch_count(void);
 
-/* 1 if the fused shared-memory kernels can take this layer shape, else 0. */
+/* 1 if the fused shared-memory kernels can take this layer shape, else 0 (no reference counterpart: dispatch query). */
 GCNB_API int gcnb_cheb_fused_supported(int B, int M, int nnz, int Fin, int Fout, int K, int p, int backward, int need_dx);
 
 /* Human-readable description of the forward kernel AUTO dispatch picks for this shape (diagnostics, bench records). */
 GCNB_API int gcnb_cheb_fwd_describe(int B, int M, int nnz, int Fin, int Fout, int K, int p, char* out, size_t n);
 
 /*
- * Operator image of a layer (see gcnb_csr.image).  rowptr / col / val are HOST arrays of the rescaled Laplacian the
+ * Operator image of a layer (see gcnb_csr.image) -- the counterpart of turning the rescaled Laplacian into a
+ * tf.SparseTensor once per graph build (models_gcn.py:590-596).  rowptr / col / val are HOST arrays of the rescaled Laplacian the
  * layer is called with -- for adjoint != 0 of its TRANSPOSE, and the image then serves the input gradient of
  * gcnb_cheb_bwd_f32 (pass it in Lt->image).  The shape arguments are the layer's (the same as in the fwd / bwd call);
  * an image is only valid for that shape on that device model.  gcnb_cheb_image_bytes returns 0 when no image-based
@@ -225,7 +226,8 @@ GCNB_API int gcnb_softmax_xent_f32(const float* logits, const int64_t* labels, f
  * Dropout: keep-probability `keep` (1 = none), counter-based masks keyed by (seed1 | seed2, adam_state[3]) -- the masks
  * gcnb_relu_dropout_fwd_f32 draws -- so CUDA-graph replays draw fresh masks.  tick != 0 advances the optimiser clock
  * {b1^t, b2^t, lr_t, t} in adam_state (as gcnb_softmax_xent_f32 does) after the masks of this step have been drawn.
- * A label outside [0, C) contributes neither loss nor gradient.  fp32 FFMA throughout; fixed-order reductions.
+ * A label outside [0, C) contributes neither loss nor gradient.  64x64 tiles on the tensor cores with both operands
+ * split (3xTF32: fp32-level products), fp32 epilogues, fixed-order reductions.
  */
 GCNB_API size_t gcnb_head_step_workspace_bytes(int B, int n0, int n1, int n2, int C); /* 0: sizes not supported */
 GCNB_API int gcnb_head_step_f32(const float* a0, const int64_t* labels, const float* W1, const float* b1, const float* W2,
@@ -236,7 +238,8 @@ GCNB_API int gcnb_head_step_f32(const float* a0, const int64_t* labels, const fl
                                 size_t workspace_bytes, gcnb_stream_t stream);
 
 /* C[M x N] = op(A) op(B) (+ bias[N]); row-major, fp32 in/out, tensor cores with a 3-pass TF32 split (fp32-level
- * accuracy).  The dense transforms of the spectral layer and the FC layers of the training step use it. */
+ * accuracy): tf.matmul of the spectral transforms (models_gcn.py:516-527) and of cgcnn.fc (:654) when the head runs
+ * launch by launch. */
 GCNB_API int gcnb_gemm_f32(const float* A, const float* B, float* C, const float* bias, int M, int N, int K, int lda,
                   int ldb, int ldc, int transA, int transB, gcnb_stream_t stream);
 
@@ -258,7 +261,8 @@ GCNB_API int gcnb_relu_dropout_fwd_f32(float* x, long long rows, int cols, int l
 /* d = (act > 0) ? d / keep : 0 in place (act = output of the forward; act > 0 <=> ReLU active and kept). */
 GCNB_API int gcnb_relu_dropout_bwd_f32(float* d, const float* act, long long rows, int cols, int ld_d, int ld_act,
                               float keep, gcnb_stream_t stream);
-/* out_i[c] = sum_r m_i[r][c] for up to 4 row-major matrices in one launch (bias gradients of the FC layers). */
+/* out_i[c] = sum_r m_i[r][c] for up to 4 row-major matrices in one launch: the bias gradients tf.gradients builds for
+ * the `+ b` of cgcnn.fc (models_gcn.py:653-654, :298-303). */
 GCNB_API int gcnb_colsum_multi_f32(const float* const* mats, float* const* outs, const int* rows, const int* cols,
                           int count, gcnb_stream_t stream);
 
