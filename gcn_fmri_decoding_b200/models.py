@@ -345,8 +345,8 @@ class cgcnn(nn.Module):
 
     # ------------------------------------------------------------------ base_model's small public methods
     def inference(self, data, dropout=1.0):
-        """Logits of a batch (models_gcn.py:224-239)."""
-        return self._inference(data, dropout)
+        """Logits of a batch (models_gcn.py:224-239); raw windows are permuted on the way in, as in ``forward``."""
+        return self.forward(data, dropout)
 
     def probabilities(self, logits):
         """Class probabilities (models_gcn.py:241-245: ``tf.nn.softmax``)."""

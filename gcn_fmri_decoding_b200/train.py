@@ -242,7 +242,8 @@ class FusedTrainer:
     """
 
     def __init__(self, model, lr=1e-3, distributed=None, use_cuda_graph=True, dropout=None, beta1=0.9, beta2=0.999,
-                 eps=1e-8, own_gemm=True, save_basis=True, fused_head=True, peer_allreduce=True, dropout_seed=None):
+                 eps=1e-8, own_gemm=True, save_basis=True, fused_head=True, peer_allreduce=True, dropout_seed=None,
+                 gather=None):
         import ctypes as C
 
         from . import _lib, ops
@@ -266,6 +267,12 @@ class FusedTrainer:
         self.dropout_seed = int(base) & 0x7FFFFFFF
         self.fused_head = fused_head
         self.save_basis = save_basis
+        # gather: True = the steps get raw [B, n_input_vertices, C] windows (permuted in the first layer's load), False =
+        # already permuted input, None = tell by the shape -- refused when the two shapes coincide (as cgcnn.forward does)
+        if gather is None and model.perm is not None and model.n_input_vertices == model.L[0].shape[0]:
+            raise ValueError("FusedTrainer: with perm set and n_input_vertices == M_0 say gather=True (raw windows) or "
+                             "gather=False (already permuted) -- the shapes are identical")
+        self.gather = gather
         self.distributed = dist.is_available() and dist.is_initialized() if distributed is None else distributed
         self.world = dist.get_world_size() if self.distributed else 1
         self.params = [p for p in model.parameters()]
@@ -351,7 +358,10 @@ class FusedTrainer:
         nconv, nfc = len(m.p), len(m.M)
         mode = m._bias_mode()
         cheb = m.filter_name != "fourier"
-        gather = m.perm is not None and x.shape[1] == m.n_input_vertices != m.L[0].shape[0]
+        gather = self.gather
+        if gather is None:
+            gather = m.perm is not None and x.shape[1] == m.n_input_vertices != m.L[0].shape[0]
+        gather = bool(gather) and m.perm is not None
         # ---- forward: conv stack (the last layer also emits the mean over its filters = the head's input) ----
         saved, h, h0 = [], x, None
         for i in range(nconv):

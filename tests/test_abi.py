@@ -349,3 +349,19 @@ def test_model_perf_harness(graph_l4, tmp_path, monkeypatch, capsys):
     perf.test(m, "cheby", dict(K=5), None, [0] * 7, None, None, None, [0] * 3)
     assert perf.names == {"cheby"} and perf.fit_accuracies["cheby"] == [50.0, 60.0] and perf.fit_time["cheby"] == 0.01
     assert perf.train_accuracy["cheby"] == 7.0 and perf.test_accuracy["cheby"] == 3.0 and perf.params["cheby"] == dict(K=5)
+
+
+def test_fused_trainer_refuses_ambiguous_input_layout(graph_l4):
+    """perm set and no fake vertices added: raw and permuted batches have the same shape -- the trainer asks (as
+    cgcnn.forward does) instead of guessing.  Raised before any device work."""
+    from gcn_fmri_decoding_b200.models import cgcnn
+    from gcn_fmri_decoding_b200.train import FusedTrainer
+
+    m = cgcnn(L=graph_l4["L"][4:], F=[4], K=[2], p=[1], M=[3], channel=2, device="cpu", perm=np.arange(25),
+              n_input_vertices=25)
+    with pytest.raises(ValueError, match="gather=True"):
+        FusedTrainer(m, distributed=False)
+    import torch
+
+    with pytest.raises(ValueError, match="gather=True"):
+        m.inference(torch.zeros(2, 25, 2))
