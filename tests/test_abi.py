@@ -365,3 +365,38 @@ def test_fused_trainer_refuses_ambiguous_input_layout(graph_l4):
 
     with pytest.raises(ValueError, match="gather=True"):
         m.inference(torch.zeros(2, 25, 2))
+
+
+def test_c_abi_from_plain_c(tmp_path):
+    """include/gcnb200.h is a C header (C99, -pedantic -Werror) and the library links and answers from plain C exactly
+    as through ctypes -- the boundary a cgo / JNI / N-API binding would use.  Host-only calls, no GPU."""
+    import shutil
+    import subprocess
+
+    from gcn_fmri_decoding_b200 import _lib
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    exe = str(tmp_path / "abi_host_calls")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "abi_c", "abi_host_calls.c"), "-o", exe, "-L", libdir,
+                    "-l:" + os.path.basename(_lib.LIB_PATH), "-Wl,-rpath," + libdir], check=True)
+    out = dict(line.split(" ", 1) for line in subprocess.run([exe], check=True, capture_output=True, text=True).stdout.splitlines())
+    lib = _lib.lib()
+    assert int(out["version"]) == lib.gcnb_version()
+    assert int(out["tap_bytes"]) == lib.gcnb_cheb_tap_image_bytes(32, 32, 5) == 2 * 5 * 32 * 32 * 4 + 5 * 32 * 32 * 2
+    assert int(out["tap_bytes_unsupported"]) == 0
+    M = 8
+    rows = [[j for j in (i - 1, i + 1) if 0 <= j < M] for i in range(M)]
+    rp = np.cumsum([0] + [len(r) for r in rows]).astype(np.int32)
+    ci = np.array([j for r in rows for j in r], np.int32)
+    v = np.full(len(ci), -0.5, np.float32)
+    n = lib.gcnb_cheb_image_bytes(rp.ctypes.data, ci.ctypes.data, 4, M, len(ci), 16, 8, 3, 2, 0)
+    img = np.zeros(n, np.uint8)
+    _lib.check(lib.gcnb_cheb_image_build(rp.ctypes.data, ci.ctypes.data, v.ctypes.data, 4, M, len(ci), 16, 8, 3, 2, 0,
+                                         img.ctypes.data, n), "image")
+    f = out["image_bytes"].split()
+    assert int(f[0]) == n > 0 and int(f[2]) == 0 and int(f[4]) == int(img.astype(np.uint64).sum())
+    assert out["wrong_size"].split() == ["rc", "-1", "error_set", "1"]
