@@ -215,3 +215,42 @@ def test_three_term_split_error_model():
     assert np.abs(z - exact).max() / np.abs(exact).max() < 2e-6                        # the parity norm: far below 1e-4
     one_pass = x_hi.astype(f8) @ w_hi.astype(f8)                                        # plain TF32 would NOT do:
     assert np.abs(one_pass - exact).max() / np.abs(exact).max() > 1e-4
+
+
+def test_host_builders_are_reentrant(graph_l4):
+    """include/gcnb200.h promises re-entrancy (no global mutable state besides the thread-local error string): eight
+    threads build operator and tap images concurrently (ctypes releases the GIL) and get the single-threaded bytes;
+    an error in one thread does not leak into another thread's error string."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from gcn_fmri_decoding_b200 import _lib, graphs
+
+    lib = _lib.lib()
+    jobs = []
+    for level, (Fin, Fout, K, p) in enumerate([(15, 32, 5, 4), (32, 32, 5, 2), (32, 32, 3, 4)]):
+        Lr = graphs.rescale_L(graph_l4["L"][level], lmax=2)
+        rp, ci, v = graphs.csr_arrays(Lr)
+        jobs.append((rp, ci, v, (64, Lr.shape[0], len(v), Fin, Fout, K, p, 0)))
+
+    def build(job):
+        rp, ci, v, args = job
+        n = lib.gcnb_cheb_image_bytes(rp.ctypes.data, ci.ctypes.data, *args)
+        img = np.zeros(n, np.uint8)
+        assert lib.gcnb_cheb_image_build(rp.ctypes.data, ci.ctypes.data, v.ctypes.data, *args, img.ctypes.data, n) == 0
+        W = np.random.RandomState(args[1]).randn(args[3] * args[5], args[4]).astype(np.float32)
+        t = np.zeros(lib.gcnb_cheb_tap_image_bytes(args[3], args[4], args[5]), np.uint8)
+        assert lib.gcnb_cheb_tap_image_build(W.ctypes.data, args[3], args[4], args[5], t.ctypes.data, t.size) == 0
+        return img.tobytes(), t.tobytes()
+
+    def fail(_):
+        rc = lib.gcnb_cheb_tap_image_build(None, 32, 32, 5, None, 0)
+        return rc, _lib.last_error()
+
+    want = [build(j) for j in jobs]
+    with ThreadPoolExecutor(8) as ex:
+        futs = [ex.submit(build, jobs[i % 3]) for i in range(48)]
+        bad = [ex.submit(fail, i) for i in range(8)]
+        got = [f.result() for f in futs]
+        errs = [f.result() for f in bad]
+    assert all(g == want[i % 3] for i, g in enumerate(got))
+    assert all(rc != 0 and "tap_image" in msg for rc, msg in errs)
