@@ -400,3 +400,27 @@ def test_c_abi_from_plain_c(tmp_path):
     f = out["image_bytes"].split()
     assert int(f[0]) == n > 0 and int(f[2]) == 0 and int(f[4]) == int(img.astype(np.uint64).sum())
     assert out["wrong_size"].split() == ["rc", "-1", "error_set", "1"]
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under gcn_fmri_decoding_b200/ may import it (only tests/,
+    __graft_entry__.smoke() and bench.py's CPU legs do), and the package has no CPU compute fallback to route through."""
+    import ast
+    import glob
+
+    pkg = os.path.join(ROOT, "gcn_fmri_decoding_b200")
+    for path in glob.glob(os.path.join(pkg, "**", "*.py"), recursive=True):
+        tree = ast.parse(open(path).read())
+        for node in ast.walk(tree):
+            names = []
+            if isinstance(node, ast.Import):
+                names = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom):
+                names = [node.module or ""]
+            assert not any(n == "oracle" or n.startswith("oracle.") for n in names), path
+    # bench.py imports the oracle only inside its CPU-baseline functions
+    tree = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
+    for node in tree.body:
+        if isinstance(node, (ast.Import, ast.ImportFrom)):
+            mod = node.module if isinstance(node, ast.ImportFrom) else ",".join(a.name for a in node.names)
+            assert "oracle" not in (mod or ""), "bench.py must not import the oracle at module level"
