@@ -424,3 +424,40 @@ def test_product_never_imports_the_oracle():
         if isinstance(node, (ast.Import, ast.ImportFrom)):
             mod = node.module if isinstance(node, ast.ImportFrom) else ",".join(a.name for a in node.names)
             assert "oracle" not in (mod or ""), "bench.py must not import the oracle at module level"
+
+
+def test_planner_queries_over_random_shapes():
+    """The host-side planners (dispatch / workspace / basis-width / describe queries) over 400 seeded random layer shapes,
+    including degenerate and oversized ones: they never fail, answer deterministically, and agree with each other --
+    the AUTO workspace is that of one of the two kernel families, sizes are multiples of 256 bytes,
+    the saved-basis width is 0, Fin, or Fin padded to a power of two, and the description names a kernel."""
+    from gcn_fmri_decoding_b200 import _lib
+
+    lib = _lib.lib()
+    rng = np.random.RandomState(77)
+    seen_fused = seen_general = 0
+    for _ in range(400):
+        B = int(rng.choice([1, 2, 7, 16, 64, 128, 512, 600]))
+        M = int(rng.choice([4, 24, 25, 100, 372, 400, 1000, 2048, 4096, 32492]))
+        p = int(rng.choice([1, 2, 4, 8]))
+        Fin, Fout = int(rng.randint(1, 65)), int(rng.randint(1, 65))
+        K = int(rng.randint(1, 31))
+        nnz = int(M * rng.randint(0, 20))
+        shape = (B, M, nnz, Fin, Fout, K, p)
+        fused = [lib.gcnb_cheb_fused_supported(*shape, bwd, dx) for bwd, dx in ((0, 0), (1, 0), (1, 1))]
+        assert all(f in (0, 1) for f in fused)
+        assert fused == [lib.gcnb_cheb_fused_supported(*shape, bwd, dx) for bwd, dx in ((0, 0), (1, 0), (1, 1))]
+        for (bwd, dx), f in zip(((0, 0), (1, 0), (1, 1)), fused):
+            auto = lib.gcnb_cheb_workspace_bytes(*shape, bwd, dx, _lib.ALGO_AUTO)
+            general = lib.gcnb_cheb_workspace_bytes(*shape, bwd, dx, _lib.ALGO_GENERAL)
+            fused_ws = lib.gcnb_cheb_workspace_bytes(*shape, bwd, dx, _lib.ALGO_FUSED)
+            assert 0 <= auto < 2 ** 48 and 0 <= general < 2 ** 48 and 0 <= fused_ws < 2 ** 48
+            assert auto in (fused_ws, general), (shape, bwd, dx, auto, fused_ws, general)
+            assert auto % 256 == 0 and general % 256 == 0
+        width = lib.gcnb_cheb_stack_width(*shape)
+        assert width == 0 or (width >= Fin and width in (Fin, 8, 16, 32, 64)), (shape, width)
+        text = _lib.describe_fwd(*shape)
+        assert text and ("k_" in text or "general" in text.lower() or "unsupported" in text.lower()), text
+        seen_fused += fused[0]
+        seen_general += 1 - fused[0]
+    assert seen_fused > 20 and seen_general > 20
