@@ -461,3 +461,41 @@ def test_planner_queries_over_random_shapes():
         seen_fused += fused[0]
         seen_general += 1 - fused[0]
     assert seen_fused > 20 and seen_general > 20
+
+
+def test_predict_pads_the_last_batch_and_returns_what_the_reference_returns(graph_l4, monkeypatch):
+    """cgcnn.predict (models_gcn.py:31-71) with the network stubbed: zero-padded last batch, predictions cropped to the
+    data set, loss = sum of batch losses * batch_size / size, and the three return forms."""
+    import torch
+
+    from gcn_fmri_decoding_b200.models import cgcnn
+
+    m = cgcnn(L=graph_l4["L"], F=[32, 32], K=[5, 5], p=[4, 4], M=[512, 256, 22], channel=15, device="cpu", batch_size=8)
+    batches = []
+
+    def fake_forward(x, dropout=1.0, gather=None):
+        batches.append(x.clone())
+        lg = torch.zeros(x.shape[0], 22)
+        lg[torch.arange(x.shape[0]), (x[:, 0, 0].long() % 22)] = 5.0     # class = first value of the window
+        return lg
+
+    monkeypatch.setattr(m, "forward", fake_forward)
+    data = np.zeros((19, 360, 15), np.float32)
+    data[:, 0, 0] = np.arange(19) + 1
+    labels = (np.arange(19) + 1) % 22
+    preds = m.predict(data)
+    assert isinstance(preds, np.ndarray) and preds.shape == (19,) and np.array_equal(preds, labels)
+    assert [tuple(b.shape) for b in batches] == [(8, 360, 15)] * 3 and float(batches[2][3:].abs().sum()) == 0.0   # padding
+    preds, loss = m.predict(data, labels)
+    per_batch = []
+    for b in range(3):
+        lab = np.zeros(8, np.int64)
+        chunk = labels[8 * b:8 * b + 8]
+        lab[:len(chunk)] = chunk
+        per_batch.append(float(m.loss(fake_forward(torch.as_tensor(np.pad(data[8 * b:8 * b + 8], ((0, 8 - len(chunk)), (0, 0), (0, 0))))),
+                                     torch.as_tensor(lab))))
+    assert abs(loss - sum(per_batch) * 8 / 19) < 1e-6
+    preds2, loss2, logits = m.predict(data, labels, return_logits=True)
+    assert np.array_equal(preds2, preds) and loss2 == loss and logits.shape == (19, 22) and np.array_equal(logits.argmax(1), labels)
+    preds3, logits3 = m.predict(data, return_logits=True)
+    assert np.array_equal(preds3, preds) and np.array_equal(logits3, logits)
