@@ -25,7 +25,8 @@ def _checkpoint_of_run(ckp_path):
     d = os.path.join(str(ckp_path), "model")
     state = os.path.join(d, "checkpoint")
     if os.path.exists(state):
-        lines = [line.rstrip("\n") for line in open(state) if line.strip()]
+        with open(state) as f:
+            lines = [line.rstrip("\n") for line in f if line.strip()]
         line = lines[1] if len(lines) > 1 else lines[0]
         return os.path.join(d, line.replace('"', "").split(" ")[-1].split("/")[-1])
     best = checkpoints.BestCheckpoints(d).best() if os.path.exists(os.path.join(d, checkpoints.INDEX_NAME)) else None
