@@ -35,3 +35,36 @@ def load():
         warnings.simplefilter("ignore")
         from lib_new import coarsening, graph  # type: ignore
     return graph, coarsening
+
+
+def load_model_builders():
+    """The reference's configuration functions of ``model.py`` (``gccn_model_common_param :148-179``,
+    ``build_fourier_graph_cnn :182-225``, ``build_chebyshev_graph_cnn :248-285``) executed as they are: the module cannot be
+    imported (TensorFlow, keras, nilearn at the top), so the three function definitions are cut out of its AST and
+    compiled in a namespace that holds what they read from their module -- NumPy, the globals of ``configure_fmri.py``
+    (``atlas_name``, ``TR_step``) and a stand-in for ``models.cgcnn`` that records its arguments.  Returns the namespace."""
+    import ast
+    import types
+
+    import numpy as np
+
+    if not available():
+        raise RuntimeError("reference sources not present at " + REFERENCE_ROOT)
+    src = open(os.path.join(REFERENCE_ROOT, "model.py")).read()
+    wanted = {"gccn_model_common_param", "build_fourier_graph_cnn", "build_chebyshev_graph_cnn"}
+    tree = ast.parse(src)
+    tree.body = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in wanted]
+    assert {n.name for n in tree.body} == wanted
+    cfg = {}
+    exec(compile(open(os.path.join(REFERENCE_ROOT, "configure_fmri.py")).read(), "configure_fmri.py", "exec"), cfg)
+
+    class RecordedModel:
+        def __init__(self, config, L, **params):
+            self.config, self.L, self.params = config, L, params
+
+    ns = {"np": np, "atlas_name": cfg["atlas_name"], "TR_step": cfg["TR_step"], "config_TF": None,
+          "models": types.SimpleNamespace(cgcnn=RecordedModel)}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        exec(compile(tree, "model.py", "exec"), ns)
+    return ns
