@@ -68,3 +68,35 @@ def load_model_builders():
         warnings.simplefilter("ignore")
         exec(compile(tree, "model.py", "exec"), ns)
     return ns
+
+
+def load_cgcnn_constructor():
+    """``cgcnn.__init__`` of the reference (models_gcn.py:445-510) as a plain function ``init(obj, config, L, F, K, p, M,
+    **kw)``: cut out of the class by AST (the module imports TensorFlow) and run on an object whose ``build_graph`` does
+    nothing and whose layer methods exist as attributes -- what remains is the reference's argument checks and its
+    Laplacian selection, executed from its own source."""
+    import ast
+
+    import numpy as np
+
+    if not available():
+        raise RuntimeError("reference sources not present at " + REFERENCE_ROOT)
+    tree = ast.parse(open(os.path.join(REFERENCE_ROOT, "lib_new", "models_gcn.py")).read())
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "cgcnn")
+    fn = next(n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name == "__init__")
+    # `super().__init__(config)` needs the class cell: drop that one statement (base_model.__init__ only stores config)
+    fn.body = [s for s in fn.body if not (isinstance(s, ast.Expr) and isinstance(s.value, ast.Call)
+                                          and "super" in ast.dump(s.value.func))]
+    fn.name = "reference_cgcnn_init"
+    mod = ast.Module(body=[fn], type_ignores=[])
+    ast.fix_missing_locations(mod)
+    ns = {"np": np}
+    exec(compile(mod, "models_gcn.py", "exec"), ns)
+
+    class Shell:
+        def build_graph(self, *a, **k):
+            self.built = a
+
+        chebyshev5 = chebyshev2 = fourier = spline = b1relu = b2relu = mpool1 = apool1 = staticmethod(lambda *a: None)
+
+    return ns["reference_cgcnn_init"], Shell

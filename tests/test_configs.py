@@ -78,3 +78,37 @@ def test_golden_configurations_are_what_the_live_reference_returns():
                 _, name, got = ns[fn](dict(commons[case["common"]]), Laplacian_list=L, **case["kwargs"])
                 assert name == case["name"]
             assert {k: _plain(v) for k, v in got.items()} == case["params"]
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference is not present (GPU box)")
+def test_constructor_checks_and_laplacian_selection_against_the_reference_source(graph_l4):
+    """cgcnn.__init__ (models_gcn.py:445-510) run from the reference's own source (TensorFlow parts cut away): the layers get
+    the same Laplacians, the stored attributes agree, and what the reference asserts on, the replacement refuses."""
+    from gcn_fmri_decoding_b200 import synth
+    from gcn_fmri_decoding_b200.models import cgcnn
+
+    init, Shell = ref_loader.load_cgcnn_constructor()
+    _, _, _, L6 = synth.brain_graph(6)
+    for L, p in ((graph_l4["L"], [4, 4]), (graph_l4["L"], [1] * 6), (L6, [1, 4, 1, 4, 1, 4]), (graph_l4["L"], [2, 2, 2]),
+                 (graph_l4["L"], [8]), (graph_l4["L"], [2, 1, 4]), (graph_l4["L"], [1, 16])):
+        n = len(p)
+        kw = dict(F=[8] * n, K=[3] * n, p=p, M=[16, 5], filter="chebyshev5", brelu="b2relu", pool="mpool1", channel=15,
+                  regularization=5e-4, dropout=0.5, batch_size=32, eval_frequency=7, dir_name="x")
+        ref = Shell()
+        with contextlib.redirect_stdout(io.StringIO()):
+            init(ref, None, L, **kw)
+        ours = cgcnn(None, L, device="cpu", **kw)
+        assert [l.shape for l in ours.L] == [l.shape for l in ref.L]
+        assert all((a != b).nnz == 0 for a, b in zip(ours.L, ref.L))
+        assert ref.built == ((L[0].shape[0], 15),)                                # placeholder shape (M_0, channel)
+        for attr in ("F", "K", "p", "M", "num_epochs", "learning_rate", "decay_rate", "decay_steps", "momentum",
+                     "regularization", "dropout", "batch_size", "eval_frequency", "dir_name", "initial"):
+            assert getattr(ours, attr) == getattr(ref, attr), attr
+    bad = [dict(p=[3], F=[8], K=[3]),                      # not a power of two
+           dict(p=[0], F=[8], K=[3]),                      # p >= 1
+           dict(p=[8, 8], F=[8, 8], K=[3, 3])]             # needs 6 coarsening levels, 5 given
+    for kw in bad:
+        with pytest.raises(AssertionError), contextlib.redirect_stdout(io.StringIO()):
+            init(Shell(), None, graph_l4["L"], M=[5], **kw)
+        with pytest.raises(ValueError):
+            cgcnn(None, graph_l4["L"], M=[5], device="cpu", **kw)
