@@ -100,3 +100,22 @@ def load_cgcnn_constructor():
         chebyshev5 = chebyshev2 = fourier = spline = b1relu = b2relu = mpool1 = apool1 = staticmethod(lambda *a: None)
 
     return ns["reference_cgcnn_init"], Shell
+
+
+def load_checkmat():
+    """``BestCheckpointSaver`` and ``get_best_checkpoint`` of the reference's ``lib_new/checkmat.py`` (the module imports
+    TensorFlow for its default saver only): the definitions are compiled from the reference source with ``tf`` left
+    undefined -- callers pass their own ``saver``.  Returns the namespace."""
+    import ast
+    import glob
+    import json
+
+    import numpy as np
+
+    if not available():
+        raise RuntimeError("reference sources not present at " + REFERENCE_ROOT)
+    tree = ast.parse(open(os.path.join(REFERENCE_ROOT, "lib_new", "checkmat.py")).read())
+    tree.body = [n for n in tree.body if isinstance(n, (ast.ClassDef, ast.FunctionDef))]
+    ns = {"os": os, "glob": glob, "json": json, "np": np}
+    exec(compile(tree, "checkmat.py", "exec"), ns)
+    return ns

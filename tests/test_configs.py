@@ -112,3 +112,48 @@ def test_constructor_checks_and_laplacian_selection_against_the_reference_source
             init(Shell(), None, graph_l4["L"], M=[5], **kw)
         with pytest.raises(ValueError):
             cgcnn(None, graph_l4["L"], M=[5], device="cpu", **kw)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference is not present (GPU box)")
+@pytest.mark.parametrize("maximize", [True, False])
+def test_best_checkpoint_bookkeeping_against_the_reference_source(graph_l4, tmp_path, maximize):
+    """checkpoints.BestCheckpoints against the reference's BestCheckpointSaver (checkmat.py:8-115, compiled from its source
+    with a file-touching stand-in for tf.train.Saver) on random value sequences with ties: after every step both keep the
+    same steps with the same values, and both name the same best checkpoint."""
+    from gcn_fmri_decoding_b200 import checkpoints
+    from gcn_fmri_decoding_b200.models import cgcnn
+
+    ns = ref_loader.load_checkmat()
+
+    class Saver:
+        def save(self, sess, path, step):
+            for ext in (".index", ".data-00000-of-00001", ".meta"):
+                open("%s-%d%s" % (path, step, ext), "w").close()
+            open(os.path.join(os.path.dirname(path), "checkpoint"), "w").close()
+
+        def set_last_checkpoints_with_time(self, files):
+            pass
+
+    class Sess:
+        def run(self, x):
+            return x
+
+    model = cgcnn(L=graph_l4["L"][4:], F=[4], K=[2], p=[1], M=[3], channel=2, device="cpu")
+    rng = np.random.RandomState(5 + maximize)
+    for trial in range(6):
+        rdir, odir = str(tmp_path / ("ref%d" % trial)), str(tmp_path / ("ours%d" % trial))
+        ref = ns["BestCheckpointSaver"](save_dir=rdir, num_to_keep=3, maximize=maximize, saver=Saver())
+        ours = checkpoints.BestCheckpoints(odir, num_to_keep=3, maximize=maximize)
+        values = rng.randint(0, 8, 14) / 8.0                     # few distinct values: ties happen
+        for step, v in enumerate(values, start=1):
+            ref.handle(v, Sess(), step * 10)
+            ours.handle(v, model, step * 10)
+            want = json.load(open(os.path.join(rdir, "best_checkpoints")))
+            got = json.load(open(os.path.join(odir, "best_checkpoints")))
+            assert {k + ".npz": x for k, x in want.items()} == got, (trial, step)
+            kept_ref = sorted(f[:-len(".index")] for f in os.listdir(rdir) if f.endswith(".index"))
+            kept_ours = sorted(f[:-len(".npz")] for f in os.listdir(odir) if f.endswith(".npz"))
+            assert kept_ref == kept_ours == sorted(want)
+        best_ref = ns["get_best_checkpoint"](rdir, select_maximum_value=maximize)
+        if best_ref is not None:                                 # (the reference's function returns a path)
+            assert os.path.basename(ours.best()) == os.path.basename(best_ref) + ".npz"
