@@ -119,3 +119,25 @@ def load_checkmat():
     ns = {"os": os, "glob": glob, "json": json, "np": np}
     exec(compile(tree, "checkmat.py", "exec"), ns)
     return ns
+
+
+def load_base_model_method(name):
+    """One method of the reference's ``base_model`` (models_gcn.py:19-355) as a plain function taking ``self`` first,
+    compiled from the reference source (the module itself imports TensorFlow).  Only methods whose body is host logic
+    around ``sess.run`` make sense here (``predict``); the caller supplies an object with the attributes they touch."""
+    import ast
+    import time
+
+    import numpy as np
+    import sklearn.metrics
+
+    if not available():
+        raise RuntimeError("reference sources not present at " + REFERENCE_ROOT)
+    tree = ast.parse(open(os.path.join(REFERENCE_ROOT, "lib_new", "models_gcn.py")).read())
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "base_model")
+    fn = next(n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name == name)
+    mod = ast.Module(body=[fn], type_ignores=[])
+    ns = {"np": np, "time": time, "sklearn": __import__("sklearn"), "os": os}
+    ns["sklearn"].metrics = sklearn.metrics
+    exec(compile(mod, "models_gcn.py", "exec"), ns)
+    return ns[name]

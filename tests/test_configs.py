@@ -157,3 +157,58 @@ def test_best_checkpoint_bookkeeping_against_the_reference_source(graph_l4, tmp_
         best_ref = ns["get_best_checkpoint"](rdir, select_maximum_value=maximize)
         if best_ref is not None:                                 # (the reference's function returns a path)
             assert os.path.basename(ours.best()) == os.path.basename(best_ref) + ".npz"
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference is not present (GPU box)")
+def test_predict_batching_against_the_reference_source(graph_l4, monkeypatch):
+    """cgcnn.predict against base_model.predict (models_gcn.py:31-71) compiled from the reference source and run on a
+    stand-in session that evaluates the SAME stub network: zero-padded last batch, labels padded with zeros, the loss
+    summed over batches and scaled by batch_size / size, a NaN batch loss counted as zero."""
+    import torch
+
+    from gcn_fmri_decoding_b200.models import cgcnn
+
+    ref_predict = ref_loader.load_base_model_method("predict")
+    m = cgcnn(L=graph_l4["L"], F=[32, 32], K=[5, 5], p=[4, 4], M=[512, 256, 22], channel=15, device="cpu", batch_size=8,
+              regularization=0)
+    rng = np.random.RandomState(3)
+    proj = torch.tensor(rng.randn(15, 22).astype(np.float32))
+    poison = {"batch": -1, "calls": 0}
+
+    def net(x):                                             # stub network: logits from the first vertex's window
+        lg = x[:, 0, :] @ proj
+        poison["calls"] += 1
+        if poison["calls"] - 1 == poison["batch"]:
+            lg = lg * float("nan")
+        return lg
+
+    monkeypatch.setattr(m, "forward", lambda x, dropout=1.0, gather=None: net(x))
+
+    class Sess:
+        def run(self, fetches, feed):
+            x = torch.tensor(np.asarray(feed["data"], np.float32))
+            lg = net(x)
+            pred = lg.argmax(1).numpy()
+            if isinstance(fetches, list):
+                lab = torch.tensor(np.asarray(feed["labels"]).astype(np.int64))
+                return pred, float(m.loss(lg, lab))
+            return pred
+
+    class Ref:
+        batch_size, ph_data, ph_labels, ph_dropout, op_prediction, op_loss = 8, "data", "labels", "dropout", "p", "l"
+
+        def _get_session(self, sess):
+            return Sess()
+
+    data = rng.randn(21, 360, 15).astype(np.float32)
+    labels = rng.randint(0, 22, 21)
+    for bad_batch in (-1, 1):                               # without / with a NaN loss in the second batch
+        poison.update(batch=bad_batch, calls=0)
+        want_pred, want_loss = ref_predict(Ref(), data, labels)
+        poison.update(calls=0)
+        got_pred, got_loss = m.predict(data, labels)
+        if bad_batch < 0:
+            assert np.array_equal(got_pred, want_pred)
+        assert abs(got_loss - want_loss) <= 1e-6 * abs(want_loss)
+    poison.update(batch=-1, calls=0)
+    assert np.array_equal(m.predict(data), ref_predict(Ref(), data))
