@@ -121,10 +121,11 @@ def load_checkmat():
     return ns
 
 
-def load_base_model_method(name):
+def load_base_model_method(name, extra=None):
     """One method of the reference's ``base_model`` (models_gcn.py:19-355) as a plain function taking ``self`` first,
     compiled from the reference source (the module itself imports TensorFlow).  Only methods whose body is host logic
-    around ``sess.run`` make sense here (``predict``); the caller supplies an object with the attributes they touch."""
+    around ``sess.run`` make sense here (``predict``, ``evaluate``, ``fit``); the caller supplies an object with the
+    attributes they touch and, through ``extra``, the module-level names the method reads (``checkmate`` for ``fit``)."""
     import ast
     import time
 
@@ -137,7 +138,12 @@ def load_base_model_method(name):
     cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "base_model")
     fn = next(n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name == name)
     mod = ast.Module(body=[fn], type_ignores=[])
-    ns = {"np": np, "time": time, "sklearn": __import__("sklearn"), "os": os}
+    import collections
+    import shutil
+
+    ns = {"np": np, "time": time, "sklearn": __import__("sklearn"), "os": os, "sys": sys, "shutil": shutil,
+          "collections": collections}
     ns["sklearn"].metrics = sklearn.metrics
+    ns.update(extra or {})
     exec(compile(mod, "models_gcn.py", "exec"), ns)
     return ns[name]

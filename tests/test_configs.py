@@ -212,3 +212,114 @@ def test_predict_batching_against_the_reference_source(graph_l4, monkeypatch):
         assert abs(got_loss - want_loss) <= 1e-6 * abs(want_loss)
     poison.update(batch=-1, calls=0)
     assert np.array_equal(m.predict(data), ref_predict(Ref(), data))
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference is not present (GPU box)")
+def test_fit_and_evaluate_host_logic_against_the_reference_source(graph_l4, tmp_path, monkeypatch):
+    """cgcnn.fit / evaluate against base_model.fit / evaluate (models_gcn.py:72-184) compiled from the reference source and
+    run on stand-ins for the TensorFlow session and saver: with the same NumPy seed both draw the SAME batches in the
+    same order, evaluate at the same steps, keep the same best checkpoints and return the same (accuracies, losses);
+    evaluate returns the same summary string and figures."""
+    import torch
+
+    from gcn_fmri_decoding_b200.models import cgcnn
+
+    ck = ref_loader.load_checkmat()
+    import types
+
+    ref_fit = ref_loader.load_base_model_method("fit", extra={"checkmate": types.SimpleNamespace(**ck)})
+    ref_evaluate = ref_loader.load_base_model_method("evaluate")
+    n, bs = 37, 8
+    data = np.zeros((n, 360, 15), np.float32)
+    data[:, 0, 0] = np.arange(n)                                   # window id, so that batches can be compared
+    labels = np.arange(n) % 5
+    val_scores = [52.0, 61.0, 58.0, 61.0, 70.0, 40.0, 66.0, 63.0, 59.0, 71.0, 30.0, 64.0]
+
+    # ---- the reference, on stand-ins
+    class Saver:
+        def save(self, sess, path, step):
+            step = sess.run(step) if isinstance(step, str) else step      # tf.train.Saver evaluates the step tensor
+            open("%s-%d.index" % (path, step), "w").close()
+            open(os.path.join(os.path.dirname(path), "checkpoint"), "w").close()
+
+        def set_last_checkpoints_with_time(self, files):
+            pass
+
+    class Sess:
+        def __init__(self):
+            self.batches, self.step = [], 0
+
+        def run(self, fetches, feed=None):
+            if fetches == "init":
+                return None
+            if fetches == "global_step":
+                return self.step
+            ids = feed["data"][:, 0, 0].astype(int).tolist()
+            assert feed["dropout"] == 0.5 and feed["labels"].tolist() == [i % 5 for i in ids]
+            self.batches.append(ids)
+            self.step += 1
+            return 0.001, 1.0 / self.step
+
+    class Ref:
+        num_epochs, batch_size, eval_frequency, dropout = 3, bs, 2, 0.5
+        ph_data, ph_labels, ph_dropout, op_train, op_loss_average, op_init = "data", "labels", "dropout", "t", "l", "init"
+        global_step, op_saver, config, graph = "global_step", Saver(), None, None
+
+        def __init__(self):
+            self.sess = Sess()
+            self.scores = iter(val_scores)
+
+        def _get_session(self, sess):
+            return sess
+
+        def _get_path(self, folder):
+            return str(tmp_path / "ref" / folder)
+
+        def evaluate(self, d, l, sess=None, isTrain=False):
+            return "accuracy: stub", next(self.scores), 0.0, 0.5
+
+    ref = Ref()
+    np.random.seed(11)
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref_acc, ref_losses, _ = ref_fit(ref, data, labels, data[:4], labels[:4])
+
+    # ---- ours, with the step and the evaluation stubbed the same way
+    m = cgcnn(L=graph_l4["L"], F=[32, 32], K=[5, 5], p=[4, 4], M=[512, 256, 22], channel=15, device="cpu",
+              batch_size=bs, num_epochs=3, eval_frequency=2, dropout=0.5)
+    seen, scores = [], iter(val_scores)
+
+    class StubTrainer:
+        def step(self, x, y, dropout=None):
+            seen.append(x[:, 0, 0].long().tolist())
+            return torch.tensor(1.0 / len(seen)), None
+
+    monkeypatch.setattr(m, "evaluate", lambda d, l, **kw: ("accuracy: stub", next(scores), 0.0, 0.5))
+    np.random.seed(11)
+    with contextlib.redirect_stdout(io.StringIO()):
+        acc, losses, _ = m.fit(data, labels, data[:4], labels[:4], best_checkpoint_dir=str(tmp_path / "ours"),
+                               trainer=StubTrainer())
+    assert seen == ref.sess.batches and len(seen) == int(3 * n / bs)      # the same windows in the same order
+    assert acc == ref_acc and losses == ref_losses
+    want = json.load(open(tmp_path / "ref" / "checkpoints" / "model" / "best_checkpoints"))
+    got = json.load(open(tmp_path / "ours" / "best_checkpoints"))
+    assert {k + ".npz": v for k, v in want.items()} == got
+
+    # ---- evaluate: summary string and figures
+    rng = np.random.RandomState(2)
+    y = rng.randint(0, 5, 60)
+    pred = np.where(rng.rand(60) < 0.7, y, rng.randint(0, 5, 60)).astype(np.float64)
+
+    class RefEval:
+        sess = object()
+
+        def _get_session(self, sess):
+            return sess
+
+        def predict(self, d, l, sess):
+            return pred, 0.4321
+
+    want = ref_evaluate(RefEval(), None, y, isTrain=True)
+    monkeypatch.undo()
+    monkeypatch.setattr(m, "predict", lambda d, l=None, **kw: (pred, 0.4321))
+    got = m.evaluate(None, y)
+    assert got[0] == want[0] and got[1:] == pytest.approx(want[1:], rel=1e-12)
