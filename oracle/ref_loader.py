@@ -147,3 +147,33 @@ def load_base_model_method(name, extra=None):
     ns.update(extra or {})
     exec(compile(mod, "models_gcn.py", "exec"), ns)
     return ns[name]
+
+
+def load_cgcnn_on_shim(variables, dtype=None):
+    """The reference's ``base_model`` and ``cgcnn`` classes (models_gcn.py:17-682) compiled from their source with ``tf``
+    bound to the NumPy stand-in of ``oracle/tf_shim.py`` and ``graph`` to the reference's own ``lib_new/graph.py``.
+    ``build_graph`` is replaced by a no-op (it creates placeholders, the optimiser and the saver), everything else --
+    ``__init__``, the layer methods, ``_inference``, ``loss``, the variable helpers -- is the reference's code.  Returns
+    ``(cgcnn class, shim)``; ``variables`` maps TF variable names (``conv1/weights`` ...) to arrays."""
+    import ast
+    import collections
+    import shutil
+    import time
+
+    import numpy as np
+    import scipy.sparse
+    import sklearn
+
+    from oracle import tf_shim
+
+    graph, _ = load()
+    shim = tf_shim.Shim(variables, dtype or np.float32)
+    tree = ast.parse(open(os.path.join(REFERENCE_ROOT, "lib_new", "models_gcn.py")).read())
+    tree.body = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name in ("base_model", "cgcnn")]
+    ns = {"tf": shim, "graph": graph, "np": np, "scipy": scipy, "sklearn": sklearn, "os": os, "sys": sys, "time": time,
+          "collections": collections, "shutil": shutil}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        exec(compile(tree, "models_gcn.py", "exec"), ns)
+    ns["cgcnn"].build_graph = lambda self, *a, **k: None
+    return ns["cgcnn"], shim
