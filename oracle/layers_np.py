@@ -14,6 +14,15 @@ wheel), so:
     PARITY UNPINNED at the TF boundary -- no reference test or golden vector
     pins the TF-executed results.
 
+What narrows that gap: the reference's own layer code (``cgcnn.__init__``,
+``chebyshev5/2``, ``fourier``, ``b1relu/b2relu``, ``mpool1``, ``fc``,
+``_inference``, ``loss``) is compiled from ``models_gcn.py`` with ``tf`` bound to
+a NumPy stand-in for the ~25 ops it calls (``oracle/tf_shim.py``) and compared
+with this module bit for bit (``tests/test_reference_on_shim.py``, build
+container only) -- so the TRANSCRIPTION (op order, transposes, reshapes, weight
+row order, variable names, L2 list) is pinned to the reference source; only
+TensorFlow's implementation of those ops is not.
+
 What *is* pinned: (i) the Chebyshev recursion against the reference's own
 NumPy implementation ``graph.chebyshev`` (``graph.py:155-172``, literally the
 body of ``chebyshev2``) executed in the build container, (ii) ``rescale_L`` /
