@@ -20,8 +20,9 @@ What narrows that gap: the reference's own layer code (``cgcnn.__init__``,
 a NumPy stand-in for the ~25 ops it calls (``oracle/tf_shim.py``) and compared
 with this module bit for bit (``tests/test_reference_on_shim.py``, build
 container only) -- so the TRANSCRIPTION (op order, transposes, reshapes, weight
-row order, variable names, L2 list) is pinned to the reference source; only
-TensorFlow's implementation of those ops is not.
+row order, variable names, L2 list) is pinned to the reference source, and the
+backward functions below agree with torch.autograd run over that same source
+(torch-backed stand-in); only TensorFlow's implementation of those ops is not.
 
 What *is* pinned: (i) the Chebyshev recursion against the reference's own
 NumPy implementation ``graph.chebyshev`` (``graph.py:155-172``, literally the

@@ -149,12 +149,14 @@ def load_base_model_method(name, extra=None):
     return ns[name]
 
 
-def load_cgcnn_on_shim(variables, dtype=None):
+def load_cgcnn_on_shim(variables, dtype=None, torch_autograd=False, dropout_masks=None):
     """The reference's ``base_model`` and ``cgcnn`` classes (models_gcn.py:17-682) compiled from their source with ``tf``
     bound to the NumPy stand-in of ``oracle/tf_shim.py`` and ``graph`` to the reference's own ``lib_new/graph.py``.
     ``build_graph`` is replaced by a no-op (it creates placeholders, the optimiser and the saver), everything else --
     ``__init__``, the layer methods, ``_inference``, ``loss``, the variable helpers -- is the reference's code.  Returns
-    ``(cgcnn class, shim)``; ``variables`` maps TF variable names (``conv1/weights`` ...) to arrays."""
+    ``(cgcnn class, shim)``; ``variables`` maps TF variable names (``conv1/weights`` ...) to arrays.  With
+    ``torch_autograd`` the stand-in works on torch tensors, so that the graph the reference code builds can be differentiated
+    (``tf_shim.TorchShim``)."""
     import ast
     import collections
     import shutil
@@ -167,7 +169,7 @@ def load_cgcnn_on_shim(variables, dtype=None):
     from oracle import tf_shim
 
     graph, _ = load()
-    shim = tf_shim.Shim(variables, dtype or np.float32)
+    shim = tf_shim.TorchShim(variables, dropout_masks) if torch_autograd else tf_shim.Shim(variables, dtype or np.float32)
     tree = ast.parse(open(os.path.join(REFERENCE_ROOT, "lib_new", "models_gcn.py")).read())
     tree.body = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name in ("base_model", "cgcnn")]
     ns = {"tf": shim, "graph": graph, "np": np, "scipy": scipy, "sklearn": sklearn, "os": os, "sys": sys, "time": time,

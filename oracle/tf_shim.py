@@ -174,3 +174,91 @@ class Shim:
 
     def py_func(self, func, inp, Tout):
         return [_t(func(*[np.asarray(a) for a in inp]))]
+
+
+class TorchShim(Shim):
+    """The same stand-in on torch tensors (CPU, float64): the reference's graph-building code then builds a torch
+    autograd graph, and ``torch.autograd.grad`` plays the part of ``tf.gradients`` (models_gcn.py:298) -- the reference
+    source differentiated by an independent engine, which is what the oracle's hand-written backward is compared with.
+    ``py_func`` (chebyshev2, :578) passes values but no gradient, exactly as in TensorFlow.  ``dropout_masks``: one 0/1
+    array per ``tf.nn.dropout`` call, applied as TF does (kept values scaled by 1 / keep_prob)."""
+
+    def __init__(self, variables, dropout_masks=None):
+        import torch
+
+        self.torch = torch
+        if not hasattr(torch.Tensor, "get_shape"):
+            torch.Tensor.get_shape = lambda t: tuple(int(s) for s in t.shape)   # static shapes (:588)
+        super().__init__({}, np.float64)
+        self.leaves = {k: torch.tensor(np.asarray(v, np.float64), requires_grad=True) for k, v in variables.items()}
+        self.variables = {k: v.detach().numpy() for k, v in self.leaves.items()}
+        masks = list(dropout_masks or [])
+
+        def max_pool(x, ksize, strides, padding):
+            assert padding == "SAME" and list(ksize) == list(strides) and ksize[0] == ksize[2] == ksize[3] == 1
+            p = int(ksize[1])
+            N, M, F, one = x.shape
+            Mo = -(-M // p)
+            pad = Mo * p - M
+            xp = torch.nn.functional.pad(x.permute(0, 2, 3, 1), (pad // 2, pad - pad // 2), value=float("-inf"))
+            return torch.nn.functional.max_pool1d(xp.reshape(N, F * one, Mo * p), p, p).reshape(N, F, one, Mo).permute(0, 3, 1, 2)
+
+        def dropout(x, keep_prob):
+            if not masks:
+                assert float(keep_prob) == 1.0, "keep probability < 1 needs dropout_masks"
+                return x
+            return x * torch.tensor(np.asarray(masks.pop(0), np.float64)) / float(keep_prob)
+
+        self.nn = types.SimpleNamespace(
+            relu=torch.relu, max_pool=max_pool, dropout=dropout,
+            sparse_softmax_cross_entropy_with_logits=lambda logits=None, labels=None: torch.nn.functional.cross_entropy(
+                logits, torch.as_tensor(np.asarray(labels), dtype=torch.long), reduction="none"),
+            l2_loss=lambda v: (v ** 2).sum() / 2)
+
+    def get_variable(self, name, shape, dtype, initializer=None):
+        super().get_variable(name, shape, dtype, initializer)      # bookkeeping and the shape check
+        out = self.leaves["/".join(self.scopes + [name])]
+        out.op = types.SimpleNamespace(name="/".join(self.scopes + [name]))
+        return out
+
+    def constant(self, value, dtype=None):
+        return self.torch.tensor(np.ascontiguousarray(np.asarray(value, np.float64)))
+
+    def to_int64(self, x):
+        return np.asarray(x).astype(np.int64)
+
+    def transpose(self, x, perm=None):
+        return x.permute(*(perm if perm is not None else reversed(range(x.dim()))))
+
+    def reshape(self, x, shape):
+        return x.reshape([int(s) for s in shape])
+
+    def expand_dims(self, x, axis):
+        return x.unsqueeze(axis)
+
+    def concat(self, values, axis):
+        return self.torch.cat(list(values), dim=axis)
+
+    def squeeze(self, x, axis):
+        for a in sorted(axis, reverse=True):
+            x = x.squeeze(a)
+        return x
+
+    def matmul(self, a, b):
+        return self.torch.matmul(a, b)
+
+    def reduce_mean(self, x, axis=None):
+        return x.mean() if axis is None else x.mean(dim=axis)
+
+    def SparseTensor(self, indices, values, dense_shape):
+        indices = np.asarray(indices)
+        return self.torch.sparse_coo_tensor(indices.T.copy(), np.asarray(values, np.float64), tuple(dense_shape)).coalesce()
+
+    def sparse_reorder(self, sp):
+        return sp
+
+    def sparse_tensor_dense_matmul(self, sp, x):
+        return self.torch.sparse.mm(sp, x)
+
+    def py_func(self, func, inp, Tout):
+        return [self.torch.tensor(np.asarray(func(*[a.detach().numpy() for a in inp])))]   # values only: no gradient

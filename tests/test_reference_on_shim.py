@@ -121,3 +121,63 @@ def test_committed_golden_layer_vectors_are_the_reference_sources_output(graph_l
                 assert np.array_equal(y, c[key]), (name, float(np.abs(y - c[key]).max()))
             else:
                 assert np.abs(y - c[key]).max() <= 1e-12 * np.abs(c[key]).max(), name
+
+
+@pytest.mark.parametrize("filt,brelu,F,K,p,Mfc", CASES)
+@pytest.mark.parametrize("keep", [1.0, 0.5])
+def test_oracle_gradients_equal_autograd_of_the_reference_source(graph_l1, graph_l4, filt, brelu, F, K, p, Mfc, keep):
+    """The training step: the reference's graph-building code (inference + loss, models_gcn.py:253-262, :658-682) run on
+    the torch-backed stand-in and differentiated by torch.autograd in place of tf.gradients (:298), against the oracle's
+    hand-written backward (``network_step``, fp64): loss to 1e-12, every gradient to 1e-10, with and without dropout
+    masks.  chebyshev2: TensorFlow's py_func has no gradient, so the reference trains conv1 of a two-layer chebyshev2
+    network with NO gradient at all -- asserted here; the oracle (and this repository) compute the
+    full gradient, and what the reference does compute must agree."""
+    g = graph_l1 if p == [1] * 6 else graph_l4
+    L = [l.astype(np.float64) for l in g["L"]]       # both sides in double precision (graph.fourier's eigh included)
+    rng = np.random.RandomState(23)
+    Ls = O.select_laplacians(L, p)
+    channel, B = 15, 4
+    if len(p) == 6:
+        F, Mfc = [6] * 6, [10, 8, 22]                      # narrower: fp64 autograd through six layers stays quick
+    var = _variables(rng, Ls, filt, brelu, channel, F, K, Mfc)
+    width = -(-Ls[-1].shape[0] // p[-1])
+    for i, m in enumerate(Mfc):
+        scope = "logits" if i == len(Mfc) - 1 else "fc%d" % (i + 1)
+        var[scope + "/weights"] = rng.randn(width, m) * 0.2
+        var[scope + "/bias"] = rng.randn(m) * 0.1 + 0.2
+        width = m
+    x = rng.randn(B, L[0].shape[0], channel)
+    labels = rng.randint(0, Mfc[-1], B)
+    masks = None if keep == 1.0 else [(rng.rand(B, m) < keep).astype(np.float64) for m in Mfc[:-1]]
+
+    cgcnn, tf = ref_loader.load_cgcnn_on_shim(var, torch_autograd=True, dropout_masks=masks)
+    torch = tf.torch
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref = cgcnn("config", L, F, K, p, Mfc, filter=filt, brelu=brelu, pool="mpool1", channel=channel,
+                    regularization=5e-4, dropout=keep, batch_size=B)
+        logits = ref._inference(torch.tensor(x), keep)
+        loss, _ = ref.loss(logits, labels, 5e-4)
+    names = list(var)
+    grads = dict(zip(names, torch.autograd.grad(loss, [tf.leaves[n] for n in names], allow_unused=True)))
+
+    params = [dict(W=var["conv%d/weights" % (i + 1)], b=var["conv%d/bias" % (i + 1)].reshape(
+        (-1, F[i]) if brelu == "b2relu" else (F[i],)), K=K[i], p=p[i]) for i in range(len(p))]
+    fc_names = ["fc%d" % (i + 1) for i in range(len(Mfc) - 1)] + ["logits"]
+    fcs = [(var[s + "/weights"], var[s + "/bias"]) for s in fc_names]
+    val, cg, fg = O.network_step(x, labels, Ls, params, fcs, 5e-4, filter=filt, brelu=brelu, dtype=np.float64,
+                                 dropout_masks=masks, keep=keep)
+    assert abs(val - float(loss)) <= 1e-12 * abs(float(loss))
+
+    def close(a, b):
+        b = b.numpy()
+        return np.abs(np.asarray(a).reshape(b.shape) - b).max() <= 1e-10 * max(np.abs(b).max(), 1e-30)
+
+    for i, s in enumerate(fc_names):
+        assert close(fg[i][0], grads[s + "/weights"]) and close(fg[i][1], grads[s + "/bias"]), s
+    last = len(p) - 1
+    for i in range(len(p)):
+        gw, gb = grads["conv%d/weights" % (i + 1)], grads["conv%d/bias" % (i + 1)]
+        if filt == "chebyshev2" and i < last:
+            assert gw is None and gb is None            # the reference's back-propagation stops at the py_func of layer i+1
+            continue
+        assert close(cg[i]["dW"], gw) and close(cg[i]["db"], gb), i
