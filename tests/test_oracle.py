@@ -282,3 +282,48 @@ def test_mpool1_ragged_against_torch_same_padding(M, p):
         yt = xt * 1
     (gx,) = torch.autograd.grad((yt * torch.tensor(dy)).sum(), xt)
     assert np.array_equal(y, yt.detach().numpy()) and np.array_equal(dx, gx.numpy())
+
+
+def test_oracle_reproduces_the_vectors_of_the_reference_source(graph_l1, graph_l4):
+    """tests/golden/ref_source_steps.npz was produced by the reference's OWN layer and loss source (models_gcn.py) run on
+    the NumPy / torch stand-ins for ``tf`` in the build container (oracle/make_golden_ref_source.py; live version:
+    tests/test_reference_on_shim.py).  The fixture carries that pin to machines without /root/reference: fp32 logits to
+    fp32 rounding, fp64 loss to 1e-12 and every gradient ``tf.gradients`` would return to 1e-10."""
+    import ast
+
+    z = np.load(os.path.join(GOLDEN, "ref_source_steps.npz"))
+    cases = sorted({k.split(".")[0] for k in z.files})
+    assert cases == ["config1", "config2", "config3a"]
+    for name in cases:
+        filt, brelu, fixture, F, K, p, Mfc, keep = z[name + ".meta"]
+        F, K, p, Mfc, keep = (ast.literal_eval(str(v)) for v in (F, K, p, Mfc, keep))
+        L = (graph_l1 if "l1" in str(fixture) else graph_l4)["L"]
+        Ls = O.select_laplacians(L, p)
+        var = {k[len(name) + 5:].replace("__", "/"): z[k] for k in z.files if k.startswith(name + ".var.")}
+        grad = {k[len(name) + 6:].replace("__", "/"): z[k] for k in z.files if k.startswith(name + ".grad.")}
+        params = [dict(W=var["conv%d/weights" % (i + 1)], b=var["conv%d/bias" % (i + 1)].reshape(
+            (-1, F[i]) if brelu == "b2relu" else (F[i],)), K=K[i], p=p[i]) for i in range(len(p))]
+        fc_names = ["fc%d" % (i + 1) for i in range(len(Mfc) - 1)] + ["logits"]
+        fcs = [(var[s + "/weights"], var[s + "/bias"]) for s in fc_names]
+        x, labels = z[name + ".x"], z[name + ".labels"]
+        logits = O.head(O.conv_stack(x, Ls, params, filter=str(filt), brelu=str(brelu), dtype=np.float32), fcs, np.float32)
+        # bit for bit where it was generated (the live test asserts exactly that); another host's BLAS may sum the
+        # fp32 GEMMs in another order, so the travelling check allows fp32 rounding
+        assert rel_inf(logits, z[name + ".logits32"]) <= 2e-6, name
+        masks = [z[name + ".mask%d" % i].astype(np.float64) for i in range(len(Mfc) - 1)] if keep < 1 else None
+        L64 = [l.astype(np.float64) for l in Ls]
+        val, cg, fg = O.network_step(x.astype(np.float64), labels, L64, params, fcs, 5e-4, filter=str(filt), brelu=str(brelu),
+                                     dtype=np.float64, dropout_masks=masks, keep=keep)
+        assert abs(val - float(z[name + ".loss64"])) <= 1e-12 * abs(val), name
+
+        def close(a, b):
+            return np.abs(np.asarray(a).reshape(b.shape) - b).max() <= 1e-10 * np.abs(b).max()
+
+        for i, s in enumerate(fc_names):
+            assert close(fg[i][0], grad[s + "/weights"]) and close(fg[i][1], grad[s + "/bias"]), (name, s)
+        for i in range(len(p)):
+            key = "conv%d/weights" % (i + 1)
+            if key not in grad:                          # chebyshev2: no gradient below a py_func in the reference
+                assert str(filt) == "chebyshev2" and i < len(p) - 1
+                continue
+            assert close(cg[i]["dW"], grad[key]) and close(cg[i]["db"], grad["conv%d/bias" % (i + 1)]), (name, i)
