@@ -64,7 +64,9 @@ class model_perf(object):
                 sub_name=None, model=None):
         """Restore the newest checkpoint under ``<ckp_path>/model/`` into ``model`` and predict ``test_data`` in zero-padded
         batches of ``batch_size`` (models_gcn.py:960-1037).  Prints the per-class report, the confusion matrix and the
-        summary line; returns ``(logits, predictions, loss, accuracy figures)`` as the reference does:
+        summary line; returns ``(logits, predictions, loss, accuracy figures)`` as the reference does (``loss`` is the sum
+        of the batch losses, as there; ``logits`` is the full ``[size, n_classes]`` array -- the reference flattens and
+        crops it to ``size`` values, :1019, which no caller uses):
         ``[accuracy]``, or with ``sub_name`` the per-subject weighted F1 table ``[n_subjects, n_classes + 1]`` (last column:
         all classes; :1039-1057, without the CSV side effect), or with ``flag_starttr`` the accuracy per class and time point
         ``[n_classes, trial_dura]`` (:1066-1075)."""
@@ -79,7 +81,10 @@ class model_perf(object):
             pred_labels, pred_loss, pred_logits = model.predict(test_data, test_labels, return_logits=True)
         finally:
             model.batch_size = keep_bs
+        # model_perf.predict reports the plain SUM of the batch losses (models_gcn.py:1016), not base_model.predict's
+        # sum * batch_size / size (:69)
         test_labels = np.asarray(test_labels)
+        pred_loss = pred_loss * len(test_labels) / int(batch_size)
         if target_name is not None:
             print(checkpoints.classification_report(test_labels, pred_labels, target_name)[0])
             print("Confusion Matrix:")

@@ -179,3 +179,25 @@ def load_cgcnn_on_shim(variables, dtype=None, torch_autograd=False, dropout_mask
         exec(compile(tree, "models_gcn.py", "exec"), ns)
     ns["cgcnn"].build_graph = lambda self, *a, **k: None
     return ns["cgcnn"], shim
+
+
+def load_model_perf(tf_stub):
+    """The reference's ``model_perf`` class (models_gcn.py:936-1200) compiled from its source with ``tf`` bound to
+    ``tf_stub`` (the caller's stand-in for the session / meta-graph calls of ``predict``).  Returns the class."""
+    import ast
+    from pathlib import Path
+
+    import numpy as np
+    import pandas as pd
+    import sklearn
+    import sklearn.metrics
+
+    if not available():
+        raise RuntimeError("reference sources not present at " + REFERENCE_ROOT)
+    tree = ast.parse(open(os.path.join(REFERENCE_ROOT, "lib_new", "models_gcn.py")).read())
+    tree.body = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "model_perf"]
+    ns = {"tf": tf_stub, "np": np, "pd": pd, "sklearn": sklearn, "os": os, "sys": sys, "Path": Path}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        exec(compile(tree, "models_gcn.py", "exec"), ns)
+    return ns["model_perf"]

@@ -316,7 +316,7 @@ def test_model_perf_harness(graph_l4, tmp_path, monkeypatch, capsys):
     lg, pl, loss, acc = perf.predict(run, np.zeros((len(y), 360, 15), np.float32), y, target_name=names, batch_size=64, model=m)
     assert calls["bs"] == 64 and m.batch_size != 64                      # the harness' batch size, then restored
     assert all(np.array_equal(v, m.state_dict_tf()[k]) for k, v in trained.state_dict_tf().items())   # best.ckpt-300
-    assert lg is logits and np.array_equal(pl, pred) and loss == 0.125
+    assert lg is logits and np.array_equal(pl, pred) and loss == 0.125 * len(y) / 64       # the SUM of the batch losses
     assert abs(acc[0] - 100 * sklearn.metrics.accuracy_score(y, pred)) < 1e-9
     out = capsys.readouterr().out
     assert "Confusion Matrix:" in out and "f1 (weighted):" in out and "best.ckpt-300" in out

@@ -323,3 +323,73 @@ def test_fit_and_evaluate_host_logic_against_the_reference_source(graph_l4, tmp_
     monkeypatch.setattr(m, "predict", lambda d, l=None, **kw: (pred, 0.4321))
     got = m.evaluate(None, y)
     assert got[0] == want[0] and got[1:] == pytest.approx(want[1:], rel=1e-12)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference is not present (GPU box)")
+def test_model_perf_predict_against_the_reference_source(graph_l4, tmp_path, monkeypatch):
+    """perf.model_perf.predict against the reference's model_perf.predict (models_gcn.py:960-1088) compiled from its source,
+    its TensorFlow session replaced by a stand-in that evaluates the same stub network: predicted labels, the reported
+    loss (the reference SUMS the batch losses here, unlike base_model.predict), the accuracy figure, the per-subject F1
+    table and the per-time-point accuracy table."""
+    import types
+
+    import torch
+
+    from gcn_fmri_decoding_b200 import tf_bundle
+    from gcn_fmri_decoding_b200.models import cgcnn
+    from gcn_fmri_decoding_b200.perf import model_perf
+
+    rng = np.random.RandomState(8)
+    C, bs, n_sub, per_sub, dura = 6, 16, 5, 34, 17
+    n = n_sub * per_sub
+    proj = torch.tensor(rng.randn(15, C).astype(np.float32))
+    m = cgcnn(L=graph_l4["L"], F=[32, 32], K=[5, 5], p=[4, 4], M=[64, 32, C], channel=15, device="cpu", regularization=0)
+
+    def net(x):
+        return x[:, 0, :] @ proj
+
+    monkeypatch.setattr(m, "forward", lambda x, dropout=1.0, gather=None: net(x))
+
+    class Sess:
+        graph = types.SimpleNamespace(get_operations=lambda: [], get_tensor_by_name=lambda name: name)
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            return False
+
+        def run(self, fetches, feed):
+            lg = net(torch.tensor(np.asarray(feed["inputs/data:0"], np.float32)))
+            lab = torch.tensor(np.asarray(feed["inputs/labels:0"]).astype(np.int64))
+            return lg.numpy(), lg.argmax(1).numpy(), float(m.loss(lg, lab))
+
+    tf_stub = types.SimpleNamespace(
+        reset_default_graph=lambda: None, Session=Sess,
+        train=types.SimpleNamespace(import_meta_graph=lambda path, clear_devices=True: types.SimpleNamespace(
+            restore=lambda sess, path: None)))
+    RefPerf = ref_loader.load_model_perf(tf_stub)
+
+    run = tmp_path / "run"
+    tf_bundle.save_tf_checkpoint(m, str(run / "model" / "best.ckpt"), step=40)
+    (run / "model" / "checkpoint").write_text('model_checkpoint_path: "best.ckpt-40"\nall_model_checkpoint_paths: "best.ckpt-40"\n')
+    (tmp_path / "train_logs").mkdir()
+    monkeypatch.chdir(tmp_path)                      # the reference writes train_logs/<...>.csv relative to the cwd
+    # labels cycle so that every subject and every time point sees every class (sklearn refuses empty groups); the windows
+    # are built so that the stub network predicts the label 70 % of the time
+    labels = (np.arange(n) // dura + np.arange(n) % dura) % C
+    wanted = np.where(rng.rand(n) < 0.7, labels, rng.randint(0, C, n))
+    data = (rng.randn(n, 360, 15) * 0.01).astype(np.float32)
+    data[:, 0, :] += (5 * np.eye(C)[wanted] @ np.linalg.pinv(proj.numpy())).astype(np.float32)
+    assert np.array_equal(net(torch.tensor(data)).argmax(1).numpy(), wanted)
+    names = ["task_%d_x" % i for i in range(C)]
+    subs = ["s%d" % i for i in range(n_sub)]
+    for kw in (dict(), dict(sub_name=subs), dict(trial_dura=dura, flag_starttr=True)):
+        with contextlib.redirect_stdout(io.StringIO()):
+            _, want_lab, want_loss, want_acc = RefPerf().predict(str(run), data, labels, target_name=names, batch_size=bs, **kw)
+            got_lg, got_lab, got_loss, got_acc = model_perf().predict(str(run), data, labels, target_name=names,
+                                                                      batch_size=bs, model=m, **kw)
+        assert np.array_equal(got_lab, want_lab)
+        assert abs(got_loss - want_loss) <= 1e-6 * abs(want_loss)
+        assert np.allclose(np.asarray(got_acc, np.float64), np.asarray(want_acc, np.float64), rtol=0, atol=1e-9), kw
+        assert got_lg.shape == (n, C) and np.array_equal(got_lg.argmax(1), want_lab)
